@@ -1,0 +1,160 @@
+// Bandwidth-bound helpers around the GEMMs: heading fusion and operand preparation.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace gg {
+
+// Heading fusion, models/super_guessr.py:347 (`layer_input.mean(dim=1)`, (N,4,C) -> (N,C)) and
+// proto_refiner.py:150-151, fused with the bf16 cast that feeds the tensor-core operands.
+// emb (B,V,D) fp32 -> x (B, ld) bf16.  split = 0: x[:, :D] = bf16(mean).  split = 1 ("bf16x3",
+// fp32-faithful): x = [hi | hi | lo] with hi = bf16(mean), lo = bf16(mean - hi), ld = 3D, to be
+// contracted against W' = [hi | lo | hi] so that x.W ~= hi.hi + hi.lo + lo.hi.
+// Optionally also writes ||hi||^2 per row (prototype retrieval needs the query norms).
+template <int SPLIT>
+__global__ void fuse_headings_kernel(const float* __restrict__ emb, bf16* __restrict__ x, int B, int V, int D, int ld,
+                                     float* __restrict__ sqnorm) {
+  const int row = blockIdx.x;
+  const float inv = 1.0f / static_cast<float>(V);
+  const float4* src = reinterpret_cast<const float4*>(emb + static_cast<size_t>(row) * V * D);
+  const int d4 = D >> 2;
+  float nrm = 0.f;
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) {
+    float4 acc = __ldcs(src + i);
+    for (int v = 1; v < V; ++v) {
+      const float4 t = __ldcs(src + static_cast<size_t>(v) * d4 + i);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (V > 1) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+    uint2 hi;
+    hi.x = pack_bf16x2(acc.x, acc.y);
+    hi.y = pack_bf16x2(acc.z, acc.w);
+    bf16* dst = x + static_cast<size_t>(row) * ld + 4 * i;
+    *reinterpret_cast<uint2*>(dst) = hi;
+    const float h0 = __uint_as_float(hi.x << 16), h1 = __uint_as_float(hi.x & 0xffff0000u);
+    const float h2 = __uint_as_float(hi.y << 16), h3 = __uint_as_float(hi.y & 0xffff0000u);
+    nrm += h0 * h0 + h1 * h1 + h2 * h2 + h3 * h3;
+    if (SPLIT) {
+      uint2 lo;
+      lo.x = pack_bf16x2(acc.x - h0, acc.y - h1);
+      lo.y = pack_bf16x2(acc.z - h2, acc.w - h3);
+      *reinterpret_cast<uint2*>(dst + D) = hi;
+      *reinterpret_cast<uint2*>(dst + 2 * D) = lo;
+    }
+  }
+  if (sqnorm) {
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) sqnorm[row] = v;
+    }
+  }
+}
+
+// W (C,D) fp32 -> bf16 operand.  split = 0: (C,D).  split = 1: (C,3D) = [hi | lo | hi].
+template <int SPLIT>
+__global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, long long n4, int d4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldcs(reinterpret_cast<const float4*>(w) + i);
+  uint2 hi;
+  hi.x = pack_bf16x2(v.x, v.y);
+  hi.y = pack_bf16x2(v.z, v.w);
+  if (!SPLIT) {
+    reinterpret_cast<uint2*>(out)[i] = hi;
+  } else {
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    uint2 lo;
+    lo.x = pack_bf16x2(v.x - __uint_as_float(hi.x << 16), v.y - __uint_as_float(hi.x & 0xffff0000u));
+    lo.y = pack_bf16x2(v.z - __uint_as_float(hi.y << 16), v.w - __uint_as_float(hi.y & 0xffff0000u));
+    uint2* o = reinterpret_cast<uint2*>(out) + row * 3 * d4;
+    o[c] = hi;
+    o[d4 + c] = lo;
+    o[2 * d4 + c] = hi;
+  }
+}
+
+__global__ void pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int C, int Cpad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Cpad) out[i] = i < C ? b[i] : 0.f;
+}
+
+// squared L2 norm of each bf16 row (prototype bank), one warp per row
+__global__ void row_sqnorm_bf16_kernel(const bf16* __restrict__ m, long long rows, int D, float* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* src = reinterpret_cast<const uint4*>(m + row * D);
+  float acc = 0.f;
+  for (int i = threadIdx.x & 31; i < (D >> 3); i += 32) {
+    const uint4 v = __ldg(src + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xffff0000u);
+      acc = fmaf(a, a, acc);
+      acc = fmaf(b, b, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) out[row] = acc;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_fuse_headings(const float* emb, void* x_bf16, int B, int V, int D, int split, float* sqnorm,
+                                gg_stream_t stream) {
+  GG_CHECK(emb && x_bf16 && B > 0 && V > 0 && D > 0, GG_ERR_ARG, "gg_fuse_headings: bad arguments");
+  GG_CHECK(D % 8 == 0, GG_ERR_ARG, "gg_fuse_headings: D=%d must be a multiple of 8", D);
+  GG_CHECK((reinterpret_cast<uintptr_t>(emb) & 15) == 0, GG_ERR_ARG, "gg_fuse_headings: emb must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = D >= 1024 ? 256 : 128;
+  if (split)
+    fuse_headings_kernel<1><<<B, threads, 0, s>>>(emb, static_cast<bf16*>(x_bf16), B, V, D, 3 * D, sqnorm);
+  else
+    fuse_headings_kernel<0><<<B, threads, 0, s>>>(emb, static_cast<bf16*>(x_bf16), B, V, D, D, sqnorm);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_prepare_head_weights(const float* w, const float* b, void* w_bf16, float* bias_pad, int C, int D,
+                                       int split, gg_stream_t stream) {
+  GG_CHECK(w && b && w_bf16 && bias_pad && C > 0 && D > 0 && D % 8 == 0, GG_ERR_ARG,
+           "gg_prepare_head_weights: bad arguments (D must be a multiple of 8)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n4 = static_cast<long long>(C) * D / 4;
+  const int blocks = static_cast<int>(ceil_div_ll(n4, 256));
+  if (split)
+    cast_weight_kernel<1><<<blocks, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4);
+  else
+    cast_weight_kernel<0><<<blocks, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4);
+  GG_LAUNCH_CHECK();
+  const int Cpad = gg_head_bias_pad(C);
+  pad_bias_kernel<<<ceil_div(Cpad, 256), 256, 0, s>>>(b, bias_pad, C, Cpad);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_cast_bf16(const float* src, void* dst_bf16, long long n, gg_stream_t stream) {
+  GG_CHECK(src && dst_bf16 && n > 0 && n % 4 == 0, GG_ERR_ARG, "gg_cast_bf16: n must be a positive multiple of 4");
+  cast_weight_kernel<0><<<static_cast<int>(ceil_div_ll(n / 4, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<bf16*>(dst_bf16), n / 4, 1);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, float* out, gg_stream_t stream) {
+  GG_CHECK(m_bf16 && out && rows > 0 && D > 0 && D % 8 == 0, GG_ERR_ARG, "gg_row_sqnorm_bf16: bad arguments");
+  row_sqnorm_bf16_kernel<<<static_cast<int>(ceil_div_ll(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(m_bf16), rows, D, out);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}

@@ -1,0 +1,239 @@
+// Geocell head backward: dW = scale * dlogits^T x  (C x D, fp32) and db = scale * sum_b dlogits.
+//
+// Replaces autograd's addmm backward for models/super_guessr.py:354 (reached from
+// main_coordinator_idun_s3.py:423).  Both operands are consumed in the layout the forward pass
+// left them in -- dlogits (B, ldc) and x (B, D), batch-major -- i.e. as MN-major UMMA operands:
+// the contraction index (batch) is the slow index of both.  TMA loads 64(k) x 64(mn) boxes with
+// the 128-byte swizzle; a 128 x 256 x 64 stage is 2 + 4 such boxes.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace gg {
+
+constexpr int kWM = 128;  // geocells per tile (UMMA M)
+constexpr int kWN = 256;  // embedding columns per tile (UMMA N)
+constexpr int kWK = 64;   // batch rows per stage
+constexpr int kWStages = 4;
+constexpr int kBwdThreads = 192;
+constexpr uint32_t kAtomBytes = kWK * 128;                 // 64 k-rows x 128 B
+constexpr uint32_t kWStageA = (kWM / 64) * kAtomBytes;     // 16 KB
+constexpr uint32_t kWStageB = (kWN / 64) * kAtomBytes;     // 32 KB
+
+struct BwdSmem {
+  uint8_t a[kWStages][kWStageA];
+  uint8_t b[kWStages][kWStageB];
+  uint64_t full[kWStages];
+  uint64_t empty[kWStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, rows B
+                const __grid_constant__ CUtensorMap tm_x,  // x:       inner D, rows B
+                float* __restrict__ dW, int C, int D, int Bk, float scale_in,
+                const float* __restrict__ grad_scale) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (C + kWM - 1) / kWM;
+  const int num_n = (D + kWN - 1) / kWN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (Bk + kWK - 1) / kWK;
+  const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sm.acc_full[a], 1);
+      mbar_init(&sm.acc_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  // tile order: the num_n column tiles of one geocell block are adjacent, so the CTAs that run
+  // concurrently share the dlogits tile through L2 and dlogits is streamed from HBM once.
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / num_n) * kWM, n0 = (t % num_n) * kWN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&sm.empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&sm.full[s], kWStageA + kWStageB);
+#pragma unroll
+          for (int i = 0; i < kWM / 64; ++i)
+            tma_load_2d(sm.a[s] + i * kAtomBytes, &tm_g, &sm.full[s], m0 + 64 * i, kb * kWK);
+#pragma unroll
+          for (int i = 0; i < kWN / 64; ++i)
+            tma_load_2d(sm.b[s] + i * kAtomBytes, &tm_x, &sm.full[s], n0 + 64 * i, kb * kWK);
+          if (++s == kWStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kWM, kWN, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kWN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&sm.full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
+#pragma unroll
+          for (int k = 0; k < kWK / 16; ++k) {
+            // 16 k-rows of 128 B per MMA; atoms (64 mn-elements) kAtomBytes apart; 8-row groups 1024 B apart
+            const uint64_t da = umma_desc_sw128(a0 + k * 2048, kAtomBytes, 1024);
+            const uint64_t db = umma_desc_sw128(b0 + k * 2048, kAtomBytes, 1024);
+            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&sm.empty[s]);
+          if (++s == kWStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&sm.acc_full[acc]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t / num_n) * kWM, n0 = (t % num_n) * kWN;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(&sm.acc_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kWN;
+#pragma unroll 1
+      for (int c = 0; c < kWN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < C) {
+          float* dst = dW + static_cast<size_t>(row) * D + col0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (col0 + 4 * q + 4 <= D) {
+              float4 o;
+              o.x = __uint_as_float(r[4 * q + 0]) * scale;
+              o.y = __uint_as_float(r[4 * q + 1]) * scale;
+              o.z = __uint_as_float(r[4 * q + 2]) * scale;
+              o.w = __uint_as_float(r[4 * q + 3]) * scale;
+              *reinterpret_cast<float4*>(dst + 4 * q) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// db: column sums of dlogits.  Block (32 x 8): each thread owns 8 adjacent columns (one 16-byte
+// load per row), 8 row lanes; grid.y row slices write partial[slice][C], reduced by a second kernel
+// (deterministic, no atomics).
+constexpr int kDbSlices = 32;
+__global__ void db_partial_kernel(const bf16* __restrict__ g, int ldc, int B, int C, float* __restrict__ partial) {
+  __shared__ float red[8][32][8];
+  const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < ldc) {
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < B; r += 8 * gridDim.y) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ldc + c0));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][i];
+      if (c0 + i < C) partial[static_cast<size_t>(blockIdx.y) * C + c0 + i] = s;
+    }
+  }
+}
+__global__ void db_final_kernel(const float* __restrict__ partial, int C, int slices, float scale_in,
+                                const float* __restrict__ grad_scale, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
+  float s = 0.f;
+  for (int i = 0; i < slices; ++i) s += partial[static_cast<size_t>(i) * C + c];
+  db[c] = s * scale;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" size_t gg_head_bwd_workspace_bytes(int C) { return static_cast<size_t>(kDbSlices) * C * sizeof(float); }
+
+extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
+                           float scale, const float* grad_scale, float* dW, float* db, void* workspace,
+                           gg_stream_t stream) {
+  GG_CHECK(B > 0 && C > 0 && D > 0, GG_ERR_ARG, "gg_head_bwd: empty problem B=%d C=%d D=%d", B, C, D);
+  GG_CHECK(dlogits_bf16 && x_bf16 && dW, GG_ERR_ARG, "gg_head_bwd: null pointer");
+  GG_CHECK(ldc >= C && ldc % 8 == 0, GG_ERR_ARG, "gg_head_bwd: ldc=%d must be >= C and a multiple of 8", ldc);
+  GG_CHECK(D % 8 == 0 && x_ld >= D && x_ld % 8 == 0, GG_ERR_ARG, "gg_head_bwd: D=%d / x_ld=%d must be multiples of 8", D, x_ld);
+  GG_CHECK(!db || workspace, GG_ERR_ARG, "gg_head_bwd: db needs the workspace");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap tm_g, tm_x;
+  int rc = make_tmap_bf16_2d(&tm_g, dlogits_bf16, C, B, static_cast<uint64_t>(ldc) * 2, 64, kWK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_x, x_bf16, D, B, static_cast<uint64_t>(x_ld) * 2, 64, kWK);
+  if (rc) return rc;
+  const int tiles = ceil_div(C, kWM) * ceil_div(D, kWN);
+  const int grid = std::min(tiles, device_sm_count());
+  const size_t smem = sizeof(BwdSmem) + 1024;
+  GG_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  head_bwd_kernel<<<grid, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
+  GG_LAUNCH_CHECK();
+  if (db) {
+    float* partial = static_cast<float*>(workspace);
+    dim3 blk(32, 8), grd(ceil_div(ldc, 256), kDbSlices);
+    db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);
+    GG_LAUNCH_CHECK();
+    db_final_kernel<<<ceil_div(C, 256), 256, 0, s>>>(partial, C, kDbSlices, scale, grad_scale, db);
+    GG_LAUNCH_CHECK();
+  }
+  return GG_OK;
+}

@@ -1,0 +1,445 @@
+// ProtoRefiner hot path: top-k geocell -> prototype retrieval + coordinate refinement.
+//
+// Replaces the Python double loop of models/proto_refiner.py:165-228 (per query, per candidate
+// cell: host->device copy of the cell's prototypes, torch.cdist, max/argmax with .item() syncs).
+//
+// Stage 0 (grouping)  : counting-sort the B*topk (query, candidate) pairs by geocell and gather
+//                       the query rows into cell order (Qs), so that every geocell sees its
+//                       queries as one contiguous bf16 matrix.
+// Stage 1 (retrieval) : persistent tcgen05 kernel.  Work item = (geocell c, chunk of <=128 pairs):
+//                       D[128 pairs, 256 prototypes] = Qs_chunk . bank_c^T over K = D, operands
+//                       streamed by TMA (the bank tile is read from HBM exactly once per chunk --
+//                       the algorithmic traffic of the path), accumulator in TMEM (2 x 256 cols).
+//                       Epilogue thread = one pair: dist^2 = |q|^2 + |p|^2 - 2 q.p, running arg-min
+//                       over the cell's prototypes (proto_refiner.py:190-194: max of -cdist), then
+//                       one 16-byte record {score, lng, lat, prototype id} per pair.
+// Stage 2 (refinement): per query temperature softmax over the k scores (no max-subtraction,
+//                       :378-389) x candidate probabilities (:210), arg-max, 1000 km guard
+//                       (:216-223, geo_utils.py:39-54), output coords / geocell (:225-228).
+// Multi-GPU: the bank is sharded by contiguous geocell ranges [cell_lo, cell_hi); a rank leaves
+// score = -inf in records of pairs whose cell it does not own; after an all-gather of the
+// record arrays stage 2 selects, per pair, the owning rank's record.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace gg {
+
+constexpr int kPM = 128;  // pairs per work item (UMMA M)
+constexpr int kPN = 256;  // prototypes per accumulation unit (UMMA N)
+constexpr int kPK = 64;
+constexpr int kPStages = 4;
+constexpr int kProtoThreads = 192;
+constexpr uint32_t kPStageA = kPM * kPK * 2;
+constexpr uint32_t kPStageB = kPN * kPK * 2;
+constexpr float kMissingScore = -100000.0f;  // proto_refiner.py:185
+
+// ------------------------------------------------------------------ stage 0: grouping
+// rec[p] initialised to "missing" (owned cell) or "not mine" (-inf); counts per owned cell.
+__global__ void proto_count_kernel(const long long* __restrict__ cand, int cand_ld, int B, int topk, int cell_lo,
+                                   int cell_hi, int* __restrict__ cnt, float4* __restrict__ rec) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B * topk) return;
+  const long long c = cand[static_cast<size_t>(p / topk) * cand_ld + (p % topk)];
+  const bool mine = c >= cell_lo && c < cell_hi;
+  rec[p] = make_float4(mine ? kMissingScore : -CUDART_INF_F, 0.f, 0.f, __int_as_float(-1));
+  if (mine) atomicAdd(&cnt[c - cell_lo], 1);
+}
+
+// Single CTA: exclusive scans over the owned cells -> pair_off (C+1), and the work list
+// (cell, chunk) for every cell that has both pairs and prototypes.  meta[0] = #work items.
+__global__ void proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off, int ncell,
+                                  int* __restrict__ pair_off, int* __restrict__ cursor, int* __restrict__ work_cell,
+                                  int* __restrict__ work_chunk, int* __restrict__ meta) {
+  __shared__ int s_pairs[1024], s_tiles[1024];
+  const int tid = threadIdx.x;
+  const int per = (ncell + 1023) / 1024;
+  const int c0 = tid * per, c1 = min(ncell, c0 + per);
+  int np = 0, nt = 0;
+  for (int c = c0; c < c1; ++c) {
+    const int n = cnt[c];
+    np += n;
+    if (cell_off[c + 1] > cell_off[c]) nt += (n + kPM - 1) / kPM;
+  }
+  s_pairs[tid] = np;
+  s_tiles[tid] = nt;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    int a = 0, b = 0;
+    if (tid >= o) { a = s_pairs[tid - o]; b = s_tiles[tid - o]; }
+    __syncthreads();
+    s_pairs[tid] += a;
+    s_tiles[tid] += b;
+    __syncthreads();
+  }
+  int pbase = s_pairs[tid] - np, tbase = s_tiles[tid] - nt;
+  for (int c = c0; c < c1; ++c) {
+    const int n = cnt[c];
+    pair_off[c] = pbase;
+    cursor[c] = 0;
+    if (cell_off[c + 1] > cell_off[c]) {
+      const int chunks = (n + kPM - 1) / kPM;
+      for (int m = 0; m < chunks; ++m) {
+        work_cell[tbase + m] = c;
+        work_chunk[tbase + m] = m;
+      }
+      tbase += chunks;
+    }
+    pbase += n;
+  }
+  if (tid == 1023) {
+    pair_off[ncell] = s_pairs[1023];
+    meta[0] = s_tiles[1023];
+    meta[1] = s_pairs[1023];
+  }
+}
+
+__global__ void proto_scatter_kernel(const long long* __restrict__ cand, int cand_ld, int B, int topk, int cell_lo,
+                                     int cell_hi, const int* __restrict__ pair_off, int* __restrict__ cursor,
+                                     int* __restrict__ pair_ids) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B * topk) return;
+  const long long c = cand[static_cast<size_t>(p / topk) * cand_ld + (p % topk)];
+  if (c < cell_lo || c >= cell_hi) return;
+  const int lc = static_cast<int>(c - cell_lo);
+  pair_ids[pair_off[lc] + atomicAdd(&cursor[lc], 1)] = p;
+}
+
+// One warp per grouped slot: copy the query row (bf16, D) and its squared norm into cell order.
+__global__ void proto_gather_kernel(const bf16* __restrict__ q, const float* __restrict__ qn,
+                                    const int* __restrict__ pair_ids, const int* __restrict__ meta, int topk, int D,
+                                    bf16* __restrict__ qs, float* __restrict__ qs_n) {
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= meta[1]) return;
+  const int qi = pair_ids[slot] / topk;
+  const uint4* src = reinterpret_cast<const uint4*>(q + static_cast<size_t>(qi) * D);
+  uint4* dst = reinterpret_cast<uint4*>(qs + static_cast<size_t>(slot) * D);
+  for (int i = threadIdx.x & 31; i < (D >> 3); i += 32) dst[i] = __ldg(src + i);
+  if ((threadIdx.x & 31) == 0) qs_n[slot] = qn[qi];
+}
+
+// ------------------------------------------------------------------ stage 1: retrieval
+struct ProtoSmem {
+  uint8_t a[kPStages][kPStageA];
+  uint8_t b[kPStages][kPStageB];
+  float pn[2][kPN];
+  uint64_t full[kPStages];
+  uint64_t empty[kPStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kProtoThreads, 1)
+proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // Qs   (slots, D)
+                      const __grid_constant__ CUtensorMap tm_bank,  // bank (P_local, D)
+                      const int* __restrict__ meta, const int* __restrict__ work_cell,
+                      const int* __restrict__ work_chunk, const int* __restrict__ pair_off,
+                      const int* __restrict__ pair_ids, const int* __restrict__ cell_off,
+                      const float* __restrict__ qs_n, const float* __restrict__ pnorm,
+                      const float* __restrict__ pcoords, int proto_base, int D, float4* __restrict__ rec) {
+  extern __shared__ uint8_t smem_raw[];
+  ProtoSmem& sm = *reinterpret_cast<ProtoSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (D + kPK - 1) / kPK;
+  const int n_work = meta[0];
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_bank);
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sm.acc_full[a], 1);
+      mbar_init(&sm.acc_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int c = work_cell[w];
+        const int a_row0 = pair_off[c] + work_chunk[w] * kPM;
+        const int p0 = cell_off[c], p1 = cell_off[c + 1];
+        for (int n0 = p0; n0 < p1; n0 += kPN) {
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(&sm.empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&sm.full[s], kPStageA + kPStageB);
+            tma_load_2d(sm.a[s], &tm_q, &sm.full[s], kb * kPK, a_row0);
+            tma_load_2d_hint(sm.b[s], &tm_bank, &sm.full[s], kb * kPK, n0, kPolicyEvictFirst);
+            if (++s == kPStages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kPM, kPN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int c = work_cell[w];
+        const int p0 = cell_off[c], p1 = cell_off[c + 1];
+        for (int n0 = p0; n0 < p1; n0 += kPN, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_ph = (it >> 1) & 1;
+          mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kPN;
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(&sm.full[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
+#pragma unroll
+            for (int k = 0; k < kPK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128(a0 + k * 32, 16, 1024);
+              const uint64_t db = umma_desc_sw128(b0 + k * 32, 16, 1024);
+              umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+            }
+            umma_commit(&sm.empty[s]);
+            if (++s == kPStages) { s = 0; ph ^= 1; }
+          }
+          umma_commit(&sm.acc_full[acc]);
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;        // pair slot within the chunk == TMEM lane
+    const int et = threadIdx.x - 64;       // 0..127 among the epilogue threads
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int c = work_cell[w];
+      const int a_row0 = pair_off[c] + work_chunk[w] * kPM;
+      const int nq = min(kPM, pair_off[c + 1] - a_row0);
+      const int p0 = cell_off[c], p1 = cell_off[c + 1];
+      float best = CUDART_INF_F;
+      int best_i = -1;
+      for (int n0 = p0; n0 < p1; n0 += kPN, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        // prototype norms of this unit -> smem (pad with +inf: prototypes of the next cell / past the bank)
+        for (int i = et; i < kPN; i += 128) sm.pn[acc][i] = (n0 + i < p1) ? __ldg(pnorm + n0 + i) : CUDART_INF_F;
+        named_bar_sync(1, 128);
+        mbar_wait(&sm.acc_full[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kPN;
+#pragma unroll 1
+        for (int cc = 0; cc < kPN / 32; ++cc) {
+          if (n0 + cc * 32 >= p1) break;  // uniform across the CTA
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + cc * 32, v);
+          tmem_ld_wait();
+          const float4* pn4 = reinterpret_cast<const float4*>(&sm.pn[acc][cc * 32]);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 pn = pn4[q4];
+            const float d0 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 0]), pn.x);
+            const float d1 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 1]), pn.y);
+            const float d2 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 2]), pn.z);
+            const float d3 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 3]), pn.w);
+            const int j = n0 + cc * 32 + 4 * q4;
+            if (d0 < best) { best = d0; best_i = j; }
+            if (d1 < best) { best = d1; best_i = j + 1; }
+            if (d2 < best) { best = d2; best_i = j + 2; }
+            if (d3 < best) { best = d3; best_i = j + 3; }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&sm.acc_empty[acc]);
+      }
+      if (r < nq && best_i >= 0) {
+        const float d2 = fmaxf(best + __ldg(qs_n + a_row0 + r), 0.f);
+        const int p = __ldg(pair_ids + a_row0 + r);
+        rec[p] = make_float4(-sqrtf(d2), __ldg(pcoords + 2 * static_cast<size_t>(best_i)),
+                             __ldg(pcoords + 2 * static_cast<size_t>(best_i) + 1),
+                             __int_as_float(proto_base + best_i));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ stage 2: refinement
+__device__ __forceinline__ float haversine_km(float lng1, float lat1, float lng2, float lat2) {
+  // preprocessing/geo_utils.py:39-54 in fp32 (the fp64 radius is a 0-dim tensor: no promotion)
+  const float d2r = 0.017453292519943295f;
+  const float x0 = lng1 * d2r, x1 = lat1 * d2r, y0 = lng2 * d2r, y1 = lat2 * d2r;
+  const float s1 = sinf((y1 - x1) * 0.5f), s0 = sinf((y0 - x0) * 0.5f);
+  const float a = s1 * s1 + cosf(x1) * cosf(y1) * s0 * s0;
+  const float c = 2.0f * asinf(sqrtf(a));
+  return (6378137.0f * c) / 1000.0f;
+}
+
+// torch.argmax semantics: NaN counts as the maximum, first occurrence wins.
+__device__ __forceinline__ int argmax_nan_first(const float* v, int k) {
+  int bi = 0;
+  float bv = v[0];
+  if (bv != bv) return 0;
+  for (int j = 1; j < k; ++j) {
+    const float x = v[j];
+    if (x != x) return j;
+    if (x > bv) { bv = x; bi = j; }
+  }
+  return bi;
+}
+
+constexpr int kMaxTopk = 16;
+
+__global__ void proto_refine_kernel(const float4* __restrict__ rec, int nranks, long long rank_stride,
+                                    const float* __restrict__ cprobs, int cprobs_ld,
+                                    const long long* __restrict__ cand, int cand_ld,
+                                    const float* __restrict__ initial, int B, int topk, float temperature,
+                                    float max_refinement_km, float* __restrict__ out_llh,
+                                    long long* __restrict__ out_cell, int* __restrict__ out_guess,
+                                    float* __restrict__ out_score, int* __restrict__ out_proto) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float score[kMaxTopk], lng[kMaxTopk], lat[kMaxTopk], cp[kMaxTopk], fin[kMaxTopk];
+  float sum = 0.f;
+  for (int j = 0; j < topk; ++j) {
+    float4 best = make_float4(-CUDART_INF_F, 0.f, 0.f, __int_as_float(-1));
+    for (int rk = 0; rk < nranks; ++rk) {
+      const float4 t = rec[rk * rank_stride + static_cast<size_t>(i) * topk + j];
+      if (t.x > best.x) best = t;  // exactly one rank owns the cell
+    }
+    if (!(best.x > -CUDART_INF_F)) best = make_float4(kMissingScore, 0.f, 0.f, __int_as_float(-1));
+    score[j] = best.x;
+    lng[j] = best.y;
+    lat[j] = best.z;
+    if (out_score) out_score[static_cast<size_t>(i) * topk + j] = best.x;
+    if (out_proto) out_proto[static_cast<size_t>(i) * topk + j] = __float_as_int(best.w);
+    cp[j] = cprobs ? cprobs[static_cast<size_t>(i) * cprobs_ld + j] : (j == 0 ? 1.f : 0.f);
+    fin[j] = expf(score[j] / temperature);  // :387, no max-subtraction
+    sum += fin[j];
+  }
+  for (int j = 0; j < topk; ++j) fin[j] = cp[j] * (fin[j] / sum);  // :389, :210 (0/0 -> NaN as in the reference)
+  const int refined = argmax_nan_first(fin, topk);                // :211
+  const float dist = haversine_km(initial[2 * i], initial[2 * i + 1], lng[refined], lat[refined]);
+  int final_id = refined;
+  if (dist > max_refinement_km) final_id = argmax_nan_first(cp, topk);  // :220-225
+  out_llh[2 * i] = lng[final_id];
+  out_llh[2 * i + 1] = lat[final_id];
+  out_cell[i] = cand[static_cast<size_t>(i) * cand_ld + final_id];
+  if (out_guess) out_guess[i] = final_id;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+// workspace layout (ints unless noted), ncell = cell_hi - cell_lo, npair = B * topk:
+//   cnt[ncell] | pair_off[ncell+1] | cursor[ncell] | work_cell[ncell + npair/128 + 1] | work_chunk[same] |
+//   meta[4] | pair_ids[npair] | qs_n[npair] (float) | pad to 256 B | Qs[npair * D] (bf16)
+struct ProtoWs {
+  int *cnt, *pair_off, *cursor, *work_cell, *work_chunk, *meta, *pair_ids;
+  float* qs_n;
+  bf16* qs;
+  size_t bytes;
+};
+static ProtoWs carve_proto_ws(void* base, int ncell, long long npair, int D) {
+  ProtoWs w;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  auto take = [&](size_t nbytes) {
+    uint8_t* r = p;
+    p += (nbytes + 255) & ~size_t(255);
+    return r;
+  };
+  const size_t nwork = static_cast<size_t>(ncell) + npair / kPM + 1;
+  w.cnt = reinterpret_cast<int*>(take(sizeof(int) * ncell));
+  w.pair_off = reinterpret_cast<int*>(take(sizeof(int) * (ncell + 1)));
+  w.cursor = reinterpret_cast<int*>(take(sizeof(int) * ncell));
+  w.work_cell = reinterpret_cast<int*>(take(sizeof(int) * nwork));
+  w.work_chunk = reinterpret_cast<int*>(take(sizeof(int) * nwork));
+  w.meta = reinterpret_cast<int*>(take(sizeof(int) * 4));
+  w.pair_ids = reinterpret_cast<int*>(take(sizeof(int) * npair));
+  w.qs_n = reinterpret_cast<float*>(take(sizeof(float) * npair));
+  w.qs = reinterpret_cast<bf16*>(take(sizeof(bf16) * static_cast<size_t>(npair + kPM) * D));
+  w.bytes = static_cast<size_t>(p - static_cast<uint8_t*>(base));
+  return w;
+}
+
+extern "C" size_t gg_proto_retrieve_workspace_bytes(int B, int topk, int D, int ncell) {
+  return carve_proto_ws(nullptr, ncell, static_cast<long long>(B) * topk, D).bytes;
+}
+
+extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int B, int D, const long long* cand,
+                                 int cand_ld, int topk, const void* bank_bf16, const float* bank_sqnorm,
+                                 const float* bank_coords, long long n_protos, const int* cell_off, int cell_lo,
+                                 int cell_hi, int proto_base, void* rec_out, void* workspace, gg_stream_t stream) {
+  GG_CHECK(B > 0 && D > 0 && topk >= 1 && topk <= kMaxTopk, GG_ERR_ARG,
+           "gg_proto_retrieve: bad sizes B=%d D=%d topk=%d (topk <= %d)", B, D, topk, kMaxTopk);
+  GG_CHECK(D % 8 == 0, GG_ERR_ARG, "gg_proto_retrieve: D=%d must be a multiple of 8", D);
+  GG_CHECK(cand_ld >= topk, GG_ERR_ARG, "gg_proto_retrieve: topk=%d exceeds the %d candidate columns", topk, cand_ld);
+  GG_CHECK(cell_hi > cell_lo && cell_lo >= 0, GG_ERR_ARG, "gg_proto_retrieve: empty cell range [%d, %d)", cell_lo, cell_hi);
+  GG_CHECK(q_bf16 && q_sqnorm && cand && cell_off && rec_out && workspace, GG_ERR_ARG, "gg_proto_retrieve: null pointer");
+  GG_CHECK(n_protos >= 0 && n_protos < (1ll << 31), GG_ERR_ARG, "gg_proto_retrieve: n_protos out of range");
+  GG_CHECK(n_protos == 0 || (bank_bf16 && bank_sqnorm && bank_coords), GG_ERR_ARG, "gg_proto_retrieve: null bank pointer");
+  GG_CHECK(static_cast<long long>(B) * topk < (1ll << 31), GG_ERR_ARG, "gg_proto_retrieve: B*topk overflows int32");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int ncell = cell_hi - cell_lo;
+  const long long npair = static_cast<long long>(B) * topk;
+  ProtoWs w = carve_proto_ws(workspace, ncell, npair, D);
+  float4* rec = static_cast<float4*>(rec_out);
+
+  GG_CUDA(cudaMemsetAsync(w.cnt, 0, sizeof(int) * ncell, s));
+  const int pb = static_cast<int>(ceil_div_ll(npair, 256));
+  proto_count_kernel<<<pb, 256, 0, s>>>(cand, cand_ld, B, topk, cell_lo, cell_hi, w.cnt, rec);
+  GG_LAUNCH_CHECK();
+  if (n_protos == 0) return GG_OK;  // this rank owns cells but no prototypes: every owned pair stays "missing"
+  proto_scan_kernel<<<1, 1024, 0, s>>>(w.cnt, cell_off, ncell, w.pair_off, w.cursor, w.work_cell, w.work_chunk, w.meta);
+  GG_LAUNCH_CHECK();
+  proto_scatter_kernel<<<pb, 256, 0, s>>>(cand, cand_ld, B, topk, cell_lo, cell_hi, w.pair_off, w.cursor, w.pair_ids);
+  GG_LAUNCH_CHECK();
+  proto_gather_kernel<<<static_cast<int>(ceil_div_ll(npair, 8)), 256, 0, s>>>(
+      static_cast<const bf16*>(q_bf16), q_sqnorm, w.pair_ids, w.meta, topk, D, w.qs, w.qs_n);
+  GG_LAUNCH_CHECK();
+
+  CUtensorMap tm_q, tm_bank;
+  int rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, kPM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPN);
+  if (rc) return rc;
+  const size_t smem = sizeof(ProtoSmem) + 1024;
+  GG_CUDA(cudaFuncSetAttribute(proto_retrieve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  proto_retrieve_kernel<<<device_sm_count(), kProtoThreads, smem, s>>>(tm_q, tm_bank, w.meta, w.work_cell, w.work_chunk,
+                                                                      w.pair_off, w.pair_ids, cell_off, w.qs_n,
+                                                                      bank_sqnorm, bank_coords, proto_base, D, rec);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_proto_refine(const void* rec, int nranks, long long rank_stride, const float* cand_probs,
+                               int cand_probs_ld, const long long* cand, int cand_ld, const float* initial_llh, int B,
+                               int topk, float temperature, float max_refinement_km, float* out_llh,
+                               long long* out_cell, int* out_guess, float* out_score, int* out_proto,
+                               gg_stream_t stream) {
+  GG_CHECK(B > 0 && topk >= 1 && topk <= kMaxTopk && nranks >= 1, GG_ERR_ARG, "gg_proto_refine: bad sizes");
+  GG_CHECK(rec && cand && initial_llh && out_llh && out_cell, GG_ERR_ARG, "gg_proto_refine: null pointer");
+  GG_CHECK(cand_ld >= topk && (!cand_probs || cand_probs_ld >= topk), GG_ERR_ARG, "gg_proto_refine: topk exceeds candidate columns");
+  proto_refine_kernel<<<ceil_div(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float4*>(rec), nranks, rank_stride, cand_probs, cand_probs_ld, cand, cand_ld, initial_llh, B,
+      topk, temperature, max_refinement_km, out_llh, out_cell, out_guess, out_score, out_proto);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}

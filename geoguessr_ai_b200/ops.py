@@ -1,0 +1,233 @@
+"""Thin tensor-level wrappers over the C ABI (include/geoguessr_b200.h).
+
+Each function allocates its outputs with torch (device memory + caching allocator are torch's
+job -- plumbing), passes raw device pointers and the current CUDA stream to one launcher of
+libgeoguessr_b200.so, and returns.  No arithmetic on the hot path happens in PyTorch here, and
+nothing here works without a CUDA device: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+
+FAR_KM_DEFAULT = 65.0 * math.log(2.0 ** 40)  # ~1802 km: targets below 2^-40 of the nearest cell's are dropped
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.GeoguessrB200Error(
+                "geoguessr_ai_b200 kernels need CUDA tensors (sm_100a); got a CPU tensor and there is no CPU fallback")
+
+
+def _u8(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- layout helpers
+def logits_ld(C: int) -> int:
+    return _lib.load().gg_head_logits_ld(C)
+
+
+def bias_pad_len(C: int) -> int:
+    return _lib.load().gg_head_bias_pad(C)
+
+
+# --------------------------------------------------------------------------- a1
+def fuse_headings(emb: torch.Tensor, split: bool = False, want_sqnorm: bool = False):
+    """(B,V,D) or (B,D) fp32 -> bf16 (B,D) [or (B,3D) hi|hi|lo]; optional ||x||^2 (B) fp32."""
+    _need_cuda(emb)
+    if emb.dtype != torch.float32:
+        emb = emb.float()
+    emb = emb.contiguous()
+    if emb.dim() == 2:
+        B, D = emb.shape
+        V = 1
+    else:
+        B, V, D = emb.shape
+    x = torch.empty((B, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
+    sq = torch.empty((B,), dtype=torch.float32, device=emb.device) if want_sqnorm else None
+    lib = _lib.load()
+    _lib.check(lib.gg_fuse_headings(_ptr(emb), _ptr(x), B, V, D, int(split), _ptr(sq), _stream()), "gg_fuse_headings")
+    return (x, sq) if want_sqnorm else x
+
+
+def prepare_head_weights(weight: torch.Tensor, bias: torch.Tensor, split: bool = False):
+    """fp32 nn.Linear parameters -> (bf16 operand (C,D) or (C,3D), zero-padded fp32 bias)."""
+    _need_cuda(weight, bias)
+    C, D = weight.shape
+    w = weight.detach().float().contiguous()
+    b = bias.detach().float().contiguous()
+    w16 = torch.empty((C, 3 * D if split else D), dtype=torch.bfloat16, device=w.device)
+    bp = torch.empty((bias_pad_len(C),), dtype=torch.float32, device=w.device)
+    lib = _lib.load()
+    _lib.check(lib.gg_prepare_head_weights(_ptr(w), _ptr(b), _ptr(w16), _ptr(bp), C, D, int(split), _stream()),
+               "gg_prepare_head_weights")
+    return w16, bp
+
+
+def row_sqnorm_bf16(m: torch.Tensor) -> torch.Tensor:
+    _need_cuda(m)
+    assert m.dtype == torch.bfloat16 and m.dim() == 2 and m.is_contiguous()
+    out = torch.empty((m.shape[0],), dtype=torch.float32, device=m.device)
+    if m.shape[0]:
+        _lib.check(_lib.load().gg_row_sqnorm_bf16(_ptr(m), m.shape[0], m.shape[1], _ptr(out), _stream()),
+                   "gg_row_sqnorm_bf16")
+    return out
+
+
+# --------------------------------------------------------------------------- a2-a4
+def head_forward(x16, w16, bias_pad, C, k, centroids, want_logits: bool):
+    """Returns dict(topk_val (B,k), topk_idx (B,k) i64, pred_cell (B) i64, pred_llh (B,2), lse (B),
+    logits (B,ldc) bf16 or None)."""
+    _need_cuda(x16, w16, bias_pad, centroids)
+    B, K = x16.shape
+    assert w16.shape == (C, K), (w16.shape, C, K)
+    dev = x16.device
+    lib = _lib.load()
+    ldc = logits_ld(C)
+    logits = torch.empty((B, ldc), dtype=torch.bfloat16, device=dev) if want_logits else None
+    ws = _u8(lib.gg_head_fwd_workspace_bytes(B, C, k), dev)
+    topk_val = torch.empty((B, k), dtype=torch.float32, device=dev)
+    topk_idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    pred_cell = torch.empty((B,), dtype=torch.int64, device=dev)
+    pred_llh = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    lse = torch.empty((B,), dtype=torch.float32, device=dev)
+    _lib.check(
+        lib.gg_head_fwd(_ptr(x16), _ptr(w16), _ptr(bias_pad), B, C, K, _ptr(logits), ldc, k, _ptr(ws),
+                        _ptr(centroids), _ptr(topk_val), _ptr(topk_idx), _ptr(pred_cell), _ptr(pred_llh), _ptr(lse),
+                        _stream()),
+        "gg_head_fwd")
+    return dict(topk_val=topk_val, topk_idx=topk_idx, pred_cell=pred_cell, pred_llh=pred_llh, lse=lse, logits=logits)
+
+
+# --------------------------------------------------------------------------- a5-a8
+def centroid_unit_vectors(centroids: torch.Tensor) -> torch.Tensor:
+    _need_cuda(centroids)
+    c = centroids.detach().float().contiguous()
+    C = c.shape[0]
+    lib = _lib.load()
+    xyz = torch.empty((3 * lib.gg_hav_cpad(C),), dtype=torch.float32, device=c.device)
+    _lib.check(lib.gg_centroid_unit_vectors(_ptr(c), _ptr(xyz), C, _stream()), "gg_centroid_unit_vectors")
+    return xyz
+
+
+def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False):
+    """Fused haversine label-smoothed CE.  Returns (dlogits bf16 (B,ldc) = p - t, loss_rows (B),
+    nearest_cell (B) i64 | None, nearest_km (B) | None)."""
+    _need_cuda(logits, lse, labels, cent_xyz)
+    B, ldc = logits.shape
+    dev = logits.device
+    lib = _lib.load()
+    labels = labels.detach().float().contiguous()
+    assert labels.shape == (B, 2), "labels must be (B, 2) (lng, lat)"
+    dlogits = torch.empty_like(logits)
+    loss_rows = torch.empty((B,), dtype=torch.float32, device=dev)
+    ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
+    nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
+    ws = _u8(lib.gg_hav_ce_workspace_bytes(B), dev)
+    _lib.check(
+        lib.gg_hav_ce_fwd_bwd(_ptr(logits), ldc, _ptr(lse), _ptr(labels), _ptr(cent_xyz), B, C, float(tau),
+                              float(far_km), _ptr(dlogits), _ptr(loss_rows), _ptr(ncell), _ptr(nkm), _ptr(ws),
+                              _stream()),
+        "gg_hav_ce_fwd_bwd")
+    return dlogits, loss_rows, ncell, nkm
+
+
+def hard_ce(logits, lse, labels_clf, C):
+    _need_cuda(logits, lse, labels_clf)
+    B, ldc = logits.shape
+    y = labels_clf.detach().to(torch.int64).contiguous()
+    assert y.shape == (B,), "labels_clf must be (B,)"
+    dlogits = torch.empty_like(logits)
+    loss_rows = torch.zeros((B,), dtype=torch.float32, device=logits.device)
+    _lib.check(
+        _lib.load().gg_hard_ce_fwd_bwd(_ptr(logits), ldc, _ptr(lse), _ptr(y), B, C, _ptr(dlogits), _ptr(loss_rows),
+                                       _stream()),
+        "gg_hard_ce_fwd_bwd")
+    return dlogits, loss_rows
+
+
+def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tensor:
+    B = loss_rows.shape[0]
+    out = torch.empty((), dtype=torch.float32, device=loss_rows.device)
+    _lib.check(_lib.load().gg_loss_mean(_ptr(loss_rows), B, float(1.0 / B if scale is None else scale), _ptr(out),
+                                        _stream()), "gg_loss_mean")
+    return out
+
+
+def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True):
+    """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C)."""
+    _need_cuda(dlogits, x16, grad_scale)
+    B, ldc = dlogits.shape
+    dev = dlogits.device
+    lib = _lib.load()
+    dW = torch.empty((C, D), dtype=torch.float32, device=dev)
+    db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
+    ws = _u8(lib.gg_head_bwd_workspace_bytes(C), dev) if want_db else None
+    if grad_scale is not None:
+        grad_scale = grad_scale.detach().float().contiguous()
+    _lib.check(
+        lib.gg_head_bwd(_ptr(dlogits), ldc, _ptr(x16), x16.shape[1], B, C, D, float(scale), _ptr(grad_scale), _ptr(dW),
+                        _ptr(db), _ptr(ws), _stream()),
+        "gg_head_bwd")
+    return dW, db
+
+
+# --------------------------------------------------------------------------- a10-a15
+def proto_retrieve(q16, q_sqnorm, cand, topk, bank16, bank_sqnorm, bank_coords, cell_off, cell_lo, cell_hi,
+                   proto_base=0):
+    """Stage 0+1.  Returns the (B*topk, 4) fp32 record array {score, lng, lat, proto id bits}."""
+    _need_cuda(q16, q_sqnorm, cand, cell_off)
+    B, D = q16.shape
+    dev = q16.device
+    lib = _lib.load()
+    cand = cand.detach().to(torch.int64).contiguous()
+    n_protos = 0 if bank16 is None else bank16.shape[0]
+    rec = torch.empty((B * topk, 4), dtype=torch.float32, device=dev)
+    ws = _u8(lib.gg_proto_retrieve_workspace_bytes(B, topk, D, cell_hi - cell_lo), dev)
+    _lib.check(
+        lib.gg_proto_retrieve(_ptr(q16), _ptr(q_sqnorm), B, D, _ptr(cand), cand.shape[1], topk, _ptr(bank16),
+                              _ptr(bank_sqnorm), _ptr(bank_coords), n_protos, _ptr(cell_off), cell_lo, cell_hi,
+                              proto_base, _ptr(rec), _ptr(ws), _stream()),
+        "gg_proto_retrieve")
+    return rec
+
+
+def proto_refine(rec, nranks, cand, cand_probs, initial, topk, temperature, max_refinement, want_debug=False):
+    """Stage 2.  rec: (nranks, B*topk, 4) or (B*topk, 4).  Returns (preds_LLH (B,2) f32, preds_geocell (B) i64,
+    guess_index (B) i32[, score (B,topk), proto (B,topk) i32])."""
+    _need_cuda(rec, cand, initial)
+    dev = rec.device
+    cand = cand.detach().to(torch.int64).contiguous()
+    B = cand.shape[0]
+    initial = initial.detach().float().contiguous()
+    assert initial.shape == (B, 2)
+    if cand_probs is not None:
+        cand_probs = cand_probs.detach().float().contiguous()
+    rec = rec.contiguous()
+    out_llh = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    out_cell = torch.empty((B,), dtype=torch.int64, device=dev)
+    out_guess = torch.empty((B,), dtype=torch.int32, device=dev)
+    out_score = torch.empty((B, topk), dtype=torch.float32, device=dev) if want_debug else None
+    out_proto = torch.empty((B, topk), dtype=torch.int32, device=dev) if want_debug else None
+    _lib.check(
+        _lib.load().gg_proto_refine(_ptr(rec), nranks, B * topk, _ptr(cand_probs),
+                                    0 if cand_probs is None else cand_probs.shape[1], _ptr(cand), cand.shape[1],
+                                    _ptr(initial), B, topk, float(temperature), float(max_refinement), _ptr(out_llh),
+                                    _ptr(out_cell), _ptr(out_guess), _ptr(out_score), _ptr(out_proto), _stream()),
+        "gg_proto_refine")
+    if want_debug:
+        return out_llh, out_cell, out_guess, out_score, out_proto
+    return out_llh, out_cell, out_guess

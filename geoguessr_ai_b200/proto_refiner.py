@@ -1,0 +1,223 @@
+"""ProtoRefiner: drop-in for the reference's proto-net refinement (models/proto_refiner.py:30-237)
+running on the sm_100a retrieval + refinement kernels.
+
+Kept from the reference: constructor keywords, ``forward(embedding, initial_preds, candidate_cells,
+candidate_probs=None) -> (loss, preds_LLH (B,2), preds_geocell (B,))``, the frozen ``temperature`` /
+``geo_scaling`` parameters (state-dict keys, :117-118), the missing-cell sentinel (-100000, (0,0)),
+the un-stabilised temperature softmax, the 1000 km guard and the "Changed geocell predictions"
+report (:231-233).  As in the executable reference the similarity is NEGATIVE EUCLIDEAN distance
+(``_euclidean_distance``; ``_cosine_similarity`` is never called), and a prototype's coordinates
+are the ones stored with it (the ``count == 0`` branch of ``_within_cluster_refinement``, the only
+one that can run: the other dereferences a ``self.dataset`` that is never assigned).
+
+The reference keeps the bank as a python list of per-cell HF datasets and copies a cell's
+prototypes host->device for every (query, candidate).  Here the bank lives in HBM once, sorted by
+geocell: ``bank`` (P, D) bf16, CSR ``cell_off`` (C+1), ``coords`` (P, 2), ``sqnorm`` (P).  With
+``shard=(rank, world)`` each rank holds a contiguous geocell range (balanced by prototype count),
+fills the candidates it owns and the per-pair records are merged with one all-gather.
+
+Out of scope here: building prototypes from images (``protos=None`` in the
+reference starts the offline embedding job, proto_refiner.py:89-103,313-345).
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+from torch.nn.parameter import Parameter
+
+from . import ops
+
+PROTO_PATH = "data/geocells/proto_df.csv"
+
+
+def shard_cells(cell_off_cpu: np.ndarray, world: int):
+    """Contiguous geocell ranges [lo, hi) per rank, balanced by prototype count."""
+    C = len(cell_off_cpu) - 1
+    P = int(cell_off_cpu[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = P * r / world
+        b = int(np.searchsorted(cell_off_cpu, target, side="left"))
+        bounds.append(min(max(b, bounds[-1]), C))
+    bounds.append(C)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+class ProtoRefiner(nn.Module):
+    def __init__(
+        self,
+        topk: int = 5,
+        max_refinement: int = 1000,
+        temperature: float = 1.6,
+        proto_path: str = PROTO_PATH,
+        protos=None,
+        verbose: bool = False,
+        clip_db_path: str = "data/sqlite/clip/dataset.sqlite",
+        tinyvit_db_path: str = "data/sqlite/tinyvit/dataset.sqlite",
+        backend: str = "clip",
+        *,
+        coords: Sequence | None = None,
+        bank: tuple | None = None,
+        shard: tuple | None = None,
+        process_group=None,
+        report_changed: bool = True,
+        device="cuda",
+    ):
+        """Reference arguments (proto_refiner.py:33-62) plus keyword-only ways to hand over a bank:
+
+        protos + coords: python lists with one ``(P_c, D)`` tensor (or None) and one ``(P_c, 2)``
+            (lng, lat) tensor per geocell -- the reference's in-memory representation.
+        protos="load": per-cell HF datasets under ``data/geocells/protos/proto_{i}`` (:104-112), rows
+            carrying ``embedding``, ``centroid_lng``, ``centroid_lat``.
+        bank=(cell_off, bank, coords): the CSR form directly (any float dtype; stored as bf16).
+        shard=(rank, world): keep only this rank's geocell range; ``process_group`` is the
+            torch.distributed group used for the all-gather (default group if None).
+        """
+        super().__init__()
+        self.topk = topk
+        self.max_refinement = max_refinement
+        self.verbose = verbose
+        self.report_changed = report_changed
+        self.process_group = process_group
+        self.temperature = Parameter(torch.tensor(float(temperature)), requires_grad=False)
+        self.geo_scaling = Parameter(torch.tensor(20.0), requires_grad=False)
+        self._temperature_host = float(temperature)
+
+        if bank is not None:
+            cell_off, mat, xy = bank
+        elif isinstance(protos, (list, tuple)):
+            if coords is None:
+                raise ValueError("protos given as a list needs the matching coords list")
+            cell_off, mat, xy = self._csr_from_lists(protos, coords)
+        elif isinstance(protos, str):
+            cell_off, mat, xy = self._csr_from_disk(proto_path)
+        else:
+            raise NotImplementedError(
+                "protos=None asks the reference to BUILD prototypes from images (embedders + S3, "
+                "proto_refiner.py:89-103); that offline job is outside this package. Pass protos='load', "
+                "protos=[...]+coords=[...], or bank=(cell_off, bank, coords).")
+        self._install_bank(cell_off, mat, xy, shard, device)
+
+    # ---- bank construction ------------------------------------------------------------------
+    @classmethod
+    def from_bank(cls, cell_off, bank, coords, **kw):
+        return cls(protos="bank", bank=(cell_off, bank, coords), **kw)
+
+    @staticmethod
+    def _csr_from_lists(protos, coords):
+        sizes = [0 if p is None else int(p.shape[0]) for p in protos]
+        off = np.zeros(len(sizes) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        mats = [p.float() for p in protos if p is not None and p.shape[0] > 0]
+        xys = [torch.as_tensor(c, dtype=torch.float32).reshape(-1, 2)
+               for p, c in zip(protos, coords) if p is not None and p.shape[0] > 0]
+        D = mats[0].shape[1] if mats else 8
+        mat = torch.cat(mats, 0) if mats else torch.zeros((0, D))
+        xy = torch.cat(xys, 0) if xys else torch.zeros((0, 2))
+        return torch.from_numpy(off.astype(np.int32)), mat, xy
+
+    @staticmethod
+    def _csr_from_disk(proto_path):
+        from datasets import Dataset  # HF datasets, as in the reference (:108-110)
+
+        root = "data/geocells/protos"
+        if os.path.exists(proto_path):
+            import pandas as pd
+
+            num = int(pd.read_csv(proto_path)["geocell_index"].astype(int).max()) + 1
+        else:
+            ids = [int(n.split("_")[1]) for n in os.listdir(root) if n.startswith("proto_")]
+            num = max(ids) + 1
+        protos, coords = [], []
+        for i in range(num):
+            try:
+                ds = Dataset.load_from_disk(f"{root}/proto_{i}").with_format("torch")
+            except FileNotFoundError:
+                protos.append(None)
+                coords.append(None)
+                continue
+            protos.append(ds["embedding"].float())
+            coords.append(torch.stack([ds["centroid_lng"].float(), ds["centroid_lat"].float()], 1))
+        return ProtoRefiner._csr_from_lists(protos, coords)
+
+    def _install_bank(self, cell_off, mat, xy, shard, device):
+        cell_off_cpu = torch.as_tensor(cell_off).to(torch.int64).cpu().numpy()
+        self.num_geocells = len(cell_off_cpu) - 1
+        self.num_protos_total = int(cell_off_cpu[-1])
+        self.embed_dim = int(mat.shape[1])
+        rank, world = shard if shard is not None else (0, 1)
+        self.rank, self.world = int(rank), int(world)
+        lo, hi = shard_cells(cell_off_cpu, self.world)[self.rank]
+        self.cell_lo, self.cell_hi = lo, hi
+        p0, p1 = int(cell_off_cpu[lo]), int(cell_off_cpu[hi])
+        self.proto_base = p0
+        local_off = torch.from_numpy((cell_off_cpu[lo:hi + 1] - p0).astype(np.int32))
+        dev = torch.device(device)
+        bank16 = mat[p0:p1].to(device=dev, dtype=torch.bfloat16).contiguous()
+        self.register_buffer("bank", bank16, persistent=False)
+        self.register_buffer("bank_coords", torch.as_tensor(xy[p0:p1], dtype=torch.float32).to(dev).contiguous(),
+                             persistent=False)
+        self.register_buffer("cell_off", local_off.to(dev), persistent=False)
+        self.register_buffer("bank_sqnorm",
+                             ops.row_sqnorm_bf16(bank16) if dev.type == "cuda" else torch.zeros(p1 - p0),
+                             persistent=False)
+
+    def __str__(self):
+        rep = "ProtoRefiner(\n"
+        rep += f"\ttopk\t\t= {self.topk}\n"
+        rep += f"\tmax_refinement\t= {self.max_refinement}\n"
+        rep += f"\ttemperature\t= {self.temperature.data.item()}\n"
+        rep += f"\tgeo_scaling\t= {self.geo_scaling.data.item()}\n"
+        rep += ")"
+        return rep
+
+    # ---- forward (proto_refiner.py:129-237) -------------------------------------------------
+    def retrieve(self, embedding: Tensor, candidate_cells: Tensor) -> Tensor:
+        """Stage 0+1 on this rank's shard: (B*topk, 4) records."""
+        q16, qn = ops.fuse_headings(embedding, split=False, want_sqnorm=True)  # :150-151 mean over headings
+        if q16.shape[1] != self.embed_dim:
+            raise ValueError(f"embedding dim {q16.shape[1]} != prototype dim {self.embed_dim}")
+        bank = self.bank if self.bank.shape[0] > 0 else None
+        return ops.proto_retrieve(q16, qn, candidate_cells, self.topk, bank, self.bank_sqnorm, self.bank_coords,
+                                  self.cell_off, self.cell_lo, self.cell_hi, self.proto_base)
+
+    def forward(self, embedding: Tensor = None, initial_preds: Tensor = None, candidate_cells: Tensor = None,
+                candidate_probs: Tensor = None, return_debug: bool = False):
+        assert self.topk <= candidate_cells.size(1), (
+            '"topk" parameter must be smaller or equal to the number of geocell candidates '
+            "passed into the forward function.")
+        if not self.bank_coords.is_cuda:
+            raise ops._lib.GeoguessrB200Error("ProtoRefiner bank is on the CPU; there is no CPU fallback (use device='cuda')")
+        dev = self.bank_coords.device
+        embedding, initial_preds, candidate_cells = (t.to(dev) for t in (embedding, initial_preds, candidate_cells))
+        if candidate_probs is not None:
+            candidate_probs = candidate_probs.to(dev)
+        temperature = self._temperature_host  # host copy of the frozen parameter: no device sync per call
+        loss = 0 if self.training else None
+
+        rec = self.retrieve(embedding, candidate_cells)
+        nranks = 1
+        if self.world > 1:
+            import torch.distributed as dist
+
+            gathered = torch.empty((self.world,) + tuple(rec.shape), dtype=rec.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, rec, group=self.process_group)
+            rec, nranks = gathered, self.world
+        out = ops.proto_refine(rec, nranks, candidate_cells, candidate_probs, initial_preds, self.topk, temperature,
+                               float(self.max_refinement), want_debug=return_debug)
+        preds_llh, preds_geocell, guess_index = out[:3]
+        if self.report_changed:  # :231-233 (one device sync, as in the reference)
+            perc_changed = (guess_index != 0).sum() / guess_index.size(0)
+            print(f"Changed geocell predictions of {perc_changed * 100:.1f} % of guesses.")
+        if return_debug:
+            return loss, preds_llh, preds_geocell, guess_index, out[3], out[4]
+        return loss, preds_llh, preds_geocell
+
+    def load_state_dict(self, state_dict, *a, **k):
+        r = super().load_state_dict(state_dict, *a, **k)
+        self._temperature_host = float(self.temperature.detach().cpu())
+        return r

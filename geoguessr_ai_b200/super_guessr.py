@@ -1,0 +1,246 @@
+"""SuperGuessr: drop-in for the reference's geocell classifier (models/super_guessr.py:20-395)
+whose post-encoder path runs on hand-written sm_100a kernels.
+
+Kept from the reference: constructor keywords, ``forward`` signature and return types
+(``ModelOutput`` in training / eval, the 3-tuple when ``serving`` in eval mode), the attribute
+names callers read (``geocell_centroid_coords``, ``num_cells``, ``cell_layer``, ``serving``,
+``num_candidates``) and the state-dict keys (``cell_layer.weight`` (C,D), ``cell_layer.bias`` (C),
+``geocell_centroid_coords`` (C,2)), so checkpoints filtered by name and shape (inference.py:134-156)
+load unchanged and torch optimisers / wandb.watch see ordinary ``.grad`` tensors.
+
+What runs where:
+  a1 fusion            -> gg_fuse_headings          a5-a7 smoothed CE      -> gg_hav_ce_fwd_bwd
+  a2-a4 head + top-k   -> gg_head_fwd (tcgen05)     a8    dW, db           -> gg_head_bwd (tcgen05)
+The vision encoder (base_model) stays PyTorch and is outside this path.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+from .geocells import resolve_centroids
+from .utils import CLIP_EMBED_DIM, LABEL_SMOOTHING_CONSTANT, ModelOutput, TopK
+
+
+class _GeocellHeadLoss(torch.autograd.Function):
+    """fusion -> head GEMM (+top-k) -> fused CE forward+gradient; backward = the dW/db GEMM."""
+
+    @staticmethod
+    def forward(ctx, embedding, weight, bias, module, labels, labels_clf, smooth):
+        st = module._operands(weight, bias)
+        x16 = ops.fuse_headings(embedding, split=st["split"])
+        C, D = weight.shape
+        head = ops.head_forward(x16, st["w16"], st["bias_pad"], C, module.num_candidates,
+                                module.geocell_centroid_coords.data, want_logits=True)
+        if smooth:
+            dlogits, loss_rows, _, _ = ops.hav_ce(head["logits"], head["lse"], labels, module._centroid_xyz(), C,
+                                                  tau=module.label_smoothing_tau, far_km=module.far_km)
+        else:
+            dlogits, loss_rows = ops.hard_ce(head["logits"], head["lse"], labels_clf, C)
+        loss = ops.loss_mean(loss_rows)
+        ctx.save_for_backward(dlogits, x16)
+        ctx.dims = (C, D, embedding.shape, embedding.requires_grad)
+        ctx.weight = weight
+        outs = (head["topk_val"], head["topk_idx"], head["pred_cell"], head["pred_llh"])
+        ctx.mark_non_differentiable(*outs)
+        return (loss,) + outs
+
+    @staticmethod
+    def backward(ctx, gloss, *_):
+        dlogits, x16 = ctx.saved_tensors
+        C, D, emb_shape, emb_needs_grad = ctx.dims
+        B = dlogits.shape[0]
+        want_w, want_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dW = db = demb = None
+        if want_w or want_b:
+            dW, db = ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=want_b)
+        if ctx.needs_input_grad[0] and emb_needs_grad:
+            # Only reached when the encoder is trained end to end (outside the BASELINE configs):
+            # dx = dlogits W through cuBLAS, then the mean's 1/V broadcast (super_guessr.py:347).
+            g = (dlogits[:, :C].float() @ ctx.weight.detach().float()) * (gloss / B)
+            demb = g if len(emb_shape) == 2 else (g / emb_shape[1]).unsqueeze(1).expand(emb_shape)
+        return demb, (dW if want_w else None), db, None, None, None, None
+
+
+class SuperGuessr(nn.Module):
+    def __init__(
+        self,
+        base_model: nn.Module = None,
+        panorama: bool = False,
+        hierarchical: bool = False,
+        should_smooth_labels: bool = False,
+        serving: bool = False,
+        freeze_base: bool = False,
+        num_candidates: int = 5,
+        embed_dim: int = CLIP_EMBED_DIM,
+        *,
+        centroids=None,
+        precision: str = "bf16",
+        label_smoothing_tau: float = LABEL_SMOOTHING_CONSTANT,
+        far_km: float = ops.FAR_KM_DEFAULT,
+        **kwargs,
+    ):
+        """Same arguments as the reference (super_guessr.py:21-54).  Keyword-only additions:
+
+        centroids: explicit (C,2) (lng,lat) table instead of the one resolved from
+            ``data/geocells`` / the packaged copy (geocells.resolve_centroids).
+        precision: "bf16" (operands rounded to bf16, fp32 accumulate; BASELINE cfg2/cfg4) or
+            "bf16x3" (hi/lo split operands, ~fp32-faithful logits for fp32 checkpoints; cfg1).
+        label_smoothing_tau: config.LABEL_SMOOTHING_CONSTANT (65 km).
+        far_km: target-mass cut-off of the fused loss (see gg_hav_ce_fwd_bwd); inf = exact.
+        """
+        super().__init__()
+        if len(kwargs) > 0:  # reference behaviour, super_guessr.py:57-59
+            print(f"Not using keyword arguments: {list(kwargs.keys())}")
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        if hierarchical:
+            raise NotImplementedError(
+                "hierarchical=True (positional encoding + 16-head attention over the 4 headings, "
+                "super_guessr.py:89-99,340-345) is not on the accelerated path yet; no reference caller enables it")
+        self.base_model = base_model
+        self.panorama = panorama
+        self.hidden_size = embed_dim
+        self.serving = serving
+        self.should_smooth_labels = should_smooth_labels
+        self.freeze_base = freeze_base
+        self.hierarchical = hierarchical
+        self.num_candidates = num_candidates
+        self.precision = precision
+        self.label_smoothing_tau = float(label_smoothing_tau)
+        self.far_km = float(far_km)
+        self._set_hidden_size()
+
+        table = resolve_centroids(centroids)
+        self.geocell_centroid_coords = nn.Parameter(table, requires_grad=False)
+        self.num_cells = table.size(0)
+        self.input_dim = self.hidden_size
+        self.cell_layer = nn.Linear(self.input_dim, self.num_cells)
+        self.softmax = nn.Softmax(dim=-1)
+        self.loss_fnc = nn.CrossEntropyLoss()
+        self._freeze_params()
+        self._op_cache = None
+        self._xyz_cache = None
+        print(f"Initialized SuperGuessr classification model with {self.num_cells} geocells.")
+
+    # ---- reference helpers (super_guessr.py:114-206) ---------------------------------------
+    def _set_hidden_size(self):
+        if self.base_model is not None:
+            try:
+                self.hidden_size = self.base_model.config.hidden_size
+                self.mode = "transformer"
+            except AttributeError:
+                self.hidden_size = self.base_model.config.hidden_sizes[-1]
+                self.mode = "convnext"
+
+    def _freeze_params(self):
+        if self.base_model is not None and self.freeze_base:
+            for p in self.base_model.parameters():
+                p.requires_grad = False
+
+    def _move_to_cuda(self, pixel_values=None, embedding=None, labels=None, labels_clf=None):
+        # the reference only moves inputs in eval mode (:187-199)
+        if not self.training and next(self.parameters()).is_cuda:
+            dev = next(self.parameters()).device
+            pixel_values, embedding, labels, labels_clf = (
+                t.to(dev) if t is not None else None for t in (pixel_values, embedding, labels, labels_clf))
+        return pixel_values, embedding, labels, labels_clf
+
+    def load_state(self, path: str):
+        own = self.state_dict()
+        for name, param in torch.load(path, map_location="cuda" if torch.cuda.is_available() else "cpu").items():
+            if name not in own:
+                print(f"Parameter {name} not in model's state.")
+                continue
+            own[name].copy_(param.data if isinstance(param, nn.Parameter) else param)
+
+    # ---- operand caches ---------------------------------------------------------------------
+    def _operands(self, weight, bias):
+        """bf16 (or hi/lo split) copy of the head weights + padded bias; rebuilt when the fp32
+        master parameters change (optimizer step, load_state_dict, .to())."""
+        key = (weight.data_ptr(), weight._version, bias.data_ptr(), bias._version, self.precision, weight.device)
+        if self._op_cache is None or self._op_cache["key"] != key:
+            split = self.precision == "bf16x3"
+            w16, bias_pad = ops.prepare_head_weights(weight, bias, split=split)
+            self._op_cache = dict(key=key, w16=w16, bias_pad=bias_pad, split=split)
+        return self._op_cache
+
+    def _centroid_xyz(self):
+        c = self.geocell_centroid_coords
+        key = (c.data_ptr(), c._version, c.device)
+        if self._xyz_cache is None or self._xyz_cache[0] != key:
+            self._xyz_cache = (key, ops.centroid_unit_vectors(c.data))
+        return self._xyz_cache[1]
+
+    # ---- forward (super_guessr.py:268-395) ---------------------------------------------------
+    def forward(self, pixel_values: Tensor = None, embedding: Tensor = None, labels: Tensor = None,
+                labels_clf: Tensor = None, index: Tensor = None):
+        if self.base_model is not None:
+            assert pixel_values is not None, 'Parameter "pixel_values" must be supplied if model has a base model.'
+        else:
+            assert embedding is not None, 'Parameter "embedding" must be supplied if model does not have a base model.'
+        pixel_values, embedding, labels, labels_clf = self._move_to_cuda(pixel_values, embedding, labels, labels_clf)
+
+        # encoder (outside the accelerated path; same handling as :308-334)
+        if self.base_model is not None and pixel_values is not None:
+            if self.panorama:
+                assert pixel_values.dim() == 5, "panorama=True expects (B, 4, C, H, W)"
+                n, v, c, h, w = pixel_values.shape
+                pixel_values = pixel_values.view(n * v, c, h, w)
+            elif pixel_values.dim() > 4:
+                pixel_values = pixel_values.squeeze(1)
+            outs = self.base_model(pixel_values=pixel_values)
+            if hasattr(outs, "last_hidden_state") and self.mode == "transformer":
+                embedding = outs.last_hidden_state.mean(dim=1)
+            elif hasattr(outs, "pooler_output"):
+                embedding = outs.pooler_output
+            else:
+                embedding = outs
+            if self.panorama:
+                embedding = embedding.view(n, v, -1)
+
+        layer_input = embedding
+        if self.panorama:
+            assert layer_input.dim() == 3, "panorama=True expects embeddings of shape (B, headings, D)"
+        else:
+            assert layer_input.dim() == 2, "panorama=False expects embeddings of shape (B, D)"
+        weight, bias = self.cell_layer.weight, self.cell_layer.bias
+        if not weight.is_cuda:
+            raise ops._lib.GeoguessrB200Error(
+                "SuperGuessr parameters are on the CPU: this implementation only runs on an sm_100a GPU "
+                "(call .cuda()); there is no CPU fallback")
+
+        serving_now = (not self.training) and self.serving
+        needs_loss = not serving_now
+        smooth = bool(getattr(self, "should_smooth_labels", False)) and labels is not None
+        if needs_loss and not smooth and labels_clf is None:
+            raise ValueError("labels_clf is required for the hard-label loss (should_smooth_labels=False or labels=None)")
+
+        if needs_loss:
+            # the fused gradient costs one extra bf16 write even under no_grad; still one code path
+            loss, tv, ti, pred_cell, pred_llh = _GeocellHeadLoss.apply(
+                layer_input, weight, bias, self, labels, labels_clf, smooth)
+            topk = TopK(tv, ti)
+            return ModelOutput(loss, loss, pred_llh, pred_cell, topk, embedding)
+
+        with torch.no_grad():
+            st = self._operands(weight, bias)
+            x16 = ops.fuse_headings(layer_input, split=st["split"])
+            head = ops.head_forward(x16, st["w16"], st["bias_pad"], self.num_cells, self.num_candidates,
+                                    self.geocell_centroid_coords.data, want_logits=False)
+        return head["pred_llh"], TopK(head["topk_val"], head["topk_idx"]), embedding
+
+    def __str__(self):
+        rep = "SuperGuessr(\n"
+        rep += f"\tbase_model\t= {self.base_model is not None}\n"
+        rep += f"\tpanorama\t= {self.panorama}\n"
+        rep += f"\thierarchical\t= {self.hierarchical}\n"
+        rep += f"\tembedding_size\t= {self.hidden_size}\n"
+        rep += f"\tinput_dim\t= {self.input_dim}\n"
+        rep += f"\tnum_geocells\t= {self.num_cells}\n"
+        rep += f"\tlabel_smoothing\t= {self.should_smooth_labels}\n"
+        rep += f"\tfreeze_base\t= {self.freeze_base}\n"
+        rep += f"\tserving\t\t= {self.serving}\n"
+        rep += ")"
+        return rep

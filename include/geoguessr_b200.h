@@ -1,0 +1,126 @@
+/* geoguessr_b200.h -- C ABI of the B200-native post-encoder geolocation path.
+ *
+ * libgeoguessr_b200.so exports exactly these symbols.  All pointers are DEVICE pointers unless
+ * noted; sizes are element counts; `stream` is a cudaStream_t passed as void*; every launcher
+ * is asynchronous on that stream, re-entrant, allocates nothing and never synchronises.  Return
+ * value: GG_OK or a GG_ERR_* code; gg_last_error() (host, thread-local) holds the message.  There
+ * is no CPU fallback: a call on a machine without an sm_100 device fails with GG_ERR_CUDA.
+ *
+ * The reference (CogitoNTNU/geoguessr-ai) has no FFI: its boundary for this path is two
+ * torch.nn.Module classes.  Each entry point below names the reference lines it replaces; the
+ * Python modules geoguessr_ai_b200.SuperGuessr / ProtoRefiner (same constructor, forward and
+ * state-dict contract) are built on top of these calls via ctypes.  See INTEGRATION.md.
+ */
+#ifndef GEOGUESSR_B200_H
+#define GEOGUESSR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_ABI_VERSION 1
+
+#define GG_OK 0
+#define GG_ERR_ARG 1         /* bad shape / alignment / null pointer */
+#define GG_ERR_CUDA 2        /* CUDA runtime or driver error (no device, launch failure, ...) */
+#define GG_ERR_UNSUPPORTED 3 /* valid request outside what the kernels cover */
+
+typedef void* gg_stream_t; /* cudaStream_t */
+
+int gg_abi_version(void);
+const char* gg_last_error(void);
+
+/* ---- layout helpers (host, pure) ---------------------------------------------------------- */
+int gg_head_logits_ld(int C); /* row pitch (elements) of the bf16 logits / dlogits buffers: C rounded up to 64 */
+int gg_head_bias_pad(int C);  /* length of the zero-padded fp32 bias vector: C rounded up to 256 */
+int gg_hav_cpad(int C);       /* geocells rounded up to 4: the centroid unit-vector table is 3 * gg_hav_cpad(C) floats */
+size_t gg_head_fwd_workspace_bytes(int B, int C, int k);
+size_t gg_head_bwd_workspace_bytes(int C);
+size_t gg_hav_ce_workspace_bytes(int B);
+size_t gg_proto_retrieve_workspace_bytes(int B, int topk, int D, int ncell);
+
+/* ---- a1: heading fusion -------------------------------------------------------------------
+ * models/super_guessr.py:347  `output = layer_input.mean(dim=1)`  ((N,4,C) -> (N,C));
+ * models/proto_refiner.py:150-151 (same mean for the refiner's queries).
+ * emb (B,V,D) fp32 -> x (B, D) bf16 [split=0] or (B, 3D) = [hi|hi|lo] [split=1, fp32-faithful
+ * "bf16x3" operands].  V=1 is the single-image pass-through (:351).  sqnorm (B) optional: ||x||^2. */
+int gg_fuse_headings(const float* emb, void* x_bf16, int B, int V, int D, int split, float* sqnorm,
+                     gg_stream_t stream);
+
+/* Operand preparation for nn.Linear(D, C) (super_guessr.py:102): W (C,D) fp32 -> bf16 (C,D), or
+ * (C,3D) = [hi|lo|hi] when split=1; b (C) -> zero-padded fp32 (gg_head_bias_pad(C)). */
+int gg_prepare_head_weights(const float* w, const float* b, void* w_bf16, float* bias_pad, int C, int D, int split,
+                            gg_stream_t stream);
+int gg_cast_bf16(const float* src, void* dst_bf16, long long n, gg_stream_t stream);
+int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, float* out, gg_stream_t stream);
+
+/* ---- a2-a4: geocell head ------------------------------------------------------------------
+ * super_guessr.py:354 logits = cell_layer(output); :355 softmax; :358-361 argmax + centroid gather;
+ * :365 torch.topk(probs, num_candidates).
+ * x (B,D) bf16, w (C,D) bf16 (D here = the K extent, 3x the embed dim in split mode).
+ * logits_bf16: (B, ldc) written only when non-null (training); serving never materialises them.
+ * Outputs: topk_val (B,k) fp32 probabilities, sorted descending; topk_idx (B,k) int64; pred_cell (B)
+ * int64 = argmax; pred_llh (B,2) fp32 = centroids[pred_cell] ((lng,lat)); lse (B) fp32 row
+ * log-sum-exp (consumed by the loss).  pred_cell / pred_llh / lse may be null.  1 <= k <= 8. */
+int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, int B, int C, int D, void* logits_bf16,
+                int ldc, int k, void* workspace, const float* centroids, float* topk_val, long long* topk_idx,
+                long long* pred_cell, float* pred_llh, float* lse, gg_stream_t stream);
+
+/* ---- a5-a8: haversine label-smoothed cross-entropy, forward + gradient ---------------------
+ * models/utils.py:39-57 haversine_matrix; :20-32 smooth_labels (tau = config.py:52 = 65 km);
+ * super_guessr.py:374-380 normalise + soft CE; autograd backward (main_coordinator_idun_s3.py:423).
+ * cent_xyz: unit vectors from gg_centroid_unit_vectors (recompute when the centroid table changes).
+ * labels (B,2) fp32 (lng,lat) degrees.  dlogits (B, ldc) bf16 = softmax(logits) - t, UNSCALED
+ * (gg_head_bwd applies 1/B).  loss_rows (B) fp32 = -sum_c t log_softmax.  Optional by-products
+ * (next-row, main_coordinator_idun_s3.py:390-391): nearest_cell (B) int64 = argmin_c d,
+ * nearest_km (B) fp32.  far_km: cells farther than dmin + far_km get t = 0 (65*ln(2^40) ~= 1802 km
+ * keeps every t > 2^-40; INFINITY evaluates every cell). */
+int gg_centroid_unit_vectors(const float* centroids, float* cent_xyz, int C, gg_stream_t stream);
+int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const float* labels, const float* cent_xyz,
+                      int B, int C, float tau, float far_km, void* dlogits_bf16, float* loss_rows,
+                      long long* nearest_cell, float* nearest_km, void* workspace, gg_stream_t stream);
+/* super_guessr.py:383 nn.CrossEntropyLoss()(logits, labels_clf) and its gradient. */
+int gg_hard_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const long long* labels_clf, int B, int C,
+                       void* dlogits_bf16, float* loss_rows, gg_stream_t stream);
+/* `.mean()` of super_guessr.py:380: loss_out[0] = scale * sum_b loss_rows[b] (deterministic). */
+int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg_stream_t stream);
+
+/* ---- a8: head backward --------------------------------------------------------------------
+ * autograd of super_guessr.py:354: dW (C,D) fp32 = scale * dlogits^T x, db (C) = scale * colsum.
+ * x (B, x_ld) bf16 (first D columns used).  scale = 1/B (1/global batch under data parallelism);
+ * grad_scale: optional DEVICE scalar (the upstream dL/dloss of autograd), multiplied in on the
+ * device so that backward needs no host synchronisation. */
+int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
+                const float* grad_scale, float* dW, float* db, void* workspace, gg_stream_t stream);
+
+/* ---- a10-a15: ProtoRefiner ----------------------------------------------------------------
+ * models/proto_refiner.py:165-203 (retrieval) -- for every (query i, candidate j < topk):
+ * score = max_p -||proto_{c,p} - q_i||_2 (:190-193, _euclidean_distance :364-376), arg-best
+ * prototype (:194) and its coordinates (:251-252); a cell without prototypes scores -100000 with
+ * coordinates (0,0) (:181-187).  Bank: prototypes sorted by geocell, CSR cell_off (ncell+1, int32,
+ * local to this rank's cell range [cell_lo, cell_hi)); bank (n_protos, D) bf16, bank_sqnorm
+ * (n_protos) fp32 from gg_row_sqnorm_bf16, bank_coords (n_protos,2) fp32 (lng,lat).  q (B,D) bf16 and
+ * q_sqnorm (B) from gg_fuse_headings.  cand (B, cand_ld) int64.  rec_out: (B*topk) 16-byte records
+ * {score f32, lng f32, lat f32, prototype id i32 (proto_base + local row, -1 if none)}; pairs whose
+ * cell lies outside [cell_lo, cell_hi) get score = -inf (another rank owns them). */
+int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int B, int D, const long long* cand, int cand_ld,
+                      int topk, const void* bank_bf16, const float* bank_sqnorm, const float* bank_coords,
+                      long long n_protos, const int* cell_off, int cell_lo, int cell_hi, int proto_base, void* rec_out,
+                      void* workspace, gg_stream_t stream);
+/* models/proto_refiner.py:205-228: temperature softmax (:378-389), x candidate probs (:210), argmax
+ * (:211), max-refinement guard with preprocessing/geo_utils.py:39-54 haversine (:216-223), outputs
+ * (:225-228).  rec: nranks record arrays rank_stride records apart (all-gather layout); cand_probs
+ * (B, cand_probs_ld) fp32 or null (= one-hot on candidate 0, :154-156).  out_llh (B,2) fp32,
+ * out_cell (B) int64; optional out_guess (B) int32 (index of the chosen candidate, :226),
+ * out_score (B,topk) fp32 and out_proto (B,topk) int32 (merged stage-1 result). */
+int gg_proto_refine(const void* rec, int nranks, long long rank_stride, const float* cand_probs, int cand_probs_ld,
+                    const long long* cand, int cand_ld, const float* initial_llh, int B, int topk, float temperature,
+                    float max_refinement_km, float* out_llh, long long* out_cell, int* out_guess, float* out_score,
+                    int* out_proto, gg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOGUESSR_B200_H */

@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the post-encoder geolocation hot path (BASELINE.json contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|retrieve]
+
+Default workload = BASELINE.json configs[1]: geocell-head training step with the haversine
+label-smoothed CE, batch 4096 per GPU, D = 1024, C = 12 647, bf16 operands, 1 x B200.  A "step" is
+what the reference's trainer does per batch (main_coordinator_idun_s3.py:393-424): zero_grad ->
+SuperGuessr.forward (fusion, head, top-5, smoothed CE) -> loss.backward() (dW, db) -> [N > 1:
+NCCL all-reduce of the gradients] -> AdamW step.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+C_CELLS = 12647
+TRAIN = dict(B=4096, D=1024, V=4, k=5)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        top = sorted(sm)[len(sm) // 2:] if sm else []  # samples under load = upper half
+        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_batches(n, B, D, V, seed0):
+    from geoguessr_ai_b200 import synth
+
+    out = []
+    for i in range(n):
+        emb, _, _, labels = synth.head_inputs(B, D, 8, V=V, seed=seed0 + i)
+        out.append((emb, labels))
+    return out
+
+
+def cpu_reference_train(steps, warmup, B, D, V, threads=None):
+    """The reference's own CPU path for the same step, restated by the oracle (eager PyTorch on the
+    host cores): forward + autograd backward + AdamW.  Returns (samples/s, ms/step, cores)."""
+    from geoguessr_ai_b200 import synth
+    from geoguessr_ai_b200.geocells import load_packaged_centroids
+    from oracle import super_guessr_oracle as sgo
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cent = load_packaged_centroids()
+    emb, W, b, labels = synth.head_inputs(B, D, C_CELLS, V=V, seed=1)
+    w = W.clone().requires_grad_(True)
+    bb = b.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([w, bb], lr=1e-4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        labels_clf, _ = sgo.nearest_centroid(labels, cent)  # trainer-side label derivation (:390-391)
+        opt.zero_grad()
+        out = sgo.forward(emb, w, bb, cent, labels, labels_clf)
+        out.loss.backward()
+        opt.step()
+        float(out.loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return B / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    cfg = TRAIN
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    val, ms, cores = cpu_reference_train(steps, warmup, cfg["B"], cfg["D"], cfg["V"])
+    line = {
+        "impl": "reference", "metric": "head-train samples/s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(args.gpus, cfg),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} full steps of batch {cfg['B']} (oracle = eager CPU PyTorch restatement of "
+                                   "models/super_guessr.py forward + autograd backward + AdamW)"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def train_config(n_gpus, cfg):
+    return {"workload": "BASELINE configs[1]: geocell head training step, haversine label-smoothed CE + backward + "
+                        "AdamW, synthetic CLIP ViT-L/14 embeddings",
+            "batch_per_gpu": cfg["B"], "global_batch": cfg["B"] * n_gpus, "embed_dim": cfg["D"], "headings": cfg["V"],
+            "geocells": C_CELLS, "num_candidates": cfg["k"], "parallelism": f"dp{n_gpus}",
+            "l2": "working set per step (~0.6 GB: embeddings, W, logits, dlogits, dW, AdamW state) exceeds the 126 MB "
+                  "L2; input batches rotate over 3 resident buffers"}
+
+
+def run_b200_train(args):
+    import torch.distributed as dist
+
+    import geoguessr_ai_b200 as gg
+    from geoguessr_ai_b200 import ops
+    from geoguessr_ai_b200.geocells import load_packaged_centroids
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = TRAIN
+    B, D, V = cfg["B"], cfg["D"], cfg["V"]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    cent = load_packaged_centroids()
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, embed_dim=D, centroids=cent,
+                               num_candidates=cfg["k"]).to(dev)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        model.cell_layer.weight.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
+        model.cell_layer.bias.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
+    model.train()
+    params = [model.cell_layer.weight, model.cell_layer.bias]
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+
+    host = make_batches(3, B, D, V, seed0=100 + 10 * rank)
+    host = [(e.pin_memory(), l.pin_memory()) for e, l in host]
+    resident = [(e.to(dev), l.to(dev)) for e, l in host]
+    dummy_clf = torch.zeros(B, dtype=torch.int64, device=dev)  # unused by the smoothed loss (as in the reference)
+
+    def step(emb, labels):
+        opt.zero_grad(set_to_none=True)
+        out = model(embedding=emb, labels=labels, labels_clf=dummy_clf)
+        out.loss.backward()
+        if world > 1:
+            for p in params:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        return out.loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---------------- device-resident throughput (`value`)
+    for i in range(Wm):
+        step(*resident[i % 3])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        loss = step(*resident[i % 3])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = world * B / (ms_step / 1e3)
+    final_loss = loss.item()
+
+    # ---------------- per-launcher CUDA-event timing over a second identical timed region
+    ops.enable_timing(True)
+    barrier()
+    for i in range(min(K, 20)):
+        step(*resident[i % 3])
+    tms = ops.timing_ms()
+    ops.enable_timing(False)
+    per = {k: sum(v) / len(v) for k, v in tms.items()}
+
+    # ---------------- end to end from host buffers (`e2e`): H2D of the batch + D2H of the loss every step
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2][0].copy_(host[i % 3][0], non_blocking=True)
+            bufs[i % 2][1].copy_(host[i % 3][1], non_blocking=True)
+            evs[i % 2].record(copy_stream)
+
+    def e2e_loop(n):
+        issue_copy(0)
+        for i in range(n):
+            torch.cuda.current_stream().wait_event(evs[i % 2])
+            l = step(*bufs[i % 2])
+            if i + 1 < n:
+                issue_copy(i + 1)  # next batch crosses PCIe while this step computes
+            l.item()  # device -> host read of the step's result
+
+    Ke = max(3, min(K, 20))
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(Ke)
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / Ke
+    e2e_val = world * B / (ms_e2e / 1e3)
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant launcher
+    peaks = measured_peaks()
+    C = C_CELLS
+    flops_gemm = 2.0 * B * C * D
+    algo = {
+        "gg_head_fwd": ("tensor", flops_gemm, "TFLOP/s"),
+        "gg_head_bwd": ("tensor", flops_gemm, "TFLOP/s"),
+        "gg_hav_ce_fwd_bwd": ("hbm", B * C * (2 + 2) + 8 * B + 12 * C, "GB/s"),
+        "gg_fuse_headings": ("hbm", B * D * (4 * V + 2), "GB/s"),
+        "gg_prepare_head_weights": ("hbm", C * D * (4 + 2) + 8 * C, "GB/s"),
+    }
+    kernels = {}
+    for name, ms in per.items():
+        if name in algo:
+            bound, work, unit = algo[name]
+            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+            peak = peaks["tf_sustained"] if bound == "tensor" else peaks["hbm"]
+            kernels[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+        else:
+            kernels[name] = {"ms": ms}
+    dom = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms"])
+    roof = dict(kernels[dom])
+    roof.pop("ms")
+    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": None,
+                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; "
+                                + ("bf16_tflops_sustained: kernel timed inside the step" if roof["bound"] == "tensor"
+                                   else "hbm_gbs") + ")"})
+
+    cpu = None
+    if world == 1 or rank == 0:
+        cval, cms, cores = cpu_reference_train(2, 1, B, D, V)
+        cpu = {"value": cval, "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": cms,
+               "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
+                         "reference forward + autograd backward + AdamW)"}
+
+    launches_per_step = 1 + 2 + 2 + 2 + 1 + 3  # fuse, prepare(cast+bias), head_fwd(+merge), hav(+labels), mean, bwd(+db x2)
+    line = {
+        "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+        "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": train_config(world, cfg), "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "steps": Ke},
+        "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+        "loss": final_loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200_train(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,33 @@ from . import _lib
 FAR_KM_DEFAULT = 65.0 * math.log(2.0 ** 40)  # ~1802 km: targets below 2^-40 of the nearest cell's are dropped
 
 
+# Optional per-launcher timing (bench.py): when enabled, every C-ABI call is bracketed by CUDA events
+# recorded on the launching stream (the current torch stream), name -> [(start, end), ...].
+_events = None
+
+
+def enable_timing(on: bool = True):
+    global _events
+    _events = {} if on else None
+
+
+def timing_ms():
+    """Synchronises and returns {launcher: [ms per call, ...]} for the calls since enable_timing()."""
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (_events or {}).items()}
+
+
+def _call(name, fn, *args):
+    if _events is None:
+        _lib.check(fn(*args), name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _lib.check(fn(*args), name)
+    b.record()
+    _events.setdefault(name, []).append((a, b))
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -59,7 +86,7 @@ def fuse_headings(emb: torch.Tensor, split: bool = False, want_sqnorm: bool = Fa
     x = torch.empty((B, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
     sq = torch.empty((B,), dtype=torch.float32, device=emb.device) if want_sqnorm else None
     lib = _lib.load()
-    _lib.check(lib.gg_fuse_headings(_ptr(emb), _ptr(x), B, V, D, int(split), _ptr(sq), _stream()), "gg_fuse_headings")
+    _call("gg_fuse_headings", lib.gg_fuse_headings, _ptr(emb), _ptr(x), B, V, D, int(split), _ptr(sq), _stream())
     return (x, sq) if want_sqnorm else x
 
 
@@ -72,8 +99,7 @@ def prepare_head_weights(weight: torch.Tensor, bias: torch.Tensor, split: bool =
     w16 = torch.empty((C, 3 * D if split else D), dtype=torch.bfloat16, device=w.device)
     bp = torch.empty((bias_pad_len(C),), dtype=torch.float32, device=w.device)
     lib = _lib.load()
-    _lib.check(lib.gg_prepare_head_weights(_ptr(w), _ptr(b), _ptr(w16), _ptr(bp), C, D, int(split), _stream()),
-               "gg_prepare_head_weights")
+    _call("gg_prepare_head_weights", lib.gg_prepare_head_weights, _ptr(w), _ptr(b), _ptr(w16), _ptr(bp), C, D, int(split), _stream())
     return w16, bp
 
 
@@ -82,8 +108,7 @@ def row_sqnorm_bf16(m: torch.Tensor) -> torch.Tensor:
     assert m.dtype == torch.bfloat16 and m.dim() == 2 and m.is_contiguous()
     out = torch.empty((m.shape[0],), dtype=torch.float32, device=m.device)
     if m.shape[0]:
-        _lib.check(_lib.load().gg_row_sqnorm_bf16(_ptr(m), m.shape[0], m.shape[1], _ptr(out), _stream()),
-                   "gg_row_sqnorm_bf16")
+        _call("gg_row_sqnorm_bf16", _lib.load().gg_row_sqnorm_bf16, _ptr(m), m.shape[0], m.shape[1], _ptr(out), _stream())
     return out
 
 
@@ -104,11 +129,9 @@ def head_forward(x16, w16, bias_pad, C, k, centroids, want_logits: bool):
     pred_cell = torch.empty((B,), dtype=torch.int64, device=dev)
     pred_llh = torch.empty((B, 2), dtype=torch.float32, device=dev)
     lse = torch.empty((B,), dtype=torch.float32, device=dev)
-    _lib.check(
-        lib.gg_head_fwd(_ptr(x16), _ptr(w16), _ptr(bias_pad), B, C, K, _ptr(logits), ldc, k, _ptr(ws),
+    _call("gg_head_fwd", lib.gg_head_fwd, _ptr(x16), _ptr(w16), _ptr(bias_pad), B, C, K, _ptr(logits), ldc, k, _ptr(ws),
                         _ptr(centroids), _ptr(topk_val), _ptr(topk_idx), _ptr(pred_cell), _ptr(pred_llh), _ptr(lse),
-                        _stream()),
-        "gg_head_fwd")
+                        _stream())
     return dict(topk_val=topk_val, topk_idx=topk_idx, pred_cell=pred_cell, pred_llh=pred_llh, lse=lse, logits=logits)
 
 
@@ -119,7 +142,7 @@ def centroid_unit_vectors(centroids: torch.Tensor) -> torch.Tensor:
     C = c.shape[0]
     lib = _lib.load()
     xyz = torch.empty((3 * lib.gg_hav_cpad(C),), dtype=torch.float32, device=c.device)
-    _lib.check(lib.gg_centroid_unit_vectors(_ptr(c), _ptr(xyz), C, _stream()), "gg_centroid_unit_vectors")
+    _call("gg_centroid_unit_vectors", lib.gg_centroid_unit_vectors, _ptr(c), _ptr(xyz), C, _stream())
     return xyz
 
 
@@ -137,11 +160,9 @@ def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, wa
     ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
     nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
     ws = _u8(lib.gg_hav_ce_workspace_bytes(B), dev)
-    _lib.check(
-        lib.gg_hav_ce_fwd_bwd(_ptr(logits), ldc, _ptr(lse), _ptr(labels), _ptr(cent_xyz), B, C, float(tau),
+    _call("gg_hav_ce_fwd_bwd", lib.gg_hav_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(labels), _ptr(cent_xyz), B, C, float(tau),
                               float(far_km), _ptr(dlogits), _ptr(loss_rows), _ptr(ncell), _ptr(nkm), _ptr(ws),
-                              _stream()),
-        "gg_hav_ce_fwd_bwd")
+                              _stream())
     return dlogits, loss_rows, ncell, nkm
 
 
@@ -152,18 +173,16 @@ def hard_ce(logits, lse, labels_clf, C):
     assert y.shape == (B,), "labels_clf must be (B,)"
     dlogits = torch.empty_like(logits)
     loss_rows = torch.zeros((B,), dtype=torch.float32, device=logits.device)
-    _lib.check(
-        _lib.load().gg_hard_ce_fwd_bwd(_ptr(logits), ldc, _ptr(lse), _ptr(y), B, C, _ptr(dlogits), _ptr(loss_rows),
-                                       _stream()),
-        "gg_hard_ce_fwd_bwd")
+    _call("gg_hard_ce_fwd_bwd", _lib.load().gg_hard_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(y), B, C, _ptr(dlogits), _ptr(loss_rows),
+                                       _stream())
     return dlogits, loss_rows
 
 
 def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tensor:
     B = loss_rows.shape[0]
     out = torch.empty((), dtype=torch.float32, device=loss_rows.device)
-    _lib.check(_lib.load().gg_loss_mean(_ptr(loss_rows), B, float(1.0 / B if scale is None else scale), _ptr(out),
-                                        _stream()), "gg_loss_mean")
+    _call("gg_loss_mean", _lib.load().gg_loss_mean, _ptr(loss_rows), B, float(1.0 / B if scale is None else scale), _ptr(out),
+                                        _stream())
     return out
 
 
@@ -178,10 +197,8 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True):
     ws = _u8(lib.gg_head_bwd_workspace_bytes(C), dev) if want_db else None
     if grad_scale is not None:
         grad_scale = grad_scale.detach().float().contiguous()
-    _lib.check(
-        lib.gg_head_bwd(_ptr(dlogits), ldc, _ptr(x16), x16.shape[1], B, C, D, float(scale), _ptr(grad_scale), _ptr(dW),
-                        _ptr(db), _ptr(ws), _stream()),
-        "gg_head_bwd")
+    _call("gg_head_bwd", lib.gg_head_bwd, _ptr(dlogits), ldc, _ptr(x16), x16.shape[1], B, C, D, float(scale), _ptr(grad_scale), _ptr(dW),
+                        _ptr(db), _ptr(ws), _stream())
     return dW, db
 
 
@@ -197,11 +214,9 @@ def proto_retrieve(q16, q_sqnorm, cand, topk, bank16, bank_sqnorm, bank_coords, 
     n_protos = 0 if bank16 is None else bank16.shape[0]
     rec = torch.empty((B * topk, 4), dtype=torch.float32, device=dev)
     ws = _u8(lib.gg_proto_retrieve_workspace_bytes(B, topk, D, cell_hi - cell_lo), dev)
-    _lib.check(
-        lib.gg_proto_retrieve(_ptr(q16), _ptr(q_sqnorm), B, D, _ptr(cand), cand.shape[1], topk, _ptr(bank16),
+    _call("gg_proto_retrieve", lib.gg_proto_retrieve, _ptr(q16), _ptr(q_sqnorm), B, D, _ptr(cand), cand.shape[1], topk, _ptr(bank16),
                               _ptr(bank_sqnorm), _ptr(bank_coords), n_protos, _ptr(cell_off), cell_lo, cell_hi,
-                              proto_base, _ptr(rec), _ptr(ws), _stream()),
-        "gg_proto_retrieve")
+                              proto_base, _ptr(rec), _ptr(ws), _stream())
     return rec
 
 
@@ -222,12 +237,10 @@ def proto_refine(rec, nranks, cand, cand_probs, initial, topk, temperature, max_
     out_guess = torch.empty((B,), dtype=torch.int32, device=dev)
     out_score = torch.empty((B, topk), dtype=torch.float32, device=dev) if want_debug else None
     out_proto = torch.empty((B, topk), dtype=torch.int32, device=dev) if want_debug else None
-    _lib.check(
-        _lib.load().gg_proto_refine(_ptr(rec), nranks, B * topk, _ptr(cand_probs),
+    _call("gg_proto_refine", _lib.load().gg_proto_refine, _ptr(rec), nranks, B * topk, _ptr(cand_probs),
                                     0 if cand_probs is None else cand_probs.shape[1], _ptr(cand), cand.shape[1],
                                     _ptr(initial), B, topk, float(temperature), float(max_refinement), _ptr(out_llh),
-                                    _ptr(out_cell), _ptr(out_guess), _ptr(out_score), _ptr(out_proto), _stream()),
-        "gg_proto_refine")
+                                    _ptr(out_cell), _ptr(out_guess), _ptr(out_score), _ptr(out_proto), _stream())
     if want_debug:
         return out_llh, out_cell, out_guess, out_score, out_proto
     return out_llh, out_cell, out_guess

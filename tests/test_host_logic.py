@@ -1,0 +1,158 @@
+"""CPU: host-side logic -- module contract (constructor, state-dict keys, error behaviour), synthetic
+input generators, geocell sharding, and the N > 1 merge protocol over gloo (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import geoguessr_ai_b200 as gg
+from geoguessr_ai_b200 import synth
+from geoguessr_ai_b200.proto_refiner import shard_cells
+from oracle import proto_refiner_oracle as pro
+
+
+def test_superguessr_contract(centroids, capsys):
+    m = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, serving=False, some_unknown_kwarg=1)
+    out = capsys.readouterr().out
+    assert "Not using keyword arguments: ['some_unknown_kwarg']" in out
+    assert "Initialized SuperGuessr classification model with 12647 geocells." in out
+    sd = m.state_dict()
+    assert set(sd) == {"geocell_centroid_coords", "cell_layer.weight", "cell_layer.bias"}
+    assert sd["cell_layer.weight"].shape == (12647, 1024) and sd["cell_layer.bias"].shape == (12647,)
+    assert sd["geocell_centroid_coords"].shape == (12647, 2) and not m.geocell_centroid_coords.requires_grad
+    assert torch.equal(m.geocell_centroid_coords.data, centroids)
+    assert (m.num_cells, m.num_candidates, m.serving, m.hidden_size) == (12647, 5, False, 1024)
+    with pytest.raises(AssertionError):
+        m(pixel_values=None, embedding=None)
+    with pytest.raises(NotImplementedError):
+        gg.SuperGuessr(None, hierarchical=True, centroids=centroids)
+    assert gg.ModelOutput._fields == ("loss", "loss_clf", "preds_LLH", "preds_geocell", "top5_geocells", "embedding")
+    v, i = gg.TopK(1, 2)
+    assert (v, i) == (1, 2)
+
+
+def test_protorefiner_contract(centroids):
+    sizes = synth.cell_sizes(50, 200, seed=0, mode="skewed", missing_frac=0.1)
+    off, bank, xy = synth.proto_bank(sizes, 16, None, seed=0)
+    r = gg.ProtoRefiner(topk=5, bank=(off, bank, xy), device="cpu")
+    assert set(r.state_dict()) == {"temperature", "geo_scaling"}
+    assert abs(r.temperature.item() - 1.6) < 1e-6 and r.geo_scaling.item() == 20.0
+    assert r.bank.dtype == torch.bfloat16 and r.bank.shape == (200, 16)
+    with pytest.raises(AssertionError):  # topk > number of candidate columns (proto_refiner.py:145)
+        r(torch.zeros(2, 16), torch.zeros(2, 2), torch.zeros(2, 3, dtype=torch.int64))
+    with pytest.raises(gg.ops._lib.GeoguessrB200Error):
+        r(torch.zeros(2, 16), torch.zeros(2, 2), torch.zeros(2, 5, dtype=torch.int64))
+    with pytest.raises(NotImplementedError):
+        gg.ProtoRefiner(protos=None)
+    protos, coords = synth.bank_as_lists(off, bank, xy)
+    r2 = gg.ProtoRefiner(topk=3, protos=protos, coords=coords, device="cpu")
+    assert torch.equal(r2.cell_off, r.cell_off) and torch.equal(r2.bank, r.bank)
+
+
+def test_synth_is_deterministic():
+    a = synth.head_inputs(4, 16, 10, seed=3)
+    b = synth.head_inputs(4, 16, 10, seed=3)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    e, W, bb, _ = synth.head_inputs(4, 16, 10, seed=3, bf16_round=True)
+    assert torch.equal(e.mean(1), e.mean(1).to(torch.bfloat16).float()) and torch.equal(W, W.to(torch.bfloat16).float())
+    s = synth.cell_sizes(100, 1000, seed=1, mode="skewed", missing_frac=0.1)
+    assert s.sum() == 1000 and (s == 0).any()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_cells_partitions_every_cell_once(world):
+    sizes = synth.cell_sizes(12647, 1_000_000, seed=2, mode="skewed", missing_frac=0.02)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    parts = shard_cells(off, world)
+    assert parts[0][0] == 0 and parts[-1][1] == 12647
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    loads = [off[hi] - off[lo] for lo, hi in parts]
+    assert max(loads) - min(loads) <= 2 * sizes.max() + 1  # balanced by prototype count
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _merge_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C, D, B, k = 300, 32, 40, 5
+    sizes = synth.cell_sizes(C, 2000, seed=4, mode="skewed", missing_frac=0.05)
+    off, bank, xy = synth.proto_bank(sizes, D, None, seed=4)
+    rng = np.random.default_rng(5)
+    emb = torch.from_numpy(rng.standard_normal((B, D), dtype=np.float32))
+    cand = torch.from_numpy(rng.integers(0, C, (B, k)))
+    protos, _ = synth.bank_as_lists(off, bank, xy)
+    lo, hi = shard_cells(off.numpy().astype(np.int64), world)[rank]
+    # what a rank's retrieval kernel produces: records for owned cells, -inf elsewhere
+    local = [p if lo <= c < hi else None for c, p in enumerate(protos)]
+    score, idx, _ = pro.best_per_candidate(emb, cand, local, k)
+    owned = (cand >= lo) & (cand < hi)
+    score = torch.where(owned, score, torch.full_like(score, -float("inf")))
+    rec = torch.stack([score, idx.float()], -1)
+    gathered = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(gathered, rec)
+    g = torch.stack(gathered)  # (world, B, k, 2): the layout gg_proto_refine consumes
+    best = g[..., 0].argmax(0)
+    merged = torch.gather(g, 0, best[None, ..., None].expand(1, B, k, 2))[0]
+    if rank == 0:
+        full_score, full_idx, _ = pro.best_per_candidate(emb, cand, protos, k)
+        q.put((torch.equal(merged[..., 0], full_score), torch.equal(merged[..., 1].long(), full_idx),
+               int((g[..., 0] > -float("inf")).sum(0).max())))
+    dist.destroy_process_group()
+
+
+def test_sharded_retrieval_merge_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_merge_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_score, same_idx, owners = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    assert same_score and same_idx and owners == 1  # exactly one rank owns each pair's cell
+
+
+def _dp_worker(rank, world, port, q):
+    """Data-parallel head step: averaged per-rank gradients == gradient of the global batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import super_guessr_oracle as sgo
+
+    C, D, B = 200, 16, 12
+    cent = torch.stack([torch.linspace(-170, 170, C), torch.linspace(-50, 70, C)], 1)
+    emb, W, b, labels = synth.head_inputs(B * world, D, C, seed=9)
+    sl = slice(rank * B, (rank + 1) * B)
+    _, gW, gb = sgo.forward_backward(emb[sl], W, b, cent, labels[sl])
+    dist.all_reduce(gW)
+    dist.all_reduce(gb)
+    gW /= world
+    gb /= world
+    if rank == 0:
+        _, fW, fb = sgo.forward_backward(emb, W, b, cent, labels)
+        q.put((float((gW - fW).abs().max()), float((gb - fb).abs().max())))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    eW, eb = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    assert eW < 1e-7 and eb < 1e-7

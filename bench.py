@@ -120,12 +120,11 @@ def cpu_reference_train(steps, warmup, B, D, V, threads=None):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        labels_clf, _ = sgo.nearest_centroid(labels, cent)  # trainer-side label derivation (:390-391)
         opt.zero_grad()
-        out = sgo.forward(emb, w, bb, cent, labels, labels_clf)
+        out = sgo.forward(emb, w, bb, cent, labels, None)  # the smoothed loss never reads labels_clf
         out.loss.backward()
         opt.step()
-        float(out.loss)
+        float(out.loss.detach())
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)

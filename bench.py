@@ -320,7 +320,7 @@ def run_b200_train(args):
                "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
                          "reference forward + autograd backward + AdamW)"}
 
-    launches_per_step = 1 + 2 + 2 + 2 + 1 + 3  # fuse, prepare(cast+bias), head_fwd(+merge), hav(+labels), mean, bwd(+db x2)
+    launches_per_step = 1 + 2 + 2 + 2 + 1 + 2  # fuse, prepare(cast+bias), head_fwd(+merge), hav(+labels), mean, bwd(+db)
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "gg_head_fwd_workspace_bytes": (c_size_t, [I, I, I]),
     "gg_head_bwd_workspace_bytes": (c_size_t, [I]),
     "gg_hav_ce_workspace_bytes": (c_size_t, [I]),
+    "gg_hav_ce_db_parts": (I, [I]),
     "gg_proto_retrieve_workspace_bytes": (c_size_t, [I, I, I, I]),
     "gg_fuse_headings": (I, [P, P, I, I, I, I, P, P]),
     "gg_prepare_head_weights": (I, [P, P, P, P, I, I, I, P]),
@@ -33,10 +34,10 @@ SIGNATURES = {
     "gg_row_sqnorm_bf16": (I, [P, L, I, P, P]),
     "gg_head_fwd": (I, [P, P, P, I, I, I, P, I, I, P, P, P, P, P, P, P, P]),
     "gg_centroid_unit_vectors": (I, [P, P, I, P]),
-    "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, F, P, P, P, P, P, P]),
+    "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, F, P, P, P, P, P, P, P]),
     "gg_hard_ce_fwd_bwd": (I, [P, I, P, P, I, I, P, P, P]),
     "gg_loss_mean": (I, [P, I, F, P, P]),
-    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, P]),
+    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P]),
     "gg_proto_retrieve": (I, [P, P, I, I, P, I, I, P, P, P, L, P, I, I, I, P, P, P]),
     "gg_proto_refine": (I, [P, I, L, P, I, P, I, P, I, I, F, F, P, P, P, P, P, P]),
 }

@@ -23,6 +23,8 @@
 // owns the same 4-cell chunks in every pass, so q / s stay in its registers.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -101,13 +103,14 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
               const float4* __restrict__ lab_xyz, const float* __restrict__ cent_xyz, int Cpad, int B, int C,
               float inv_tau, float cos_half_far, float sin_half_far, bf16* __restrict__ dlogits,
               float* __restrict__ loss_rows, long long* __restrict__ nearest_cell,
-              float* __restrict__ nearest_km) {
+              float* __restrict__ nearest_km, float* __restrict__ db_partials) {
   extern __shared__ float4 smem_f4[];
   const int nchunks = Cpad >> 2;
   float4* cx = smem_f4;
   float4* cy = cx + nchunks;
   float4* cz = cy + nchunks;
-  float* red_min = reinterpret_cast<float*>(cz + nchunks);  // [32]
+  float4* dbs = cz + nchunks;  // per-CTA column sums of the gradient (bias gradient), owned per thread
+  float* red_min = reinterpret_cast<float*>(dbs + nchunks);  // [32]
   float* red_sum = red_min + 32;                      // [32]
   float* red_loss = red_sum + 32;                     // [2][32]
   int* s_argmin = reinterpret_cast<int*>(red_loss + 64);
@@ -118,6 +121,7 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
   {  // centroid table -> shared memory (L2 hits after the first CTA)
     const float4* gx = reinterpret_cast<const float4*>(cent_xyz);
     for (int i = tid; i < 3 * nchunks; i += nthr) smem_f4[i] = __ldg(gx + i);
+    for (int i = tid; i < nchunks; i += nthr) dbs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (tid == 0) *s_argmin = 0x7fffffff;
   __syncthreads();
@@ -127,18 +131,31 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
   int prev_row = -1;
   float prev_lse = 0.f, prev_valid = 0.f;
 
-  for (int row = blockIdx.x; row < B; row += gridDim.x, parity ^= 1) {
-    const bf16* lrow = logits + static_cast<size_t>(row) * ldc;
-    bf16* grow = dlogits + static_cast<size_t>(row) * ldc;
-    // prefetch this row's logits (the only HBM read) before the distance passes
-    uint2 lraw[SLOTS];
+  // software pipeline over rows: the next row's logits (the only HBM read), label vector and lse are
+  // requested while the current row is processed
+  uint2 lraw_next[SLOTS];
+  float4 u_next = make_float4(0.f, 0.f, 1.f, 0.f);
+  float lse_next = 0.f;
+  auto fetch_row = [&](int r) {
+    const uint2* lrow = reinterpret_cast<const uint2*>(logits + static_cast<size_t>(r) * ldc);
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
       const int g = j * nthr + tid;
-      lraw[j] = (g < nchunks) ? __ldcs(reinterpret_cast<const uint2*>(lrow) + g) : make_uint2(0u, 0u);
+      lraw_next[j] = (j < SLOTS - 1 || g < nchunks) ? __ldcs(lrow + g) : make_uint2(0u, 0u);
     }
-    const float4 u = __ldg(lab_xyz + row);
-    const float row_lse = __ldg(lse + row);
+    u_next = __ldg(lab_xyz + r);
+    lse_next = __ldg(lse + r);
+  };
+  if (blockIdx.x < B) fetch_row(blockIdx.x);
+
+  for (int row = blockIdx.x; row < B; row += gridDim.x, parity ^= 1) {
+    bf16* grow = dlogits + static_cast<size_t>(row) * ldc;
+    uint2 lraw[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) lraw[j] = lraw_next[j];
+    const float4 u = u_next;
+    const float row_lse = lse_next;
+    if (row + gridDim.x < B) fetch_row(row + gridDim.x);
 
     // ---- pass 1a: squared chords to every centroid, row minimum
     float qmin = CUDART_INF_F;
@@ -147,7 +164,7 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
     for (int j = 0; j < SLOTS; ++j) {
       const int g = j * nthr + tid;
       qs[j] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
-      if (g < nchunks) {
+      if (j < SLOTS - 1 || g < nchunks) {
         const float4 x = cx[g], y = cy[g], z = cz[g];
         float4 q;
         float dx, dy, dz;
@@ -244,7 +261,7 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
       const int g = j * nthr + tid;
-      if (g < nchunks) {
+      if (j < SLOTS - 1 || g < nchunks) {
         float l0 = __uint_as_float(lraw[j].x << 16), l1 = __uint_as_float(lraw[j].x & 0xffff0000u);
         float l2 = __uint_as_float(lraw[j].y << 16), l3 = __uint_as_float(lraw[j].y & 0xffff0000u);
         float g0 = ex2_approx(fmaf(l0, kLog2eF, -lse2));
@@ -267,6 +284,12 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
         o.x = pack_bf16x2(g0, g1);
         o.y = pack_bf16x2(g2, g3);
         __stcs(reinterpret_cast<uint2*>(grow) + g, o);
+        if (db_partials != nullptr) {  // sum the bf16-rounded values the dW GEMM will see
+          float4 a = dbs[g];
+          a.x += __uint_as_float(o.x << 16); a.y += __uint_as_float(o.x & 0xffff0000u);
+          a.z += __uint_as_float(o.y << 16); a.w += __uint_as_float(o.y & 0xffff0000u);
+          dbs[g] = a;
+        }
       }
     }
     sl = warp_sum(sl);
@@ -281,6 +304,14 @@ hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict_
     if (lane >= nwarps) sl = 0.f;
     sl = warp_sum(sl);
     if (lane == 0) loss_rows[prev_row] = prev_valid != 0.f ? prev_lse - sl : 0.f;
+  }
+  if (db_partials != nullptr) {  // each chunk was only ever touched by its owning thread
+    float4* out = reinterpret_cast<float4*>(db_partials + static_cast<size_t>(blockIdx.x) * Cpad);
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+      const int g = j * nthr + tid;
+      if (j < SLOTS - 1 || g < nchunks) out[g] = dbs[g];
+    }
   }
 }
 
@@ -346,11 +377,14 @@ extern "C" int gg_centroid_unit_vectors(const float* centroids, float* cent_xyz,
 }
 
 extern "C" size_t gg_hav_ce_workspace_bytes(int B) { return static_cast<size_t>(B) * sizeof(float4); }
+// db_partials is (gg_hav_ce_db_parts(B), gg_hav_cpad(C)) fp32: one row of column sums per CTA
+extern "C" int gg_hav_ce_db_parts(int B) { return std::min(B, device_sm_count()); }
 
 template <int SLOTS>
 static int launch_hav(const void* logits, int ldc, const float* lse, const float4* lab, const float* cent_xyz,
                       int Cpad, int B, int C, float tau, float far_km, void* dlogits, float* loss_rows,
-                      long long* nearest_cell, float* nearest_km, int nthr, size_t smem, cudaStream_t s) {
+                      long long* nearest_cell, float* nearest_km, float* db_partials, int nthr, size_t smem,
+                      cudaStream_t s) {
   auto kern = hav_ce_kernel<SLOTS>;
   GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = std::min(B, device_sm_count());
@@ -359,15 +393,15 @@ static int launch_hav(const void* logits, int ldc, const float* lse, const float
   if (!(half_phi < 1.5707963267948966)) half_phi = 1.5707963267948966;
   kern<<<grid, nthr, smem, s>>>(static_cast<const bf16*>(logits), ldc, lse, lab, cent_xyz, Cpad, B, C, 1.0f / tau,
                                 static_cast<float>(cos(half_phi)), static_cast<float>(sin(half_phi)),
-                                static_cast<bf16*>(dlogits), loss_rows, nearest_cell, nearest_km);
+                                static_cast<bf16*>(dlogits), loss_rows, nearest_cell, nearest_km, db_partials);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const float* labels,
                                  const float* cent_xyz, int B, int C, float tau, float far_km, void* dlogits_bf16,
-                                 float* loss_rows, long long* nearest_cell, float* nearest_km, void* workspace,
-                                 gg_stream_t stream) {
+                                 float* loss_rows, long long* nearest_cell, float* nearest_km, float* db_partials,
+                                 void* workspace, gg_stream_t stream) {
   GG_CHECK(B > 0 && C > 0, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: empty problem B=%d C=%d", B, C);
   GG_CHECK(logits_bf16 && lse && labels && cent_xyz && dlogits_bf16 && loss_rows && workspace, GG_ERR_ARG,
            "gg_hav_ce_fwd_bwd: null pointer");
@@ -377,10 +411,10 @@ extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Cpad = gg_hav_cpad(C);
   const int nchunks = Cpad / 4;
-  const size_t smem = static_cast<size_t>(nchunks) * 3 * sizeof(float4) + 160 * sizeof(float);
+  const size_t smem = static_cast<size_t>(nchunks) * 4 * sizeof(float4) + 160 * sizeof(float);
   GG_CHECK(smem <= 227 * 1024, GG_ERR_UNSUPPORTED,
            "gg_hav_ce_fwd_bwd: C=%d needs %zu B of shared memory for the resident centroid table (max 232448); "
-           "geocell tables above ~19k cells are not supported yet", C, smem);
+           "geocell tables above ~14.5k cells are not supported yet", C, smem);
   float4* lab = static_cast<float4*>(workspace);
   label_xyz_kernel<<<ceil_div(B, 256), 256, 0, s>>>(labels, lab, B);
   GG_LAUNCH_CHECK();
@@ -388,10 +422,10 @@ extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* 
   int nthr = ceil_div(ceil_div(nchunks, slots), 32) * 32;
   if (nthr < 128) nthr = 128;
   switch (slots) {
-    case 1: return launch_hav<1>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, nthr, smem, s);
-    case 2: return launch_hav<2>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, nthr, smem, s);
-    case 3: return launch_hav<3>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, nthr, smem, s);
-    default: return launch_hav<4>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, nthr, smem, s);
+    case 1: return launch_hav<1>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
+    case 2: return launch_hav<2>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
+    case 3: return launch_hav<3>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
+    default: return launch_hav<4>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
   }
 }
 

@@ -191,14 +191,21 @@ __global__ void db_partial_kernel(const bf16* __restrict__ g, int ldc, int B, in
     }
   }
 }
-__global__ void db_final_kernel(const float* __restrict__ partial, int C, int slices, float scale_in,
+__global__ void db_final_kernel(const float* __restrict__ partial, int C, int ld, int slices, float scale_in,
                                 const float* __restrict__ grad_scale, float* __restrict__ db) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
-  float s = 0.f;
-  for (int i = 0; i < slices; ++i) s += partial[static_cast<size_t>(i) * C + c];
-  db[c] = s * scale;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // fixed order: deterministic
+  int i = 0;
+  for (; i + 4 <= slices; i += 4) {
+    s0 += partial[static_cast<size_t>(i) * ld + c];
+    s1 += partial[static_cast<size_t>(i + 1) * ld + c];
+    s2 += partial[static_cast<size_t>(i + 2) * ld + c];
+    s3 += partial[static_cast<size_t>(i + 3) * ld + c];
+  }
+  for (; i < slices; ++i) s0 += partial[static_cast<size_t>(i) * ld + c];
+  db[c] = ((s0 + s1) + (s2 + s3)) * scale;
 }
 
 }  // namespace gg
@@ -208,13 +215,14 @@ using namespace gg;
 extern "C" size_t gg_head_bwd_workspace_bytes(int C) { return static_cast<size_t>(kDbSlices) * C * sizeof(float); }
 
 extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
-                           float scale, const float* grad_scale, float* dW, float* db, void* workspace,
-                           gg_stream_t stream) {
+                           float scale, const float* grad_scale, float* dW, float* db, const float* db_partials,
+                           int db_parts, int db_ld, void* workspace, gg_stream_t stream) {
   GG_CHECK(B > 0 && C > 0 && D > 0, GG_ERR_ARG, "gg_head_bwd: empty problem B=%d C=%d D=%d", B, C, D);
   GG_CHECK(dlogits_bf16 && x_bf16 && dW, GG_ERR_ARG, "gg_head_bwd: null pointer");
   GG_CHECK(ldc >= C && ldc % 8 == 0, GG_ERR_ARG, "gg_head_bwd: ldc=%d must be >= C and a multiple of 8", ldc);
   GG_CHECK(D % 8 == 0 && x_ld >= D && x_ld % 8 == 0, GG_ERR_ARG, "gg_head_bwd: D=%d / x_ld=%d must be multiples of 8", D, x_ld);
-  GG_CHECK(!db || workspace, GG_ERR_ARG, "gg_head_bwd: db needs the workspace");
+  GG_CHECK(!db || workspace || db_partials, GG_ERR_ARG, "gg_head_bwd: db needs the workspace or db_partials");
+  GG_CHECK(!db_partials || (db_parts > 0 && db_ld >= C), GG_ERR_ARG, "gg_head_bwd: bad db_partials shape");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUtensorMap tm_g, tm_x;
   int rc = make_tmap_bf16_2d(&tm_g, dlogits_bf16, C, B, static_cast<uint64_t>(ldc) * 2, 64, kWK);
@@ -227,12 +235,15 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   GG_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   head_bwd_kernel<<<grid, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
   GG_LAUNCH_CHECK();
-  if (db) {
+  if (db && db_partials) {  // column sums already accumulated by the loss kernel (one row per CTA)
+    db_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(db_partials, C, db_ld, db_parts, scale, grad_scale, db);
+    GG_LAUNCH_CHECK();
+  } else if (db) {
     float* partial = static_cast<float*>(workspace);
     dim3 blk(32, 8), grd(ceil_div(ldc, 256), kDbSlices);
     db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);
     GG_LAUNCH_CHECK();
-    db_final_kernel<<<ceil_div(C, 256), 256, 0, s>>>(partial, C, kDbSlices, scale, grad_scale, db);
+    db_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(partial, C, C, kDbSlices, scale, grad_scale, db);
     GG_LAUNCH_CHECK();
   }
   return GG_OK;

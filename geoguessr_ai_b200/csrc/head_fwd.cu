@@ -2,14 +2,23 @@
 //
 // Replaces  models/super_guessr.py:354 (nn.Linear), :355 (softmax), :358-361 (argmax + centroid
 // gather) and :365 (top-k) of the reference.  Per 128x256 output tile the accumulator lives in
-// TMEM (2 x 256 fp32 columns, double buffered); the epilogue warps add the bias, optionally
-// write the bf16 logits (training only) and keep, per row, an online (max, sum-exp) and the top-K
-// logits of the tile, so that in serving the (B, C) logit / probability matrices never reach HBM.
-// A small merge kernel combines the per-tile partials into top-k probabilities and indices,
-// argmax, predicted centroid and the row log-sum-exp.
+// TMEM (2 x 256 fp32 columns, double buffered); eight epilogue warps (two per TMEM lane quadrant,
+// 128 columns each) add the bias, optionally write the bf16 logits (training only) and keep, per
+// row, an online (max, sum-exp) and the running top-K logits, so that in serving the (B, C) logit /
+// probability matrices never reach HBM.
+//
+// Tile schedule: tiles are ordered geocell-tile-fastest within a 128-row block and every CTA owns a
+// CONTIGUOUS range of that order, i.e. it sweeps many geocell tiles of the same rows back to back.
+// The per-row state therefore stays in registers across tiles ("run") and is flushed once per
+// (CTA, row block): after the first tile the running 5th-best logit rejects almost every 32-column
+// chunk by its maximum alone (which the softmax needs anyway), so the top-k costs ~1 compare per
+// chunk.  A warp-per-row merge kernel combines the few partials of a row into top-k probabilities
+// and indices, argmax, predicted centroid and the row log-sum-exp.
 //
 // Layout: x (M=B, K=D) bf16 row-major; W (N=C, K=D) bf16 row-major (both K-major operands, 128 B
 // swizzled TMA boxes of 64 K-elements); logits (B, ldc) bf16, ldc >= C padded to a multiple of 64.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -19,7 +28,8 @@ constexpr int kBM = 128;        // rows of x per tile (UMMA M)
 constexpr int kBN = 256;        // geocells per tile   (UMMA N)
 constexpr int kBK = 64;         // K elements per stage (128 B of bf16 = one swizzle span)
 constexpr int kStages = 4;      // 4 x (16 KB + 32 KB) = 192 KB
-constexpr int kFwdThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kFwdThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kStageBytesA = kBM * kBK * 2;
 constexpr uint32_t kStageBytesB = kBN * kBK * 2;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -33,6 +43,27 @@ struct FwdSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
 };
+
+// Static schedule shared by the kernel, the merge kernel and the host.
+struct FwdSched {
+  int num_m, num_n, tiles, grid, base, rem, runs;  // runs = max row blocks a CTA can touch
+  __host__ __device__ int start(int c) const { return c * base + (c < rem ? c : rem); }
+  __host__ __device__ int owner(int t) const {
+    const int cut = rem * (base + 1);
+    return t < cut ? t / (base + 1) : rem + (t - cut) / base;
+  }
+};
+static FwdSched make_sched(int M, int N, int sms) {
+  FwdSched s;
+  s.num_m = ceil_div(M, kBM);
+  s.num_n = ceil_div(N, kBN);
+  s.tiles = s.num_m * s.num_n;
+  s.grid = std::min(s.tiles, sms);
+  s.base = s.tiles / s.grid;
+  s.rem = s.tiles % s.grid;
+  s.runs = ceil_div(s.base + 1, s.num_n) + 1;
+  return s;
+}
 
 template <int KTOP>
 __device__ __forceinline__ void topk_insert(float (&tv)[KTOP], int (&ti)[KTOP], float v, int idx) {
@@ -55,16 +86,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                 const float* __restrict__ bias_pad, bf16* __restrict__ logits, int ldc,
                 float* __restrict__ pmax, float* __restrict__ psum, float* __restrict__ ptopv,
-                int* __restrict__ ptopi, int M, int N, int K, int Mpad) {
+                int* __restrict__ ptopi, int M, int N, int K, FwdSched sc) {
   extern __shared__ uint8_t smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + kBM - 1) / kBM;
-  const int num_n = (N + kBN - 1) / kBN;
-  const int num_tiles = num_m * num_n;
   const int num_k = (K + kBK - 1) / kBK;
+  const int t_begin = sc.start(blockIdx.x), t_end = sc.start(blockIdx.x + 1);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
@@ -75,7 +104,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm.acc_full[a], 1);
-      mbar_init(&sm.acc_empty[a], 128);
+      mbar_init(&sm.acc_empty[a], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -93,8 +122,8 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % num_m) * kBM, n0 = (t / num_m) * kBN;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int m0 = (t / sc.num_n) * kBM, n0 = (t % sc.num_n) * kBN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&sm.empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
@@ -111,7 +140,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = t_begin; t < t_end; ++t, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
@@ -134,28 +163,33 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (128 threads, one row each) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (256 threads: row = TMEM lane, 128 columns each) ==========
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which 128 columns of the 256-wide tile
     const int row_in_tile = quad * 32 + lane;
+    constexpr int kColsPerWarp = kBN / 2;
+
+    float run_max = -INFINITY, run_sum = 0.f;
+    float tv[KTOP];
+    int ti[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+    const int mb_first = t_begin / sc.num_n;
+
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int mb = t % num_m, nb = t / num_m;
-      const int m0 = mb * kBM, n0 = nb * kBN;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int mb = t / sc.num_n, nb = t % sc.num_n;
+      const int m0 = mb * kBM, n0 = nb * kBN + half * kColsPerWarp;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const int row = m0 + row_in_tile;
       mbar_wait(&sm.acc_full[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN;
-
-      float run_max = -INFINITY, run_sum = 0.f;
-      float tv[KTOP];
-      int ti[KTOP];
-#pragma unroll
-      for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + half * kColsPerWarp;
 
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -195,33 +229,44 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
         for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
         if (cmax > run_max) {
-          run_sum *= ex2_approx((run_max - cmax) * kLog2e);  // run_max=-inf -> 0 * 0
+          run_sum *= ex2_approx((run_max - cmax) * kLog2e);  // run_max = -inf -> 0 * 0
           run_max = cmax;
         }
         if (run_max > -INFINITY) {
           const float ms = run_max * kLog2e;
-          float acc_s = 0.f;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc_s += ex2_approx(fmaf(v[i], kLog2e, -ms));
-          run_sum += acc_s;
+          for (int i = 0; i < 32; i += 4) {
+            s0 += ex2_approx(fmaf(v[i + 0], kLog2e, -ms));
+            s1 += ex2_approx(fmaf(v[i + 1], kLog2e, -ms));
+            s2 += ex2_approx(fmaf(v[i + 2], kLog2e, -ms));
+            s3 += ex2_approx(fmaf(v[i + 3], kLog2e, -ms));
+          }
+          run_sum += (s0 + s1) + (s2 + s3);
         }
+        if (cmax > tv[KTOP - 1]) {  // rare once the list has seen a few hundred columns
 #pragma unroll
-        for (int i = 0; i < 32; ++i) topk_insert<KTOP>(tv, ti, v[i], col0 + i);
+          for (int i = 0; i < 32; ++i) topk_insert<KTOP>(tv, ti, v[i], col0 + i);
+        }
       }
       // TMEM accumulator drained -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&sm.acc_empty[acc]);
 
-      if (row < M) {
-        const size_t p = static_cast<size_t>(nb) * Mpad + row;
-        pmax[p] = run_max;
-        psum[p] = run_sum;
+      // end of this CTA's run over row block mb: flush the row state
+      if (nb == sc.num_n - 1 || t == t_end - 1) {
+        const size_t p = (static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first)) * 2 + half;
+        pmax[p * kBM + row_in_tile] = run_max;
+        psum[p * kBM + row_in_tile] = run_sum;
 #pragma unroll
         for (int j = 0; j < KTOP; ++j) {
-          const size_t pj = (static_cast<size_t>(nb) * KTOP + j) * Mpad + row;
-          ptopv[pj] = tv[j];
-          ptopi[pj] = ti[j];
+          ptopv[(p * KTOP + j) * kBM + row_in_tile] = tv[j];
+          ptopi[(p * KTOP + j) * kBM + row_in_tile] = ti[j];
         }
+        run_max = -INFINITY;
+        run_sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
       }
     }
   }
@@ -234,52 +279,101 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   }
 }
 
-// Per row: merge the per-tile (max, sumexp, top-K) partials.
+// One warp per row: merge the row's partials (one per (CTA run, column half)).
 //   topk_val = softmax probabilities exp(l - max) / sum   (super_guessr.py:355,365)
 //   pred_cell = argmax (:358), pred_llh = centroids[pred_cell] (:359-361), lse = max + log(sum)
 template <int KTOP>
 __global__ void head_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum,
-                                  const float* __restrict__ ptopv, const int* __restrict__ ptopi, int num_n,
-                                  int Mpad, int M, int k, const float* __restrict__ centroids,
-                                  float* __restrict__ topk_val, long long* __restrict__ topk_idx,
-                                  long long* __restrict__ pred_cell, float* __restrict__ pred_llh,
-                                  float* __restrict__ lse) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+                                  const float* __restrict__ ptopv, const int* __restrict__ ptopi, FwdSched sc, int M,
+                                  int k, const float* __restrict__ centroids, float* __restrict__ topk_val,
+                                  long long* __restrict__ topk_idx, long long* __restrict__ pred_cell,
+                                  float* __restrict__ pred_llh, float* __restrict__ lse) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  float gmax = -INFINITY;
-  for (int nb = 0; nb < num_n; ++nb) gmax = fmaxf(gmax, pmax[static_cast<size_t>(nb) * Mpad + row]);
-  float gsum = 0.f;
+  const int mb = row / kBM, rit = row % kBM;
+  const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
+  const int nparts = (c_hi - c_lo + 1) * 2;
+
+  float lmax = -INFINITY, lsum = 0.f;
   float tv[KTOP];
   int ti[KTOP];
 #pragma unroll
   for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  for (int nb = 0; nb < num_n; ++nb) {
-    const size_t p = static_cast<size_t>(nb) * Mpad + row;
-    const float m = pmax[p];
-    if (m > -INFINITY) gsum += psum[p] * expf(m - gmax);
+  for (int i = lane; i < nparts; i += 32) {
+    const int c = c_lo + (i >> 1);
+    const int run = mb - sc.start(c) / sc.num_n;
+    const size_t p = (static_cast<size_t>(c) * sc.runs + run) * 2 + (i & 1);
+    const float m = pmax[p * kBM + rit];
+    if (m > -INFINITY) {
+      const float s = psum[p * kBM + rit];
+      if (m > lmax) { lsum = lsum * expf(lmax - m) + s; lmax = m; }
+      else lsum += s * expf(m - lmax);
+    }
 #pragma unroll
     for (int j = 0; j < KTOP; ++j) {
-      const size_t pj = (static_cast<size_t>(nb) * KTOP + j) * Mpad + row;
-      const float v = ptopv[pj];
-      if (!(v > tv[KTOP - 1])) break;  // partial lists are sorted descending
-      topk_insert<KTOP>(tv, ti, v, ptopi[pj]);
+      const float v = ptopv[(p * KTOP + j) * kBM + rit];
+      if (!(v > tv[KTOP - 1]) && !(v == tv[KTOP - 1] && v > -INFINITY)) break;  // lists are sorted descending
+      const int id = ptopi[(p * KTOP + j) * kBM + rit];
+      // equal values across partials: keep the lower geocell index first
+      if (v > tv[KTOP - 1] || id < ti[KTOP - 1]) {
+        tv[KTOP - 1] = v;
+        ti[KTOP - 1] = id;
+#pragma unroll
+        for (int q = KTOP - 1; q > 0; --q) {
+          if (tv[q] > tv[q - 1] || (tv[q] == tv[q - 1] && ti[q] < ti[q - 1])) {
+            float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+            int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+          }
+        }
+      }
     }
   }
+  // warp-wide log-sum-exp
+  float gmax = lmax;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  float gsum = lmax > -INFINITY ? lsum * expf(lmax - gmax) : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
   const float inv = 1.f / gsum;
+  // k rounds: the best head among the lanes' sorted lists wins and is popped
+  int best0 = 0;
   for (int j = 0; j < k; ++j) {
-    topk_val[static_cast<size_t>(row) * k + j] = expf(tv[j] - gmax) * inv;
-    topk_idx[static_cast<size_t>(row) * k + j] = ti[j];
+    float bv = tv[0];
+    int bi = ti[0], bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bl = ol; }
+    }
+    if (lane == bl) {  // pop
+#pragma unroll
+      for (int q = 0; q < KTOP - 1; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+      tv[KTOP - 1] = -INFINITY;
+      ti[KTOP - 1] = 0x7fffffff;
+    }
+    if (j == 0) best0 = bi;
+    if (lane == 0) {
+      topk_val[static_cast<size_t>(row) * k + j] = expf(bv - gmax) * inv;
+      topk_idx[static_cast<size_t>(row) * k + j] = bi;
+    }
   }
-  const int best = ti[0];
-  if (pred_cell) pred_cell[row] = best;
-  if (pred_llh) {
-    pred_llh[2 * row + 0] = centroids[2 * best + 0];
-    pred_llh[2 * row + 1] = centroids[2 * best + 1];
+  if (lane == 0) {
+    if (pred_cell) pred_cell[row] = best0;
+    if (pred_llh) {
+      pred_llh[2 * row + 0] = centroids[2 * best0 + 0];
+      pred_llh[2 * row + 1] = centroids[2 * best0 + 1];
+    }
+    if (lse) lse[row] = gmax + logf(gsum);
   }
-  if (lse) lse[row] = gmax + logf(gsum);
 }
 
 static size_t fwd_smem_bytes() { return sizeof(FwdSmem) + 1024; }
+
+static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(sc.grid) * sc.runs * 2; }
 
 template <int KTOP>
 static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, int B, int C, int D, void* logits,
@@ -291,29 +385,28 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_w, W, D, C, static_cast<uint64_t>(D) * 2, kBK, kBN);
   if (rc) return rc;
-  const int num_m = ceil_div(B, kBM), num_n = ceil_div(C, kBN);
-  const int Mpad = num_m * kBM;
+  const FwdSched sc = make_sched(B, C, device_sm_count());
+  const size_t np = fwd_partials(sc) * kBM;
   float* pmax = static_cast<float*>(workspace);
-  float* psum = pmax + static_cast<size_t>(num_n) * Mpad;
-  float* ptopv = psum + static_cast<size_t>(num_n) * Mpad;
-  int* ptopi = reinterpret_cast<int*>(ptopv + static_cast<size_t>(num_n) * KTOP * Mpad);
-  const int grid = std::min(num_m * num_n, device_sm_count());
+  float* psum = pmax + np;
+  float* ptopv = psum + np;
+  int* ptopi = reinterpret_cast<int*>(ptopv + np * KTOP);
   const size_t smem = fwd_smem_bytes();
+  // every (CTA, run, half) slot the merge reads is flushed by the CTA that owns those tiles
   if (logits) {
     auto kern = head_fwd_kernel<KTOP, true>;
     GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, static_cast<bf16*>(logits), ldc, pmax, psum,
-                                              ptopv, ptopi, B, C, D, Mpad);
+    kern<<<sc.grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, static_cast<bf16*>(logits), ldc, pmax, psum,
+                                                 ptopv, ptopi, B, C, D, sc);
   } else {
     auto kern = head_fwd_kernel<KTOP, false>;
     GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, nullptr, ldc, pmax, psum, ptopv, ptopi, B, C,
-                                              D, Mpad);
+    kern<<<sc.grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, nullptr, ldc, pmax, psum, ptopv, ptopi, B, C,
+                                                 D, sc);
   }
   GG_LAUNCH_CHECK();
-  head_merge_kernel<KTOP><<<ceil_div(B, 128), 128, 0, stream>>>(pmax, psum, ptopv, ptopi, num_n, Mpad, B, k,
-                                                               centroids, topk_val, topk_idx, pred_cell,
-                                                               pred_llh, lse);
+  head_merge_kernel<KTOP><<<ceil_div(B, 8), 256, 0, stream>>>(pmax, psum, ptopv, ptopi, sc, B, k, centroids,
+                                                              topk_val, topk_idx, pred_cell, pred_llh, lse);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -324,8 +417,8 @@ using namespace gg;
 
 extern "C" size_t gg_head_fwd_workspace_bytes(int B, int C, int k) {
   const int ktop = k <= 5 ? 5 : 8;
-  const size_t num_n = ceil_div(C, kBN), Mpad = static_cast<size_t>(ceil_div(B, kBM)) * kBM;
-  return num_n * Mpad * (2 + 2 * ktop) * sizeof(float);
+  const FwdSched sc = make_sched(B, C, device_sm_count());
+  return fwd_partials(sc) * kBM * (2 + 2 * ktop) * sizeof(float);
 }
 
 extern "C" int gg_head_logits_ld(int C) { return ceil_div(C, 64) * 64; }

@@ -146,9 +146,9 @@ def centroid_unit_vectors(centroids: torch.Tensor) -> torch.Tensor:
     return xyz
 
 
-def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False):
+def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False, want_db=False):
     """Fused haversine label-smoothed CE.  Returns (dlogits bf16 (B,ldc) = p - t, loss_rows (B),
-    nearest_cell (B) i64 | None, nearest_km (B) | None)."""
+    nearest_cell (B) i64 | None, nearest_km (B) | None[, db_partials (parts, Cpad) fp32 if want_db])."""
     _need_cuda(logits, lse, labels, cent_xyz)
     B, ldc = logits.shape
     dev = logits.device
@@ -160,9 +160,13 @@ def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, wa
     ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
     nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
     ws = _u8(lib.gg_hav_ce_workspace_bytes(B), dev)
+    dbp = (torch.empty((lib.gg_hav_ce_db_parts(B), lib.gg_hav_cpad(C)), dtype=torch.float32, device=dev)
+           if want_db else None)
     _call("gg_hav_ce_fwd_bwd", lib.gg_hav_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(labels), _ptr(cent_xyz), B, C, float(tau),
-                              float(far_km), _ptr(dlogits), _ptr(loss_rows), _ptr(ncell), _ptr(nkm), _ptr(ws),
+                              float(far_km), _ptr(dlogits), _ptr(loss_rows), _ptr(ncell), _ptr(nkm), _ptr(dbp), _ptr(ws),
                               _stream())
+    if want_db:
+        return dlogits, loss_rows, ncell, nkm, dbp
     return dlogits, loss_rows, ncell, nkm
 
 
@@ -186,19 +190,23 @@ def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tens
     return out
 
 
-def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True):
-    """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C)."""
+def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None):
+    """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C) (from the loss kernel's column-sum
+    partials when given, else from a pass over dlogits)."""
     _need_cuda(dlogits, x16, grad_scale)
     B, ldc = dlogits.shape
     dev = dlogits.device
     lib = _lib.load()
     dW = torch.empty((C, D), dtype=torch.float32, device=dev)
     db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
-    ws = _u8(lib.gg_head_bwd_workspace_bytes(C), dev) if want_db else None
+    ws = _u8(lib.gg_head_bwd_workspace_bytes(C), dev) if (want_db and db_partials is None) else None
+    if not want_db:
+        db_partials = None
     if grad_scale is not None:
         grad_scale = grad_scale.detach().float().contiguous()
     _call("gg_head_bwd", lib.gg_head_bwd, _ptr(dlogits), ldc, _ptr(x16), x16.shape[1], B, C, D, float(scale), _ptr(grad_scale), _ptr(dW),
-                        _ptr(db), _ptr(ws), _stream())
+                        _ptr(db), _ptr(db_partials), 0 if db_partials is None else db_partials.shape[0],
+                        0 if db_partials is None else db_partials.shape[1], _ptr(ws), _stream())
     return dW, db
 
 

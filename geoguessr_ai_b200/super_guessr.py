@@ -33,13 +33,17 @@ class _GeocellHeadLoss(torch.autograd.Function):
         C, D = weight.shape
         head = ops.head_forward(x16, st["w16"], st["bias_pad"], C, module.num_candidates,
                                 module.geocell_centroid_coords.data, want_logits=True)
+        dbp = None
         if smooth:
-            dlogits, loss_rows, _, _ = ops.hav_ce(head["logits"], head["lse"], labels, module._centroid_xyz(), C,
-                                                  tau=module.label_smoothing_tau, far_km=module.far_km)
+            dlogits, loss_rows, _, _, dbp = ops.hav_ce(head["logits"], head["lse"], labels, module._centroid_xyz(), C,
+                                                       tau=module.label_smoothing_tau, far_km=module.far_km,
+                                                       want_db=True)
         else:
             dlogits, loss_rows = ops.hard_ce(head["logits"], head["lse"], labels_clf, C)
         loss = ops.loss_mean(loss_rows)
         ctx.save_for_backward(dlogits, x16)
+        ctx.dbp = dbp
+        ctx.set_materialize_grads(False)  # no zero-filled grads for the non-differentiable outputs
         ctx.dims = (C, D, embedding.shape, embedding.requires_grad)
         ctx.weight = weight
         outs = (head["topk_val"], head["topk_idx"], head["pred_cell"], head["pred_llh"])
@@ -54,7 +58,8 @@ class _GeocellHeadLoss(torch.autograd.Function):
         want_w, want_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dW = db = demb = None
         if want_w or want_b:
-            dW, db = ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=want_b)
+            dW, db = ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=want_b,
+                                       db_partials=ctx.dbp)
         if ctx.needs_input_grad[0] and emb_needs_grad:
             # Only reached when the encoder is trained end to end (outside the BASELINE configs):
             # dx = dlogits W through cuBLAS, then the mean's 1/V broadcast (super_guessr.py:347).
@@ -157,10 +162,12 @@ class SuperGuessr(nn.Module):
 
     # ---- operand caches ---------------------------------------------------------------------
     def _operands(self, weight, bias):
-        """bf16 (or hi/lo split) copy of the head weights + padded bias; rebuilt when the fp32
-        master parameters change (optimizer step, load_state_dict, .to())."""
+        """bf16 (or hi/lo split) copy of the head weights + padded bias.  In training mode it is
+        rebuilt every step (fused optimisers update parameters without bumping ``_version``, so a
+        version key cannot be trusted while weights are moving); in eval mode it is cached and
+        rebuilt when the fp32 parameters change (load_state_dict, .to(), manual edits)."""
         key = (weight.data_ptr(), weight._version, bias.data_ptr(), bias._version, self.precision, weight.device)
-        if self._op_cache is None or self._op_cache["key"] != key:
+        if self.training or self._op_cache is None or self._op_cache["key"] != key:
             split = self.precision == "bf16x3"
             w16, bias_pad = ops.prepare_head_weights(weight, bias, split=split)
             self._op_cache = dict(key=key, w16=w16, bias_pad=bias_pad, split=split)

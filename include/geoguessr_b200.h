@@ -39,6 +39,7 @@ int gg_hav_cpad(int C);       /* geocells rounded up to 4: the centroid unit-vec
 size_t gg_head_fwd_workspace_bytes(int B, int C, int k);
 size_t gg_head_bwd_workspace_bytes(int C);
 size_t gg_hav_ce_workspace_bytes(int B);
+int gg_hav_ce_db_parts(int B); /* rows of the loss kernel's bias-gradient partial sums (one per CTA) */
 size_t gg_proto_retrieve_workspace_bytes(int B, int topk, int D, int ncell);
 
 /* ---- a1: heading fusion -------------------------------------------------------------------
@@ -75,12 +76,15 @@ int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, i
  * labels (B,2) fp32 (lng,lat) degrees.  dlogits (B, ldc) bf16 = softmax(logits) - t, UNSCALED
  * (gg_head_bwd applies 1/B).  loss_rows (B) fp32 = -sum_c t log_softmax.  Optional by-products
  * (next-row, main_coordinator_idun_s3.py:390-391): nearest_cell (B) int64 = argmin_c d,
- * nearest_km (B) fp32.  far_km: cells farther than dmin + far_km get t = 0 (65*ln(2^40) ~= 1802 km
- * keeps every t > 2^-40; INFINITY evaluates every cell). */
+ * nearest_km (B) fp32; db_partials (gg_hav_ce_db_parts(B), gg_hav_cpad(C)) fp32 = per-CTA column sums of
+ * dlogits, finished by gg_head_bwd (saves a second pass over dlogits for the bias gradient).
+ * far_km: cells farther than dmin + far_km get t = 0 (65*ln(2^40) ~= 1802 km keeps every
+ * t > 2^-40; INFINITY evaluates every cell). */
 int gg_centroid_unit_vectors(const float* centroids, float* cent_xyz, int C, gg_stream_t stream);
 int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const float* labels, const float* cent_xyz,
                       int B, int C, float tau, float far_km, void* dlogits_bf16, float* loss_rows,
-                      long long* nearest_cell, float* nearest_km, void* workspace, gg_stream_t stream);
+                      long long* nearest_cell, float* nearest_km, float* db_partials, void* workspace,
+                      gg_stream_t stream);
 /* super_guessr.py:383 nn.CrossEntropyLoss()(logits, labels_clf) and its gradient. */
 int gg_hard_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const long long* labels_clf, int B, int C,
                        void* dlogits_bf16, float* loss_rows, gg_stream_t stream);
@@ -91,9 +95,11 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * autograd of super_guessr.py:354: dW (C,D) fp32 = scale * dlogits^T x, db (C) = scale * colsum.
  * x (B, x_ld) bf16 (first D columns used).  scale = 1/B (1/global batch under data parallelism);
  * grad_scale: optional DEVICE scalar (the upstream dL/dloss of autograd), multiplied in on the
- * device so that backward needs no host synchronisation. */
+ * device so that backward needs no host synchronisation.  db_partials (db_parts, db_ld): column
+ * sums from gg_hav_ce_fwd_bwd; when null, db is computed from dlogits (needs workspace). */
 int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
-                const float* grad_scale, float* dW, float* db, void* workspace, gg_stream_t stream);
+                const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
+                void* workspace, gg_stream_t stream);
 
 /* ---- a10-a15: ProtoRefiner ----------------------------------------------------------------
  * models/proto_refiner.py:165-203 (retrieval) -- for every (query i, candidate j < topk):

@@ -108,9 +108,10 @@ def hav_ce():
         lg[:, :C] = logits
         lse = torch.logsumexp(logits.float(), -1)
         xyz = ops.centroid_unit_vectors(cent.to(dev))
-        dl, loss_rows, ncell, nkm = ops.hav_ce(lg.to(dev), lse.to(dev), labels.to(dev), xyz, C, far_km=far,
-                                               want_nearest=True)
+        dl, loss_rows, ncell, nkm, dbp = ops.hav_ce(lg.to(dev), lse.to(dev), labels.to(dev), xyz, C, far_km=far,
+                                                    want_nearest=True, want_db=True)
         torch.cuda.synchronize()
+        report("db partial sum vs colsum(dlogits)", dbp.sum(0)[:C], dl[:, :C].float().sum(0), 1e-5)
         t = sgo.soft_targets(labels, cent)
         logp = torch.log_softmax(logits.float(), -1)
         ref_rows = -(t * logp).sum(-1)

@@ -63,7 +63,9 @@ def test_train_step_matches_reference_golden(name, precision, centroids):
     scale = np.abs(g["gW_sample"]).max()
     np.testing.assert_allclose(gW[torch.from_numpy(g["gW_rows"])].numpy(), g["gW_sample"], atol=2e-2 * scale)
     np.testing.assert_allclose(m.cell_layer.bias.grad.cpu().numpy(), g["gb"], atol=2e-2 * np.abs(g["gb"]).max())
-    np.testing.assert_allclose(gW.sum(0).numpy(), g["gW_colsum"], atol=2e-2 * np.abs(g["gW_colsum"]).max() + 1e-6)
+    # (the class-sum of dW cancels to ~1e-7 in exact arithmetic -- not a usable check under bf16 gradients;
+    #  the total gradient mass is)
+    assert abs(gW.double().abs().sum().item() - float(g["gW_abs_sum"])) <= 2e-2 * float(g["gW_abs_sum"])
 
 
 @pytest.mark.parametrize("name,precision", [("cfg1", "bf16x3"), ("bf16_b256", "bf16")])

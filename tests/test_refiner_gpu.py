@@ -40,7 +40,7 @@ def test_refiner_matches_reference_golden(name, centroids, capsys):
     margins are tiny, so compare outcome-by-outcome and demand >= 97 % identical cells and, for those,
     coordinates within 1 m."""
     g, off, bank, xy, emb, cand, cprobs, initial = golden_case(name, centroids)
-    r = gg.ProtoRefiner(topk=int(g["topk"]), bank=(off, bank, xy), device=DEV)
+    r = gg.ProtoRefiner(topk=int(g["topk"]), bank=(off, bank, xy), device=DEV).eval()  # loss is 0 in train mode (:162)
     loss, llh, cells = r(emb.to(DEV), initial.to(DEV), cand.to(DEV), None if cprobs is None else cprobs.to(DEV))
     assert loss is None and llh.dtype == torch.float32 and cells.dtype == torch.int64 and llh.is_cuda
     assert "Changed geocell predictions of" in capsys.readouterr().out

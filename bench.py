@@ -314,7 +314,7 @@ def run_b200_train(args):
                                    else "hbm_gbs") + ")"})
 
     cpu = None
-    if world == 1 or rank == 0:
+    if not args.no_cpu:
         cval, cms, cores = cpu_reference_train(2, 1, B, D, V)
         cpu = {"value": cval, "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": cms,
                "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,6 +39,14 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
                       uint32_t box_inner, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return GG_ERR_CUDA;
+  // The encode call is a DRIVER entry point: it needs a context current on the calling thread.
+  // Threads that have only used the runtime lazily (e.g. torch's autograd worker threads) may not
+  // have one bound yet; cudaFree(0) binds the device's primary context, once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    GG_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   GG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, GG_ERR_ARG, "TMA base %p is not 16-byte aligned", base);
   GG_CHECK(pitch_bytes % 16 == 0, GG_ERR_ARG, "TMA row pitch %llu is not a multiple of 16 bytes",
            (unsigned long long)pitch_bytes);

@@ -1,0 +1,27 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, bench (both arms), ncu launch list + full capture of the three hot kernels.
+# Usage (from the repo root, under gpurun): bash tools/gpu_check.sh [tests] [bench] [launches] [ncu]
+set -u
+mkdir -p gpurun_out
+what="${*:-tests bench launches ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi.txt
+cp MEASURED_PEAKS.json gpurun_out/ 2>/dev/null
+for w in $what; do
+  case $w in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
+      echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log ;;
+    smoke)
+      timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log ;;
+    bench)
+      timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json
+      timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
+    ncu)
+      timeout 1200 ncu --set full --clock-control none --import-source on \
+        -k regex:'head_fwd_kernel|hav_ce_kernel|head_bwd_kernel' -s 9 -c 3 -f -o gpurun_out/prof_train \
+        python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
+  esac
+done

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgeoguessr_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
@@ -23,18 +23,22 @@ SIGNATURES = {
     "gg_head_logits_ld": (I, [I]),
     "gg_head_bias_pad": (I, [I]),
     "gg_hav_cpad": (I, [I]),
+    "gg_centroid_table_floats": (c_size_t, [I]),
+    "gg_centroid_table_workspace_bytes": (c_size_t, [I]),
+    "gg_hav_row_stats_bytes": (c_size_t, [I, I]),
     "gg_head_fwd_workspace_bytes": (c_size_t, [I, I, I]),
     "gg_head_bwd_workspace_bytes": (c_size_t, [I]),
-    "gg_hav_ce_workspace_bytes": (c_size_t, [I]),
-    "gg_hav_ce_db_parts": (I, [I]),
+    "gg_hav_ce_workspace_bytes": (c_size_t, [I, I]),
+    "gg_hav_ce_db_parts": (I, [I, I]),
     "gg_proto_retrieve_workspace_bytes": (c_size_t, [I, I, I, I]),
     "gg_fuse_headings": (I, [P, P, I, I, I, I, P, P]),
     "gg_prepare_head_weights": (I, [P, P, P, P, I, I, I, P]),
     "gg_cast_bf16": (I, [P, P, L, P]),
     "gg_row_sqnorm_bf16": (I, [P, L, I, P, P]),
     "gg_head_fwd": (I, [P, P, P, I, I, I, P, I, I, P, P, P, P, P, P, P, P]),
-    "gg_centroid_unit_vectors": (I, [P, P, I, P]),
-    "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, F, P, P, P, P, P, P, P]),
+    "gg_centroid_unit_vectors": (I, [P, P, I, P, P]),
+    "gg_hav_row_stats": (I, [P, P, I, I, F, F, P, P, P, P]),
+    "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, P, P, P, P, P, F, P]),
     "gg_hard_ce_fwd_bwd": (I, [P, I, P, P, I, I, P, P, P]),
     "gg_loss_mean": (I, [P, I, F, P, P]),
     "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P]),

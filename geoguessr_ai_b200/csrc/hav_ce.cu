@@ -1,4 +1,4 @@
-// Fused haversine label-smoothed geocell cross-entropy, forward + gradient in one kernel.
+// Fused haversine label-smoothed geocell cross-entropy, forward + gradient.
 //
 // Replaces, per training step, the reference's
 //   haversine_matrix(labels, centroids.t())        models/utils.py:39-57   (B x C distances)
@@ -6,21 +6,31 @@
 //   t = s / max(sum_c s, 1e-12)                     models/super_guessr.py:377
 //   loss_b = -sum_c t * log_softmax(logits)         models/super_guessr.py:379-380
 //   dlogits = softmax(logits) - t                   (autograd, main_coordinator_idun_s3.py:423)
-// without materialising any B x C distance / target / probability matrix: per row the only HBM
+// without materialising any B x C distance / target / probability matrix: the only B x C HBM
 // traffic is one read of the bf16 logits and one write of the bf16 gradient.
 //
 // Distance: with unit vectors u (label) and v_c (centroid), haversine's a = |u - v_c|^2 / 4 exactly,
-// so q = |u - v_c|^2 (3 sub + 3 fma from registers / shared memory, no per-element trig, no
-// cancellation at small distances) and d = 2R asin(sqrt(q)/2).  q is monotone in d, so the row
-// minimum and the "can this cell carry any target mass" test run on q; sqrt/asin/exp are only
-// evaluated for cells with d < dmin + far_km, where far_km = 65 km * ln(2^40) by default: beyond
-// it exp(-(d-dmin)/65) < 2^-40 relative to the nearest cell's weight of 1 (far_km = inf disables
-// the skip).  Geocells are ordered by (country, admin1, id), so chunks of 4 x 32 consecutive
-// cells are geographically coherent and the skip is close to warp-uniform.
+// so q = |u - v_c|^2 (3 sub + 3 fma, no per-element trig, no cancellation at small distances) and
+// d = 2R asin(sqrt(q)/2).  q is monotone in d, so row minimum and "can this cell carry target mass"
+// run on q; sqrt/asin/exp are evaluated only for cells with d < dmin + far_km (the caller's cut-off:
+// beyond it exp(-(d-dmin)/65) is below the chosen fraction of the nearest cell's weight; inf = off).
 //
-// One persistent CTA per SM keeps the whole centroid unit-vector table (3 x C fp32 = 152 KB at
-// C = 12 647) resident in shared memory and walks rows b = blockIdx.x, +gridDim.x, ...; a thread
-// owns the same 4-cell chunks in every pass, so q / s stay in its registers.
+// Kernels:
+//  (T) centroid table (once per table): unit vectors in class order, plus a copy sorted along a
+//      Morton curve in 64-cell spatial groups with one bounding cap (centre, angular radius) each and,
+//      per spatial group, the bitmask of the 64-column class groups its members fall in.
+//  (A) gg_hav_row_stats, no B x C data: label unit vectors (fp64 trig, one thread per row), then one
+//      warp per row bounds every spatial group's distance from its cap, evaluates exact q only in
+//      the groups that can hold the nearest cell / a near cell, and emits {u, q_thr, dmin, 1/sum s}
+//      plus the bitmask of class groups that contain near cells (and argmin_c d as a by-product).
+//  (B) hav_ce_stream_kernel, the HBM-bound pass.  A warp owns 256 adjacent classes (4 groups = one
+//      nibble of the near mask) and walks a block of rows; a lane owns one bf16 pair in each of the
+//      four groups (unit vectors and bias-gradient column sums in registers), so every warp-level
+//      load/store is one full 128-byte line and a near group costs every lane exactly two target
+//      evaluations -- no divergence.  Per row: p = exp(l - lse), minus t in the near groups, and
+//      the row's sum_c t*l.  No block-wide synchronisation, 4 rows of loads in flight per lane.
+//  (C) hav_loss_finish_kernel: loss_b = lse_b - sum_c t*l (fixed-order sum of the per-warp
+//      partials), and optionally the batch mean (deterministic two-level sum, last block finishes).
 #include <math_constants.h>
 
 #include <algorithm>
@@ -32,9 +42,55 @@ namespace gg {
 
 constexpr float kEarthRadiusKm = 6378.137f;  // models/utils.py:55 (6378137 m) / 1000
 constexpr float kLog2eF = 1.4426950408889634f;
+constexpr int kCellsPerGroup = 64;   // spatial group (one cap) and class group (one near-mask bit)
+constexpr int kColsPerWarp = 256;    // kernel B: 4 class groups = one nibble of the near mask
+constexpr int kMaxSlots = 8;         // kernel A keeps one group bound per lane per slot: <= 256 groups
+constexpr int kMaxMaskWords = 8;     // near mask words per row: 256 class groups
+constexpr int kStreamThreads = 128, kStreamCtasPerSm = 5;  // kernel B: 20 warps per SM at <= 102 registers
+constexpr float kCapMargin = 1.0e-5f;  // rad (64 m): absorbs fp32 rounding in the cap tests
 
-// theta = 2 asin(sqrt(q)/2), q = squared chord in [0, 4].  Cephes-style asinf (abs err ~1e-7).
-__device__ __forceinline__ float asin_poly(float r, float z) {  // asin(r) for r <= 0.5, z = r*r
+struct RowRec {  // 32 bytes per row, written by (A), read by (B)/(C)
+  float ux, uy, uz, q_thr;
+  float off, inv_s, valid, dmin;
+};
+
+// Centroid table layout, in 4-byte words (see (T)):
+//   x[Cpad] y[Cpad] z[Cpad]                       class order, Cpad = C rounded up to 256
+//   sx[Cs] sy[Cs] sz[Cs] sidx[Cs] (int)            Morton order, Cs = C rounded up to 64
+//   caps[4 * Cs/64] = {cx, cy, cz, radius}         radius 4 = anywhere, < 0 = empty group
+//   gmask[kMaxMaskWords * Cs/64] (uint)            class groups touched by each spatial group
+struct TableView {
+  int Cpad, Cs, ngroups;
+  const float *x, *y, *z, *sx, *sy, *sz;
+  const int* sidx;
+  const float4* caps;
+  const uint32_t* gmask;
+};
+__host__ __device__ inline int table_cpad(int C) { return (C + 255) / 256 * 256; }
+__host__ __device__ inline int table_cs(int C) { return (C + 63) / 64 * 64; }
+__host__ __device__ inline size_t table_words(int C) {
+  const size_t Cpad = table_cpad(C), Cs = table_cs(C);
+  return 3 * Cpad + 4 * Cs + (4 + kMaxMaskWords) * (Cs / kCellsPerGroup);
+}
+__host__ __device__ inline TableView view_table(const float* t, int C) {
+  TableView v;
+  v.Cpad = table_cpad(C);
+  v.Cs = table_cs(C);
+  v.ngroups = v.Cs / kCellsPerGroup;
+  v.x = t;
+  v.y = v.x + v.Cpad;
+  v.z = v.y + v.Cpad;
+  v.sx = v.z + v.Cpad;
+  v.sy = v.sx + v.Cs;
+  v.sz = v.sy + v.Cs;
+  v.sidx = reinterpret_cast<const int*>(v.sz + v.Cs);
+  v.caps = reinterpret_cast<const float4*>(v.sz + 2 * static_cast<size_t>(v.Cs));
+  v.gmask = reinterpret_cast<const uint32_t*>(v.caps + v.ngroups);
+  return v;
+}
+
+// asin(r) for r <= 0.5, z = r*r.  Cephes-style (abs err ~1e-7).
+__device__ __forceinline__ float asin_poly(float r, float z) {
   float p = 4.2163199048e-2f;
   p = fmaf(p, z, 2.4181311049e-2f);
   p = fmaf(p, z, 4.5470025998e-2f);
@@ -42,6 +98,12 @@ __device__ __forceinline__ float asin_poly(float r, float z) {  // asin(r) for r
   p = fmaf(p, z, 1.6666752422e-1f);
   return fmaf(p * z, r, r);
 }
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// theta = 2 asin(sqrt(q)/2), q = squared chord in [0, 4]; IEEE sqrt (row minima, cap radii)
 __device__ __forceinline__ float theta_from_q(float q) {
   const float h = fminf(0.25f * q, 1.0f);  // = sin^2(theta/2) = haversine 'a'
   if (h <= 0.25f) {
@@ -51,29 +113,166 @@ __device__ __forceinline__ float theta_from_q(float q) {
   const float z = 0.5f * (1.0f - x);
   return CUDART_PI_F - 4.0f * asin_poly(sqrtf(z), z);
 }
+// same, branch-free with the approximate square root (cap bounds: their margins absorb the error)
+__device__ __forceinline__ float theta_from_q_fast(float q) {
+  const float h = fminf(0.25f * q, 1.0f);
+  const float x = sqrt_approx(h);
+  const float z = 0.5f * (1.0f - x);
+  const float near_half = 2.0f * asin_poly(x, h);
+  const float far_half = CUDART_PI_F - 4.0f * asin_poly(sqrt_approx(z), z);
+  return h <= 0.25f ? near_half : far_half;
+}
+// Unnormalised target s = exp(-(d - dmin)/tau) = 2^(neg_rk2 * theta + off) of a cell at squared chord
+// q, or 0 when q >= q_thr.  (A) sums it and (B) applies it: both call exactly this function.
+// WIDE = false assumes q_thr <= 1 (d < 6672 km: every row unless dmin + far_km exceeds that), so a
+// cell that passes the test is on the first asin branch and nothing diverges.
+template <bool WIDE>
+__device__ __forceinline__ float target_weight(float q, float q_thr, float neg_rk2, float off) {
+  float theta;
+  if (!WIDE) {
+    const float h = 0.25f * fminf(q, 1.0f);
+    theta = 2.0f * asin_poly(sqrt_approx(h), h);
+  } else {
+    theta = theta_from_q_fast(q);
+  }
+  const float s = ex2_approx(fmaf(neg_rk2, theta, off));
+  return q < q_thr ? s : 0.f;
+}
+// squared chord; (A) and (B) must evaluate it identically (same threshold decisions)
+__device__ __forceinline__ float chord2(float ux, float uy, float uz, float x, float y, float z) {
+  const float dx = ux - x, dy = uy - y, dz = uz - z;
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
 
-// Unit vectors of the geocell centroids, SoA [x(0..Cpad) | y | z], fp64 trig rounded to fp32.
-// Pad entries sit far outside the unit sphere so that their q is huge ("infinitely far").
-__global__ void centroid_xyz_kernel(const float* __restrict__ centroids, float* __restrict__ xyz, int C, int Cpad) {
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ (T) centroid table
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {  // abcd -> 0a0b0c0d
+  v &= 0xffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+// class-order unit vectors (fp64 trig rounded to fp32; pad cells far outside the unit sphere, so
+// their q is huge: "infinitely far") and Morton keys of (lat, lng)
+__global__ void table_unit_kernel(const float* __restrict__ centroids, float* __restrict__ table, int C,
+                                  uint32_t* __restrict__ keys) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Cpad = table_cpad(C);
   if (c >= Cpad) return;
   float x = 1.0e9f, y = 1.0e9f, z = 1.0e9f;
   if (c < C) {
-    const double lng = static_cast<double>(centroids[2 * c]) * (CUDART_PI / 180.0);
-    const double lat = static_cast<double>(centroids[2 * c + 1]) * (CUDART_PI / 180.0);
+    const float lngf = centroids[2 * c], latf = centroids[2 * c + 1];
+    const double lng = static_cast<double>(lngf) * (CUDART_PI / 180.0);
+    const double lat = static_cast<double>(latf) * (CUDART_PI / 180.0);
     x = static_cast<float>(cos(lat) * cos(lng));
     y = static_cast<float>(cos(lat) * sin(lng));
     z = static_cast<float>(sin(lat));
+    const float fx = fminf(fmaxf((lngf + 180.0f) * (1.0f / 360.0f), 0.f), 1.f);
+    const float fy = fminf(fmaxf((latf + 90.0f) * (1.0f / 180.0f), 0.f), 1.f);
+    const uint32_t qx = static_cast<uint32_t>(fx * 65535.0f), qy = static_cast<uint32_t>(fy * 65535.0f);
+    keys[c] = (fx == fx && fy == fy) ? (spread16(qx) | (spread16(qy) << 1)) : 0xffffffffu;
   }
-  xyz[c] = x;
-  xyz[Cpad + c] = y;
-  xyz[2 * Cpad + c] = z;
+  table[c] = x;
+  table[Cpad + c] = y;
+  table[2 * static_cast<size_t>(Cpad) + c] = z;
+}
+// rank of every class along the Morton curve (O(C^2) compares, C ~ 1e4, once per table)
+__global__ void table_rank_kernel(const uint32_t* __restrict__ keys, int C, int* __restrict__ sidx) {
+  __shared__ uint32_t tile[256];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t mine = c < C ? keys[c] : 0u;
+  int rank = 0;
+  for (int base = 0; base < C; base += 256) {
+    const int n = min(256, C - base);
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < n) tile[threadIdx.x] = keys[base + threadIdx.x];
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+      const uint32_t k = tile[i];
+      rank += (k < mine || (k == mine && base + i < c)) ? 1 : 0;
+    }
+  }
+  if (c < C) sidx[rank] = c;
+}
+// sorted copy, one warp per spatial group (2 cells per lane): centre = normalised mean of the
+// members, radius = largest member angle + margin; class-group bitmask of the members
+__global__ void table_group_kernel(float* __restrict__ table, int C) {
+  const TableView tv = view_table(table, C);
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= tv.ngroups) return;
+  float* sx = const_cast<float*>(tv.sx);
+  float* sy = const_cast<float*>(tv.sy);
+  float* sz = const_cast<float*>(tv.sz);
+  int* sidx = const_cast<int*>(tv.sidx);
+  float x[2], y[2], z[2];
+  int idx[2];
+  float n = 0.f, mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = g * kCellsPerGroup + lane + 32 * h;
+    x[h] = y[h] = z[h] = 1.0e9f;
+    idx[h] = 0x7fffffff;
+    if (p < C) {
+      idx[h] = sidx[p];
+      x[h] = tv.x[idx[h]]; y[h] = tv.y[idx[h]]; z[h] = tv.z[idx[h]];
+      n += 1.f; mx += x[h]; my += y[h]; mz += z[h];
+    } else {
+      sidx[p] = 0x7fffffff;
+    }
+    sx[p] = x[h]; sy[p] = y[h]; sz[p] = z[h];
+  }
+  n = warp_sum(n); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
+  const float len = sqrtf(mx * mx + my * my + mz * mz);
+  float rad;
+  if (n == 0.f) {
+    mx = 0.f; my = 0.f; mz = 1.f; rad = -1.f;
+  } else if (len < 1.0e-3f * n || !(len == len)) {
+    mx = 0.f; my = 0.f; mz = 1.f; rad = 4.f;
+  } else {
+    mx /= len; my /= len; mz /= len;
+    float a = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (idx[h] != 0x7fffffff) a = fmaxf(a, theta_from_q(chord2(mx, my, mz, x[h], y[h], z[h])));
+    rad = warp_max(a) * (1.0f + 1.0e-6f) + kCapMargin;
+  }
+  if (lane == 0) const_cast<float4*>(tv.caps)[g] = make_float4(mx, my, mz, rad);
+  uint32_t* gm = const_cast<uint32_t*>(tv.gmask) + static_cast<size_t>(g) * kMaxMaskWords;
+  for (int w = 0; w < kMaxMaskWords; ++w) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (idx[h] != 0x7fffffff && (idx[h] >> 11) == w) bits |= 1u << ((idx[h] >> 6) & 31);
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    if (lane == 0) gm[w] = bits;
+  }
 }
 
-// Unit vectors of the labels: (B,4) = {x, y, z, valid}.  Non-finite labels give valid = 0
-// (the reference's nan_to_num turns such a row's targets into zeros, utils.py:31).
-__global__ void label_xyz_kernel(const float* __restrict__ labels, float4* __restrict__ out, int B) {
+// ------------------------------------------------------------------ (A) per-row statistics
+// Unit vectors of the labels: (B,4) = {x, y, z, valid}.  Non-finite labels give valid = 0 (the
+// reference's nan_to_num turns such a row's targets into zeros, utils.py:31).
+__global__ void label_xyz_kernel(const float* __restrict__ labels, float4* __restrict__ out, int B,
+                                 unsigned int* __restrict__ counter) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *counter = 0u;  // ticket of the finishing kernel
   if (b >= B) return;
   const float lngf = labels[2 * b], latf = labels[2 * b + 1];
   float4 o = make_float4(0.f, 0.f, 1.f, 0.f);
@@ -86,231 +285,311 @@ __global__ void label_xyz_kernel(const float* __restrict__ labels, float4* __res
   out[b] = o;
 }
 
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 template <int SLOTS>
-__global__ void __launch_bounds__(1024, 1)
-hav_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict__ lse,
-              const float4* __restrict__ lab_xyz, const float* __restrict__ cent_xyz, int Cpad, int B, int C,
-              float inv_tau, float cos_half_far, float sin_half_far, bf16* __restrict__ dlogits,
-              float* __restrict__ loss_rows, long long* __restrict__ nearest_cell,
-              float* __restrict__ nearest_km, float* __restrict__ db_partials) {
-  extern __shared__ float4 smem_f4[];
-  const int nchunks = Cpad >> 2;
-  float4* cx = smem_f4;
-  float4* cy = cx + nchunks;
-  float4* cz = cy + nchunks;
-  float4* dbs = cz + nchunks;  // per-CTA column sums of the gradient (bias gradient), owned per thread
-  float* red_min = reinterpret_cast<float*>(dbs + nchunks);  // [32]
-  float* red_sum = red_min + 32;                      // [32]
-  float* red_loss = red_sum + 32;                     // [2][32]
-  int* s_argmin = reinterpret_cast<int*>(red_loss + 64);
+__global__ void __launch_bounds__(128)
+hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict__ table, int C, int B, float k2,
+                     float cos_half_far, float sin_half_far, float phi, RowRec* __restrict__ rec,
+                     uint32_t* __restrict__ near, int nwp, long long* __restrict__ nearest_cell,
+                     float* __restrict__ nearest_km) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const TableView tv = view_table(table, C);
+  const float4 u = __ldg(lab_xyz + row);
+  const float ux = u.x, uy = u.y, uz = u.z;
+  const bool valid = u.w != 0.f;
 
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-
-  {  // centroid table -> shared memory (L2 hits after the first CTA)
-    const float4* gx = reinterpret_cast<const float4*>(cent_xyz);
-    for (int i = tid; i < 3 * nchunks; i += nthr) smem_f4[i] = __ldg(gx + i);
-    for (int i = tid; i < nchunks; i += nthr) dbs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (tid == 0) *s_argmin = 0x7fffffff;
-  __syncthreads();
-
-  const float k2 = inv_tau * kLog2eF;  // s = 2^((dmin - d) * k2)
-  int parity = 0;
-  int prev_row = -1;
-  float prev_lse = 0.f, prev_valid = 0.f;
-
-  // software pipeline over rows: the next row's logits (the only HBM read), label vector and lse are
-  // requested while the current row is processed
-  uint2 lraw_next[SLOTS];
-  float4 u_next = make_float4(0.f, 0.f, 1.f, 0.f);
-  float lse_next = 0.f;
-  auto fetch_row = [&](int r) {
-    const uint2* lrow = reinterpret_cast<const uint2*>(logits + static_cast<size_t>(r) * ldc);
+  // phase 1: distance bounds of every spatial group from its cap
+  float lo[SLOTS];
+  float lo_min = CUDART_INF_F;
+  int g_best = 0;
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j) {
-      const int g = j * nthr + tid;
-      lraw_next[j] = (j < SLOTS - 1 || g < nchunks) ? __ldcs(lrow + g) : make_uint2(0u, 0u);
+  for (int k = 0; k < SLOTS; ++k) {
+    const int g = lane + 32 * k;
+    lo[k] = CUDART_INF_F;
+    if (g < tv.ngroups) {
+      const float4 cap = __ldg(tv.caps + g);
+      if (cap.w >= 0.f) {
+        const float a = theta_from_q_fast(chord2(ux, uy, uz, cap.x, cap.y, cap.z));
+        lo[k] = fmaxf(a - cap.w, 0.f);
+        if (lo[k] < lo_min) { lo_min = lo[k]; g_best = g; }
+      }
     }
-    u_next = __ldg(lab_xyz + r);
-    lse_next = __ldg(lse + r);
+  }
+  // the most promising group gives a real cell distance = a tight upper bound of the row minimum
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ol = __shfl_xor_sync(0xffffffffu, lo_min, o);
+    const int og = __shfl_xor_sync(0xffffffffu, g_best, o);
+    if (ol < lo_min || (ol == lo_min && og < g_best)) { lo_min = ol; g_best = og; }
+  }
+  float qmin = CUDART_INF_F;
+  int imin = 0x7fffffff;
+  auto scan_group = [&](int g) {
+    const int p = g * kCellsPerGroup + lane;
+    const float q0 = chord2(ux, uy, uz, __ldg(tv.sx + p), __ldg(tv.sy + p), __ldg(tv.sz + p));
+    const float q1 = chord2(ux, uy, uz, __ldg(tv.sx + p + 32), __ldg(tv.sy + p + 32), __ldg(tv.sz + p + 32));
+    const int i0 = __ldg(tv.sidx + p), i1 = __ldg(tv.sidx + p + 32);
+    if (q0 < qmin || (q0 == qmin && i0 < imin)) { qmin = q0; imin = i0; }  // first class index on ties
+    if (q1 < qmin || (q1 == qmin && i1 < imin)) { qmin = q1; imin = i1; }
   };
-  if (blockIdx.x < B) fetch_row(blockIdx.x);
+  scan_group(g_best);
+  const float ub = theta_from_q_fast(warp_min(qmin)) + kCapMargin;
 
-  for (int row = blockIdx.x; row < B; row += gridDim.x, parity ^= 1) {
-    bf16* grow = dlogits + static_cast<size_t>(row) * ldc;
-    uint2 lraw[SLOTS];
+  // phase 2: exact nearest cell among the groups that can still contain it
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j) lraw[j] = lraw_next[j];
-    const float4 u = u_next;
-    const float row_lse = lse_next;
-    if (row + gridDim.x < B) fetch_row(row + gridDim.x);
-
-    // ---- pass 1a: squared chords to every centroid, row minimum
-    float qmin = CUDART_INF_F;
-    float4 qs[SLOTS];  // q, then s for the near chunks; a thread only ever touches its own chunks
-#pragma unroll
-    for (int j = 0; j < SLOTS; ++j) {
-      const int g = j * nthr + tid;
-      qs[j] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
-      if (j < SLOTS - 1 || g < nchunks) {
-        const float4 x = cx[g], y = cy[g], z = cz[g];
-        float4 q;
-        float dx, dy, dz;
-        dx = u.x - x.x; dy = u.y - y.x; dz = u.z - z.x; q.x = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        dx = u.x - x.y; dy = u.y - y.y; dz = u.z - z.y; q.y = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        dx = u.x - x.z; dy = u.y - y.z; dz = u.z - z.z; q.z = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        dx = u.x - x.w; dy = u.y - y.w; dz = u.z - z.w; q.w = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        qs[j] = q;
-        qmin = fminf(qmin, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
-      }
+  for (int k = 0; k < SLOTS; ++k) {
+    uint32_t m = __ballot_sync(0xffffffffu, lo[k] <= ub && lane + 32 * k != g_best);
+#pragma unroll 1
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      scan_group(j + 32 * k);
     }
-    qmin = warp_min(qmin);
-    if (lane == 0) red_min[warp] = qmin;
-    __syncthreads();  // (1)
-    {
-      float m = red_min[lane < nwarps ? lane : 0];
-      qmin = warp_min(m);
-    }
-    // previous row's loss: its partials were published before barrier (1)
-    if (tid < 32 && prev_row >= 0) {
-      float sl = red_loss[(parity ^ 1) * 32 + (lane < nwarps ? lane : 0)];
-      if (lane >= nwarps) sl = 0.f;
-      sl = warp_sum(sl);
-      if (lane == 0) loss_rows[prev_row] = prev_valid != 0.f ? prev_lse - sl : 0.f;
-    }
-    const float dmin = kEarthRadiusKm * theta_from_q(qmin);
-    // near test on q: d < dmin + far  <=>  q < 4 sin^2((theta_min + phi)/2), phi = far / R, expanded
-    // with sin(theta_min/2) = sqrt(qmin)/2 so that no trig runs per row; everything is "near"
-    // once theta_min + phi reaches pi.
-    float q_thr = CUDART_INF_F;
-    {
-      const float hmin = fminf(0.25f * qmin, 1.0f);
-      const float sa = sqrtf(hmin), ca = sqrtf(1.0f - hmin);
-      if (ca * cos_half_far - sa * sin_half_far > 0.f) {
-        const float sh = fmaf(sa, cos_half_far, ca * sin_half_far);
-        q_thr = 4.0f * sh * sh;
-      }
-    }
-
-    // ---- pass 1b: unnormalised targets s for the cells that can carry mass, and their sum
-    uint32_t near_mask = 0;
-    float ssum = 0.f;
-    const float off = dmin * k2;
-#pragma unroll
-    for (int j = 0; j < SLOTS; ++j) {
-      const int g = j * nthr + tid;
-      {
-        const float4 q = qs[j];  // +inf for slots past the table
-        if (fminf(fminf(q.x, q.y), fminf(q.z, q.w)) < q_thr) {
-          float4 s;
-          s.x = ex2_approx(fmaf(-kEarthRadiusKm * k2, theta_from_q(q.x), off));
-          s.y = ex2_approx(fmaf(-kEarthRadiusKm * k2, theta_from_q(q.y), off));
-          s.z = ex2_approx(fmaf(-kEarthRadiusKm * k2, theta_from_q(q.z), off));
-          s.w = ex2_approx(fmaf(-kEarthRadiusKm * k2, theta_from_q(q.w), off));
-          if (4 * g + 3 >= C) {  // pad cells of the last chunk
-            if (4 * g + 0 >= C) s.x = 0.f;
-            if (4 * g + 1 >= C) s.y = 0.f;
-            if (4 * g + 2 >= C) s.z = 0.f;
-            s.w = 0.f;
-          }
-          if (nearest_cell != nullptr) {
-            int hit = 0x7fffffff;
-            if (q.w == qmin) hit = 4 * g + 3;
-            if (q.z == qmin) hit = 4 * g + 2;
-            if (q.y == qmin) hit = 4 * g + 1;
-            if (q.x == qmin) hit = 4 * g + 0;
-            if (hit != 0x7fffffff) atomicMin(s_argmin, hit);
-          }
-          qs[j] = s;
-          near_mask |= 1u << j;
-          ssum += (s.x + s.y) + (s.z + s.w);
-        }
-      }
-    }
-    ssum = warp_sum(ssum);
-    if (lane == 0) red_sum[warp] = ssum;
-    __syncthreads();  // (2)
-    {
-      float m = red_sum[lane < nwarps ? lane : 0];
-      if (lane >= nwarps) m = 0.f;
-      ssum = warp_sum(m);
-    }
-    // s / max(sum, 1e-12) (super_guessr.py:377); invalid label -> zero targets
-    const float inv_s = u.w != 0.f ? 1.0f / fmaxf(ssum, 1e-12f) : 0.f;
-    if (tid == 0 && nearest_cell != nullptr) {
-      nearest_cell[row] = *s_argmin;
-      if (nearest_km) nearest_km[row] = dmin;
-      *s_argmin = 0x7fffffff;  // next atomicMin on it happens after the next barrier (1)
-    }
-
-    // ---- pass 2: p = exp(l - lse), gradient p - t, loss partial sum_c t * l
-    const float lse2 = row_lse * kLog2eF;
-    float sl = 0.f;
-#pragma unroll
-    for (int j = 0; j < SLOTS; ++j) {
-      const int g = j * nthr + tid;
-      if (j < SLOTS - 1 || g < nchunks) {
-        float l0 = __uint_as_float(lraw[j].x << 16), l1 = __uint_as_float(lraw[j].x & 0xffff0000u);
-        float l2 = __uint_as_float(lraw[j].y << 16), l3 = __uint_as_float(lraw[j].y & 0xffff0000u);
-        float g0 = ex2_approx(fmaf(l0, kLog2eF, -lse2));
-        float g1 = ex2_approx(fmaf(l1, kLog2eF, -lse2));
-        float g2 = ex2_approx(fmaf(l2, kLog2eF, -lse2));
-        float g3 = ex2_approx(fmaf(l3, kLog2eF, -lse2));
-        if (near_mask & (1u << j)) {
-          const float4 s = qs[j];
-          if (4 * g + 3 >= C) {  // pad logits are never defined
-            if (4 * g + 0 >= C) l0 = 0.f;
-            if (4 * g + 1 >= C) l1 = 0.f;
-            if (4 * g + 2 >= C) l2 = 0.f;
-            l3 = 0.f;
-          }
-          const float t0 = s.x * inv_s, t1 = s.y * inv_s, t2 = s.z * inv_s, t3 = s.w * inv_s;
-          sl = fmaf(t0, l0, sl); sl = fmaf(t1, l1, sl); sl = fmaf(t2, l2, sl); sl = fmaf(t3, l3, sl);
-          g0 -= t0; g1 -= t1; g2 -= t2; g3 -= t3;
-        }
-        uint2 o;
-        o.x = pack_bf16x2(g0, g1);
-        o.y = pack_bf16x2(g2, g3);
-        __stcs(reinterpret_cast<uint2*>(grow) + g, o);
-        if (db_partials != nullptr) {  // sum the bf16-rounded values the dW GEMM will see
-          float4 a = dbs[g];
-          a.x += __uint_as_float(o.x << 16); a.y += __uint_as_float(o.x & 0xffff0000u);
-          a.z += __uint_as_float(o.y << 16); a.w += __uint_as_float(o.y & 0xffff0000u);
-          dbs[g] = a;
-        }
-      }
-    }
-    sl = warp_sum(sl);
-    if (lane == 0) red_loss[parity * 32 + warp] = sl;
-    prev_row = row;
-    prev_lse = row_lse;
-    prev_valid = u.w;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oq = __shfl_xor_sync(0xffffffffu, qmin, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+    if (oq < qmin || (oq == qmin && oi < imin)) { qmin = oq; imin = oi; }
+  }
+  const float theta_min = theta_from_q(qmin);
+  const float dmin = kEarthRadiusKm * theta_min;
+  // near test on q: d < dmin + far  <=>  q < 4 sin^2((theta_min + phi)/2), phi = far / R, expanded
+  // with sin(theta_min/2) = sqrt(qmin)/2 so that no trig runs per row; everything is "near" once
+  // theta_min + phi reaches pi.
+  float q_thr = CUDART_INF_F;
+  {
+    const float hmin = fminf(0.25f * qmin, 1.0f);
+    const float sa = sqrtf(hmin), ca = sqrtf(1.0f - hmin);
+    if (ca * cos_half_far - sa * sin_half_far > 0.f) {
+      const float sh = fmaf(sa, cos_half_far, ca * sin_half_far);
+      q_thr = 4.0f * sh * sh;
+    }
+  }
+  const float a_thr = q_thr < CUDART_INF_F ? theta_min + phi + kCapMargin : CUDART_INF_F;
+  const float off = dmin * k2;  // s = 2^((dmin - d) * k2)
+  const float neg_rk2 = -kEarthRadiusKm * k2;
+  const bool wide = !(q_thr <= 1.0f);  // warp-uniform
+
+  // phase 3: sum of the unnormalised targets; lane w accumulates word w of the class-group mask
+  float ssum = 0.f;
+  uint32_t mask_word = 0u;
+#pragma unroll
+  for (int k = 0; k < SLOTS; ++k) {
+    uint32_t m = valid ? __ballot_sync(0xffffffffu, lo[k] < a_thr) : 0u;  // lo = inf for absent groups
+#pragma unroll 1
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const int g = j + 32 * k;
+      const int p = g * kCellsPerGroup + lane;
+      const float q0 = chord2(ux, uy, uz, __ldg(tv.sx + p), __ldg(tv.sy + p), __ldg(tv.sz + p));
+      const float q1 = chord2(ux, uy, uz, __ldg(tv.sx + p + 32), __ldg(tv.sy + p + 32), __ldg(tv.sz + p + 32));
+      // pad cells sit at 1e9: q ~ 3e18 fails every finite threshold; with q_thr = inf they are cut by index
+      const bool ok0 = p < C, ok1 = p + 32 < C;
+      float s0, s1;
+      if (!wide) {
+        s0 = target_weight<false>(q0, q_thr, neg_rk2, off);
+        s1 = target_weight<false>(q1, q_thr, neg_rk2, off);
+      } else {
+        s0 = target_weight<true>(q0, q_thr, neg_rk2, off);
+        s1 = target_weight<true>(q1, q_thr, neg_rk2, off);
+      }
+      s0 = ok0 ? s0 : 0.f;
+      s1 = ok1 ? s1 : 0.f;
+      ssum += s0 + s1;
+      if (__any_sync(0xffffffffu, (ok0 && q0 < q_thr) || (ok1 && q1 < q_thr))) {
+        if (lane < kMaxMaskWords) mask_word |= __ldg(tv.gmask + static_cast<size_t>(g) * kMaxMaskWords + lane);
+      }
+    }
+  }
+  if (lane < nwp) near[static_cast<size_t>(row) * nwp + lane] = lane < kMaxMaskWords ? mask_word : 0u;
+  ssum = warp_sum(ssum);
+  if (lane == 0) {
+    RowRec r;
+    r.ux = ux; r.uy = uy; r.uz = uz; r.q_thr = q_thr;
+    r.off = off;
+    r.inv_s = valid ? 1.0f / fmaxf(ssum, 1e-12f) : 0.f;  // s / max(sum, 1e-12) (super_guessr.py:377)
+    r.valid = valid ? 1.f : 0.f;
+    r.dmin = dmin;
+    rec[row] = r;
+    if (nearest_cell) nearest_cell[row] = imin;
+    if (nearest_km) nearest_km[row] = dmin;
+  }
+}
+
+// ------------------------------------------------------------------ (B) streaming pass
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Lane l of warp slice ws owns the bf16 pairs at columns ws*256 + 64*j + 2*l + {0,1}, j = 0..3: one
+// pair in each of the slice's four 64-class groups.  Rows are padded to a multiple of 256 columns
+// (ldc >= Cpad), so nothing in the row loop is predicated; pad columns carry p only and are never
+// read downstream.
+template <bool WANT_DB>
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
+hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict__ lse,
+                     const RowRec* __restrict__ rec, const uint32_t* __restrict__ near, int nwp,
+                     const float* __restrict__ table, int B, int C, int rows_per_block, int nslices, int nrb,
+                     float neg_rk2, bf16* __restrict__ dlogits, float* __restrict__ loss_part,
+                     float* __restrict__ db_part) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= nslices * nrb) return;
+  const int rb = gw / nslices, ws = gw - rb * nslices;
+  const int Cpad = table_cpad(C);
+  const int cbase = ws * kColsPerWarp + 2 * lane;  // + 64 j
+  const int near_word = ws >> 3, near_shift = 4 * (ws & 7);
+
+  float vx[8], vy[8], vz[8], db[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(table + cbase + 64 * j));
+    const float2 b = __ldg(reinterpret_cast<const float2*>(table + Cpad + cbase + 64 * j));
+    const float2 c = __ldg(reinterpret_cast<const float2*>(table + 2 * static_cast<size_t>(Cpad) + cbase + 64 * j));
+    vx[2 * j] = a.x; vx[2 * j + 1] = a.y;
+    vy[2 * j] = b.x; vy[2 * j + 1] = b.y;
+    vz[2 * j] = c.x; vz[2 * j + 1] = c.y;
+    db[2 * j] = db[2 * j + 1] = 0.f;
+  }
+  // pad classes (column >= C, last slice only) carry no target mass even when q_thr = inf
+  uint32_t cell_ok = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cell_ok |= (cbase + 64 * (i >> 1) + (i & 1) < C) ? (1u << i) : 0u;
+
+  const int row0 = rb * rows_per_block, row1 = min(B, row0 + rows_per_block);
+  const size_t pitch = static_cast<size_t>(ldc);
+  const bf16* lptr = logits + cbase;
+  bf16* gptr = dlogits + cbase;
+  constexpr int kDepth = 4;  // rows of loads in flight per lane
+
+  for (int rbase = row0; rbase < row1; rbase += 32) {
+    const int nr = min(32, row1 - rbase);
+    // lane j carries row rbase + j's scalars; broadcast by shuffle when the row is processed
+    float my_lse2 = 0.f, my_sl = 0.f;
+    uint32_t my_near = 0u;
+    if (lane < nr) {
+      my_lse2 = __ldg(lse + rbase + lane) * kLog2eF;
+      my_near = (__ldg(near + static_cast<size_t>(rbase + lane) * nwp + near_word) >> near_shift) & 0xfu;
+    }
+    uint32_t pre[kDepth][4];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        pre[d][j] = d < nr ? ld_stream_u32(lptr + (rbase + d) * pitch + 64 * j) : 0u;
+    }
+    for (int r4 = 0; r4 < nr; r4 += kDepth) {
+#pragma unroll
+      for (int d = 0; d < kDepth; ++d) {
+        const int r = r4 + d;
+        if (r >= nr) break;  // warp-uniform
+        const int row = rbase + r;
+        uint32_t cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cur[j] = pre[d][j];
+          if (r + kDepth < nr) pre[d][j] = ld_stream_u32(lptr + (row + kDepth) * pitch + 64 * j);
+        }
+        const float lse2 = __shfl_sync(0xffffffffu, my_lse2, r);
+        const uint32_t nb = __shfl_sync(0xffffffffu, my_near, r);
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // softmax probability
+          g[2 * j] = ex2_approx(fmaf(__uint_as_float(cur[j] << 16), kLog2eF, -lse2));
+          g[2 * j + 1] = ex2_approx(fmaf(__uint_as_float(cur[j] & 0xffff0000u), kLog2eF, -lse2));
+        }
+        if (nb != 0u) {  // some group of this warp's 256 classes holds a near cell (warp-uniform)
+          const float4 ra = __ldg(reinterpret_cast<const float4*>(rec + row));
+          const float4 rb4 = __ldg(reinterpret_cast<const float4*>(rec + row) + 1);
+          const bool wide = !(ra.w <= 1.0f);
+          float sl = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((nb >> j) & 1u) {  // warp-uniform
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * j + h;
+                const float q = chord2(ra.x, ra.y, ra.z, vx[i], vy[i], vz[i]);
+                float t = wide ? target_weight<true>(q, ra.w, neg_rk2, rb4.x)
+                               : target_weight<false>(q, ra.w, neg_rk2, rb4.x);
+                t = ((cell_ok >> i) & 1u) ? t * rb4.y : 0.f;
+                g[i] -= t;
+                const float l = h ? __uint_as_float(cur[j] & 0xffff0000u) : __uint_as_float(cur[j] << 16);
+                sl = fmaf(t, l, sl);
+              }
+            }
+          }
+          sl = warp_sum(sl);
+          if (lane == r) my_sl = sl;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_stream_u32(gptr + row * pitch + 64 * j, pack_bf16x2(g[2 * j], g[2 * j + 1]));
+        if (WANT_DB) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) db[i] += g[i];
+        }
+      }
+    }
+    if (lane < nr) loss_part[static_cast<size_t>(ws) * B + rbase + lane] = my_sl;
+  }
+  if (WANT_DB) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float2*>(db_part + static_cast<size_t>(rb) * Cpad + cbase + 64 * j) =
+          make_float2(db[2 * j], db[2 * j + 1]);
+  }
+}
+
+// ------------------------------------------------------------------ (C) per-row loss, batch mean
+// Block (32 rows x 8 slice lanes).  loss_b = lse_b - sum over warp slices of sum_c t*l, summed in a
+// fixed order; the batch mean is a fixed-order sum of block partials done by whichever block
+// finishes last (deterministic).
+__global__ void __launch_bounds__(256)
+hav_loss_finish_kernel(const float* __restrict__ loss_part, int nslices, const float* __restrict__ lse,
+                       const RowRec* __restrict__ rec, int B, float* __restrict__ loss_rows,
+                       float* __restrict__ block_part, unsigned int* __restrict__ counter, float mean_scale,
+                       float* __restrict__ loss_mean) {
+  __shared__ float red[8][33];
+  __shared__ bool last;
+  const int row = blockIdx.x * 32 + threadIdx.x;
+  float sl = 0.f;
+  if (row < B)
+    for (int s = threadIdx.y; s < nslices; s += 8) sl += loss_part[static_cast<size_t>(s) * B + row];
+  red[threadIdx.y][threadIdx.x] = sl;
   __syncthreads();
-  if (tid < 32 && prev_row >= 0) {
-    float sl = red_loss[(parity ^ 1) * 32 + (lane < nwarps ? lane : 0)];
-    if (lane >= nwarps) sl = 0.f;
-    sl = warp_sum(sl);
-    if (lane == 0) loss_rows[prev_row] = prev_valid != 0.f ? prev_lse - sl : 0.f;
-  }
-  if (db_partials != nullptr) {  // each chunk was only ever touched by its owning thread
-    float4* out = reinterpret_cast<float4*>(db_partials + static_cast<size_t>(blockIdx.x) * Cpad);
+  if (threadIdx.y != 0) return;
+  float v = 0.f;
+  if (row < B) {
+    sl = 0.f;
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j) {
-      const int g = j * nthr + tid;
-      if (j < SLOTS - 1 || g < nchunks) out[g] = dbs[g];
+    for (int y = 0; y < 8; ++y) sl += red[y][threadIdx.x];
+    v = rec[row].valid != 0.f ? lse[row] - sl : 0.f;
+    loss_rows[row] = v;
+  }
+  if (loss_mean == nullptr) return;
+  v = warp_sum(v);  // threadIdx.y == 0: exactly one warp
+  if (threadIdx.x == 0) {
+    block_part[blockIdx.x] = v;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncwarp();
+  if (last) {  // block partials summed in block order whichever block is last
+    __threadfence();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) s += __ldcg(block_part + i);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+      loss_mean[0] = s * mean_scale;
+      *counter = 0u;  // ready for the next launch on the same row statistics
     }
   }
 }
@@ -362,71 +641,152 @@ __global__ void loss_mean_kernel(const float* __restrict__ loss_rows, int B, flo
   }
 }
 
+// ------------------------------------------------------------------ host-side planning
+// Row statistics buffer (gg_hav_row_stats -> gg_hav_ce_fwd_bwd): rec[B] | near[B * nwp] | counter | lab_xyz[B]
+struct StatsPlan {
+  int nwp;
+  size_t off_rec, off_near, off_counter, off_lab, bytes;
+};
+static StatsPlan make_stats_plan(int B, int C) {
+  StatsPlan p;
+  const int Cpad = table_cpad(C);
+  const int class_groups = Cpad / kCellsPerGroup;
+  p.nwp = ceil_div(ceil_div(class_groups, 32), 4) * 4;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~size_t(255); return r; };
+  p.off_rec = take(sizeof(RowRec) * static_cast<size_t>(B));
+  p.off_near = take(sizeof(uint32_t) * static_cast<size_t>(B) * p.nwp);
+  p.off_counter = take(sizeof(unsigned int));
+  p.off_lab = take(sizeof(float4) * static_cast<size_t>(B));
+  p.bytes = o;
+  return p;
+}
+struct HavPlan {
+  int Cpad, nslices, rows_per_block, nrb, finish_blocks;
+  size_t off_loss_part, off_block_part, bytes;
+};
+static HavPlan make_hav_plan(int B, int C) {
+  HavPlan p;
+  p.Cpad = table_cpad(C);
+  p.nslices = p.Cpad / kColsPerWarp;
+  // one resident wave of warps
+  const int capacity = std::max(1, device_sm_count() * kStreamCtasPerSm * (kStreamThreads / 32) / p.nslices);
+  p.rows_per_block = std::max(8, ceil_div(B, capacity));
+  p.nrb = ceil_div(B, p.rows_per_block);
+  p.finish_blocks = ceil_div(B, 32);
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~size_t(255); return r; };
+  p.off_loss_part = take(sizeof(float) * static_cast<size_t>(B) * p.nslices);
+  p.off_block_part = take(sizeof(float) * p.finish_blocks);
+  p.bytes = o;
+  return p;
+}
+
 }  // namespace gg
 
 using namespace gg;
 
-extern "C" int gg_hav_cpad(int C) { return ceil_div(C, 4) * 4; }
+extern "C" int gg_hav_cpad(int C) { return table_cpad(C); }
+extern "C" size_t gg_centroid_table_floats(int C) { return table_words(C); }
+extern "C" size_t gg_centroid_table_workspace_bytes(int C) { return sizeof(uint32_t) * static_cast<size_t>(C); }
 
-extern "C" int gg_centroid_unit_vectors(const float* centroids, float* cent_xyz, int C, gg_stream_t stream) {
-  GG_CHECK(centroids && cent_xyz && C > 0, GG_ERR_ARG, "gg_centroid_unit_vectors: bad arguments");
-  const int Cpad = gg_hav_cpad(C);
-  centroid_xyz_kernel<<<ceil_div(Cpad, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(centroids, cent_xyz, C, Cpad);
-  GG_LAUNCH_CHECK();
-  return GG_OK;
-}
-
-extern "C" size_t gg_hav_ce_workspace_bytes(int B) { return static_cast<size_t>(B) * sizeof(float4); }
-// db_partials is (gg_hav_ce_db_parts(B), gg_hav_cpad(C)) fp32: one row of column sums per CTA
-extern "C" int gg_hav_ce_db_parts(int B) { return std::min(B, device_sm_count()); }
-
-template <int SLOTS>
-static int launch_hav(const void* logits, int ldc, const float* lse, const float4* lab, const float* cent_xyz,
-                      int Cpad, int B, int C, float tau, float far_km, void* dlogits, float* loss_rows,
-                      long long* nearest_cell, float* nearest_km, float* db_partials, int nthr, size_t smem,
-                      cudaStream_t s) {
-  auto kern = hav_ce_kernel<SLOTS>;
-  GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int grid = std::min(B, device_sm_count());
-  // phi/2 = far / (2R); far = inf (skip disabled) or >= pi R  ->  cos <= 0  ->  everything is near
-  double half_phi = 0.5 * static_cast<double>(far_km) / 6378.137;
-  if (!(half_phi < 1.5707963267948966)) half_phi = 1.5707963267948966;
-  kern<<<grid, nthr, smem, s>>>(static_cast<const bf16*>(logits), ldc, lse, lab, cent_xyz, Cpad, B, C, 1.0f / tau,
-                                static_cast<float>(cos(half_phi)), static_cast<float>(sin(half_phi)),
-                                static_cast<bf16*>(dlogits), loss_rows, nearest_cell, nearest_km, db_partials);
-  GG_LAUNCH_CHECK();
-  return GG_OK;
-}
-
-extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const float* labels,
-                                 const float* cent_xyz, int B, int C, float tau, float far_km, void* dlogits_bf16,
-                                 float* loss_rows, long long* nearest_cell, float* nearest_km, float* db_partials,
-                                 void* workspace, gg_stream_t stream) {
-  GG_CHECK(B > 0 && C > 0, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: empty problem B=%d C=%d", B, C);
-  GG_CHECK(logits_bf16 && lse && labels && cent_xyz && dlogits_bf16 && loss_rows && workspace, GG_ERR_ARG,
-           "gg_hav_ce_fwd_bwd: null pointer");
-  GG_CHECK(ldc >= C && ldc % 4 == 0, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: ldc=%d must be >= C and a multiple of 4", ldc);
-  GG_CHECK(tau > 0.f, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: tau must be positive");
-  GG_CHECK(far_km >= 1.0f, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: far_km must be >= 1 km (inf disables the skip)");
+extern "C" int gg_centroid_unit_vectors(const float* centroids, float* cent_table, int C, void* workspace,
+                                        gg_stream_t stream) {
+  GG_CHECK(centroids && cent_table && workspace && C > 0, GG_ERR_ARG, "gg_centroid_unit_vectors: bad arguments");
+  GG_CHECK(table_cpad(C) / kCellsPerGroup <= 32 * kMaxMaskWords, GG_ERR_UNSUPPORTED,
+           "gg_centroid_unit_vectors: C=%d exceeds the %d geocells the loss kernels cover", C,
+           32 * kMaxMaskWords * kCellsPerGroup);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int Cpad = gg_hav_cpad(C);
-  const int nchunks = Cpad / 4;
-  const size_t smem = static_cast<size_t>(nchunks) * 4 * sizeof(float4) + 160 * sizeof(float);
-  GG_CHECK(smem <= 227 * 1024, GG_ERR_UNSUPPORTED,
-           "gg_hav_ce_fwd_bwd: C=%d needs %zu B of shared memory for the resident centroid table (max 232448); "
-           "geocell tables above ~14.5k cells are not supported yet", C, smem);
-  float4* lab = static_cast<float4*>(workspace);
-  label_xyz_kernel<<<ceil_div(B, 256), 256, 0, s>>>(labels, lab, B);
+  uint32_t* keys = static_cast<uint32_t*>(workspace);
+  const TableView tv = view_table(cent_table, C);
+  table_unit_kernel<<<ceil_div(tv.Cpad, 256), 256, 0, s>>>(centroids, cent_table, C, keys);
   GG_LAUNCH_CHECK();
-  int slots = ceil_div(nchunks, 1024);
-  int nthr = ceil_div(ceil_div(nchunks, slots), 32) * 32;
-  if (nthr < 128) nthr = 128;
-  switch (slots) {
-    case 1: return launch_hav<1>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
-    case 2: return launch_hav<2>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
-    case 3: return launch_hav<3>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
-    default: return launch_hav<4>(logits_bf16, ldc, lse, lab, cent_xyz, Cpad, B, C, tau, far_km, dlogits_bf16, loss_rows, nearest_cell, nearest_km, db_partials, nthr, smem, s);
-  }
+  table_rank_kernel<<<ceil_div(C, 256), 256, 0, s>>>(keys, C, const_cast<int*>(tv.sidx));
+  GG_LAUNCH_CHECK();
+  table_group_kernel<<<ceil_div(tv.ngroups, 8), 256, 0, s>>>(cent_table, C);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" size_t gg_hav_row_stats_bytes(int B, int C) { return make_stats_plan(B, C).bytes; }
+
+extern "C" int gg_hav_row_stats(const float* labels, const float* cent_table, int B, int C, float tau, float far_km,
+                                void* row_stats, long long* nearest_cell, float* nearest_km, gg_stream_t stream) {
+  GG_CHECK(B > 0 && C > 0 && labels && cent_table && row_stats, GG_ERR_ARG, "gg_hav_row_stats: bad arguments");
+  GG_CHECK(tau > 0.f, GG_ERR_ARG, "gg_hav_row_stats: tau must be positive");
+  GG_CHECK(far_km >= 1.0f, GG_ERR_ARG, "gg_hav_row_stats: far_km must be >= 1 km (inf disables the skip)");
+  const TableView tv = view_table(cent_table, C);
+  GG_CHECK(tv.ngroups <= 32 * kMaxSlots && tv.Cpad / kCellsPerGroup <= 32 * kMaxMaskWords, GG_ERR_UNSUPPORTED,
+           "gg_hav_row_stats: C=%d exceeds the %d geocells the row-statistics kernel covers", C,
+           32 * kMaxSlots * kCellsPerGroup);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const StatsPlan p = make_stats_plan(B, C);
+  uint8_t* base = static_cast<uint8_t*>(row_stats);
+  RowRec* rec = reinterpret_cast<RowRec*>(base + p.off_rec);
+  uint32_t* near = reinterpret_cast<uint32_t*>(base + p.off_near);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(base + p.off_counter);
+  float4* lab = reinterpret_cast<float4*>(base + p.off_lab);
+  label_xyz_kernel<<<ceil_div(B, 128), 128, 0, s>>>(labels, lab, B, counter);
+  GG_LAUNCH_CHECK();
+  // phi = far / R; far = inf (skip disabled) or >= pi R  ->  cos(phi/2) <= 0  ->  everything is near
+  double phi = static_cast<double>(far_km) / 6378.137;
+  if (!(phi < 3.141592653589793)) phi = 3.141592653589793;
+  const float k2 = (1.0f / tau) * kLog2eF;
+  const float chf = static_cast<float>(cos(0.5 * phi)), shf = static_cast<float>(sin(0.5 * phi));
+  const int slots = ceil_div(tv.ngroups, 32);
+  const int grid_a = ceil_div(B, 4);
+#define GG_HAV_A(S)                                                                                          \
+  hav_row_stats_kernel<S><<<grid_a, 128, 0, s>>>(lab, cent_table, C, B, k2, chf, shf, static_cast<float>(phi), \
+                                                 rec, near, p.nwp, nearest_cell, nearest_km)
+  if (slots <= 2) GG_HAV_A(2);
+  else if (slots <= 4) GG_HAV_A(4);
+  else GG_HAV_A(kMaxSlots);
+#undef GG_HAV_A
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" size_t gg_hav_ce_workspace_bytes(int B, int C) { return make_hav_plan(B, C).bytes; }
+// db_partials is (gg_hav_ce_db_parts(B, C), gg_hav_cpad(C)) fp32: one row of column sums per row block
+extern "C" int gg_hav_ce_db_parts(int B, int C) { return make_hav_plan(B, C).nrb; }
+
+extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const void* row_stats,
+                                 const float* cent_table, int B, int C, float tau, void* dlogits_bf16,
+                                 float* loss_rows, float* db_partials, void* workspace, float* loss_mean,
+                                 float mean_scale, gg_stream_t stream) {
+  GG_CHECK(B > 0 && C > 0, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: empty problem B=%d C=%d", B, C);
+  GG_CHECK(logits_bf16 && lse && row_stats && cent_table && dlogits_bf16 && loss_rows && workspace, GG_ERR_ARG,
+           "gg_hav_ce_fwd_bwd: null pointer");
+  const HavPlan p = make_hav_plan(B, C);
+  const StatsPlan sp = make_stats_plan(B, C);
+  GG_CHECK(ldc >= p.Cpad && ldc % 2 == 0, GG_ERR_ARG,
+           "gg_hav_ce_fwd_bwd: ldc=%d must be >= %d (C rounded up to 256) and even", ldc, p.Cpad);
+  GG_CHECK(tau > 0.f, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: tau must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint8_t* sb = static_cast<const uint8_t*>(row_stats);
+  const RowRec* rec = reinterpret_cast<const RowRec*>(sb + sp.off_rec);
+  const uint32_t* near = reinterpret_cast<const uint32_t*>(sb + sp.off_near);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(const_cast<uint8_t*>(sb) + sp.off_counter);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* loss_part = reinterpret_cast<float*>(ws + p.off_loss_part);
+  float* block_part = reinterpret_cast<float*>(ws + p.off_block_part);
+  const float neg_rk2 = -kEarthRadiusKm * (1.0f / tau) * kLog2eF;
+
+  const int warps = p.nslices * p.nrb;
+  const int grid_b = ceil_div(warps, kStreamThreads / 32);
+  if (db_partials)
+    hav_ce_stream_kernel<true><<<grid_b, kStreamThreads, 0, s>>>(
+        static_cast<const bf16*>(logits_bf16), ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
+        p.nslices, p.nrb, neg_rk2, static_cast<bf16*>(dlogits_bf16), loss_part, db_partials);
+  else
+    hav_ce_stream_kernel<false><<<grid_b, kStreamThreads, 0, s>>>(
+        static_cast<const bf16*>(logits_bf16), ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
+        p.nslices, p.nrb, neg_rk2, static_cast<bf16*>(dlogits_bf16), loss_part, nullptr);
+  GG_LAUNCH_CHECK();
+  hav_loss_finish_kernel<<<p.finish_blocks, dim3(32, 8), 0, s>>>(loss_part, p.nslices, lse, rec, B, loss_rows,
+                                                                 block_part, counter, mean_scale, loss_mean);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
 }
 
 extern "C" int gg_hard_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const long long* labels_clf,

@@ -5,6 +5,8 @@
 // left them in -- dlogits (B, ldc) and x (B, D), batch-major -- i.e. as MN-major UMMA operands:
 // the contraction index (batch) is the slow index of both.  TMA loads 64(k) x 64(mn) boxes with
 // the 128-byte swizzle; a 128 x 256 x 64 stage is 2 + 4 such boxes.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -191,21 +193,30 @@ __global__ void db_partial_kernel(const bf16* __restrict__ g, int ldc, int B, in
     }
   }
 }
+// Block (32 columns x 8 slice lanes): lane y sums slices y, y+8, ... (coalesced 128-byte rows), then a
+// fixed-order reduction over y in shared memory: deterministic, and wide enough to hide the latency.
 __global__ void db_final_kernel(const float* __restrict__ partial, int C, int ld, int slices, float scale_in,
                                 const float* __restrict__ grad_scale, float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // fixed order: deterministic
-  int i = 0;
-  for (; i + 4 <= slices; i += 4) {
-    s0 += partial[static_cast<size_t>(i) * ld + c];
-    s1 += partial[static_cast<size_t>(i + 1) * ld + c];
-    s2 += partial[static_cast<size_t>(i + 2) * ld + c];
-    s3 += partial[static_cast<size_t>(i + 3) * ld + c];
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    int i = threadIdx.y;
+    for (; i + 8 < slices; i += 16) {
+      s0 += partial[static_cast<size_t>(i) * ld + c];
+      s1 += partial[static_cast<size_t>(i + 8) * ld + c];
+    }
+    if (i < slices) s0 += partial[static_cast<size_t>(i) * ld + c];
   }
-  for (; i < slices; ++i) s0 += partial[static_cast<size_t>(i) * ld + c];
-  db[c] = ((s0 + s1) + (s2 + s3)) * scale;
+  red[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+    db[c] = s * scale;
+  }
 }
 
 }  // namespace gg
@@ -236,14 +247,14 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   head_bwd_kernel<<<grid, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
   GG_LAUNCH_CHECK();
   if (db && db_partials) {  // column sums already accumulated by the loss kernel (one row per CTA)
-    db_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(db_partials, C, db_ld, db_parts, scale, grad_scale, db);
+    db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(db_partials, C, db_ld, db_parts, scale, grad_scale, db);
     GG_LAUNCH_CHECK();
   } else if (db) {
     float* partial = static_cast<float*>(workspace);
     dim3 blk(32, 8), grd(ceil_div(ldc, 256), kDbSlices);
     db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);
     GG_LAUNCH_CHECK();
-    db_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(partial, C, C, kDbSlices, scale, grad_scale, db);
+    db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(partial, C, C, kDbSlices, scale, grad_scale, db);
     GG_LAUNCH_CHECK();
   }
   return GG_OK;

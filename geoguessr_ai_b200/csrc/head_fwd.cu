@@ -81,6 +81,21 @@ __device__ __forceinline__ void topk_insert(float (&tv)[KTOP], int (&ti)[KTOP], 
   }
 }
 
+// v[i] for a run-time i without spilling v[] to local memory: 5-level select tree (31 FSEL).
+__device__ __forceinline__ float select32(const float (&v)[32], int i) {
+  float a[16], b[8], c[4], d[2];
+  const bool b0 = i & 1, b1 = i & 2, b2 = i & 4, b3 = i & 8, b4 = i & 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = b0 ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = b1 ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c[j] = b2 ? b[2 * j + 1] : b[2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) d[j] = b3 ? c[2 * j + 1] : c[2 * j];
+  return b4 ? d[1] : d[0];
+}
+
 template <int KTOP, bool WRITE_LOGITS>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -244,9 +259,20 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           }
           run_sum += (s0 + s1) + (s2 + s3);
         }
-        if (cmax > tv[KTOP - 1]) {  // rare once the list has seen a few hundred columns
+        if (cmax > tv[KTOP - 1]) {
+          // Lanes are different rows, so which of the 32 columns qualify differs per lane: an unrolled
+          // "insert if larger" chain makes the whole warp walk all 32 insert bodies.  Instead build a
+          // per-thread bitmask of the qualifying columns (predicated, branch-free) and pop it in a
+          // data-driven loop whose trip count is the largest popcount in the warp (usually 1-2).
+          const float thr = tv[KTOP - 1];
+          uint32_t mask = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) topk_insert<KTOP>(tv, ti, v[i], col0 + i);
+          for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;
+          while (mask) {  // ascending column order: on ties the lower geocell index stays first
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            topk_insert<KTOP>(tv, ti, select32(v, i), col0 + i);
+          }
         }
       }
       // TMEM accumulator drained -> hand it back to the MMA warp
@@ -421,7 +447,7 @@ extern "C" size_t gg_head_fwd_workspace_bytes(int B, int C, int k) {
   return fwd_partials(sc) * kBM * (2 + 2 * ktop) * sizeof(float);
 }
 
-extern "C" int gg_head_logits_ld(int C) { return ceil_div(C, 64) * 64; }
+extern "C" int gg_head_logits_ld(int C) { return ceil_div(C, 256) * 256; }
 extern "C" int gg_head_bias_pad(int C) { return ceil_div(C, kBN) * kBN; }
 
 extern "C" int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, int B, int C, int D,

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-FAR_KM_DEFAULT = 65.0 * math.log(2.0 ** 40)  # ~1802 km: targets below 2^-40 of the nearest cell's are dropped
+FAR_KM_DEFAULT = 65.0 * math.log(2.0 ** 32)  # ~1442 km: targets below 2^-32 of the nearest cell's are dropped
 
 
 # Optional per-launcher timing (bench.py): when enabled, every C-ABI call is bracketed by CUDA events
@@ -137,37 +137,61 @@ def head_forward(x16, w16, bias_pad, C, k, centroids, want_logits: bool):
 
 # --------------------------------------------------------------------------- a5-a8
 def centroid_unit_vectors(centroids: torch.Tensor) -> torch.Tensor:
+    """(C,2) (lng,lat) -> the loss kernels' centroid table (unit vectors + spatial index)."""
     _need_cuda(centroids)
     c = centroids.detach().float().contiguous()
     C = c.shape[0]
     lib = _lib.load()
-    xyz = torch.empty((3 * lib.gg_hav_cpad(C),), dtype=torch.float32, device=c.device)
-    _call("gg_centroid_unit_vectors", lib.gg_centroid_unit_vectors, _ptr(c), _ptr(xyz), C, _stream())
-    return xyz
+    table = torch.empty((lib.gg_centroid_table_floats(C),), dtype=torch.float32, device=c.device)
+    ws = _u8(lib.gg_centroid_table_workspace_bytes(C), c.device)
+    _call("gg_centroid_unit_vectors", lib.gg_centroid_unit_vectors, _ptr(c), _ptr(table), C, _ptr(ws), _stream())
+    return table
 
 
-def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False, want_db=False):
+def hav_row_stats(labels, cent_table, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False):
+    """Label-only half of the smoothed loss.  Returns (row_stats buffer, nearest_cell (B) i64 | None,
+    nearest_km (B) | None)."""
+    _need_cuda(labels, cent_table)
+    labels = labels.detach().float().contiguous()
+    B = labels.shape[0]
+    assert labels.shape == (B, 2), "labels must be (B, 2) (lng, lat)"
+    dev = labels.device
+    lib = _lib.load()
+    stats = _u8(lib.gg_hav_row_stats_bytes(B, C), dev)
+    ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
+    nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
+    _call("gg_hav_row_stats", lib.gg_hav_row_stats, _ptr(labels), _ptr(cent_table), B, C, float(tau), float(far_km),
+          _ptr(stats), _ptr(ncell), _ptr(nkm), _stream())
+    return stats, ncell, nkm
+
+
+def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False, want_db=False,
+           want_mean=False, row_stats=None):
     """Fused haversine label-smoothed CE.  Returns (dlogits bf16 (B,ldc) = p - t, loss_rows (B),
-    nearest_cell (B) i64 | None, nearest_km (B) | None[, db_partials (parts, Cpad) fp32 if want_db])."""
-    _need_cuda(logits, lse, labels, cent_xyz)
+    nearest_cell (B) i64 | None, nearest_km (B) | None[, db_partials (parts, Cpad) fp32 if want_db]
+    [, loss_mean () fp32 if want_mean]).  row_stats: result of hav_row_stats() when it was computed
+    ahead (then labels / far_km / want_nearest are not used here)."""
+    _need_cuda(logits, lse, cent_xyz)
     B, ldc = logits.shape
     dev = logits.device
     lib = _lib.load()
-    labels = labels.detach().float().contiguous()
-    assert labels.shape == (B, 2), "labels must be (B, 2) (lng, lat)"
+    ncell = nkm = None
+    if row_stats is None:
+        row_stats, ncell, nkm = hav_row_stats(labels, cent_xyz, C, tau, far_km, want_nearest)
     dlogits = torch.empty_like(logits)
     loss_rows = torch.empty((B,), dtype=torch.float32, device=dev)
-    ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
-    nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
-    ws = _u8(lib.gg_hav_ce_workspace_bytes(B), dev)
-    dbp = (torch.empty((lib.gg_hav_ce_db_parts(B), lib.gg_hav_cpad(C)), dtype=torch.float32, device=dev)
+    ws = _u8(lib.gg_hav_ce_workspace_bytes(B, C), dev)
+    dbp = (torch.empty((lib.gg_hav_ce_db_parts(B, C), lib.gg_hav_cpad(C)), dtype=torch.float32, device=dev)
            if want_db else None)
-    _call("gg_hav_ce_fwd_bwd", lib.gg_hav_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(labels), _ptr(cent_xyz), B, C, float(tau),
-                              float(far_km), _ptr(dlogits), _ptr(loss_rows), _ptr(ncell), _ptr(nkm), _ptr(dbp), _ptr(ws),
-                              _stream())
+    mean = torch.empty((), dtype=torch.float32, device=dev) if want_mean else None
+    _call("gg_hav_ce_fwd_bwd", lib.gg_hav_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(row_stats), _ptr(cent_xyz), B, C,
+          float(tau), _ptr(dlogits), _ptr(loss_rows), _ptr(dbp), _ptr(ws), _ptr(mean), 1.0 / B, _stream())
+    out = (dlogits, loss_rows, ncell, nkm)
     if want_db:
-        return dlogits, loss_rows, ncell, nkm, dbp
-    return dlogits, loss_rows, ncell, nkm
+        out += (dbp,)
+    if want_mean:
+        out += (mean,)
+    return out
 
 
 def hard_ce(logits, lse, labels_clf, C):

@@ -35,12 +35,12 @@ class _GeocellHeadLoss(torch.autograd.Function):
                                 module.geocell_centroid_coords.data, want_logits=True)
         dbp = None
         if smooth:
-            dlogits, loss_rows, _, _, dbp = ops.hav_ce(head["logits"], head["lse"], labels, module._centroid_xyz(), C,
-                                                       tau=module.label_smoothing_tau, far_km=module.far_km,
-                                                       want_db=True)
+            dlogits, loss_rows, _, _, dbp, loss = ops.hav_ce(head["logits"], head["lse"], labels, module._centroid_xyz(),
+                                                             C, tau=module.label_smoothing_tau, far_km=module.far_km,
+                                                             want_db=True, want_mean=True)
         else:
             dlogits, loss_rows = ops.hard_ce(head["logits"], head["lse"], labels_clf, C)
-        loss = ops.loss_mean(loss_rows)
+            loss = ops.loss_mean(loss_rows)
         ctx.save_for_backward(dlogits, x16)
         ctx.dbp = dbp
         ctx.set_materialize_grads(False)  # no zero-filled grads for the non-differentiable outputs

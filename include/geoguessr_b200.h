@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 1
+#define GG_ABI_VERSION 2
 
 #define GG_OK 0
 #define GG_ERR_ARG 1         /* bad shape / alignment / null pointer */
@@ -33,13 +33,17 @@ int gg_abi_version(void);
 const char* gg_last_error(void);
 
 /* ---- layout helpers (host, pure) ---------------------------------------------------------- */
-int gg_head_logits_ld(int C); /* row pitch (elements) of the bf16 logits / dlogits buffers: C rounded up to 64 */
+int gg_head_logits_ld(int C); /* row pitch (elements) of the bf16 logits / dlogits buffers: C rounded up to 256 */
 int gg_head_bias_pad(int C);  /* length of the zero-padded fp32 bias vector: C rounded up to 256 */
-int gg_hav_cpad(int C);       /* geocells rounded up to 4: the centroid unit-vector table is 3 * gg_hav_cpad(C) floats */
+int gg_hav_cpad(int C);       /* geocells rounded up to 256: column pitch of the centroid table and of db_partials */
+size_t gg_centroid_table_floats(int C); /* 4-byte words in the table gg_centroid_unit_vectors fills: unit vectors in
+                                           class order + a Morton-sorted copy with one bounding cap per 64 cells */
+size_t gg_centroid_table_workspace_bytes(int C);
+size_t gg_hav_row_stats_bytes(int B, int C);
 size_t gg_head_fwd_workspace_bytes(int B, int C, int k);
 size_t gg_head_bwd_workspace_bytes(int C);
-size_t gg_hav_ce_workspace_bytes(int B);
-int gg_hav_ce_db_parts(int B); /* rows of the loss kernel's bias-gradient partial sums (one per CTA) */
+size_t gg_hav_ce_workspace_bytes(int B, int C);
+int gg_hav_ce_db_parts(int B, int C); /* rows of the loss kernel's bias-gradient partial sums (one per row block) */
 size_t gg_proto_retrieve_workspace_bytes(int B, int topk, int D, int ncell);
 
 /* ---- a1: heading fusion -------------------------------------------------------------------
@@ -72,19 +76,33 @@ int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, i
 /* ---- a5-a8: haversine label-smoothed cross-entropy, forward + gradient ---------------------
  * models/utils.py:39-57 haversine_matrix; :20-32 smooth_labels (tau = config.py:52 = 65 km);
  * super_guessr.py:374-380 normalise + soft CE; autograd backward (main_coordinator_idun_s3.py:423).
- * cent_xyz: unit vectors from gg_centroid_unit_vectors (recompute when the centroid table changes).
- * labels (B,2) fp32 (lng,lat) degrees.  dlogits (B, ldc) bf16 = softmax(logits) - t, UNSCALED
- * (gg_head_bwd applies 1/B).  loss_rows (B) fp32 = -sum_c t log_softmax.  Optional by-products
- * (next-row, main_coordinator_idun_s3.py:390-391): nearest_cell (B) int64 = argmin_c d,
- * nearest_km (B) fp32; db_partials (gg_hav_ce_db_parts(B), gg_hav_cpad(C)) fp32 = per-CTA column sums of
- * dlogits, finished by gg_head_bwd (saves a second pass over dlogits for the bias gradient).
- * far_km: cells farther than dmin + far_km get t = 0 (65*ln(2^40) ~= 1802 km keeps every
- * t > 2^-40; INFINITY evaluates every cell). */
-int gg_centroid_unit_vectors(const float* centroids, float* cent_xyz, int C, gg_stream_t stream);
-int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const float* labels, const float* cent_xyz,
-                      int B, int C, float tau, float far_km, void* dlogits_bf16, float* loss_rows,
-                      long long* nearest_cell, float* nearest_km, float* db_partials, void* workspace,
-                      gg_stream_t stream);
+ *
+ * gg_centroid_unit_vectors: once per centroid table ((C,2) fp32 (lng,lat) degrees) -> cent_table
+ * (gg_centroid_table_floats(C) words).  Geocell tables up to 16384 cells.
+ *
+ * gg_hav_row_stats: everything that depends on the labels only -- per row the label unit vector, the
+ * nearest centroid (row minimum of the haversine matrix, utils.py:29), sum_c exp(-(d - dmin)/tau)
+ * (super_guessr.py:377) and which 64-class groups hold cells with d < dmin + far_km.  labels (B,2) fp32
+ * (lng,lat) degrees; row_stats: gg_hav_row_stats_bytes(B,C) bytes, consumed by gg_hav_ce_fwd_bwd.  It reads
+ * no logits, so it can run before / beside the head GEMM.  By-products = the trainer's label derivation
+ * (main_coordinator_idun_s3.py:390-391): nearest_cell (B) int64 = argmin_c d (first index on ties),
+ * nearest_km (B) fp32; either may be null.
+ * far_km: cells farther than dmin + far_km get t = 0 (65*ln(2^32) ~= 1442 km, the Python default,
+ * keeps every target above 2^-32 of the nearest cell's, i.e. below the fp32 rounding of the reference's
+ * own row sum; INFINITY evaluates every cell).
+ *
+ * gg_hav_ce_fwd_bwd: the B x C pass.  logits / dlogits (B, ldc) bf16 with ldc >= gg_hav_cpad(C);
+ * dlogits = softmax(logits) - t, UNSCALED (gg_head_bwd applies 1/B).  loss_rows (B) fp32 =
+ * -sum_c t log_softmax; loss_mean (optional, 1 float) = mean_scale * sum_b loss_rows, summed in a fixed
+ * order (deterministic) -- the `.mean()` of super_guessr.py:380 with mean_scale = 1/B.  db_partials
+ * (optional, (gg_hav_ce_db_parts(B,C), gg_hav_cpad(C)) fp32) = per-row-block column sums of dlogits,
+ * finished by gg_head_bwd (saves a second pass over dlogits for the bias gradient). */
+int gg_centroid_unit_vectors(const float* centroids, float* cent_table, int C, void* workspace, gg_stream_t stream);
+int gg_hav_row_stats(const float* labels, const float* cent_table, int B, int C, float tau, float far_km,
+                     void* row_stats, long long* nearest_cell, float* nearest_km, gg_stream_t stream);
+int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const void* row_stats,
+                      const float* cent_table, int B, int C, float tau, void* dlogits_bf16, float* loss_rows,
+                      float* db_partials, void* workspace, float* loss_mean, float mean_scale, gg_stream_t stream);
 /* super_guessr.py:383 nn.CrossEntropyLoss()(logits, labels_clf) and its gradient. */
 int gg_hard_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* lse, const long long* labels_clf, int B, int C,
                        void* dlogits_bf16, float* loss_rows, gg_stream_t stream);

@@ -29,9 +29,10 @@ def test_library_loads_and_exports_header_symbols():
 
 def test_layout_helpers():
     lib = _lib.load()
-    assert lib.gg_head_logits_ld(12647) == 12672 and lib.gg_head_logits_ld(64) == 64
+    assert lib.gg_head_logits_ld(12647) == 12800 and lib.gg_head_logits_ld(64) == 256
     assert lib.gg_head_bias_pad(12647) == 12800
-    assert lib.gg_hav_cpad(12647) == 12648
+    assert lib.gg_hav_cpad(12647) == 12800
+    assert lib.gg_centroid_table_floats(12647) == 3 * 12800 + 4 * 12672 + 12 * 198
     assert lib.gg_head_fwd_workspace_bytes(4096, 12647, 5) >= 148 * 2 * 128 * 12 * 4
     assert lib.gg_proto_retrieve_workspace_bytes(64, 5, 1024, 12647) > 64 * 5 * 1024 * 2
 
@@ -40,7 +41,7 @@ def test_argument_errors_are_reported_not_crashed():
     lib = _lib.load()
     rc = lib.gg_head_fwd(0, 0, 0, 16, 100, 12, 0, 0, 5, 0, 0, 0, 0, 0, 0, 0, 0)  # D % 8 != 0
     assert rc == 1 and b"multiple of 8" in lib.gg_last_error()
-    rc = lib.gg_hav_ce_fwd_bwd(0, 0, 0, 0, 0, 0, 10, 65.0, 100.0, 0, 0, 0, 0, 0, 0, 0)
+    rc = lib.gg_hav_ce_fwd_bwd(0, 0, 0, 0, 0, 0, 10, 65.0, 0, 0, 0, 0, 0, 1.0, 0)
     assert rc == 1
 
 

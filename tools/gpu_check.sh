@@ -21,7 +21,7 @@ for w in $what; do
         python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on \
-        -k regex:'head_fwd_kernel|hav_ce_kernel|head_bwd_kernel' -s 9 -c 3 -f -o gpurun_out/prof_train \
+        -k regex:"${NCU_KERNELS:-head_fwd_kernel|hav_ce_stream_kernel|head_bwd_kernel|hav_row_stats_kernel}" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-4} -f -o gpurun_out/prof_train \
         python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
   esac
 done

@@ -155,7 +155,7 @@ def train_config(n_gpus, cfg):
     return {"workload": "BASELINE configs[1]: geocell head training step, haversine label-smoothed CE + backward + "
                         "AdamW, synthetic CLIP ViT-L/14 embeddings",
             "batch_per_gpu": cfg["B"], "global_batch": cfg["B"] * n_gpus, "embed_dim": cfg["D"], "headings": cfg["V"],
-            "geocells": C_CELLS, "num_candidates": cfg["k"], "parallelism": f"dp{n_gpus}",
+            "geocells": C_CELLS, "num_candidates": cfg["k"], "parallelism": f"dp{n_gpus}", "cuda_graph": None,
             "l2": "working set per step (~0.6 GB: embeddings, W, logits, dlogits, dW, AdamW state) exceeds the 126 MB "
                   "L2; input batches rotate over 3 resident buffers"}
 
@@ -192,7 +192,8 @@ def run_b200_train(args):
         model.cell_layer.bias.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
     model.train()
     params = [model.cell_layer.weight, model.cell_layer.bias]
-    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=use_graph)
 
     host = make_batches(3, B, D, V, seed0=100 + 10 * rank)
     host = [(e.pin_memory(), l.pin_memory()) for e, l in host]
@@ -221,9 +222,45 @@ def run_b200_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    # One CUDA graph per input buffer: the ~25 launches of a step (ours, the fused AdamW, the NCCL
+    # all-reduce) replay without host work in between.  Falls back to eager launches if capture fails.
+    graphs = {}
+
+    def capture(key, emb, labels):
+        g = torch.cuda.CUDAGraph()
+        pool = next(iter(graphs.values()))[0].pool() if graphs else None
+        with torch.cuda.graph(g, pool=pool):
+            loss = step(emb, labels)
+        graphs[key] = (g, loss)
+
+    def run(key, emb, labels):
+        if key in graphs:
+            g, loss = graphs[key]
+            g.replay()
+            return loss
+        return step(emb, labels)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # eager warm-up off the default stream (required before capture)
+        for i in range(3):
+            step(*resident[i % 3])
+    torch.cuda.current_stream().wait_stream(side)
+    barrier()
+    if use_graph:
+        try:
+            for i in range(3):
+                capture(("res", i), *resident[i])
+        except Exception as e:  # noqa: BLE001
+            graphs.clear()
+            use_graph = False
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+
     # ---------------- device-resident throughput (`value`)
     for i in range(Wm):
-        step(*resident[i % 3])
+        run(("res", i % 3), *resident[i % 3])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -232,7 +269,7 @@ def run_b200_train(args):
     barrier()
     e0.record()
     for i in range(K):
-        loss = step(*resident[i % 3])
+        loss = run(("res", i % 3), *resident[i % 3])
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -261,11 +298,20 @@ def run_b200_train(args):
             bufs[i % 2][1].copy_(host[i % 3][1], non_blocking=True)
             evs[i % 2].record(copy_stream)
 
+    if use_graph:
+        try:
+            for i in range(2):
+                capture(("e2e", i), *bufs[i])
+        except Exception:  # noqa: BLE001
+            for i in range(2):
+                graphs.pop(("e2e", i), None)
+            torch.cuda.synchronize()
+
     def e2e_loop(n):
         issue_copy(0)
         for i in range(n):
             torch.cuda.current_stream().wait_event(evs[i % 2])
-            l = step(*bufs[i % 2])
+            l = run(("e2e", i % 2), *bufs[i % 2])
             if i + 1 < n:
                 issue_copy(i + 1)  # next batch crosses PCIe while this step computes
             l.item()  # device -> host read of the step's result
@@ -320,11 +366,11 @@ def run_b200_train(args):
                "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
                          "reference forward + autograd backward + AdamW)"}
 
-    launches_per_step = 1 + 2 + 2 + 2 + 1 + 2  # fuse, prepare(cast+bias), head_fwd(+merge), hav(+labels), mean, bwd(+db)
+    launches_per_step = 1 + 2 + 2 + 2 + 2 + 2  # fuse, prepare(cast+bias), head_fwd(+merge), row_stats(labels+stats), hav(stream+finish), bwd(+db)
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": train_config(world, cfg), "clocks": clocks,
+        "dtype": "bf16", "data": "synthetic", "config": dict(train_config(world, cfg), cuda_graph=use_graph), "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "steps": Ke},
         "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
@@ -343,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

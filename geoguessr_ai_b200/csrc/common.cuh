@@ -40,7 +40,20 @@ void set_error(const char* fmt, ...);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                       uint32_t box_inner, uint32_t box_rows);
 
+// Same without swizzle: box = {box_inner elements (<= 256, multiple of 8), box_rows}, rows land
+// contiguously (box_inner * 2 bytes apart) in shared memory.
+int make_tmap_bf16_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                            uint32_t box_inner, uint32_t box_rows);
+
 int device_sm_count();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): keeps the launch path free
+// of driver calls (and legal inside CUDA-graph stream capture).
+int set_max_dynamic_smem_once_impl(const void* kernel, size_t bytes);
+template <typename K>
+int set_max_dynamic_smem_once(K kernel, size_t bytes) {
+  return set_max_dynamic_smem_once_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -44,9 +44,8 @@ constexpr float kEarthRadiusKm = 6378.137f;  // models/utils.py:55 (6378137 m) /
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr int kCellsPerGroup = 64;   // spatial group (one cap) and class group (one near-mask bit)
 constexpr int kColsPerWarp = 256;    // kernel B: 4 class groups = one nibble of the near mask
-constexpr int kMaxSlots = 8;         // kernel A keeps one group bound per lane per slot: <= 256 groups
+constexpr int kMaxSlots = 2;         // kernel A keeps one group bound per thread per slot: <= 256 groups
 constexpr int kMaxMaskWords = 8;     // near mask words per row: 256 class groups
-constexpr int kStreamThreads = 128, kStreamCtasPerSm = 5;  // kernel B: 20 warps per SM at <= 102 registers
 constexpr float kCapMargin = 1.0e-5f;  // rad (64 m): absorbs fp32 rounding in the cap tests
 
 struct RowRec {  // 32 bytes per row, written by (A), read by (B)/(C)
@@ -56,13 +55,13 @@ struct RowRec {  // 32 bytes per row, written by (A), read by (B)/(C)
 
 // Centroid table layout, in 4-byte words (see (T)):
 //   x[Cpad] y[Cpad] z[Cpad]                       class order, Cpad = C rounded up to 256
-//   sx[Cs] sy[Cs] sz[Cs] sidx[Cs] (int)            Morton order, Cs = C rounded up to 64
-//   caps[4 * Cs/64] = {cx, cy, cz, radius}         radius 4 = anywhere, < 0 = empty group
+//   scell[Cs] = {x, y, z, class index (int bits)}  Morton order, Cs = C rounded up to 64 (pad: 1e9, INT_MAX)
+//   caps[Cs/64] = {cx, cy, cz, radius}             radius 4 = anywhere, < 0 = empty group
 //   gmask[kMaxMaskWords * Cs/64] (uint)            class groups touched by each spatial group
 struct TableView {
   int Cpad, Cs, ngroups;
-  const float *x, *y, *z, *sx, *sy, *sz;
-  const int* sidx;
+  const float *x, *y, *z;
+  const float4* scell;
   const float4* caps;
   const uint32_t* gmask;
 };
@@ -80,11 +79,8 @@ __host__ __device__ inline TableView view_table(const float* t, int C) {
   v.x = t;
   v.y = v.x + v.Cpad;
   v.z = v.y + v.Cpad;
-  v.sx = v.z + v.Cpad;
-  v.sy = v.sx + v.Cs;
-  v.sz = v.sy + v.Cs;
-  v.sidx = reinterpret_cast<const int*>(v.sz + v.Cs);
-  v.caps = reinterpret_cast<const float4*>(v.sz + 2 * static_cast<size_t>(v.Cs));
+  v.scell = reinterpret_cast<const float4*>(v.z + v.Cpad);  // 3 * Cpad words: 16-byte aligned (Cpad % 256 == 0)
+  v.caps = v.scell + v.Cs;
   v.gmask = reinterpret_cast<const uint32_t*>(v.caps + v.ngroups);
   return v;
 }
@@ -123,19 +119,17 @@ __device__ __forceinline__ float theta_from_q_fast(float q) {
   return h <= 0.25f ? near_half : far_half;
 }
 // Unnormalised target s = exp(-(d - dmin)/tau) = 2^(neg_rk2 * theta + off) of a cell at squared chord
-// q, or 0 when q >= q_thr.  (A) sums it and (B) applies it: both call exactly this function.
-// WIDE = false assumes q_thr <= 1 (d < 6672 km: every row unless dmin + far_km exceeds that), so a
-// cell that passes the test is on the first asin branch and nothing diverges.
-template <bool WIDE>
+// q, or 0 when q >= q_thr.  (A) sums it and (B) applies it: both call exactly this function (the same
+// bits), so the targets of a row sum to one.  Branch-free.
 __device__ __forceinline__ float target_weight(float q, float q_thr, float neg_rk2, float off) {
-  float theta;
-  if (!WIDE) {
-    const float h = 0.25f * fminf(q, 1.0f);
-    theta = 2.0f * asin_poly(sqrt_approx(h), h);
-  } else {
-    theta = theta_from_q_fast(q);
-  }
-  const float s = ex2_approx(fmaf(neg_rk2, theta, off));
+  const float s = ex2_approx(fmaf(neg_rk2, theta_from_q_fast(q), off));
+  return q < q_thr ? s : 0.f;
+}
+// Same bits as target_weight for q < q_thr <= 1 (d < 6672 km: the near half of theta_from_q_fast, evaluated
+// by the same operations), 0 otherwise: lets (A) skip the far-half polynomial on almost every row.
+__device__ __forceinline__ float target_weight_narrow(float q, float q_thr, float neg_rk2, float off) {
+  const float h = fminf(0.25f * q, 1.0f);
+  const float s = ex2_approx(fmaf(neg_rk2, 2.0f * asin_poly(sqrt_approx(h), h), off));
   return q < q_thr ? s : 0.f;
 }
 // squared chord; (A) and (B) must evaluate it identically (same threshold decisions)
@@ -194,7 +188,7 @@ __global__ void table_unit_kernel(const float* __restrict__ centroids, float* __
   table[2 * static_cast<size_t>(Cpad) + c] = z;
 }
 // rank of every class along the Morton curve (O(C^2) compares, C ~ 1e4, once per table)
-__global__ void table_rank_kernel(const uint32_t* __restrict__ keys, int C, int* __restrict__ sidx) {
+__global__ void table_rank_kernel(const uint32_t* __restrict__ keys, int C, float4* __restrict__ scell) {
   __shared__ uint32_t tile[256];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t mine = c < C ? keys[c] : 0u;
@@ -209,7 +203,7 @@ __global__ void table_rank_kernel(const uint32_t* __restrict__ keys, int C, int*
       rank += (k < mine || (k == mine && base + i < c)) ? 1 : 0;
     }
   }
-  if (c < C) sidx[rank] = c;
+  if (c < C) scell[rank].w = __int_as_float(c);
 }
 // sorted copy, one warp per spatial group (2 cells per lane): centre = normalised mean of the
 // members, radius = largest member angle + margin; class-group bitmask of the members
@@ -218,10 +212,7 @@ __global__ void table_group_kernel(float* __restrict__ table, int C) {
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (g >= tv.ngroups) return;
-  float* sx = const_cast<float*>(tv.sx);
-  float* sy = const_cast<float*>(tv.sy);
-  float* sz = const_cast<float*>(tv.sz);
-  int* sidx = const_cast<int*>(tv.sidx);
+  float4* scell = const_cast<float4*>(tv.scell);
   float x[2], y[2], z[2];
   int idx[2];
   float n = 0.f, mx = 0.f, my = 0.f, mz = 0.f;
@@ -231,13 +222,11 @@ __global__ void table_group_kernel(float* __restrict__ table, int C) {
     x[h] = y[h] = z[h] = 1.0e9f;
     idx[h] = 0x7fffffff;
     if (p < C) {
-      idx[h] = sidx[p];
+      idx[h] = __float_as_int(scell[p].w);
       x[h] = tv.x[idx[h]]; y[h] = tv.y[idx[h]]; z[h] = tv.z[idx[h]];
       n += 1.f; mx += x[h]; my += y[h]; mz += z[h];
-    } else {
-      sidx[p] = 0x7fffffff;
     }
-    sx[p] = x[h]; sy[p] = y[h]; sz[p] = z[h];
+    scell[p] = make_float4(x[h], y[h], z[h], __int_as_float(idx[h]));
   }
   n = warp_sum(n); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
   const float len = sqrtf(mx * mx + my * my + mz * mz);
@@ -285,72 +274,96 @@ __global__ void label_xyz_kernel(const float* __restrict__ labels, float4* __res
   out[b] = o;
 }
 
+// One CTA (4 warps) per row.  Thread t owns the caps of spatial groups 4*(t%32) + t/32 + 128*s, so
+// Morton-adjacent groups belong to different warps and each warp walks only its own groups.
 template <int SLOTS>
 __global__ void __launch_bounds__(128)
 hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict__ table, int C, int B, float k2,
                      float cos_half_far, float sin_half_far, float phi, RowRec* __restrict__ rec,
                      uint32_t* __restrict__ near, int nwp, long long* __restrict__ nearest_cell,
                      float* __restrict__ nearest_km) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= B) return;
+  __shared__ float s_f[4];
+  __shared__ int s_i[4];
+  __shared__ uint32_t s_mask[4][kMaxMaskWords];
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TableView tv = view_table(table, C);
   const float4 u = __ldg(lab_xyz + row);
   const float ux = u.x, uy = u.y, uz = u.z;
   const bool valid = u.w != 0.f;
 
-  // phase 1: distance bounds of every spatial group from its cap
+  // phase 1: distance bounds of my spatial groups from their caps
   float lo[SLOTS];
-  float lo_min = CUDART_INF_F;
-  int g_best = 0;
+  float lo_min = CUDART_INF_F;  // (smallest a + radius: the group that guarantees the closest cell)
+  int g_best = 0x7fffffff;
 #pragma unroll
   for (int k = 0; k < SLOTS; ++k) {
-    const int g = lane + 32 * k;
+    const int g = 4 * lane + warp + 128 * k;
     lo[k] = CUDART_INF_F;
     if (g < tv.ngroups) {
       const float4 cap = __ldg(tv.caps + g);
       if (cap.w >= 0.f) {
         const float a = theta_from_q_fast(chord2(ux, uy, uz, cap.x, cap.y, cap.z));
         lo[k] = fmaxf(a - cap.w, 0.f);
-        if (lo[k] < lo_min) { lo_min = lo[k]; g_best = g; }
+        if (a + cap.w < lo_min) { lo_min = a + cap.w; g_best = g; }
       }
     }
   }
-  // the most promising group gives a real cell distance = a tight upper bound of the row minimum
+  // scanning that group gives a real cell distance = a tight upper bound of the row minimum
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ol = __shfl_xor_sync(0xffffffffu, lo_min, o);
     const int og = __shfl_xor_sync(0xffffffffu, g_best, o);
     if (ol < lo_min || (ol == lo_min && og < g_best)) { lo_min = ol; g_best = og; }
   }
+  if (lane == 0) { s_f[warp] = lo_min; s_i[warp] = g_best; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float ol = s_f[w];
+    const int og = s_i[w];
+    if (ol < lo_min || (ol == lo_min && og < g_best)) { lo_min = ol; g_best = og; }
+  }
+  __syncthreads();  // s_f / s_i are reused below
+
   float qmin = CUDART_INF_F;
   int imin = 0x7fffffff;
-  auto scan_group = [&](int g) {
-    const int p = g * kCellsPerGroup + lane;
-    const float q0 = chord2(ux, uy, uz, __ldg(tv.sx + p), __ldg(tv.sy + p), __ldg(tv.sz + p));
-    const float q1 = chord2(ux, uy, uz, __ldg(tv.sx + p + 32), __ldg(tv.sy + p + 32), __ldg(tv.sz + p + 32));
-    const int i0 = __ldg(tv.sidx + p), i1 = __ldg(tv.sidx + p + 32);
+  auto scan_cells = [&](const float4& c0, const float4& c1) {
+    const float q0 = chord2(ux, uy, uz, c0.x, c0.y, c0.z), q1 = chord2(ux, uy, uz, c1.x, c1.y, c1.z);
+    const int i0 = __float_as_int(c0.w), i1 = __float_as_int(c1.w);
     if (q0 < qmin || (q0 == qmin && i0 < imin)) { qmin = q0; imin = i0; }  // first class index on ties
     if (q1 < qmin || (q1 == qmin && i1 < imin)) { qmin = q1; imin = i1; }
   };
-  scan_group(g_best);
+  {
+    const float4* p = tv.scell + g_best * kCellsPerGroup + lane;
+    scan_cells(__ldg(p), __ldg(p + 32));
+  }
   const float ub = theta_from_q_fast(warp_min(qmin)) + kCapMargin;
 
-  // phase 2: exact nearest cell among the groups that can still contain it
+  // phase 2: exact nearest cell among my groups that can still contain it
 #pragma unroll
   for (int k = 0; k < SLOTS; ++k) {
-    uint32_t m = __ballot_sync(0xffffffffu, lo[k] <= ub && lane + 32 * k != g_best);
+    uint32_t m = __ballot_sync(0xffffffffu, lo[k] <= ub && 4 * lane + warp + 128 * k != g_best);
 #pragma unroll 1
     while (m) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      scan_group(j + 32 * k);
+      const float4* p = tv.scell + (4 * j + warp + 128 * k) * kCellsPerGroup + lane;
+      scan_cells(__ldg(p), __ldg(p + 32));
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float oq = __shfl_xor_sync(0xffffffffu, qmin, o);
     const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+    if (oq < qmin || (oq == qmin && oi < imin)) { qmin = oq; imin = oi; }
+  }
+  if (lane == 0) { s_f[warp] = qmin; s_i[warp] = imin; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float oq = s_f[w];
+    const int oi = s_i[w];
     if (oq < qmin || (oq == qmin && oi < imin)) { qmin = oq; imin = oi; }
   }
   const float theta_min = theta_from_q(qmin);
@@ -370,9 +383,10 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
   const float a_thr = q_thr < CUDART_INF_F ? theta_min + phi + kCapMargin : CUDART_INF_F;
   const float off = dmin * k2;  // s = 2^((dmin - d) * k2)
   const float neg_rk2 = -kEarthRadiusKm * k2;
-  const bool wide = !(q_thr <= 1.0f);  // warp-uniform
+  const bool narrow = q_thr <= 1.0f;  // CTA-uniform: every near cell is on the first asin branch
 
-  // phase 3: sum of the unnormalised targets; lane w accumulates word w of the class-group mask
+  // phase 3: sum of the unnormalised targets over my near groups; lane w accumulates word w of the
+  // class-group mask
   float ssum = 0.f;
   uint32_t mask_word = 0u;
 #pragma unroll
@@ -382,19 +396,19 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
     while (m) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      const int g = j + 32 * k;
-      const int p = g * kCellsPerGroup + lane;
-      const float q0 = chord2(ux, uy, uz, __ldg(tv.sx + p), __ldg(tv.sy + p), __ldg(tv.sz + p));
-      const float q1 = chord2(ux, uy, uz, __ldg(tv.sx + p + 32), __ldg(tv.sy + p + 32), __ldg(tv.sz + p + 32));
-      // pad cells sit at 1e9: q ~ 3e18 fails every finite threshold; with q_thr = inf they are cut by index
-      const bool ok0 = p < C, ok1 = p + 32 < C;
+      const int g = 4 * j + warp + 128 * k;
+      const float4* p = tv.scell + g * kCellsPerGroup + lane;
+      const float4 c0 = __ldg(p), c1 = __ldg(p + 32);
+      const float q0 = chord2(ux, uy, uz, c0.x, c0.y, c0.z), q1 = chord2(ux, uy, uz, c1.x, c1.y, c1.z);
+      // pad cells sit at 1e9 (q ~ 3e18) with index INT_MAX: cut by index when q_thr = inf
+      const bool ok0 = __float_as_int(c0.w) < C, ok1 = __float_as_int(c1.w) < C;
       float s0, s1;
-      if (!wide) {
-        s0 = target_weight<false>(q0, q_thr, neg_rk2, off);
-        s1 = target_weight<false>(q1, q_thr, neg_rk2, off);
+      if (narrow) {
+        s0 = target_weight_narrow(q0, q_thr, neg_rk2, off);
+        s1 = target_weight_narrow(q1, q_thr, neg_rk2, off);
       } else {
-        s0 = target_weight<true>(q0, q_thr, neg_rk2, off);
-        s1 = target_weight<true>(q1, q_thr, neg_rk2, off);
+        s0 = target_weight(q0, q_thr, neg_rk2, off);
+        s1 = target_weight(q1, q_thr, neg_rk2, off);
       }
       s0 = ok0 ? s0 : 0.f;
       s1 = ok1 ? s1 : 0.f;
@@ -404,9 +418,17 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
       }
     }
   }
-  if (lane < nwp) near[static_cast<size_t>(row) * nwp + lane] = lane < kMaxMaskWords ? mask_word : 0u;
   ssum = warp_sum(ssum);
+  __syncthreads();  // every warp has read s_f / s_i
+  if (lane == 0) s_f[warp] = ssum;
+  if (lane < kMaxMaskWords) s_mask[warp][lane] = mask_word;
+  __syncthreads();
+  if (warp != 0) return;
+  if (lane < nwp)
+    near[static_cast<size_t>(row) * nwp + lane] =
+        lane < kMaxMaskWords ? (s_mask[0][lane] | s_mask[1][lane] | s_mask[2][lane] | s_mask[3][lane]) : 0u;
   if (lane == 0) {
+    ssum = (s_f[0] + s_f[1]) + (s_f[2] + s_f[3]);
     RowRec r;
     r.ux = ux; r.uy = uy; r.uz = uz; r.q_thr = q_thr;
     r.off = off;
@@ -420,30 +442,83 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
 }
 
 // ------------------------------------------------------------------ (B) streaming pass
-__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-  return r;
-}
 __device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
   asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 
-// Lane l of warp slice ws owns the bf16 pairs at columns ws*256 + 64*j + 2*l + {0,1}, j = 0..3: one
-// pair in each of the slice's four 64-class groups.  Rows are padded to a multiple of 256 columns
-// (ldc >= Cpad), so nothing in the row loop is predicated; pad columns carry p only and are never
-// read downstream.
+constexpr int kStripWarps = 4;                       // consumer warps per CTA: a strip of 1024 classes
+constexpr int kStripCols = kStripWarps * kColsPerWarp;
+constexpr int kStageRows = 8;                        // rows per pipeline stage
+constexpr int kStreamStages = 4;
+constexpr int kStreamThreads = 32 * (kStripWarps + 1);  // + one TMA producer warp
+constexpr int kStreamCtasPerSm = 3;
+constexpr uint32_t kSliceTileBytes = kStageRows * kColsPerWarp * 2;  // one TMA box: 8 rows x 512 B
+constexpr uint32_t kStageBytes = kStripWarps * kSliceTileBytes;      // 16 KB
+
+struct StreamSmem {
+  uint8_t tile[kStreamStages][kStageBytes];
+  uint64_t full[kStreamStages];
+  uint64_t empty[kStreamStages];
+};
+
+// CTA = (row block rb, strip of 4 warp slices).  The producer warp streams the strip's logits through a
+// 4-stage TMA -> shared-memory ring (8 rows x 1024 classes per stage, 64 KB in flight per CTA, three
+// CTAs per SM), so the depth of the memory pipeline does not depend on registers or occupancy.
+// Consumer warp w owns classes [256 (4 strip + w), +256): lane l holds the bf16 pairs at 64 j + 2 l +
+// {0,1}, j = 0..3 -- one pair in each of the slice's four 64-class groups -- so a near group costs
+// every lane exactly two target evaluations (no divergence), shared-memory reads are conflict-free
+// and every global store is one full 128-byte line.  Rows are padded to a multiple of 256 columns
+// (ldc >= Cpad): nothing in the row loop is predicated; pad columns carry p only and are never read
+// downstream.
 template <bool WANT_DB>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
-hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict__ lse,
+hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, const float* __restrict__ lse,
                      const RowRec* __restrict__ rec, const uint32_t* __restrict__ near, int nwp,
-                     const float* __restrict__ table, int B, int C, int rows_per_block, int nslices, int nrb,
+                     const float* __restrict__ table, int B, int C, int rows_per_block, int nslices, int nstrips,
                      float neg_rk2, bf16* __restrict__ dlogits, float* __restrict__ loss_part,
                      float* __restrict__ db_part) {
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= nslices * nrb) return;
-  const int rb = gw / nslices, ws = gw - rb * nslices;
+  extern __shared__ uint8_t smem_raw[];
+  StreamSmem& sm = *reinterpret_cast<StreamSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = blockIdx.x / nstrips, strip = blockIdx.x - rb * nstrips;
+  const int nactive = min(kStripWarps, nslices - strip * kStripWarps);  // consumer warps with a slice
+  const int row0 = rb * rows_per_block, row1 = min(B, row0 + rows_per_block);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_logits);
+    for (int s = 0; s < kStreamStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], nactive);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kStripWarps) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int row = row0; row < row1; row += kStageRows) {
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&sm.full[s], nactive * kSliceTileBytes);
+        for (int w = 0; w < nactive; ++w)
+          tma_load_2d_hint(sm.tile[s] + w * kSliceTileBytes, &tm_logits, &sm.full[s],
+                           (strip * kStripWarps + w) * kColsPerWarp, row, kPolicyEvictFirst);
+        if (++s == kStreamStages) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  if (warp >= nactive) return;
+
+  // ===================== consumers =====================
+  const int ws = strip * kStripWarps + warp;
   const int Cpad = table_cpad(C);
   const int cbase = ws * kColsPerWarp + 2 * lane;  // + 64 j
   const int near_word = ws >> 3, near_shift = 4 * (ws & 7);
@@ -464,11 +539,11 @@ hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __re
 #pragma unroll
   for (int i = 0; i < 8; ++i) cell_ok |= (cbase + 64 * (i >> 1) + (i & 1) < C) ? (1u << i) : 0u;
 
-  const int row0 = rb * rows_per_block, row1 = min(B, row0 + rows_per_block);
   const size_t pitch = static_cast<size_t>(ldc);
-  const bf16* lptr = logits + cbase;
   bf16* gptr = dlogits + cbase;
-  constexpr int kDepth = 4;  // rows of loads in flight per lane
+  const uint32_t my_tile = smem_u32(sm.tile[0]) + warp * kSliceTileBytes + 4 * lane;
+  int stage = 0;
+  uint32_t phase = 0;
 
   for (int rbase = row0; rbase < row1; rbase += 32) {
     const int nr = min(32, row1 - rbase);
@@ -479,25 +554,17 @@ hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __re
       my_lse2 = __ldg(lse + rbase + lane) * kLog2eF;
       my_near = (__ldg(near + static_cast<size_t>(rbase + lane) * nwp + near_word) >> near_shift) & 0xfu;
     }
-    uint32_t pre[kDepth][4];
-#pragma unroll
-    for (int d = 0; d < kDepth; ++d) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        pre[d][j] = d < nr ? ld_stream_u32(lptr + (rbase + d) * pitch + 64 * j) : 0u;
-    }
-    for (int r4 = 0; r4 < nr; r4 += kDepth) {
-#pragma unroll
-      for (int d = 0; d < kDepth; ++d) {
-        const int r = r4 + d;
+    for (int r8 = 0; r8 < nr; r8 += kStageRows) {
+      mbar_wait(&sm.full[stage], phase);
+      const uint32_t tile = my_tile + stage * kStageBytes;
+#pragma unroll 2
+      for (int rr = 0; rr < kStageRows; ++rr) {
+        const int r = r8 + rr;
         if (r >= nr) break;  // warp-uniform
         const int row = rbase + r;
         uint32_t cur[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          cur[j] = pre[d][j];
-          if (r + kDepth < nr) pre[d][j] = ld_stream_u32(lptr + (row + kDepth) * pitch + 64 * j);
-        }
+        for (int j = 0; j < 4; ++j) cur[j] = lds_u32(tile + rr * (kColsPerWarp * 2) + 128 * j);
         const float lse2 = __shfl_sync(0xffffffffu, my_lse2, r);
         const uint32_t nb = __shfl_sync(0xffffffffu, my_near, r);
         float g[8];
@@ -509,7 +576,6 @@ hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __re
         if (nb != 0u) {  // some group of this warp's 256 classes holds a near cell (warp-uniform)
           const float4 ra = __ldg(reinterpret_cast<const float4*>(rec + row));
           const float4 rb4 = __ldg(reinterpret_cast<const float4*>(rec + row) + 1);
-          const bool wide = !(ra.w <= 1.0f);
           float sl = 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -518,8 +584,7 @@ hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __re
               for (int h = 0; h < 2; ++h) {
                 const int i = 2 * j + h;
                 const float q = chord2(ra.x, ra.y, ra.z, vx[i], vy[i], vz[i]);
-                float t = wide ? target_weight<true>(q, ra.w, neg_rk2, rb4.x)
-                               : target_weight<false>(q, ra.w, neg_rk2, rb4.x);
+                float t = target_weight(q, ra.w, neg_rk2, rb4.x);
                 t = ((cell_ok >> i) & 1u) ? t * rb4.y : 0.f;
                 g[i] -= t;
                 const float l = h ? __uint_as_float(cur[j] & 0xffff0000u) : __uint_as_float(cur[j] << 16);
@@ -537,6 +602,9 @@ hav_ce_stream_kernel(const bf16* __restrict__ logits, int ldc, const float* __re
           for (int i = 0; i < 8; ++i) db[i] += g[i];
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);  // this warp is done with the stage
+      if (++stage == kStreamStages) { stage = 0; phase ^= 1; }
     }
     if (lane < nr) loss_part[static_cast<size_t>(ws) * B + rbase + lane] = my_sl;
   }
@@ -662,16 +730,17 @@ static StatsPlan make_stats_plan(int B, int C) {
   return p;
 }
 struct HavPlan {
-  int Cpad, nslices, rows_per_block, nrb, finish_blocks;
+  int Cpad, nslices, nstrips, rows_per_block, nrb, finish_blocks;
   size_t off_loss_part, off_block_part, bytes;
 };
 static HavPlan make_hav_plan(int B, int C) {
   HavPlan p;
   p.Cpad = table_cpad(C);
   p.nslices = p.Cpad / kColsPerWarp;
-  // one resident wave of warps
-  const int capacity = std::max(1, device_sm_count() * kStreamCtasPerSm * (kStreamThreads / 32) / p.nslices);
-  p.rows_per_block = std::max(8, ceil_div(B, capacity));
+  p.nstrips = ceil_div(p.nslices, kStripWarps);
+  // one resident wave of CTAs: row blocks x strips <= SMs x CTAs per SM, row blocks of whole stages
+  const int capacity = std::max(1, device_sm_count() * kStreamCtasPerSm / p.nstrips);
+  p.rows_per_block = ceil_div(std::max(kStageRows, ceil_div(B, capacity)), kStageRows) * kStageRows;
   p.nrb = ceil_div(B, p.rows_per_block);
   p.finish_blocks = ceil_div(B, 32);
   size_t o = 0;
@@ -701,7 +770,7 @@ extern "C" int gg_centroid_unit_vectors(const float* centroids, float* cent_tabl
   const TableView tv = view_table(cent_table, C);
   table_unit_kernel<<<ceil_div(tv.Cpad, 256), 256, 0, s>>>(centroids, cent_table, C, keys);
   GG_LAUNCH_CHECK();
-  table_rank_kernel<<<ceil_div(C, 256), 256, 0, s>>>(keys, C, const_cast<int*>(tv.sidx));
+  table_rank_kernel<<<ceil_div(C, 256), 256, 0, s>>>(keys, C, const_cast<float4*>(tv.scell));
   GG_LAUNCH_CHECK();
   table_group_kernel<<<ceil_div(tv.ngroups, 8), 256, 0, s>>>(cent_table, C);
   GG_LAUNCH_CHECK();
@@ -716,9 +785,9 @@ extern "C" int gg_hav_row_stats(const float* labels, const float* cent_table, in
   GG_CHECK(tau > 0.f, GG_ERR_ARG, "gg_hav_row_stats: tau must be positive");
   GG_CHECK(far_km >= 1.0f, GG_ERR_ARG, "gg_hav_row_stats: far_km must be >= 1 km (inf disables the skip)");
   const TableView tv = view_table(cent_table, C);
-  GG_CHECK(tv.ngroups <= 32 * kMaxSlots && tv.Cpad / kCellsPerGroup <= 32 * kMaxMaskWords, GG_ERR_UNSUPPORTED,
+  GG_CHECK(tv.ngroups <= 128 * kMaxSlots && tv.Cpad / kCellsPerGroup <= 32 * kMaxMaskWords, GG_ERR_UNSUPPORTED,
            "gg_hav_row_stats: C=%d exceeds the %d geocells the row-statistics kernel covers", C,
-           32 * kMaxSlots * kCellsPerGroup);
+           128 * kMaxSlots * kCellsPerGroup);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const StatsPlan p = make_stats_plan(B, C);
   uint8_t* base = static_cast<uint8_t*>(row_stats);
@@ -733,14 +802,13 @@ extern "C" int gg_hav_row_stats(const float* labels, const float* cent_table, in
   if (!(phi < 3.141592653589793)) phi = 3.141592653589793;
   const float k2 = (1.0f / tau) * kLog2eF;
   const float chf = static_cast<float>(cos(0.5 * phi)), shf = static_cast<float>(sin(0.5 * phi));
-  const int slots = ceil_div(tv.ngroups, 32);
-  const int grid_a = ceil_div(B, 4);
+  const int slots = ceil_div(tv.ngroups, 128);
+  const int grid_a = B;
 #define GG_HAV_A(S)                                                                                          \
   hav_row_stats_kernel<S><<<grid_a, 128, 0, s>>>(lab, cent_table, C, B, k2, chf, shf, static_cast<float>(phi), \
                                                  rec, near, p.nwp, nearest_cell, nearest_km)
-  if (slots <= 2) GG_HAV_A(2);
-  else if (slots <= 4) GG_HAV_A(4);
-  else GG_HAV_A(kMaxSlots);
+  if (slots <= 1) GG_HAV_A(1);
+  else GG_HAV_A(2);
 #undef GG_HAV_A
   GG_LAUNCH_CHECK();
   return GG_OK;
@@ -759,8 +827,8 @@ extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* 
            "gg_hav_ce_fwd_bwd: null pointer");
   const HavPlan p = make_hav_plan(B, C);
   const StatsPlan sp = make_stats_plan(B, C);
-  GG_CHECK(ldc >= p.Cpad && ldc % 2 == 0, GG_ERR_ARG,
-           "gg_hav_ce_fwd_bwd: ldc=%d must be >= %d (C rounded up to 256) and even", ldc, p.Cpad);
+  GG_CHECK(ldc >= p.Cpad && ldc % 8 == 0, GG_ERR_ARG,
+           "gg_hav_ce_fwd_bwd: ldc=%d must be >= %d (C rounded up to 256) and a multiple of 8", ldc, p.Cpad);
   GG_CHECK(tau > 0.f, GG_ERR_ARG, "gg_hav_ce_fwd_bwd: tau must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint8_t* sb = static_cast<const uint8_t*>(row_stats);
@@ -772,16 +840,25 @@ extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* 
   float* block_part = reinterpret_cast<float*>(ws + p.off_block_part);
   const float neg_rk2 = -kEarthRadiusKm * (1.0f / tau) * kLog2eF;
 
-  const int warps = p.nslices * p.nrb;
-  const int grid_b = ceil_div(warps, kStreamThreads / 32);
-  if (db_partials)
-    hav_ce_stream_kernel<true><<<grid_b, kStreamThreads, 0, s>>>(
-        static_cast<const bf16*>(logits_bf16), ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
-        p.nslices, p.nrb, neg_rk2, static_cast<bf16*>(dlogits_bf16), loss_part, db_partials);
-  else
-    hav_ce_stream_kernel<false><<<grid_b, kStreamThreads, 0, s>>>(
-        static_cast<const bf16*>(logits_bf16), ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
-        p.nslices, p.nrb, neg_rk2, static_cast<bf16*>(dlogits_bf16), loss_part, nullptr);
+  CUtensorMap tm_logits;
+  int rc = make_tmap_bf16_2d_plain(&tm_logits, logits_bf16, static_cast<uint64_t>(p.Cpad), static_cast<uint64_t>(B),
+                                   static_cast<uint64_t>(ldc) * 2, kColsPerWarp, kStageRows);
+  if (rc) return rc;
+  const int grid_b = p.nrb * p.nstrips;
+  const size_t smem = sizeof(StreamSmem) + 128;
+  if (db_partials) {
+    auto kern = hav_ce_stream_kernel<true>;
+    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
+    kern<<<grid_b, kStreamThreads, smem, s>>>(tm_logits, ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
+                                              p.nslices, p.nstrips, neg_rk2, static_cast<bf16*>(dlogits_bf16),
+                                              loss_part, db_partials);
+  } else {
+    auto kern = hav_ce_stream_kernel<false>;
+    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
+    kern<<<grid_b, kStreamThreads, smem, s>>>(tm_logits, ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
+                                              p.nslices, p.nstrips, neg_rk2, static_cast<bf16*>(dlogits_bf16),
+                                              loss_part, nullptr);
+  }
   GG_LAUNCH_CHECK();
   hav_loss_finish_kernel<<<p.finish_blocks, dim3(32, 8), 0, s>>>(loss_part, p.nslices, lse, rec, B, loss_rows,
                                                                  block_part, counter, mean_scale, loss_mean);

@@ -243,7 +243,7 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   const int tiles = ceil_div(C, kWM) * ceil_div(D, kWN);
   const int grid = std::min(tiles, device_sm_count());
   const size_t smem = sizeof(BwdSmem) + 1024;
-  GG_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (int e = set_max_dynamic_smem_once(head_bwd_kernel, smem)) return e;
   head_bwd_kernel<<<grid, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
   GG_LAUNCH_CHECK();
   if (db && db_partials) {  // column sums already accumulated by the loss kernel (one row per CTA)

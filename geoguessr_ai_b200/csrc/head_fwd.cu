@@ -421,12 +421,12 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
   // every (CTA, run, half) slot the merge reads is flushed by the CTA that owns those tiles
   if (logits) {
     auto kern = head_fwd_kernel<KTOP, true>;
-    GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
     kern<<<sc.grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, static_cast<bf16*>(logits), ldc, pmax, psum,
                                                  ptopv, ptopi, B, C, D, sc);
   } else {
     auto kern = head_fwd_kernel<KTOP, false>;
-    GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
     kern<<<sc.grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, nullptr, ldc, pmax, psum, ptopv, ptopi, B, C,
                                                  D, sc);
   }

@@ -421,7 +421,7 @@ extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int 
   rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPN);
   if (rc) return rc;
   const size_t smem = sizeof(ProtoSmem) + 1024;
-  GG_CUDA(cudaFuncSetAttribute(proto_retrieve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (int e = set_max_dynamic_smem_once(proto_retrieve_kernel, smem)) return e;
   proto_retrieve_kernel<<<device_sm_count(), kProtoThreads, smem, s>>>(tm_q, tm_bank, w.meta, w.work_cell, w.work_chunk,
                                                                       w.pair_off, w.pair_ids, cell_off, w.qs_n,
                                                                       bank_sqnorm, bank_coords, proto_base, D, rec);

@@ -148,16 +148,20 @@ def centroid_unit_vectors(centroids: torch.Tensor) -> torch.Tensor:
     return table
 
 
-def hav_row_stats(labels, cent_table, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False):
+def row_stats_buffer(B, C, device):
+    return _u8(_lib.load().gg_hav_row_stats_bytes(B, C), device)
+
+
+def hav_row_stats(labels, cent_table, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False, out=None):
     """Label-only half of the smoothed loss.  Returns (row_stats buffer, nearest_cell (B) i64 | None,
-    nearest_km (B) | None)."""
+    nearest_km (B) | None).  out: a buffer from row_stats_buffer() (e.g. allocated on another stream)."""
     _need_cuda(labels, cent_table)
     labels = labels.detach().float().contiguous()
     B = labels.shape[0]
     assert labels.shape == (B, 2), "labels must be (B, 2) (lng, lat)"
     dev = labels.device
     lib = _lib.load()
-    stats = _u8(lib.gg_hav_row_stats_bytes(B, C), dev)
+    stats = out if out is not None else row_stats_buffer(B, C, dev)
     ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
     nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
     _call("gg_hav_row_stats", lib.gg_hav_row_stats, _ptr(labels), _ptr(cent_table), B, C, float(tau), float(far_km),

@@ -28,16 +28,22 @@ class _GeocellHeadLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, embedding, weight, bias, module, labels, labels_clf, smooth):
+        C, D = weight.shape
+        stats = None
+        if smooth:
+            # the label-only half of the loss (nearest centroid, sum of smoothed targets, near-group
+            # mask) reads no logits: it runs on a side stream next to the head GEMM
+            stats = module._row_stats_async(labels, C)
         st = module._operands(weight, bias)
         x16 = ops.fuse_headings(embedding, split=st["split"])
-        C, D = weight.shape
         head = ops.head_forward(x16, st["w16"], st["bias_pad"], C, module.num_candidates,
                                 module.geocell_centroid_coords.data, want_logits=True)
         dbp = None
         if smooth:
-            dlogits, loss_rows, _, _, dbp, loss = ops.hav_ce(head["logits"], head["lse"], labels, module._centroid_xyz(),
-                                                             C, tau=module.label_smoothing_tau, far_km=module.far_km,
-                                                             want_db=True, want_mean=True)
+            torch.cuda.current_stream().wait_stream(module._side_stream)
+            dlogits, loss_rows, _, _, dbp, loss = ops.hav_ce(head["logits"], head["lse"], None, module._centroid_xyz(),
+                                                             C, tau=module.label_smoothing_tau, want_db=True,
+                                                             want_mean=True, row_stats=stats)
         else:
             dlogits, loss_rows = ops.hard_ce(head["logits"], head["lse"], labels_clf, C)
             loss = ops.loss_mean(loss_rows)
@@ -127,6 +133,7 @@ class SuperGuessr(nn.Module):
         self._freeze_params()
         self._op_cache = None
         self._xyz_cache = None
+        self._side_stream = None
         print(f"Initialized SuperGuessr classification model with {self.num_cells} geocells.")
 
     # ---- reference helpers (super_guessr.py:114-206) ---------------------------------------
@@ -172,6 +179,22 @@ class SuperGuessr(nn.Module):
             w16, bias_pad = ops.prepare_head_weights(weight, bias, split=split)
             self._op_cache = dict(key=key, w16=w16, bias_pad=bias_pad, split=split)
         return self._op_cache
+
+    def _row_stats_async(self, labels, C):
+        """gg_hav_row_stats on a side stream (joined by the caller before the loss kernel)."""
+        cur = torch.cuda.current_stream()
+        table = self._centroid_xyz()
+        if self._side_stream is None or self._side_stream.device != labels.device:
+            self._side_stream = torch.cuda.Stream(device=labels.device)
+        side = self._side_stream
+        # the buffer belongs to the main stream (which joins the side stream before the loss kernel reads
+        # it and before anything later could reuse it); labels are made fp32-contiguous there as well
+        labels = labels.detach().float().contiguous()
+        stats = ops.row_stats_buffer(labels.shape[0], C, labels.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.hav_row_stats(labels, table, C, tau=self.label_smoothing_tau, far_km=self.far_km, out=stats)
+        return stats
 
     def _centroid_xyz(self):
         c = self.geocell_centroid_coords

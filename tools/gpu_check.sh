@@ -18,10 +18,10 @@ for w in $what; do
       timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-        python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
+        python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on \
-        -k regex:"${NCU_KERNELS:-head_fwd_kernel|hav_ce_stream_kernel|head_bwd_kernel|hav_row_stats_kernel}" -s ${NCU_SKIP:-12} -c ${NCU_COUNT:-4} -f -o gpurun_out/prof_train \
-        python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
+        -k regex:"${NCU_KERNELS:-gg::}" -s ${NCU_SKIP:-42} -c ${NCU_COUNT:-14} -f -o gpurun_out/prof_train \
+        python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
   esac
 done

@@ -5,6 +5,11 @@
 // left them in -- dlogits (B, ldc) and x (B, D), batch-major -- i.e. as MN-major UMMA operands:
 // the contraction index (batch) is the slow index of both.  TMA loads 64(k) x 64(mn) boxes with
 // the 128-byte swizzle; a 128 x 256 x 64 stage is 2 + 4 such boxes.
+//
+// CTA pairs (clusters of two): the CTAs of a pair own vertically adjacent geocell blocks of the same 256
+// embedding columns, so they contract against the SAME x tile.  Each loads two of its four boxes and TMA
+// multicasts them into both CTAs' shared memory: 32 KB instead of 48 KB per CTA and k-block through the
+// L2 -> SM fabric.  A stage is recycled when both CTAs' MMAs have read it (tcgen05.commit multicast).
 #include <algorithm>
 
 #include "common.cuh"
@@ -31,7 +36,7 @@ struct BwdSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
 head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, rows B
                 const __grid_constant__ CUtensorMap tm_x,  // x:       inner D, rows B
                 float* __restrict__ dW, int C, int D, int Bk, float scale_in,
@@ -39,9 +44,11 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (C + kWM - 1) / kWM;
+  const int num_m = (C + 2 * kWM - 1) / (2 * kWM);  // pairs of geocell blocks
   const int num_n = (D + kWN - 1) / kWN;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = num_m * num_n;              // pair-tiles
+  const int crank = static_cast<int>(cluster_ctarank());
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int num_k = (Bk + kWK - 1) / kWK;
   const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
 
@@ -50,7 +57,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
     tma_prefetch_desc(&tm_x);
     for (int s = 0; s < kWStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], 2);  // this CTA's MMAs and the partner's
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm.acc_full[a], 1);
@@ -63,65 +70,71 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();  // the partner's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
   // tile order: the num_n column tiles of one geocell block are adjacent, so the CTAs that run
   // concurrently share the dlogits tile through L2 and dlogits is streamed from HBM once.
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / num_n) * kWM, n0 = (t % num_n) * kWN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&sm.empty[s], ph ^ 1);
+    // TMA producer: warp-uniform loop, one elected lane issues
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = pair; t < num_tiles; t += npairs) {
+      const int m0 = (2 * (t / num_n) + crank) * kWM, n0 = (t % num_n) * kWN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&sm.full[s], kWStageA + kWStageB);
 #pragma unroll
           for (int i = 0; i < kWM / 64; ++i)
             tma_load_2d(sm.a[s] + i * kAtomBytes, &tm_g, &sm.full[s], m0 + 64 * i, kb * kWK);
 #pragma unroll
-          for (int i = 0; i < kWN / 64; ++i)
-            tma_load_2d(sm.b[s] + i * kAtomBytes, &tm_x, &sm.full[s], n0 + 64 * i, kb * kWK);
-          if (++s == kWStages) { s = 0; ph ^= 1; }
+          for (int i = 0; i < kWN / 128; ++i) {  // my half of the x tile's boxes, delivered to both CTAs
+            const int atom = crank * (kWN / 128) + i;
+            tma_load_2d_multicast(sm.b[s] + atom * kAtomBytes, &tm_x, &sm.full[s], n0 + 64 * atom, kb * kWK, 0x3);
+          }
         }
+        __syncwarp();
+        if (++s == kWStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kWM, kWN, 1, 1);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_ph = (it >> 1) & 1;
-        mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    constexpr uint32_t idesc = umma_idesc_bf16(kWM, kWN, 1, 1);
+    // 16 k-rows of 128 B per MMA; atoms (64 mn-elements) kAtomBytes apart; 8-row groups 1024 B apart
+    const uint64_t da_base = umma_desc_sw128(smem_u32(sm.a[0]), kAtomBytes, 1024);
+    const uint64_t db_base = umma_desc_sw128(smem_u32(sm.b[0]), kAtomBytes, 1024);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kWN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&sm.full[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kWN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&sm.full[s], ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
+        if (elect_one()) {
+          const uint64_t da = da_base + static_cast<uint64_t>(s * (kWStageA >> 4));
+          const uint64_t db = db_base + static_cast<uint64_t>(s * (kWStageB >> 4));
+          umma_f16(d_tmem, da, db, idesc, kb != 0);
 #pragma unroll
-          for (int k = 0; k < kWK / 16; ++k) {
-            // 16 k-rows of 128 B per MMA; atoms (64 mn-elements) kAtomBytes apart; 8-row groups 1024 B apart
-            const uint64_t da = umma_desc_sw128(a0 + k * 2048, kAtomBytes, 1024);
-            const uint64_t db = umma_desc_sw128(b0 + k * 2048, kAtomBytes, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
-          }
-          umma_commit(&sm.empty[s]);
-          if (++s == kWStages) { s = 0; ph ^= 1; }
+          for (int k = 1; k < kWK / 16; ++k) umma_f16_acc(d_tmem, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc);
+          umma_commit_multicast(&sm.empty[s], 0x3);
+          if (kb == num_k - 1) umma_commit(&sm.acc_full[acc]);
         }
-        umma_commit(&sm.acc_full[acc]);
+        __syncwarp();
+        if (++s == kWStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
     const int quad = warp & 3;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m0 = (t / num_n) * kWM, n0 = (t % num_n) * kWN;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int m0 = (2 * (t / num_n) + crank) * kWM, n0 = (t % num_n) * kWN;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const int row = m0 + quad * 32 + lane;
@@ -154,7 +167,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
     }
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();  // the partner may still be multicasting into / arriving on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -240,11 +253,12 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_x, x_bf16, D, B, static_cast<uint64_t>(x_ld) * 2, 64, kWK);
   if (rc) return rc;
-  const int tiles = ceil_div(C, kWM) * ceil_div(D, kWN);
-  const int grid = std::min(tiles, device_sm_count());
+  const int pair_tiles = ceil_div(C, 2 * kWM) * ceil_div(D, kWN);
+  const int pairs = std::max(1, std::min(pair_tiles, device_sm_count() / 2));
   const size_t smem = sizeof(BwdSmem) + 1024;
   if (int e = set_max_dynamic_smem_once(head_bwd_kernel, smem)) return e;
-  head_bwd_kernel<<<grid, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
+  // cluster shape (2,1,1) is compiled into the kernel
+  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
   GG_LAUNCH_CHECK();
   if (db && db_partials) {  // column sums already accumulated by the loss kernel (one row per CTA)
     db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(db_partials, C, db_ld, db_parts, scale, grad_scale, db);

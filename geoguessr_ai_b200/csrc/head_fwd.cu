@@ -2,13 +2,21 @@
 //
 // Replaces  models/super_guessr.py:354 (nn.Linear), :355 (softmax), :358-361 (argmax + centroid
 // gather) and :365 (top-k) of the reference.  Per 128x256 output tile the accumulator lives in
-// TMEM (2 x 256 fp32 columns, double buffered); eight epilogue warps (two per TMEM lane quadrant,
-// 128 columns each) add the bias, optionally write the bf16 logits (training only) and keep, per
+// TMEM (2 x 256 fp32 columns, double buffered); sixteen epilogue warps (four per TMEM lane quadrant,
+// 64 columns each) add the bias, optionally write the bf16 logits (training only) and keep, per
 // row, an online (max, sum-exp) and the running top-K logits, so that in serving the (B, C) logit /
 // probability matrices never reach HBM.
 //
-// Tile schedule: tiles are ordered geocell-tile-fastest within a 128-row block and every CTA owns a
-// CONTIGUOUS range of that order, i.e. it sweeps many geocell tiles of the same rows back to back.
+// CTA pairs: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (rows
+// m0 .. m0+127 and m0+128 .. m0+255 of the same 256 geocells).  Each CTA loads its own x tile and HALF of
+// the shared W tile, multicast by TMA into both CTAs' shared memory, so every W byte crosses the
+// L2 -> SM fabric once per pair: 32 KB instead of 48 KB per CTA and k-block, which is what lets the
+// tensor pipe run ahead of operand delivery.  A stage is recycled when BOTH CTAs' MMAs have read it
+// (tcgen05.commit multicast onto the `empty` barriers of the pair).
+//
+// Tile schedule: pair-tiles (256 rows x 256 geocells) are ordered geocell-tile-fastest within a 256-row
+// block and every pair owns a CONTIGUOUS range of that order, i.e. it sweeps many geocell tiles of the
+// same rows back to back.
 // The per-row state therefore stays in registers across tiles ("run") and is flushed once per
 // (CTA, row block): after the first tile the running 5th-best logit rejects almost every 32-column
 // chunk by its maximum alone (which the softmax needs anyway), so the top-k costs ~1 compare per
@@ -27,16 +35,23 @@ namespace gg {
 constexpr int kBM = 128;        // rows of x per tile (UMMA M)
 constexpr int kBN = 256;        // geocells per tile   (UMMA N)
 constexpr int kBK = 64;         // K elements per stage (128 B of bf16 = one swizzle span)
-constexpr int kStages = 4;      // 4 x (16 KB + 32 KB) = 192 KB
-constexpr int kEpiWarps = 8;
-constexpr int kFwdThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kStages = 3;      // 3 x (16 KB + 32 KB) = 144 KB (+ 64 KB of logits staging for the TMA stores)
+constexpr int kEpiWarps = 16;
+constexpr int kColGroups = kEpiWarps / 4;       // column groups of a tile (one warp per TMEM lane quadrant each)
+constexpr int kColsPerEpiWarp = kBN / kColGroups;
+constexpr int kFwdThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr uint32_t kStageBytesA = kBM * kBK * 2;
 constexpr uint32_t kStageBytesB = kBN * kBK * 2;
 constexpr float kLog2e = 1.4426950408889634f;
 
+constexpr int kThrSlots = 8;    // shared top-k thresholds are kept per run, in a ring of run slots
+constexpr int kKeyMin = static_cast<int>(0x80000000u);
+
 struct FwdSmem {
   uint8_t a[kStages][kStageBytesA];
   uint8_t b[kStages][kStageBytesB];
+  uint8_t out[kEpiWarps][32 * 128];  // per epilogue warp: 32 rows x 64 bf16 logits, 128-byte swizzled (TMA store box)
+  int thr[kThrSlots][kBM];           // per row: best known lower bound of the run's k-th largest logit (ordered key)
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full[2];
@@ -44,9 +59,11 @@ struct FwdSmem {
   uint32_t tmem_base;
 };
 
-// Static schedule shared by the kernel, the merge kernel and the host.
+// Static schedule shared by the kernel, the merge kernel and the host.  Units are CTA PAIRS and
+// pair-tiles: num_m = 256-row blocks, grid = number of pairs (clusters); CTA 2c + r of pair c works on
+// row block 2 * mb + r.
 struct FwdSched {
-  int num_m, num_n, tiles, grid, base, rem, runs;  // runs = max row blocks a CTA can touch
+  int num_m, num_n, tiles, grid, base, rem, runs;  // runs = max row blocks a pair can touch
   __host__ __device__ int start(int c) const { return c * base + (c < rem ? c : rem); }
   __host__ __device__ int owner(int t) const {
     const int cut = rem * (base + 1);
@@ -55,10 +72,10 @@ struct FwdSched {
 };
 static FwdSched make_sched(int M, int N, int sms) {
   FwdSched s;
-  s.num_m = ceil_div(M, kBM);
+  s.num_m = ceil_div(M, 2 * kBM);
   s.num_n = ceil_div(N, kBN);
   s.tiles = s.num_m * s.num_n;
-  s.grid = std::min(s.tiles, sms);
+  s.grid = std::max(1, std::min(s.tiles, sms / 2));
   s.base = s.tiles / s.grid;
   s.rem = s.tiles % s.grid;
   s.runs = ceil_div(s.base + 1, s.num_n) + 1;
@@ -96,10 +113,17 @@ __device__ __forceinline__ float select32(const float (&v)[32], int i) {
   return b4 ? d[1] : d[0];
 }
 
+// float <-> int key with the same ordering (involution)
+__device__ __forceinline__ int ordered_key(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_to_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
 template <int KTOP, bool WRITE_LOGITS>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                const float* __restrict__ bias_pad, bf16* __restrict__ logits, int ldc,
+                const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias_pad,
                 float* __restrict__ pmax, float* __restrict__ psum, float* __restrict__ ptopv,
                 int* __restrict__ ptopi, int M, int N, int K, FwdSched sc) {
   extern __shared__ uint8_t smem_raw[];
@@ -108,14 +132,17 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_k = (K + kBK - 1) / kBK;
-  const int t_begin = sc.start(blockIdx.x), t_end = sc.start(blockIdx.x + 1);
+  const int crank = static_cast<int>(cluster_ctarank());  // == blockIdx.x & 1
+  const int pair = blockIdx.x >> 1;
+  const int t_begin = sc.start(pair), t_end = sc.start(pair + 1);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
+    if (WRITE_LOGITS) tma_prefetch_desc(&tm_out);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], 2);  // this CTA's MMAs and the partner's (both read what this CTA multicasts)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm.acc_full[a], 1);
@@ -127,62 +154,68 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tmem_alloc(&sm.tmem_base, 512);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < kThrSlots * kBM; i += kFwdThreads) (&sm.thr[0][0])[i] = kKeyMin;
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();  // the partner's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int m0 = (t / sc.num_n) * kBM, n0 = (t % sc.num_n) * kBN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&sm.empty[s], ph ^ 1);
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int m0 = (2 * (t / sc.num_n) + crank) * kBM, n0 = (t % sc.num_n) * kBN + crank * (kBN / 2);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&sm.empty[s], ph ^ 1);  // free in BOTH CTAs
+        if (elect_one()) {
           mbar_arrive_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
           tma_load_2d(sm.a[s], &tm_x, &sm.full[s], kb * kBK, m0);
-          tma_load_2d(sm.b[s], &tm_w, &sm.full[s], kb * kBK, n0);
-          if (++s == kStages) { s = 0; ph ^= 1; }
+          // my half of the W tile (128 geocells), delivered to both CTAs of the pair
+          tma_load_2d_multicast(sm.b[s] + crank * (kStageBytesB / 2), &tm_w, &sm.full[s], kb * kBK, n0, 0x3);
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_ph = (it >> 1) & 1;
-        mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
+    const uint64_t da_base = umma_desc_sw128(smem_u32(sm.a[0]), 16, 1024);
+    const uint64_t db_base = umma_desc_sw128(smem_u32(sm.b[0]), 16, 1024);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kBN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&sm.full[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kBN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&sm.full[s], ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
+        if (elect_one()) {
+          // descriptors differ only in the start-address field: stage s, then 32 bytes per 16-wide k step
+          const uint64_t da = da_base + static_cast<uint64_t>(s * (kStageBytesA >> 4));
+          const uint64_t db = db_base + static_cast<uint64_t>(s * (kStageBytesB >> 4));
+          umma_f16(d_tmem, da, db, idesc, kb != 0);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a0 + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b0 + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
-          }
-          umma_commit(&sm.empty[s]);  // smem slot reusable once these MMAs have read it
-          if (++s == kStages) { s = 0; ph ^= 1; }
+          for (int k = 1; k < kBK / 16; ++k) umma_f16_acc(d_tmem, da + 2 * k, db + 2 * k, idesc);
+          umma_commit_multicast(&sm.empty[s], 0x3);  // slot reusable once these MMAs have read it
+          if (kb == num_k - 1) umma_commit(&sm.acc_full[acc]);  // accumulator complete
         }
-        umma_commit(&sm.acc_full[acc]);  // accumulator complete
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue warps (256 threads: row = TMEM lane, 128 columns each) ==========
-    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;   // which 128 columns of the 256-wide tile
+    // ===================== epilogue warps (512 threads: row = TMEM lane, 64 columns each) ==========
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int cg = (warp - 2) >> 2;   // which 64 columns of the 256-wide tile
     const int row_in_tile = quad * 32 + lane;
-    constexpr int kColsPerWarp = kBN / 2;
+    uint8_t* const my_out = sm.out[warp - 2];
+    const uint32_t my_out_row = smem_u32(my_out) + lane * 128;
 
     float run_max = -INFINITY, run_sum = 0.f;
     float tv[KTOP];
@@ -190,49 +223,52 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
     const int mb_first = t_begin / sc.num_n;
+    int run_id = 0;
+    sm.thr[4][row_in_tile] = kKeyMin;  // slot of run 4 (see the flush below); slots 0..3 start clean
 
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const int mb = t / sc.num_n, nb = t % sc.num_n;
-      const int m0 = mb * kBM, n0 = nb * kBN + half * kColsPerWarp;
+      const int m0 = (2 * mb + crank) * kBM, n0 = nb * kBN + cg * kColsPerEpiWarp;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      const int row = m0 + row_in_tile;
+      int* const thr_slot = &sm.thr[run_id & (kThrSlots - 1)][row_in_tile];
       mbar_wait(&sm.acc_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + half * kColsPerWarp;
+          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + cg * kColsPerEpiWarp;
+      if (WRITE_LOGITS) {  // the previous tile's TMA store has finished reading the staging buffer
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
 
 #pragma unroll 1
-      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+      for (int c = 0; c < kColsPerEpiWarp / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        float v[32];
+        float4 bq[8];
         const float4* bp = reinterpret_cast<const float4*>(bias_pad + col0);
 #pragma unroll
+        for (int q = 0; q < 8; ++q) bq[q] = __ldg(bp + q);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 bq = __ldg(bp + q);
-          v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bq.x;
-          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
-          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z;
-          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+          v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bq[q].x;
+          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq[q].y;
+          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq[q].z;
+          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq[q].w;
         }
         if (WRITE_LOGITS) {
-          if (row < M) {
-            bf16* dst = logits + static_cast<size_t>(row) * ldc + col0;
+          // 16-byte piece j of row r sits at piece j ^ (r & 7): the 128-byte TMA swizzle, and conflict-free
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (col0 + 8 * q + 8 <= ldc) {
-                uint4 pk;
-                pk.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-                pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-                pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-                pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-                *reinterpret_cast<uint4*>(dst + 8 * q) = pk;
-              }
-            }
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t dst = my_out_row + (((4 * c + q) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                         "r"(pack_bf16x2(v[8 * q + 0], v[8 * q + 1])), "r"(pack_bf16x2(v[8 * q + 2], v[8 * q + 3])),
+                         "r"(pack_bf16x2(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16x2(v[8 * q + 6], v[8 * q + 7]))
+                         : "memory");
           }
         }
         if (col0 + 32 > N) {  // tail tile: geocells >= C do not exist
@@ -259,20 +295,42 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           }
           run_sum += (s0 + s1) + (s2 + s3);
         }
-        if (cmax > tv[KTOP - 1]) {
-          // Lanes are different rows, so which of the 32 columns qualify differs per lane: an unrolled
-          // "insert if larger" chain makes the whole warp walk all 32 insert bodies.  Instead build a
-          // per-thread bitmask of the qualifying columns (predicated, branch-free) and pop it in a
-          // data-driven loop whose trip count is the largest popcount in the warp (usually 1-2).
-          const float thr = tv[KTOP - 1];
+        // Top-k.  A logit can only matter if it beats a lower bound of the row's k-th best in this run:
+        // this warp's own k-th best, or the one any of the three other warps of the row has published.
+        // (Strict '>': a logit exactly equal to the bound may be dropped -- below the score-gap tolerance.)
+        const float thr = fmaxf(tv[KTOP - 1], key_to_float(*reinterpret_cast<volatile int*>(thr_slot)));
+        if (__any_sync(0xffffffffu, cmax > thr)) {
           uint32_t mask = 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;
-          while (mask) {  // ascending column order: on ties the lower geocell index stays first
-            const int i = __ffs(mask) - 1;
-            mask &= mask - 1;
-            topk_insert<KTOP>(tv, ti, select32(v, i), col0 + i);
+          const bool mine = mask != 0u;
+          // Lanes are different rows, so WHICH columns qualify differs per lane.  Few per lane (steady
+          // state): pop each lane's own bits, v[i] by a select tree.  Many (start of a run): walk the
+          // union's columns in a warp-uniform, compile-time-indexed loop instead.
+          if (__reduce_max_sync(0xffffffffu, __popc(mask)) >= 8u) {
+            const uint32_t any_mask = __reduce_or_sync(0xffffffffu, mask);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {  // ascending column order: on ties the lower geocell index stays first
+              if ((any_mask >> i) & 1u) {
+                if ((mask >> i) & 1u) topk_insert<KTOP>(tv, ti, v[i], col0 + i);
+              }
+            }
+          } else {
+            while (mask) {
+              const int i = __ffs(mask) - 1;
+              mask &= mask - 1;
+              topk_insert<KTOP>(tv, ti, select32(v, i), col0 + i);
+            }
           }
+          if (mine && tv[KTOP - 1] > -INFINITY) atomicMax(thr_slot, ordered_key(tv[KTOP - 1]));
+        }
+      }
+      if (WRITE_LOGITS) {
+        fence_proxy_async_smem();  // staging writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_out, my_out, n0, m0 + quad * 32);  // rows >= M / columns >= ldc are clipped
+          tma_store_commit();
         }
       }
       // TMEM accumulator drained -> hand it back to the MMA warp
@@ -281,7 +339,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
       // end of this CTA's run over row block mb: flush the row state
       if (nb == sc.num_n - 1 || t == t_end - 1) {
-        const size_t p = (static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first)) * 2 + half;
+        const size_t p = (static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first)) * kColGroups + cg;
         pmax[p * kBM + row_in_tile] = run_max;
         psum[p * kBM + row_in_tile] = run_sum;
 #pragma unroll
@@ -293,19 +351,27 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         run_sum = 0.f;
 #pragma unroll
         for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+        // Threshold slots: the warps of a CTA are never more than two tiles (hence two runs) apart --
+        // the accumulators are double buffered -- so while this warp is in run r the others use slots
+        // r-2 .. r+2 (mod 8); slot r+4 is free and is cleaned here, long before anyone enters run r+4.
+        ++run_id;
+        sm.thr[(run_id + 4) & (kThrSlots - 1)][row_in_tile] = kKeyMin;
       }
+    }
+    if (WRITE_LOGITS) {
+      if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last bulk store
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync();  // the partner may still be multicasting into / arriving on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-// One warp per row: merge the row's partials (one per (CTA run, column half)).
+// One warp per row: merge the row's partials (one per (CTA run, column group)).
 //   topk_val = softmax probabilities exp(l - max) / sum   (super_guessr.py:355,365)
 //   pred_cell = argmax (:358), pred_llh = centroids[pred_cell] (:359-361), lse = max + log(sum)
 template <int KTOP>
@@ -317,9 +383,9 @@ __global__ void head_merge_kernel(const float* __restrict__ pmax, const float* _
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const int mb = row / kBM, rit = row % kBM;
+  const int mb = row / (2 * kBM), crank = (row / kBM) & 1, rit = row % kBM;  // pair row block, CTA of the pair
   const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
-  const int nparts = (c_hi - c_lo + 1) * 2;
+  const int nparts = (c_hi - c_lo + 1) * kColGroups;
 
   float lmax = -INFINITY, lsum = 0.f;
   float tv[KTOP];
@@ -327,9 +393,9 @@ __global__ void head_merge_kernel(const float* __restrict__ pmax, const float* _
 #pragma unroll
   for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
   for (int i = lane; i < nparts; i += 32) {
-    const int c = c_lo + (i >> 1);
+    const int c = c_lo + i / kColGroups;
     const int run = mb - sc.start(c) / sc.num_n;
-    const size_t p = (static_cast<size_t>(c) * sc.runs + run) * 2 + (i & 1);
+    const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + (i % kColGroups);
     const float m = pmax[p * kBM + rit];
     if (m > -INFINITY) {
       const float s = psum[p * kBM + rit];
@@ -399,7 +465,17 @@ __global__ void head_merge_kernel(const float* __restrict__ pmax, const float* _
 
 static size_t fwd_smem_bytes() { return sizeof(FwdSmem) + 1024; }
 
-static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(sc.grid) * sc.runs * 2; }
+static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(2 * sc.grid) * sc.runs * kColGroups; }
+
+template <typename Kern, typename... Args>
+static cudaError_t launch_pairs(Kern kern, int pairs, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);  // cluster shape (2,1,1) is compiled into the kernel
+  cfg.blockDim = dim3(kFwdThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 template <int KTOP>
 static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, int B, int C, int D, void* logits,
@@ -409,8 +485,13 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
   CUtensorMap tm_x, tm_w;
   int rc = make_tmap_bf16_2d(&tm_x, x, D, B, static_cast<uint64_t>(D) * 2, kBK, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_w, W, D, C, static_cast<uint64_t>(D) * 2, kBK, kBN);
+  rc = make_tmap_bf16_2d(&tm_w, W, D, C, static_cast<uint64_t>(D) * 2, kBK, kBN / 2);  // one CTA's half
   if (rc) return rc;
+  CUtensorMap tm_out = tm_x;  // placeholder in serving (never dereferenced)
+  if (logits) {
+    rc = make_tmap_bf16_2d(&tm_out, logits, ldc, B, static_cast<uint64_t>(ldc) * 2, 64, 32);
+    if (rc) return rc;
+  }
   const FwdSched sc = make_sched(B, C, device_sm_count());
   const size_t np = fwd_partials(sc) * kBM;
   float* pmax = static_cast<float*>(workspace);
@@ -422,13 +503,13 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
   if (logits) {
     auto kern = head_fwd_kernel<KTOP, true>;
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
-    kern<<<sc.grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, static_cast<bf16*>(logits), ldc, pmax, psum,
-                                                 ptopv, ptopi, B, C, D, sc);
+    GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, pmax, psum, ptopv, ptopi, B, C, D,
+                         sc));
   } else {
     auto kern = head_fwd_kernel<KTOP, false>;
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
-    kern<<<sc.grid, kFwdThreads, smem, stream>>>(tm_x, tm_w, bias_pad, nullptr, ldc, pmax, psum, ptopv, ptopi, B, C,
-                                                 D, sc);
+    GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, pmax, psum, ptopv, ptopi, B, C, D,
+                         sc));
   }
   GG_LAUNCH_CHECK();
   head_merge_kernel<KTOP><<<ceil_div(B, 8), 256, 0, stream>>>(pmax, psum, ptopv, ptopi, sc, B, k, centroids,

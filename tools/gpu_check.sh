@@ -16,12 +16,17 @@ for w in $what; do
     bench)
       timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json
       timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
+    kbench)
+      timeout 300 python tools/kbench.py 30 > gpurun_out/kbench.log 2>&1; cat gpurun_out/kbench.log ;;
+    ncufwd)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-^head_fwd}" -s 4 -c 2 -f -o gpurun_out/prof_k \
+        python tools/kbench.py 2 > gpurun_out/ncu_k.log 2>&1; echo "ncuk rc=$?" ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on \
-        -k regex:"${NCU_KERNELS:-gg::}" -s ${NCU_SKIP:-42} -c ${NCU_COUNT:-14} -f -o gpurun_out/prof_train \
+        -k regex:"${NCU_KERNELS:-^(cast_weight|fuse_headings|hav_|head_|label_xyz|pad_bias|db_final)}" -s ${NCU_SKIP:-44} -c ${NCU_COUNT:-11} -f -o gpurun_out/prof_train \
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
   esac
 done

@@ -279,9 +279,12 @@ def run_b200_train(args):
     final_loss = loss.item()
 
     # ---------------- per-launcher CUDA-event timing over a second identical timed region
+    # Eager launches; a ~1 ms device-side spin queued ahead of every step lets the host run a whole step
+    # ahead, so the events bracket device time only (no launch gaps inside the brackets).
     ops.enable_timing(True)
     barrier()
     for i in range(min(K, 20)):
+        torch.cuda._sleep(2_000_000)
         step(*resident[i % 3])
     tms = ops.timing_ms()
     ops.enable_timing(False)

@@ -34,6 +34,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -462,19 +463,30 @@ constexpr uint32_t kStageBytes = kStripWarps * kSliceTileBytes;      // 16 KB
 
 struct StreamSmem {
   uint8_t tile[kStreamStages][kStageBytes];
+  float4 rec[kStreamStages][kStageRows][2];   // the stage's row records (RowRec)
+  float lse2[kStreamStages][kStageRows];      // row log-sum-exp * log2(e)
+  uint32_t near[kStreamStages][kStageRows];   // the strip's word of the row's near mask (4 bits per consumer warp)
   uint64_t full[kStreamStages];
   uint64_t empty[kStreamStages];
 };
 
+__device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
 // CTA = (row block rb, strip of 4 warp slices).  The producer warp streams the strip's logits through a
 // 4-stage TMA -> shared-memory ring (8 rows x 1024 classes per stage, 64 KB in flight per CTA, three
-// CTAs per SM), so the depth of the memory pipeline does not depend on registers or occupancy.
+// CTAs per SM), so the depth of the memory pipeline does not depend on registers or occupancy; its
+// lanes 0..7 also stage the 8 rows' scalars (record, lse, near bits), fetched one stage ahead, so the
+// consumers never touch global memory for per-row data.
 // Consumer warp w owns classes [256 (4 strip + w), +256): lane l holds the bf16 pairs at 64 j + 2 l +
 // {0,1}, j = 0..3 -- one pair in each of the slice's four 64-class groups -- so a near group costs
 // every lane exactly two target evaluations (no divergence), shared-memory reads are conflict-free
 // and every global store is one full 128-byte line.  Rows are padded to a multiple of 256 columns
 // (ldc >= Cpad): nothing in the row loop is predicated; pad columns carry p only and are never read
-// downstream.
+// downstream.  Pairs are processed with the packed fp32x2 pipe (fma / add on both halves at once).
 template <bool WANT_DB>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, const float* __restrict__ lse,
@@ -500,18 +512,42 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
   __syncthreads();
 
   if (warp == kStripWarps) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int row = row0; row < row1; row += kStageRows) {
-        mbar_wait(&sm.empty[s], ph ^ 1);
+    // ===================== producer warp =====================
+    const int near_word = (strip * kStripWarps) >> 3;  // the strip's 16 bits live in one mask word
+    const int near_shift = 4 * ((strip * kStripWarps) & 7);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    float l2 = 0.f;
+    uint32_t nw = 0u;
+    auto fetch = [&](int row) {  // lanes 0..7: one row each
+      r0 = make_float4(0.f, 0.f, 0.f, 0.f); r1 = r0; l2 = 0.f; nw = 0u;
+      if (lane < kStageRows && row + lane < row1) {
+        const float4* rp = reinterpret_cast<const float4*>(rec + row + lane);
+        r0 = __ldg(rp);
+        r1 = __ldg(rp + 1);
+        l2 = __ldg(lse + row + lane) * kLog2eF;
+        nw = (__ldg(near + static_cast<size_t>(row + lane) * nwp + near_word) >> near_shift) & 0xffffu;
+      }
+    };
+    fetch(row0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int row = row0; row < row1; row += kStageRows) {
+      mbar_wait_relaxed(&sm.empty[s], ph ^ 1);
+      if (lane < kStageRows) {
+        sm.rec[s][lane][0] = r0;
+        sm.rec[s][lane][1] = r1;
+        sm.lse2[s][lane] = l2;
+        sm.near[s][lane] = nw;
+      }
+      __syncwarp();  // lanes' stores ordered before lane 0's releasing arrive
+      if (lane == 0) {
         mbar_arrive_expect_tx(&sm.full[s], nactive * kSliceTileBytes);
         for (int w = 0; w < nactive; ++w)
           tma_load_2d_hint(sm.tile[s] + w * kSliceTileBytes, &tm_logits, &sm.full[s],
                            (strip * kStripWarps + w) * kColsPerWarp, row, kPolicyEvictFirst);
-        if (++s == kStreamStages) { s = 0; ph ^= 1; }
       }
+      fetch(row + kStageRows);  // next stage's scalars: in flight while we wait for its slot
+      if (++s == kStreamStages) { s = 0; ph ^= 1; }
     }
     return;
   }
@@ -521,9 +557,10 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
   const int ws = strip * kStripWarps + warp;
   const int Cpad = table_cpad(C);
   const int cbase = ws * kColsPerWarp + 2 * lane;  // + 64 j
-  const int near_word = ws >> 3, near_shift = 4 * (ws & 7);
+  const uint32_t near_shift = 4 * warp;
 
-  float vx[8], vy[8], vz[8], db[8];
+  float vx[8], vy[8], vz[8];
+  float2 db[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 a = __ldg(reinterpret_cast<const float2*>(table + cbase + 64 * j));
@@ -532,7 +569,7 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
     vx[2 * j] = a.x; vx[2 * j + 1] = a.y;
     vy[2 * j] = b.x; vy[2 * j + 1] = b.y;
     vz[2 * j] = c.x; vz[2 * j + 1] = c.y;
-    db[2 * j] = db[2 * j + 1] = 0.f;
+    db[j] = make_float2(0.f, 0.f);
   }
   // pad classes (column >= C, last slice only) carry no target mass even when q_thr = inf
   uint32_t cell_ok = 0;
@@ -540,79 +577,86 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
   for (int i = 0; i < 8; ++i) cell_ok |= (cbase + 64 * (i >> 1) + (i & 1) < C) ? (1u << i) : 0u;
 
   const size_t pitch = static_cast<size_t>(ldc);
-  bf16* gptr = dlogits + cbase;
-  const uint32_t my_tile = smem_u32(sm.tile[0]) + warp * kSliceTileBytes + 4 * lane;
+  uint32_t* gptr = reinterpret_cast<uint32_t*>(dlogits + static_cast<size_t>(row0) * pitch + cbase);
+  const size_t pitch_w = pitch / 2;  // row pitch in 32-bit words (ldc is even)
+  const uint32_t tile0 = smem_u32(sm.tile[0]) + warp * kSliceTileBytes + 4 * lane;
+  const uint32_t rec0 = smem_u32(&sm.rec[0][0][0]), lse0 = smem_u32(&sm.lse2[0][0]), near0 = smem_u32(&sm.near[0][0]);
+  const float2 log2e2 = make_float2(kLog2eF, kLog2eF);
   int stage = 0;
   uint32_t phase = 0;
 
-  for (int rbase = row0; rbase < row1; rbase += 32) {
-    const int nr = min(32, row1 - rbase);
-    // lane j carries row rbase + j's scalars; broadcast by shuffle when the row is processed
-    float my_lse2 = 0.f, my_sl = 0.f;
-    uint32_t my_near = 0u;
-    if (lane < nr) {
-      my_lse2 = __ldg(lse + rbase + lane) * kLog2eF;
-      my_near = (__ldg(near + static_cast<size_t>(rbase + lane) * nwp + near_word) >> near_shift) & 0xfu;
-    }
-    for (int r8 = 0; r8 < nr; r8 += kStageRows) {
-      mbar_wait(&sm.full[stage], phase);
-      const uint32_t tile = my_tile + stage * kStageBytes;
+  for (int rbase = row0; rbase < row1; rbase += kStageRows) {
+    const int nr = min(kStageRows, row1 - rbase);
+    mbar_wait(&sm.full[stage], phase);
+    const uint32_t tile = tile0 + stage * kStageBytes;
+    float my_sl = 0.f;  // lane r keeps row r's sum_c t*l of this warp's classes
 #pragma unroll 2
-      for (int rr = 0; rr < kStageRows; ++rr) {
-        const int r = r8 + rr;
-        if (r >= nr) break;  // warp-uniform
-        const int row = rbase + r;
-        uint32_t cur[4];
+    for (int rr = 0; rr < kStageRows; ++rr) {
+      if (rr >= nr) break;  // warp-uniform
+      uint32_t cur[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = lds_u32(tile + rr * (kColsPerWarp * 2) + 128 * j);
-        const float lse2 = __shfl_sync(0xffffffffu, my_lse2, r);
-        const uint32_t nb = __shfl_sync(0xffffffffu, my_near, r);
-        float g[8];
+      for (int j = 0; j < 4; ++j) cur[j] = lds_u32(tile + rr * (kColsPerWarp * 2) + 128 * j);
+      const float nlse2 = -__uint_as_float(lds_u32(lse0 + (stage * kStageRows + rr) * 4));
+      const uint32_t nb = (lds_u32(near0 + (stage * kStageRows + rr) * 4) >> near_shift) & 0xfu;
+      const float2 nl = make_float2(nlse2, nlse2);
+      float2 g[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // softmax probability
-          g[2 * j] = ex2_approx(fmaf(__uint_as_float(cur[j] << 16), kLog2eF, -lse2));
-          g[2 * j + 1] = ex2_approx(fmaf(__uint_as_float(cur[j] & 0xffff0000u), kLog2eF, -lse2));
-        }
-        if (nb != 0u) {  // some group of this warp's 256 classes holds a near cell (warp-uniform)
-          const float4 ra = __ldg(reinterpret_cast<const float4*>(rec + row));
-          const float4 rb4 = __ldg(reinterpret_cast<const float4*>(rec + row) + 1);
-          float sl = 0.f;
+      for (int j = 0; j < 4; ++j) {  // softmax probability 2^(l log2e - lse log2e), both halves of the pair at once
+        const float2 a = __ffma2_rn(make_float2(__uint_as_float(cur[j] << 16), __uint_as_float(cur[j] & 0xffff0000u)),
+                                    log2e2, nl);
+        g[j] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+      }
+      if (nb != 0u) {  // some group of this warp's 256 classes holds a near cell (warp-uniform)
+        const uint4 ua = lds_u128(rec0 + (stage * kStageRows + rr) * 32);
+        const uint4 ub = lds_u128(rec0 + (stage * kStageRows + rr) * 32 + 16);
+        const float ux = __uint_as_float(ua.x), uy = __uint_as_float(ua.y), uz = __uint_as_float(ua.z);
+        const float q_thr = __uint_as_float(ua.w), off = __uint_as_float(ub.x), inv_s = __uint_as_float(ub.y);
+        float sl = 0.f;
+        auto near_groups = [&](auto narrow_tag) {
+          constexpr bool kNarrow = decltype(narrow_tag)::value;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if ((nb >> j) & 1u) {  // warp-uniform
+              float t[2];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int i = 2 * j + h;
-                const float q = chord2(ra.x, ra.y, ra.z, vx[i], vy[i], vz[i]);
-                float t = target_weight(q, ra.w, neg_rk2, rb4.x);
-                t = ((cell_ok >> i) & 1u) ? t * rb4.y : 0.f;
-                g[i] -= t;
-                const float l = h ? __uint_as_float(cur[j] & 0xffff0000u) : __uint_as_float(cur[j] << 16);
-                sl = fmaf(t, l, sl);
+                const float q = chord2(ux, uy, uz, vx[i], vy[i], vz[i]);
+                // same bits either way (see target_weight_narrow); (A) summed exactly these values
+                const float w = kNarrow ? target_weight_narrow(q, q_thr, neg_rk2, off)
+                                        : target_weight(q, q_thr, neg_rk2, off);
+                t[h] = ((cell_ok >> i) & 1u) ? w * inv_s : 0.f;
               }
+              g[j].x -= t[0];
+              g[j].y -= t[1];
+              sl = fmaf(t[0], __uint_as_float(cur[j] << 16), sl);
+              sl = fmaf(t[1], __uint_as_float(cur[j] & 0xffff0000u), sl);
             }
           }
-          sl = warp_sum(sl);
-          if (lane == r) my_sl = sl;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) st_stream_u32(gptr + row * pitch + 64 * j, pack_bf16x2(g[2 * j], g[2 * j + 1]));
-        if (WANT_DB) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) db[i] += g[i];
-        }
+        };
+        // row-uniform: with q_thr <= 1 every near cell is on the first asin branch
+        if (q_thr <= 1.0f) near_groups(std::true_type{});
+        else near_groups(std::false_type{});
+        sl = warp_sum(sl);
+        if (lane == rr) my_sl = sl;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[stage]);  // this warp is done with the stage
-      if (++stage == kStreamStages) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) __stcs(gptr + 32 * j, pack_bf16x2(g[j].x, g[j].y));
+      gptr += pitch_w;
+      if (WANT_DB) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) db[j] = __fadd2_rn(db[j], g[j]);
+      }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);  // this warp is done with the stage
     if (lane < nr) loss_part[static_cast<size_t>(ws) * B + rbase + lane] = my_sl;
+    if (++stage == kStreamStages) { stage = 0; phase ^= 1; }
   }
   if (WANT_DB) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<float2*>(db_part + static_cast<size_t>(rb) * Cpad + cbase + 64 * j) =
-          make_float2(db[2 * j], db[2 * j + 1]);
+      *reinterpret_cast<float2*>(db_part + static_cast<size_t>(rb) * Cpad + cbase + 64 * j) = db[j];
   }
 }
 

@@ -396,17 +396,25 @@ __global__ void head_merge_kernel(const float* __restrict__ pmax, const float* _
     const int c = c_lo + i / kColGroups;
     const int run = mb - sc.start(c) / sc.num_n;
     const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + (i % kColGroups);
+    // all loads of this partial first (independent: one memory latency), then the merge
     const float m = pmax[p * kBM + rit];
+    const float s = psum[p * kBM + rit];
+    float pv[KTOP];
+    int pi[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) {
+      pv[j] = ptopv[(p * KTOP + j) * kBM + rit];
+      pi[j] = ptopi[(p * KTOP + j) * kBM + rit];
+    }
     if (m > -INFINITY) {
-      const float s = psum[p * kBM + rit];
       if (m > lmax) { lsum = lsum * expf(lmax - m) + s; lmax = m; }
       else lsum += s * expf(m - lmax);
     }
 #pragma unroll
     for (int j = 0; j < KTOP; ++j) {
-      const float v = ptopv[(p * KTOP + j) * kBM + rit];
+      const float v = pv[j];
       if (!(v > tv[KTOP - 1]) && !(v == tv[KTOP - 1] && v > -INFINITY)) break;  // lists are sorted descending
-      const int id = ptopi[(p * KTOP + j) * kBM + rit];
+      const int id = pi[j];
       // equal values across partials: keep the lower geocell index first
       if (v > tv[KTOP - 1] || id < ti[KTOP - 1]) {
         tv[KTOP - 1] = v;

@@ -57,6 +57,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same for waits that are EXPECTED to be long (a producer that runs ahead of its consumers): back off between
+// polls so that the spinning thread does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(96);
+    if (clock64() - t0 > 8000000000LL) {
+      printf("gg: mbarrier timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

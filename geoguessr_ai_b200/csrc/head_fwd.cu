@@ -7,12 +7,13 @@
 // row, an online (max, sum-exp) and the running top-K logits, so that in serving the (B, C) logit /
 // probability matrices never reach HBM.
 //
-// CTA pairs: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (rows
-// m0 .. m0+127 and m0+128 .. m0+255 of the same 256 geocells).  Each CTA loads its own x tile and HALF of
-// the shared W tile, multicast by TMA into both CTAs' shared memory, so every W byte crosses the
-// L2 -> SM fabric once per pair: 32 KB instead of 48 KB per CTA and k-block, which is what lets the
-// tensor pipe run ahead of operand delivery.  A stage is recycled when BOTH CTAs' MMAs have read it
-// (tcgen05.commit multicast onto the `empty` barriers of the pair).
+// CTA pairs (tcgen05 cta_group::2): the kernel runs as clusters of two CTAs on the two SMs of a TPC, which
+// execute ONE 256 x 256 x 16 MMA together: each CTA holds its own 128 rows of x and HALF of the W tile (128
+// geocells) in shared memory, and its 128 x 256 half of the accumulator in its own TMEM.  Per CTA and k-block
+// 32 KB instead of 48 KB cross the L2 -> SM fabric and sit in shared memory, which is what lets the tensor
+// pipe run ahead of operand delivery.  The leader CTA (cluster rank 0) issues the MMAs; both CTAs' TMA loads
+// signal the leader's `full` barrier; tcgen05.commit (multicast) releases the stage / publishes the
+// accumulator in both CTAs; both CTAs' epilogue warps hand the accumulator back on the leader's barrier.
 //
 // Tile schedule: pair-tiles (256 rows x 256 geocells) are ordered geocell-tile-fastest within a 256-row
 // block and every pair owns a CONTIGUOUS range of that order, i.e. it sweeps many geocell tiles of the
@@ -35,13 +36,13 @@ namespace gg {
 constexpr int kBM = 128;        // rows of x per tile (UMMA M)
 constexpr int kBN = 256;        // geocells per tile   (UMMA N)
 constexpr int kBK = 64;         // K elements per stage (128 B of bf16 = one swizzle span)
-constexpr int kStages = 3;      // 3 x (16 KB + 32 KB) = 144 KB (+ 64 KB of logits staging for the TMA stores)
+constexpr int kStages = 4;      // 4 x (16 KB + 16 KB) = 128 KB per CTA (+ 64 KB of logits staging for the TMA stores)
 constexpr int kEpiWarps = 16;
 constexpr int kColGroups = kEpiWarps / 4;       // column groups of a tile (one warp per TMEM lane quadrant each)
 constexpr int kColsPerEpiWarp = kBN / kColGroups;
 constexpr int kFwdThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr uint32_t kStageBytesA = kBM * kBK * 2;
-constexpr uint32_t kStageBytesB = kBN * kBK * 2;
+constexpr uint32_t kStageBytesB = (kBN / 2) * kBK * 2;  // this CTA's half of the W tile
 constexpr float kLog2e = 1.4426950408889634f;
 
 constexpr int kThrSlots = 8;    // shared top-k thresholds are kept per run, in a ring of run slots
@@ -141,72 +142,74 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tma_prefetch_desc(&tm_w);
     if (WRITE_LOGITS) tma_prefetch_desc(&tm_out);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 2);  // this CTA's MMAs and the partner's (both read what this CTA multicasts)
+      mbar_init(&sm.full[s], 1);   // leader's: its own arrive.expect_tx, bytes from both CTAs' loads
+      mbar_init(&sm.empty[s], 1);  // one multicast commit per round
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm.acc_full[a], 1);
-      mbar_init(&sm.acc_empty[a], 32 * kEpiWarps);
+      mbar_init(&sm.acc_empty[a], 2 * kEpiWarps);  // leader's: one arrive per epilogue warp of BOTH CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(&sm.tmem_base, 512);
-    tmem_relinquish();
+  if (warp == 1) {  // collective over the pair: one warp in each CTA
+    tmem_alloc_pair(&sm.tmem_base, 512);
+    tmem_relinquish_pair();
   }
   for (int i = threadIdx.x; i < kThrSlots * kBM; i += kFwdThreads) (&sm.thr[0][0])[i] = kKeyMin;
   tc_fence_before();
-  cluster_sync();  // the partner's barriers are initialised before anything is multicast to them
+  cluster_sync();  // the partner's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t leader_full = mapa_u32(smem_u32(&sm.full[0]), 0);
     int s = 0;
     uint32_t ph = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int m0 = (2 * (t / sc.num_n) + crank) * kBM, n0 = (t % sc.num_n) * kBN + crank * (kBN / 2);
       for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&sm.empty[s], ph ^ 1);  // free in BOTH CTAs
+        mbar_wait(&sm.empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&sm.full[s], kStageBytesA + kStageBytesB);
-          tma_load_2d(sm.a[s], &tm_x, &sm.full[s], kb * kBK, m0);
-          // my half of the W tile (128 geocells), delivered to both CTAs of the pair
-          tma_load_2d_multicast(sm.b[s] + crank * (kStageBytesB / 2), &tm_w, &sm.full[s], kb * kBK, n0, 0x3);
+          if (crank == 0) mbar_arrive_expect_tx(&sm.full[s], 2 * (kStageBytesA + kStageBytesB));
+          tma_load_2d_pair(sm.a[s], &tm_x, leader_full + 8 * s, kb * kBK, m0);  // my 128 rows of x
+          tma_load_2d_pair(sm.b[s], &tm_w, leader_full + 8 * s, kb * kBK, n0);  // my 128 of the 256 geocells
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, 0, 0);
-    const uint64_t da_base = umma_desc_sw128(smem_u32(sm.a[0]), 16, 1024);
-    const uint64_t db_base = umma_desc_sw128(smem_u32(sm.b[0]), 16, 1024);
-    int s = 0;
-    uint32_t ph = 0;
-    int it = 0;
-    for (int t = t_begin; t < t_end; ++t, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
-      mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kBN;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&sm.full[s], ph);
+    // ===================== MMA issuer (pair leader only; warp-uniform loop, one elected lane issues) =======
+    if (crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, kBN, 0, 0);
+      const uint64_t da_base = umma_desc_sw128(smem_u32(sm.a[0]), 16, 1024);
+      const uint64_t db_base = umma_desc_sw128(smem_u32(sm.b[0]), 16, 1024);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
-          // descriptors differ only in the start-address field: stage s, then 32 bytes per 16-wide k step
-          const uint64_t da = da_base + static_cast<uint64_t>(s * (kStageBytesA >> 4));
-          const uint64_t db = db_base + static_cast<uint64_t>(s * (kStageBytesB >> 4));
-          umma_f16(d_tmem, da, db, idesc, kb != 0);
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&sm.full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            // descriptors differ only in the start-address field: stage s, then 32 bytes per 16-wide k step
+            const uint64_t da = da_base + static_cast<uint64_t>(s * (kStageBytesA >> 4));
+            const uint64_t db = db_base + static_cast<uint64_t>(s * (kStageBytesB >> 4));
+            umma_pair_f16(d_tmem, da, db, idesc, kb != 0);
 #pragma unroll
-          for (int k = 1; k < kBK / 16; ++k) umma_f16_acc(d_tmem, da + 2 * k, db + 2 * k, idesc);
-          umma_commit_multicast(&sm.empty[s], 0x3);  // slot reusable once these MMAs have read it
-          if (kb == num_k - 1) umma_commit(&sm.acc_full[acc]);  // accumulator complete
+            for (int k = 1; k < kBK / 16; ++k) umma_pair_f16_acc(d_tmem, da + 2 * k, db + 2 * k, idesc);
+            umma_pair_commit(&sm.empty[s], 0x3);  // slot reusable in both CTAs once these MMAs have read it
+            if (kb == num_k - 1) umma_pair_commit(&sm.acc_full[acc], 0x3);  // accumulator complete (both halves)
+          }
+          __syncwarp();
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -215,6 +218,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int cg = (warp - 2) >> 2;   // which 64 columns of the 256-wide tile
     const int row_in_tile = quad * 32 + lane;
     uint8_t* const my_out = sm.out[warp - 2];
+    const uint32_t leader_acc_empty = mapa_u32(smem_u32(&sm.acc_empty[0]), 0);
     const uint32_t my_out_row = smem_u32(my_out) + lane * 128;
 
     float run_max = -INFINITY, run_sum = 0.f;
@@ -333,9 +337,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           tma_store_commit();
         }
       }
-      // TMEM accumulator drained -> hand it back to the MMA warp
+      // TMEM accumulator drained -> hand it back to the leader's MMA warp
       tc_fence_before();
-      mbar_arrive(&sm.acc_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
 
       // end of this CTA's run over row block mb: flush the row state
       if (nb == sc.num_n - 1 || t == t_end - 1) {
@@ -364,10 +369,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   }
 
   tc_fence_before();
-  cluster_sync();  // the partner may still be multicasting into / arriving on this CTA's shared memory
+  cluster_sync();  // the partner may still be signalling this CTA's barriers / the leader reading its operands
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 

@@ -156,6 +156,7 @@ def train_config(n_gpus, cfg):
                         "AdamW, synthetic CLIP ViT-L/14 embeddings",
             "batch_per_gpu": cfg["B"], "global_batch": cfg["B"] * n_gpus, "embed_dim": cfg["D"], "headings": cfg["V"],
             "geocells": C_CELLS, "num_candidates": cfg["k"], "parallelism": f"dp{n_gpus}", "cuda_graph": None,
+            "grad_allreduce": None,
             "l2": "working set per step (~0.6 GB: embeddings, W, logits, dlogits, dW, AdamW state) exceeds the 126 MB "
                   "L2; input batches rotate over 3 resident buffers"}
 
@@ -191,6 +192,9 @@ def run_b200_train(args):
         model.cell_layer.weight.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
         model.cell_layer.bias.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
     model.train()
+    if world > 1:  # gradients are averaged inside backward(), range by range, overlapped with the dW GEMM
+        model.enable_data_parallel(chunks=args.dp_chunks,
+                                   comm_dtype=torch.bfloat16 if args.dp_bf16 else None)
     params = [model.cell_layer.weight, model.cell_layer.bias]
     use_graph = not args.no_graph
     opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=use_graph)
@@ -204,9 +208,6 @@ def run_b200_train(args):
         opt.zero_grad(set_to_none=True)
         out = model(embedding=emb, labels=labels, labels_clf=dummy_clf)
         out.loss.backward()
-        if world > 1:
-            for p in params:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
         opt.step()
         return out.loss
 
@@ -330,8 +331,7 @@ def run_b200_train(args):
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     # ---------------- roofline of the dominant launcher
@@ -373,15 +373,27 @@ def run_b200_train(args):
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": dict(train_config(world, cfg), cuda_graph=use_graph), "clocks": clocks,
+        "dtype": "bf16", "data": "synthetic", "config": dict(train_config(world, cfg), cuda_graph=use_graph,
+                                            grad_allreduce=(None if world == 1 else
+                                                            f"nccl avg, {'bf16' if args.dp_bf16 else 'fp32'}, {args.dp_chunks} "
+                                                            "geocell ranges overlapped with the dW GEMM")), "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "steps": Ke},
         "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
         "loss": final_loss,
     }
     print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Multi-rank exit: tearing NCCL communicators down while CUDA graphs that captured collectives are alive can
+    block; everything is measured and printed by now, so leave without running destructors."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -392,6 +404,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
+    ap.add_argument("--dp-chunks", type=int, default=3, help="geocell ranges of the overlapped dW GEMM + all-reduce (N > 1)")
+    ap.add_argument("--dp-bf16", action="store_true", help="all-reduce the gradients in bf16 (opt-in, N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -8,8 +8,8 @@ CUDA: TMA + tcgen05/TMEM GEMMs, fused bandwidth-bound kernels) behind the C ABI 
 ``include/geoguessr_b200.h``.  No Triton, no torch.compile, no CPU fallback.
 """
 from .utils import ModelOutput, TopK  # noqa: F401
-from .super_guessr import SuperGuessr  # noqa: F401
+from .super_guessr import SuperGuessr, dp_chunk_bounds  # noqa: F401
 from .proto_refiner import ProtoRefiner, shard_cells  # noqa: F401
 from . import ops, synth  # noqa: F401
 
-__all__ = ["SuperGuessr", "ProtoRefiner", "ModelOutput", "TopK", "ops", "synth", "shard_cells"]
+__all__ = ["SuperGuessr", "ProtoRefiner", "ModelOutput", "TopK", "ops", "synth", "shard_cells", "dp_chunk_bounds"]

@@ -218,23 +218,35 @@ def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tens
     return out
 
 
-def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None):
+def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None, c_range=None, out=None):
     """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C) (from the loss kernel's column-sum
-    partials when given, else from a pass over dlogits)."""
+    partials when given, else from a pass over dlogits).
+
+    c_range=(c0, c1) computes only geocells [c0, c1) (c0 a multiple of 8) into rows c0..c1 of ``out=(dW, db)``:
+    the data-parallel path runs the GEMM range by range and all-reduces each range while the next one runs."""
     _need_cuda(dlogits, x16, grad_scale)
     B, ldc = dlogits.shape
     dev = dlogits.device
     lib = _lib.load()
-    dW = torch.empty((C, D), dtype=torch.float32, device=dev)
-    db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
-    ws = _u8(lib.gg_head_bwd_workspace_bytes(C), dev) if (want_db and db_partials is None) else None
+    if out is None:
+        dW = torch.empty((C, D), dtype=torch.float32, device=dev)
+        db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
+    else:
+        dW, db = out
+        if not want_db:
+            db = None
+    c0, c1 = (0, C) if c_range is None else c_range
+    assert 0 <= c0 < c1 <= C and c0 % 8 == 0, "geocell range must start at a multiple of 8"
+    ws = _u8(lib.gg_head_bwd_workspace_bytes(c1 - c0), dev) if (want_db and db_partials is None) else None
     if not want_db:
         db_partials = None
     if grad_scale is not None:
         grad_scale = grad_scale.detach().float().contiguous()
-    _call("gg_head_bwd", lib.gg_head_bwd, _ptr(dlogits), ldc, _ptr(x16), x16.shape[1], B, C, D, float(scale), _ptr(grad_scale), _ptr(dW),
-                        _ptr(db), _ptr(db_partials), 0 if db_partials is None else db_partials.shape[0],
-                        0 if db_partials is None else db_partials.shape[1], _ptr(ws), _stream())
+    esz = dlogits.element_size()
+    _call("gg_head_bwd", lib.gg_head_bwd, _ptr(dlogits) + c0 * esz, ldc, _ptr(x16), x16.shape[1], B, c1 - c0, D, float(scale),
+          _ptr(grad_scale), _ptr(dW) + c0 * D * 4, 0 if db is None else _ptr(db) + c0 * 4,
+          0 if db_partials is None else _ptr(db_partials) + c0 * 4, 0 if db_partials is None else db_partials.shape[0],
+          0 if db_partials is None else db_partials.shape[1], _ptr(ws), _stream())
     return dW, db
 
 

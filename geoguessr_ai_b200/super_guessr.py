@@ -52,6 +52,7 @@ class _GeocellHeadLoss(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # no zero-filled grads for the non-differentiable outputs
         ctx.dims = (C, D, embedding.shape, embedding.requires_grad)
         ctx.weight = weight
+        ctx.module = module
         outs = (head["topk_val"], head["topk_idx"], head["pred_cell"], head["pred_llh"])
         ctx.mark_non_differentiable(*outs)
         return (loss,) + outs
@@ -64,14 +65,45 @@ class _GeocellHeadLoss(torch.autograd.Function):
         want_w, want_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dW = db = demb = None
         if want_w or want_b:
-            dW, db = ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=want_b,
-                                       db_partials=ctx.dbp)
+            dp = ctx.module._dp
+            if dp is None:
+                dW, db = ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=want_b,
+                                           db_partials=ctx.dbp)
+            else:
+                dW, db = ctx.module._backward_data_parallel(dlogits, x16, C, D, B, gloss, want_b, ctx.dbp)
         if ctx.needs_input_grad[0] and emb_needs_grad:
             # Only reached when the encoder is trained end to end (outside the BASELINE configs):
             # dx = dlogits W through cuBLAS, then the mean's 1/V broadcast (super_guessr.py:347).
             g = (dlogits[:, :C].float() @ ctx.weight.detach().float()) * (gloss / B)
             demb = g if len(emb_shape) == 2 else (g / emb_shape[1]).unsqueeze(1).expand(emb_shape)
         return demb, (dW if want_w else None), db, None, None, None, None
+
+
+def dp_chunk_bounds(C: int, chunks: int, align: int = 256):
+    """Geocell ranges [c0, c1) for the chunked dW GEMM + all-reduce: boundaries on multiples of ``align``
+    (one CTA pair's 2 x 128 geocell blocks), sizes as equal as the alignment allows, never empty."""
+    blocks = -(-C // align)
+    chunks = max(1, min(int(chunks), blocks))
+    base, rem = divmod(blocks, chunks)
+    out, b0 = [], 0
+    for i in range(chunks):
+        b1 = b0 + base + (1 if i < rem else 0)
+        out.append((b0 * align, min(b1 * align, C)))
+        b0 = b1
+    return out
+
+
+def _all_reduce_avg(t: Tensor, group, comm_dtype):
+    import torch.distributed as dist
+
+    c = t if comm_dtype is None or comm_dtype == t.dtype else t.to(comm_dtype)
+    if c.is_cuda:
+        dist.all_reduce(c, op=dist.ReduceOp.AVG, group=group)  # NCCL
+    else:  # gloo (CPU tests of the host logic) has no AVG
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+        c /= dist.get_world_size(group)
+    if c is not t:
+        t.copy_(c)
 
 
 class SuperGuessr(nn.Module):
@@ -134,6 +166,7 @@ class SuperGuessr(nn.Module):
         self._op_cache = None
         self._xyz_cache = None
         self._side_stream = None
+        self._dp = None
         print(f"Initialized SuperGuessr classification model with {self.num_cells} geocells.")
 
     # ---- reference helpers (super_guessr.py:114-206) ---------------------------------------
@@ -202,6 +235,47 @@ class SuperGuessr(nn.Module):
         if self._xyz_cache is None or self._xyz_cache[0] != key:
             self._xyz_cache = (key, ops.centroid_unit_vectors(c.data))
         return self._xyz_cache[1]
+
+    # ---- data-parallel head training --------------------------------------------
+    def enable_data_parallel(self, process_group=None, chunks: int = 3, comm_dtype=None):
+        """Average the head gradients over the ranks of ``process_group`` INSIDE ``backward()`` (what the
+        reference leaves to DDP / Accelerate): the dW GEMM runs in ``chunks`` geocell ranges and every range
+        is all-reduced (NCCL, AVG) on a communication stream while the next range is being computed, so only
+        the last range's transfer is exposed.  ``chunks=3`` keeps each range at one full wave of CTA pairs
+        at C = 12 647 (see dp_chunk_bounds).  ``comm_dtype=torch.bfloat16`` halves the bytes on NVLink by
+        rounding each rank's gradient before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
+        After this call ``.grad`` is already the global average: do not wrap the module in DDP as well."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("enable_data_parallel needs an initialised torch.distributed process group")
+        self._dp = dict(group=process_group, chunks=int(chunks), comm_dtype=comm_dtype, stream=None)
+        return self
+
+    def _backward_data_parallel(self, dlogits, x16, C, D, B, gloss, want_b, dbp):
+        import torch.distributed as dist
+
+        dp = self._dp
+        dev = dlogits.device
+        if dp["stream"] is None or dp["stream"].device != dev:
+            dp["stream"] = torch.cuda.Stream(device=dev)
+        comm, cur = dp["stream"], torch.cuda.current_stream()
+        dW = torch.empty((C, D), dtype=torch.float32, device=dev)
+        db = torch.empty((C,), dtype=torch.float32, device=dev) if want_b else None
+        comm.wait_stream(cur)  # orders the allocator's reuse of dW / db memory behind earlier work
+        for c0, c1 in dp_chunk_bounds(C, dp["chunks"]):
+            ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=want_b, db_partials=dbp,
+                              c_range=(c0, c1), out=(dW, db))
+            done = torch.cuda.Event()
+            done.record(cur)
+            comm.wait_event(done)
+            with torch.cuda.stream(comm):
+                _all_reduce_avg(dW[c0:c1], dp["group"], dp["comm_dtype"])
+        if db is not None:
+            with torch.cuda.stream(comm):
+                _all_reduce_avg(db, dp["group"], None)
+        cur.wait_stream(comm)
+        return dW, db
 
     # ---- forward (super_guessr.py:268-395) ---------------------------------------------------
     def forward(self, pixel_values: Tensor = None, embedding: Tensor = None, labels: Tensor = None,

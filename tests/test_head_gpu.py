@@ -180,6 +180,28 @@ def test_ragged_shapes_through_c_abi(B, Cc, D, k):
     np.testing.assert_allclose(db.cpu().numpy(), (dl.float().sum(0) / B).numpy(), atol=1e-6)
 
 
+def test_head_backward_by_geocell_ranges_equals_one_launch():
+    """The data-parallel path computes dW / db range by range (then all-reduces each): same bits as one launch."""
+    from geoguessr_ai_b200 import dp_chunk_bounds
+
+    B, Cc, D = 200, 1500, 192
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, D, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    dlp = torch.zeros((B, ops.logits_ld(Cc)), dtype=torch.bfloat16)
+    dlp[:, :Cc] = (torch.randn(B, Cc, generator=g) * 1e-2).to(torch.bfloat16)
+    dlp = dlp.to(DEV)
+    dbp = torch.randn(3, ops.logits_ld(Cc), generator=g).to(DEV)  # stand-in for the loss kernel's column-sum partials
+    for partials in (None, dbp):
+        dW, db = ops.head_backward(dlp, x, Cc, D, scale=0.25, db_partials=partials)
+        dW2 = torch.full_like(dW, float("nan"))
+        db2 = torch.full_like(db, float("nan"))
+        bounds = dp_chunk_bounds(Cc, 3)
+        assert len(bounds) == 3
+        for c0, c1 in bounds:
+            ops.head_backward(dlp, x, Cc, D, scale=0.25, db_partials=partials, c_range=(c0, c1), out=(dW2, db2))
+        assert torch.equal(dW, dW2) and torch.equal(db, db2)
+
+
 def test_training_loop_matches_reference_optimizer_trajectory(centroids):
     """Three AdamW steps through the module (operand cache must follow the fp32 master weights)."""
     B, D = 64, 128

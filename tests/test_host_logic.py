@@ -145,6 +145,50 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _dp_chunk_worker(rank, world, port, q):
+    """The module's range-by-range gradient averaging (dp_chunk_bounds + _all_reduce_avg) == one all-reduce."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from geoguessr_ai_b200.super_guessr import _all_reduce_avg, dp_chunk_bounds
+
+    C, D = 1000, 24
+    g = torch.from_numpy(np.random.default_rng(rank).standard_normal((C, D), dtype=np.float32))
+    whole = g.clone()
+    dist.all_reduce(whole)
+    whole /= world
+    for c0, c1 in dp_chunk_bounds(C, 3):
+        _all_reduce_avg(g[c0:c1], None, None)
+    g16 = whole.clone()
+    _all_reduce_avg(g16, None, torch.bfloat16)  # opt-in compressed transfer: bf16 rounding only
+    if rank == 0:
+        q.put((torch.equal(g, whole), float((g16 - whole).abs().max() / whole.abs().max())))
+    dist.destroy_process_group()
+
+
+def test_dp_chunk_bounds_cover_every_geocell_once():
+    from geoguessr_ai_b200 import dp_chunk_bounds
+
+    for C, n in [(12647, 3), (12647, 4), (200, 3), (1000, 8), (256, 2), (257, 2)]:
+        b = dp_chunk_bounds(C, n)
+        assert b[0][0] == 0 and b[-1][1] == C and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert all(c0 % 256 == 0 and c1 > c0 for c0, c1 in b) and len(b) <= n
+    # cfg2: every range fits one wave of the 74 CTA pairs (pair tile = 256 geocells x 256 embedding columns)
+    assert all(-(-(c1 - c0) // 256) * 4 <= 74 for c0, c1 in dp_chunk_bounds(12647, 3))
+
+
+def test_chunked_gradient_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_chunk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same, err16 = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    assert same and err16 < 1e-2
+
+
 def test_data_parallel_gradient_average_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

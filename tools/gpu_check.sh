@@ -21,6 +21,9 @@ for w in $what; do
     ncufwd)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-^head_fwd}" -s 4 -c 2 -f -o gpurun_out/prof_k \
         python tools/kbench.py 2 > gpurun_out/ncu_k.log 2>&1; echo "ncuk rc=$?" ;;
+    klaunch)
+      timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -s 30 -c 60 --csv --log-file gpurun_out/klaunch.csv \
+        python tools/kbench.py 3 > gpurun_out/klaunch.log 2>&1; echo "klaunch rc=$?" ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;

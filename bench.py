@@ -404,7 +404,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
-    ap.add_argument("--dp-chunks", type=int, default=3, help="geocell ranges of the overlapped dW GEMM + all-reduce (N > 1)")
+    ap.add_argument("--dp-chunks", type=int, default=1, help="geocell ranges of the overlapped dW GEMM + all-reduce (N > 1)")
     ap.add_argument("--dp-bf16", action="store_true", help="all-reduce the gradients in bf16 (opt-in, N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()

@@ -237,13 +237,15 @@ class SuperGuessr(nn.Module):
         return self._xyz_cache[1]
 
     # ---- data-parallel head training --------------------------------------------
-    def enable_data_parallel(self, process_group=None, chunks: int = 3, comm_dtype=None):
+    def enable_data_parallel(self, process_group=None, chunks: int = 1, comm_dtype=None):
         """Average the head gradients over the ranks of ``process_group`` INSIDE ``backward()`` (what the
-        reference leaves to DDP / Accelerate): the dW GEMM runs in ``chunks`` geocell ranges and every range
-        is all-reduced (NCCL, AVG) on a communication stream while the next range is being computed, so only
-        the last range's transfer is exposed.  ``chunks=3`` keeps each range at one full wave of CTA pairs
-        at C = 12 647 (see dp_chunk_bounds).  ``comm_dtype=torch.bfloat16`` halves the bytes on NVLink by
-        rounding each rank's gradient before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
+        reference leaves to DDP / Accelerate): NCCL all-reduce (AVG) of dW and db on a communication stream.
+        With ``chunks`` > 1 the dW GEMM runs in that many geocell ranges (dp_chunk_bounds) and every range is
+        all-reduced while the next one is computed.  Measured on 2 x B200 (r01) this does NOT pay with NCCL:
+        its kernels cannot co-reside with the persistent 148-CTA GEMM (registers), so the ranges serialise and
+        three small all-reduces cost more than one large one -- hence the default of 1; the knob stays for
+        communication back-ends that do not need SMs.  ``comm_dtype=torch.bfloat16`` halves the bytes on
+        NVLink by rounding each rank's gradient before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
         After this call ``.grad`` is already the global average: do not wrap the module in DDP as well."""
         import torch.distributed as dist
 

@@ -46,6 +46,17 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def profile_traffic(launcher):
+    """dram read + write bytes per launch of the launcher's main kernel, from the committed ncu capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py from `ncu --set full`); None if not captured."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(launcher, {}).get("dram_bytes")
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -357,7 +368,7 @@ def run_b200_train(args):
     dom = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms"])
     roof = dict(kernels[dom])
     roof.pop("ms")
-    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": None,
+    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom),
                  "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; "
                                 + ("bf16_tflops_sustained: kernel timed inside the step" if roof["bound"] == "tensor"
                                    else "hbm_gbs") + ")"})
@@ -386,6 +397,236 @@ def run_b200_train(args):
     finish(world)
 
 
+# ------------------------------------------------------------------------------------------------
+# Serving workload (BASELINE configs[2] / [4]): SuperGuessr serving forward -> ProtoRefiner on a geocell-sharded
+# prototype bank.  Not the default bench line (configs[1] is); run with --workload infer.
+INFER = dict(B=65536, D=1024, V=4, k=5)
+
+
+def infer_config(n_gpus, cfg, P, B):
+    return {"workload": f"BASELINE configs[{2 if P <= 1_000_000 else 4}]: SuperGuessr serving + ProtoRefiner retrieval vs "
+                        f"{P} synthetic prototypes sharded by geocell, top-{cfg['k']} cells",
+            "queries_per_batch": B, "prototypes": P, "embed_dim": cfg["D"], "headings": cfg["V"], "geocells": C_CELLS,
+            "parallelism": f"queries split {n_gpus}-way in front of a bank sharded {n_gpus}-way by geocell",
+            "l2": "every batch streams the whole local bank shard (>= 0.25 GB) and 1 GB of embeddings: far beyond the "
+                  "126 MB L2"}
+
+
+def make_local_bank(P, D, rank, world, dev, cent):
+    """Synthetic CSR bank, rows of this rank's geocell range only (generated on the device)."""
+    from geoguessr_ai_b200 import shard_cells, synth
+
+    sizes = synth.cell_sizes(C_CELLS, P, seed=0, mode="skewed")
+    off = np.zeros(C_CELLS + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    lo, hi = shard_cells(off, world)[rank]
+    p0, p1 = int(off[lo]), int(off[hi])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    bank = torch.empty((p1 - p0, D), dtype=torch.bfloat16, device=dev)
+    for a in range(0, p1 - p0, 1 << 20):
+        b = min(p1 - p0, a + (1 << 20))
+        bank[a:b] = torch.randn((b - a, D), device=dev, generator=gen).to(torch.bfloat16)
+    cell_of = torch.repeat_interleave(torch.arange(lo, hi, device=dev), torch.from_numpy(sizes[lo:hi]).to(dev))
+    coords = cent.to(dev)[cell_of] + (torch.rand((p1 - p0, 2), device=dev, generator=gen) - 0.5)
+    return torch.from_numpy(off.astype(np.int32)), bank, coords.float(), (lo, hi, p0, p1)
+
+
+def cpu_reference_infer(model_w, model_b, cent, emb, refiner, nq):
+    """The reference's serving path restated by the oracle on `nq` queries: eager CPU head + the Python
+    (query x candidate) loop of ProtoRefiner.forward.  Prototypes of the cells those queries touch are copied
+    back from the device bank.  Returns (queries/s, cores)."""
+    from oracle import proto_refiner_oracle as pro
+    from oracle import super_guessr_oracle as sgo
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    e = emb[:nq].float().cpu()
+    W, b = model_w.detach().float().cpu(), model_b.detach().float().cpu()
+    out = sgo.forward(e, W, b, cent, None, torch.zeros(nq, dtype=torch.int64))  # warm-up + candidates
+    cells = sorted(set(out.top5_geocells.indices.flatten().tolist()))
+    off = refiner.cell_off.cpu().tolist()
+    protos, coords = [None] * C_CELLS, [None] * C_CELLS
+    for c in cells:
+        if refiner.cell_lo <= c < refiner.cell_hi:
+            a, z = off[c - refiner.cell_lo], off[c - refiner.cell_lo + 1]
+            if z > a:
+                protos[c] = refiner.bank[a:z].float().cpu()
+                coords[c] = refiner.bank_coords[a:z].cpu()
+    t0 = time.perf_counter()
+    out = sgo.forward(e, W, b, cent, None, torch.zeros(nq, dtype=torch.int64))
+    pro.forward(e, out.preds_LLH, out.top5_geocells.indices, out.top5_geocells.values.detach(), protos, coords, topk=5)
+    dt = time.perf_counter() - t0
+    return nq / dt, torch.get_num_threads()
+
+
+def run_b200_infer(args):
+    import contextlib
+    import io
+
+    import torch.distributed as dist
+
+    import geoguessr_ai_b200 as gg
+    from geoguessr_ai_b200 import ops
+    from geoguessr_ai_b200.geocells import load_packaged_centroids
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = INFER
+    D, V, k = cfg["D"], cfg["V"], cfg["k"]
+    B, P = args.batch, args.protos
+    assert B % world == 0
+    Bl = B // world
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    cent = load_packaged_centroids()
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = gg.SuperGuessr(None, panorama=True, serving=True, embed_dim=D, centroids=cent, num_candidates=k).to(dev)
+    torch.manual_seed(0)  # same head on every rank
+    with torch.no_grad():
+        model.cell_layer.weight.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
+        model.cell_layer.bias.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
+    model.eval()
+    off, bank, coords, (lo, hi, p0, p1) = make_local_bank(P, D, rank, world, dev, cent)
+    refiner = gg.ProtoRefiner(topk=k, protos="bank", bank=(off, bank, coords), shard=(rank, world),
+                              split_queries=world > 1, bank_is_local=True, report_changed=False, device=dev)
+    del bank, coords
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77 + rank)
+    resident = [torch.randn((Bl, V, D), device=dev, generator=gen) for _ in range(2)]
+    host = [r.cpu().pin_memory() for r in resident[:1]]
+
+    def step(emb):
+        llh, topk, _ = model(embedding=emb)
+        _, r_llh, r_cell = refiner(emb, llh, topk.indices, topk.values)
+        return r_llh, r_cell
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    for i in range(Wm):
+        step(resident[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        out = step(resident[i % 2])
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / K
+    clocks = sampler.stop() if rank == 0 else None
+    value = B / (ms_step / 1e3)
+
+    ops.enable_timing(True)
+    barrier()
+    for i in range(min(K, 5)):
+        torch.cuda._sleep(40_000_000)
+        step(resident[i % 2])
+    tms = ops.timing_ms()
+    ops.enable_timing(False)
+    per = {kk: sum(v) / len(v) for kk, v in tms.items()}
+    calls = {kk: len(v) // min(K, 5) for kk, v in tms.items()}
+
+    # end to end: the batch crosses PCIe from pinned memory, results come back to the host
+    copy_stream = torch.cuda.Stream()
+    bufs = [torch.empty_like(resident[0]) for _ in range(2)]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    res_host = (torch.empty((Bl, 2), dtype=torch.float32).pin_memory(), torch.empty((Bl,), dtype=torch.int64).pin_memory())
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2].copy_(host[0], non_blocking=True)
+            evs[i % 2].record(copy_stream)
+
+    def e2e_loop(n):
+        issue_copy(0)
+        for i in range(n):
+            torch.cuda.current_stream().wait_event(evs[i % 2])
+            r_llh, r_cell = step(bufs[i % 2])
+            if i + 1 < n:
+                issue_copy(i + 1)
+            res_host[0].copy_(r_llh, non_blocking=True)
+            res_host[1].copy_(r_cell, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    Ke = max(3, min(K, 10))
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(Ke)
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / Ke
+    h2d = host[0].numel() * 4
+    d2h = Bl * (8 + 8)
+
+    if rank != 0:
+        finish(world)
+        return
+
+    peaks = measured_peaks()
+    P_local = p1 - p0
+    algo = {
+        "gg_head_fwd": ("tensor", 2.0 * Bl * C_CELLS * D, "TFLOP/s"),
+        # bank shard read once + grouped queries written and read + records
+        "gg_proto_retrieve": ("hbm", P_local * D * 2.0 + 3.0 * B * k * D * 2 + B * k * 16, "GB/s"),
+        "gg_fuse_headings": ("hbm", Bl * D * (4 * V + 2.0), "GB/s"),
+        "gg_proto_refine": ("hbm", (world * k * 16 + k * 12 + 24.0) * Bl, "GB/s"),
+    }
+    kernels = {}
+    for name, ms in per.items():
+        n = max(1, calls.get(name, 1))
+        if name in algo:
+            bound, work, unit = algo[name]
+            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+            peak = peaks["tf_sustained"] if bound == "tensor" else peaks["hbm"]
+            kernels[name] = {"ms": ms, "calls_per_step": n, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                             "frac": ach / peak}
+        else:
+            kernels[name] = {"ms": ms, "calls_per_step": n}
+    dom = max((kk for kk in kernels if "frac" in kernels[kk]), key=lambda kk: kernels[kk]["ms"] * kernels[kk]["calls_per_step"])
+    roof = {kk: v for kk, v in kernels[dom].items() if kk not in ("ms", "calls_per_step")}
+    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom),
+                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})"})
+    cpu = None
+    if not args.no_cpu:
+        nq = 256
+        cval, cores = cpu_reference_infer(model.cell_layer.weight, model.cell_layer.bias, cent, resident[0], refiner, nq)
+        cpu = {"value": cval, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{nq} queries of the same batch through the oracle (eager CPU head + the reference's Python "
+                         "(query x candidate) refiner loop); prototypes of the touched cells copied from the device bank"
+                         + ("" if world == 1 else "; cells owned by other ranks count as missing")}
+    launches = 2 + 2 + 1 + 6 + 1  # fuse, head (GEMM + merge), refiner fuse, retrieval (memset + 5 kernels), refine
+    line = {
+        "metric": "geolocation queries/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": infer_config(world, cfg, P, B), "clocks": clocks,
+        "e2e": {"value": B / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": Ke},
+        "gpu_launches": launches * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    finish(world)
+
+
 def finish(world):
     """Multi-rank exit: tearing NCCL communicators down while CUDA graphs that captured collectives are alive can
     block; everything is measured and printed by now, so leave without running destructors."""
@@ -402,7 +643,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train = BASELINE configs[1] (the bench line); infer = serving + sharded prototype retrieval")
+    ap.add_argument("--protos", type=int, default=1_000_000, help="infer: total prototypes (configs[2]: 1e6, configs[4]: 1e7)")
+    ap.add_argument("--batch", type=int, default=65536, help="infer: queries per batch over all GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
     ap.add_argument("--dp-chunks", type=int, default=1, help="geocell ranges of the overlapped dW GEMM + all-reduce (N > 1)")
     ap.add_argument("--dp-bf16", action="store_true", help="all-reduce the gradients in bf16 (opt-in, N > 1)")
@@ -410,6 +654,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        run_b200_infer(args)
     else:
         run_b200_train(args)
 

@@ -64,6 +64,8 @@ class ProtoRefiner(nn.Module):
         bank: tuple | None = None,
         shard: tuple | None = None,
         process_group=None,
+        split_queries: bool = False,
+        bank_is_local: bool = False,
         report_changed: bool = True,
         device="cuda",
     ):
@@ -75,7 +77,13 @@ class ProtoRefiner(nn.Module):
             carrying ``embedding``, ``centroid_lng``, ``centroid_lat``.
         bank=(cell_off, bank, coords): the CSR form directly (any float dtype; stored as bf16).
         shard=(rank, world): keep only this rank's geocell range; ``process_group`` is the
-            torch.distributed group used for the all-gather (default group if None).
+            torch.distributed group used for the exchange (default group if None).
+        split_queries: with a sharded bank, every rank passes a DIFFERENT, equally sized slice of the query
+            batch (data-parallel serving in front of the refiner).  forward() then all-gathers the fused bf16
+            queries + candidate lists, retrieves on the local shard for all of them, and returns each rank
+            the records of its own queries with one all-to-all.  False: every rank passes the same batch
+            (records merged with one all-gather).
+        bank_is_local: ``bank`` / ``coords`` already hold only this rank's rows (``cell_off`` stays global).
         """
         super().__init__()
         self.topk = topk
@@ -83,6 +91,7 @@ class ProtoRefiner(nn.Module):
         self.verbose = verbose
         self.report_changed = report_changed
         self.process_group = process_group
+        self.split_queries = bool(split_queries)
         self.temperature = Parameter(torch.tensor(float(temperature)), requires_grad=False)
         self.geo_scaling = Parameter(torch.tensor(20.0), requires_grad=False)
         self._temperature_host = float(temperature)
@@ -100,7 +109,7 @@ class ProtoRefiner(nn.Module):
                 "protos=None asks the reference to BUILD prototypes from images (embedders + S3, "
                 "proto_refiner.py:89-103); that offline job is outside this package. Pass protos='load', "
                 "protos=[...]+coords=[...], or bank=(cell_off, bank, coords).")
-        self._install_bank(cell_off, mat, xy, shard, device)
+        self._install_bank(cell_off, mat, xy, shard, device, bank_is_local)
 
     # ---- bank construction ------------------------------------------------------------------
     @classmethod
@@ -144,7 +153,7 @@ class ProtoRefiner(nn.Module):
             coords.append(torch.stack([ds["centroid_lng"].float(), ds["centroid_lat"].float()], 1))
         return ProtoRefiner._csr_from_lists(protos, coords)
 
-    def _install_bank(self, cell_off, mat, xy, shard, device):
+    def _install_bank(self, cell_off, mat, xy, shard, device, bank_is_local=False):
         cell_off_cpu = torch.as_tensor(cell_off).to(torch.int64).cpu().numpy()
         self.num_geocells = len(cell_off_cpu) - 1
         self.num_protos_total = int(cell_off_cpu[-1])
@@ -157,9 +166,13 @@ class ProtoRefiner(nn.Module):
         self.proto_base = p0
         local_off = torch.from_numpy((cell_off_cpu[lo:hi + 1] - p0).astype(np.int32))
         dev = torch.device(device)
-        bank16 = mat[p0:p1].to(device=dev, dtype=torch.bfloat16).contiguous()
+        if bank_is_local:
+            assert mat.shape[0] == p1 - p0 and len(xy) == p1 - p0, "local bank does not match this rank's geocell range"
+        else:
+            mat, xy = mat[p0:p1], xy[p0:p1]
+        bank16 = mat.to(device=dev, dtype=torch.bfloat16).contiguous()
         self.register_buffer("bank", bank16, persistent=False)
-        self.register_buffer("bank_coords", torch.as_tensor(xy[p0:p1], dtype=torch.float32).to(dev).contiguous(),
+        self.register_buffer("bank_coords", torch.as_tensor(xy, dtype=torch.float32).to(dev).contiguous(),
                              persistent=False)
         self.register_buffer("cell_off", local_off.to(dev), persistent=False)
         self.register_buffer("bank_sqnorm",
@@ -176,14 +189,21 @@ class ProtoRefiner(nn.Module):
         return rep
 
     # ---- forward (proto_refiner.py:129-237) -------------------------------------------------
-    def retrieve(self, embedding: Tensor, candidate_cells: Tensor) -> Tensor:
-        """Stage 0+1 on this rank's shard: (B*topk, 4) records."""
+    def _fuse(self, embedding: Tensor):
         q16, qn = ops.fuse_headings(embedding, split=False, want_sqnorm=True)  # :150-151 mean over headings
         if q16.shape[1] != self.embed_dim:
             raise ValueError(f"embedding dim {q16.shape[1]} != prototype dim {self.embed_dim}")
+        return q16, qn
+
+    def _retrieve(self, q16, qn, candidate_cells):
         bank = self.bank if self.bank.shape[0] > 0 else None
         return ops.proto_retrieve(q16, qn, candidate_cells, self.topk, bank, self.bank_sqnorm, self.bank_coords,
                                   self.cell_off, self.cell_lo, self.cell_hi, self.proto_base)
+
+    def retrieve(self, embedding: Tensor, candidate_cells: Tensor) -> Tensor:
+        """Stage 0+1 on this rank's shard: (B*topk, 4) records."""
+        q16, qn = self._fuse(embedding)
+        return self._retrieve(q16, qn, candidate_cells)
 
     def forward(self, embedding: Tensor = None, initial_preds: Tensor = None, candidate_cells: Tensor = None,
                 candidate_probs: Tensor = None, return_debug: bool = False):
@@ -199,14 +219,33 @@ class ProtoRefiner(nn.Module):
         temperature = self._temperature_host  # host copy of the frozen parameter: no device sync per call
         loss = 0 if self.training else None
 
-        rec = self.retrieve(embedding, candidate_cells)
+        q16, qn = self._fuse(embedding)
         nranks = 1
-        if self.world > 1:
+        if self.world == 1:
+            rec = self._retrieve(q16, qn, candidate_cells)
+        else:
             import torch.distributed as dist
 
-            gathered = torch.empty((self.world,) + tuple(rec.shape), dtype=rec.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, rec, group=self.process_group)
-            rec, nranks = gathered, self.world
+            pg, N = self.process_group, self.world
+            if self.split_queries:
+                # every rank holds B/N of the queries: all ranks need all fused queries + candidate lists
+                Bl = q16.shape[0]
+                cand_l = candidate_cells[:, :self.topk].to(torch.int64).contiguous()
+                q_all = torch.empty((N * Bl, q16.shape[1]), dtype=q16.dtype, device=dev)
+                qn_all = torch.empty((N * Bl,), dtype=qn.dtype, device=dev)
+                cand_all = torch.empty((N * Bl, self.topk), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(q_all, q16, group=pg)
+                dist.all_gather_into_tensor(qn_all, qn, group=pg)
+                dist.all_gather_into_tensor(cand_all, cand_l, group=pg)
+                rec_all = self._retrieve(q_all, qn_all, cand_all)  # (N*Bl*topk, 4), rank-major over query owners
+                rec = torch.empty_like(rec_all)  # chunk i = rank i's records of MY queries
+                dist.all_to_all_single(rec, rec_all, group=pg)
+                rec = rec.view(N, Bl * self.topk, 4)
+            else:
+                local = self._retrieve(q16, qn, candidate_cells)
+                rec = torch.empty((N,) + tuple(local.shape), dtype=local.dtype, device=dev)
+                dist.all_gather_into_tensor(rec, local, group=pg)
+            nranks = N
         out = ops.proto_refine(rec, nranks, candidate_cells, candidate_probs, initial_preds, self.topk, temperature,
                                float(self.max_refinement), want_debug=return_debug)
         preds_llh, preds_geocell, guess_index = out[:3]

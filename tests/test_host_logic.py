@@ -124,6 +124,56 @@ def test_sharded_retrieval_merge_gloo_world2():
     assert same_score and same_idx and owners == 1  # exactly one rank owns each pair's cell
 
 
+def _split_worker(rank, world, port, q):
+    """split_queries=True exchange (ProtoRefiner.forward): all-gather queries, retrieve on the shard for all of
+    them, all-to-all the records back to the query owners, merge by selection."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C, D, Bl, k = 300, 32, 24, 5
+    sizes = synth.cell_sizes(C, 2000, seed=4, mode="skewed", missing_frac=0.05)
+    off, bank, xy = synth.proto_bank(sizes, D, None, seed=4)
+    rng = np.random.default_rng(5)
+    emb_all = torch.from_numpy(rng.standard_normal((world * Bl, D), dtype=np.float32))
+    cand_all_ref = torch.from_numpy(rng.integers(0, C, (world * Bl, k)))
+    emb, cand = emb_all[rank * Bl:(rank + 1) * Bl].contiguous(), cand_all_ref[rank * Bl:(rank + 1) * Bl].contiguous()
+    protos, _ = synth.bank_as_lists(off, bank, xy)
+    lo, hi = shard_cells(off.numpy().astype(np.int64), world)[rank]
+    local = [p if lo <= c < hi else None for c, p in enumerate(protos)]
+    # forward(): gather queries + candidates
+    q_all, c_all = torch.empty(world * Bl, D), torch.empty(world * Bl, k, dtype=torch.int64)
+    dist.all_gather_into_tensor(q_all, emb)
+    dist.all_gather_into_tensor(c_all, cand)
+    score, idx, _ = pro.best_per_candidate(q_all, c_all, local, k)  # what the retrieval kernel leaves on this shard
+    owned = (c_all >= lo) & (c_all < hi)
+    score = torch.where(owned, score, torch.full_like(score, -float("inf")))
+    rec_all = torch.stack([score, idx.float()], -1).reshape(world * Bl * k, 2).contiguous()
+    rec = torch.empty_like(rec_all)
+    dist.all_to_all_single(rec, rec_all)
+    g = rec.view(world, Bl, k, 2)  # the layout gg_proto_refine consumes for this rank's queries
+    best = g[..., 0].argmax(0)
+    merged = torch.gather(g, 0, best[None, ..., None].expand(1, Bl, k, 2))[0]
+    full_score, full_idx, _ = pro.best_per_candidate(emb, cand, protos, k)
+    ok = torch.equal(q_all, emb_all) and torch.equal(merged[..., 0], full_score) and torch.equal(merged[..., 1].long(), full_idx)
+    res = torch.tensor([1 if ok else 0])
+    dist.all_reduce(res)
+    if rank == 0:
+        q.put(int(res))
+    dist.destroy_process_group()
+
+
+def test_split_query_exchange_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    oks = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    assert oks == 2  # both ranks recover, for their own queries, exactly the unsharded result
+
+
 def _dp_worker(rank, world, port, q):
     """Data-parallel head step: averaged per-rank gradients == gradient of the global batch."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

@@ -638,6 +638,9 @@ def finish(world):
 
 
 def main():
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; the bench contract is ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

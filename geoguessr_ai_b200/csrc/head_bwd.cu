@@ -4,12 +4,24 @@
 // main_coordinator_idun_s3.py:423).  Both operands are consumed in the layout the forward pass
 // left them in -- dlogits (B, ldc) and x (B, D), batch-major -- i.e. as MN-major UMMA operands:
 // the contraction index (batch) is the slow index of both.  TMA loads 64(k) x 64(mn) boxes with
-// the 128-byte swizzle; a 128 x 256 x 64 stage is 2 + 4 such boxes.
+// the 128-byte swizzle.
 //
-// CTA pairs (clusters of two): the CTAs of a pair own vertically adjacent geocell blocks of the same 256
-// embedding columns, so they contract against the SAME x tile.  Each loads two of its four boxes and TMA
-// multicasts them into both CTAs' shared memory: 32 KB instead of 48 KB per CTA and k-block through the
-// L2 -> SM fabric.  A stage is recycled when both CTAs' MMAs have read it (tcgen05.commit multicast).
+// CTA pairs (tcgen05 cta_group::2): a cluster of two CTAs on the two SMs of a TPC executes one
+// 256 (geocells) x 256 (embedding columns) x 16 MMA; each CTA holds its own 128 geocells of dlogits
+// (2 boxes) and HALF of the x tile (2 of 4 boxes) per 64-row k-block -- 32 KB per CTA and stage, six
+// stages -- and its 128 x 256 half of the accumulator in its own TMEM (double buffered).  The pair
+// leader issues the MMAs; both CTAs' loads signal the leader's `full` barrier.
+//
+// Schedule: whole rounds of pair-tiles are handed out round-robin (pair p takes tiles p, p + P, ...: the
+// pairs that run concurrently work on the few geocell blocks whose dlogits then sit in L2, so dlogits is
+// streamed from HBM once).  The last, incomplete round is cut stream-K style: its (tile, k-block) units
+// are split into one contiguous, equally long range per pair (at cfg2: 200 pair-tiles over 74 pairs = 2
+// whole rounds + 52 tiles x 64 k-blocks = 45 units per pair instead of a third, 70 %-idle round).  A pair
+// walks its range downwards.  A tile that straddles two ranges is finished by the HIGHER pair: the lower
+// pair meets its part first, parks the raw fp32 partial in the workspace and raises a flag; the higher pair
+// reaches its part last, adds the parked partial in its epilogue and writes dW.  Waits therefore only ever
+// point at lower-numbered, earlier-scheduled pairs that did the awaited work first: no deadlock, and a fixed
+// summation order (deterministic).
 #include <algorithm>
 
 #include "common.cuh"
@@ -17,14 +29,15 @@
 
 namespace gg {
 
-constexpr int kWM = 128;  // geocells per tile (UMMA M)
-constexpr int kWN = 256;  // embedding columns per tile (UMMA N)
+constexpr int kWM = 128;  // geocells per CTA (UMMA M = 256 over the pair)
+constexpr int kWN = 256;  // embedding columns per pair tile (UMMA N; 128 per CTA in shared memory)
 constexpr int kWK = 64;   // batch rows per stage
-constexpr int kWStages = 4;
+constexpr int kWStages = 6;
 constexpr int kBwdThreads = 192;
 constexpr uint32_t kAtomBytes = kWK * 128;                 // 64 k-rows x 128 B
-constexpr uint32_t kWStageA = (kWM / 64) * kAtomBytes;     // 16 KB
-constexpr uint32_t kWStageB = (kWN / 64) * kAtomBytes;     // 32 KB
+constexpr uint32_t kWStageA = (kWM / 64) * kAtomBytes;     // 16 KB: my 128 geocells
+constexpr uint32_t kWStageB = (kWN / 128) * kAtomBytes;    // 16 KB: my half of the embedding columns
+constexpr size_t kPartialFloats = static_cast<size_t>(kWM) * kWN;  // one CTA's parked accumulator half
 
 struct BwdSmem {
   uint8_t a[kWStages][kWStageA];
@@ -36,11 +49,45 @@ struct BwdSmem {
   uint32_t tmem_base;
 };
 
+// A pair's work list: `rounds` whole tiles (pair, pair + P, ...), then its range of the tail round's units.
+struct PairSchedule {
+  int pair, npairs, num_k, rounds, tail_base;
+  long long tail_total;
+  long long u0, u1;  // tail units [u0, u1): unit = tail_tile * num_k + k-block
+  __device__ PairSchedule(int pair_, int npairs_, int num_tiles, int nk)
+      : pair(pair_), npairs(npairs_), num_k(nk) {
+    rounds = num_tiles / npairs;
+    tail_base = rounds * npairs;
+    tail_total = static_cast<long long>(num_tiles - tail_base) * nk;
+    u0 = tail_total * pair / npairs;
+    u1 = tail_total * (pair + 1) / npairs;
+  }
+  // the pair whose range ends where mine begins (owner of tail unit u0 - 1): with few tail units most ranges
+  // are empty, so this need not be pair - 1
+  __device__ int lower_neighbour() const {
+    const long long total = tail_total;
+    if (u0 <= 0 || total <= 0) return -1;
+    return static_cast<int>((u0 * npairs + total - 1) / total) - 1;  // ceil(u0 * P / total) - 1
+  }
+  __device__ int segments() const {
+    return rounds + (u1 > u0 ? static_cast<int>((u1 - 1) / num_k - u0 / num_k) + 1 : 0);
+  }
+  // i-th segment: tile and k-block range [k0, k1)
+  __device__ void get(int i, int& tile, int& k0, int& k1) const {
+    if (i < rounds) { tile = i * npairs + pair; k0 = 0; k1 = num_k; return; }
+    const int t = static_cast<int>((u1 - 1) / num_k) - (i - rounds);  // tail tiles from the top of the range down
+    const long long base = static_cast<long long>(t) * num_k;
+    k0 = static_cast<int>((u0 > base ? u0 : base) - base);
+    k1 = static_cast<int>((u1 < base + num_k ? u1 : base + num_k) - base);
+    tile = tail_base + t;
+  }
+};
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
 head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, rows B
                 const __grid_constant__ CUtensorMap tm_x,  // x:       inner D, rows B
                 float* __restrict__ dW, int C, int D, int Bk, float scale_in,
-                const float* __restrict__ grad_scale) {
+                const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -51,126 +98,170 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int num_k = (Bk + kWK - 1) / kWK;
   const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
+  const PairSchedule ps(pair, npairs, num_tiles, num_k);
+  const int nseg = ps.segments();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_g);
     tma_prefetch_desc(&tm_x);
     for (int s = 0; s < kWStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 2);  // this CTA's MMAs and the partner's
+      mbar_init(&sm.full[s], 1);   // leader's: its own arrive.expect_tx, bytes from both CTAs' loads
+      mbar_init(&sm.empty[s], 1);  // one multicast commit per round
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sm.acc_full[a], 1);
-      mbar_init(&sm.acc_empty[a], 128);
+      mbar_init(&sm.acc_empty[a], 2 * 4);  // leader's: one arrive per epilogue warp of BOTH CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(&sm.tmem_base, 512);
-    tmem_relinquish();
+  if (warp == 1) {  // collective over the pair: one warp in each CTA
+    tmem_alloc_pair(&sm.tmem_base, 512);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
-  cluster_sync();  // the partner's barriers exist before anything is multicast to them
+  cluster_sync();  // the partner's barriers exist before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
-  // tile order: the num_n column tiles of one geocell block are adjacent, so the CTAs that run
-  // concurrently share the dlogits tile through L2 and dlogits is streamed from HBM once.
-  if (warp == 0) {
-    // TMA producer: warp-uniform loop, one elected lane issues
-    int s = 0;
-    uint32_t ph = 0;
-    for (int t = pair; t < num_tiles; t += npairs) {
-      const int m0 = (2 * (t / num_n) + crank) * kWM, n0 = (t % num_n) * kWN;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&sm.empty[s], ph ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&sm.full[s], kWStageA + kWStageB);
+  {
+    if (warp == 0) {
+      // ===== TMA producer: warp-uniform loop, one elected lane issues =====
+      const uint32_t leader_full = mapa_u32(smem_u32(&sm.full[0]), 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nseg; ++i) {
+        int t, k0, k1;
+        ps.get(i, t, k0, k1);
+        const int m0 = (2 * (t / num_n) + crank) * kWM, n0 = (t % num_n) * kWN + crank * (kWN / 2);
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(&sm.empty[s], ph ^ 1);
+          if (elect_one()) {
+            if (crank == 0) mbar_arrive_expect_tx(&sm.full[s], 2 * (kWStageA + kWStageB));
 #pragma unroll
-          for (int i = 0; i < kWM / 64; ++i)
-            tma_load_2d(sm.a[s] + i * kAtomBytes, &tm_g, &sm.full[s], m0 + 64 * i, kb * kWK);
+            for (int i = 0; i < kWM / 64; ++i)  // my 128 geocells
+              tma_load_2d_pair(sm.a[s] + i * kAtomBytes, &tm_g, leader_full + 8 * s, m0 + 64 * i, kb * kWK);
 #pragma unroll
-          for (int i = 0; i < kWN / 128; ++i) {  // my half of the x tile's boxes, delivered to both CTAs
-            const int atom = crank * (kWN / 128) + i;
-            tma_load_2d_multicast(sm.b[s] + atom * kAtomBytes, &tm_x, &sm.full[s], n0 + 64 * atom, kb * kWK, 0x3);
+            for (int i = 0; i < kWN / 128; ++i)  // my half of the embedding columns
+              tma_load_2d_pair(sm.b[s] + i * kAtomBytes, &tm_x, leader_full + 8 * s, n0 + 64 * i, kb * kWK);
+          }
+          __syncwarp();
+          if (++s == kWStages) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer: pair leader only; warp-uniform loop, one elected lane issues =====
+      if (crank == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * kWM, kWN, 1, 1);
+        // 16 k-rows of 128 B per MMA; atoms (64 mn-elements) kAtomBytes apart; 8-row groups 1024 B apart
+        const uint64_t da_base = umma_desc_sw128(smem_u32(sm.a[0]), kAtomBytes, 1024);
+        const uint64_t db_base = umma_desc_sw128(smem_u32(sm.b[0]), kAtomBytes, 1024);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (; it < nseg; ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_ph = (it >> 1) & 1;
+          int t, k0, k1;
+          ps.get(it, t, k0, k1);
+          mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);  // both CTAs' epilogues have drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kWN;
+          for (int kb = k0; kb < k1; ++kb) {
+            mbar_wait(&sm.full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = da_base + static_cast<uint64_t>(s * (kWStageA >> 4));
+              const uint64_t db = db_base + static_cast<uint64_t>(s * (kWStageB >> 4));
+              umma_pair_f16(d_tmem, da, db, idesc, kb != k0);
+#pragma unroll
+              for (int k = 1; k < kWK / 16; ++k)
+                umma_pair_f16_acc(d_tmem, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc);
+              umma_pair_commit(&sm.empty[s], 0x3);
+              if (kb == k1 - 1) umma_pair_commit(&sm.acc_full[acc], 0x3);
+            }
+            __syncwarp();
+            if (++s == kWStages) { s = 0; ph ^= 1; }
           }
         }
-        __syncwarp();
-        if (++s == kWStages) { s = 0; ph ^= 1; }
       }
-    }
-  } else if (warp == 1) {
-    // MMA issuer: warp-uniform loop, one elected lane issues
-    constexpr uint32_t idesc = umma_idesc_bf16(kWM, kWN, 1, 1);
-    // 16 k-rows of 128 B per MMA; atoms (64 mn-elements) kAtomBytes apart; 8-row groups 1024 B apart
-    const uint64_t da_base = umma_desc_sw128(smem_u32(sm.a[0]), kAtomBytes, 1024);
-    const uint64_t db_base = umma_desc_sw128(smem_u32(sm.b[0]), kAtomBytes, 1024);
-    int s = 0;
-    uint32_t ph = 0;
-    int it = 0;
-    for (int t = pair; t < num_tiles; t += npairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
-      mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kWN;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&sm.full[s], ph);
+    } else {
+      // ===== epilogue: 4 warps, thread = one geocell row of this CTA's accumulator half =====
+      const int quad = warp & 3;
+      const int rit = quad * 32 + lane;  // row in tile
+      const uint32_t leader_acc_empty = mapa_u32(smem_u32(&sm.acc_empty[0]), 0);
+      // parked partials: [pair][cta][column][row] so that a warp's accesses are contiguous
+      float* const my_park = parked + (static_cast<size_t>(pair) * 2 + crank) * kPartialFloats + rit;
+      const int lower = ps.lower_neighbour();  // whose parked partial a straddling first tile continues
+      const float* const prev_park = parked + (static_cast<size_t>(lower < 0 ? 0 : lower) * 2 + crank) * kPartialFloats + rit;
+      int it = 0;
+      for (; it < nseg; ++it) {
+        int t, k0, k1;
+        ps.get(it, t, k0, k1);
+        const int m0 = (2 * (t / num_n) + crank) * kWM, n0 = (t % num_n) * kWN;
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        const int row = m0 + rit;
+        const bool add_prev = k0 > 0;      // the lower pair parked the first k-blocks of this tile
+        const bool park = k1 < num_k;      // the higher pair finishes this tile
+        mbar_wait(&sm.acc_full[acc], acc_ph);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = da_base + static_cast<uint64_t>(s * (kWStageA >> 4));
-          const uint64_t db = db_base + static_cast<uint64_t>(s * (kWStageB >> 4));
-          umma_f16(d_tmem, da, db, idesc, kb != 0);
-#pragma unroll
-          for (int k = 1; k < kWK / 16; ++k) umma_f16_acc(d_tmem, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc);
-          umma_commit_multicast(&sm.empty[s], 0x3);
-          if (kb == num_k - 1) umma_commit(&sm.acc_full[acc]);
+        if (add_prev) {  // (set long ago: the lower pair did that part first)
+          if (threadIdx.x == 64) {
+            const long long t0 = clock64();
+            while (atomicAdd(&flags[lower * 2 + crank], 0) == 0) {
+              __nanosleep(64);
+              if (clock64() - t0 > 8000000000LL) { printf("gg: head_bwd partial of pair %d never arrived\n", lower); __trap(); }
+            }
+            __threadfence();
+          }
+          named_bar_sync(1, 128);
         }
-        __syncwarp();
-        if (++s == kWStages) { s = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    const int quad = warp & 3;
-    int it = 0;
-    for (int t = pair; t < num_tiles; t += npairs, ++it) {
-      const int m0 = (2 * (t / num_n) + crank) * kWM, n0 = (t % num_n) * kWN;
-      const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
-      const int row = m0 + quad * 32 + lane;
-      mbar_wait(&sm.acc_full[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kWN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kWN;
 #pragma unroll 1
-      for (int c = 0; c < kWN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < C) {
-          float* dst = dW + static_cast<size_t>(row) * D + col0;
+        for (int c = 0; c < kWN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (add_prev) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (col0 + 4 * q + 4 <= D) {
-              float4 o;
-              o.x = __uint_as_float(r[4 * q + 0]) * scale;
-              o.y = __uint_as_float(r[4 * q + 1]) * scale;
-              o.z = __uint_as_float(r[4 * q + 2]) * scale;
-              o.w = __uint_as_float(r[4 * q + 3]) * scale;
-              *reinterpret_cast<float4*>(dst + 4 * q) = o;
+            for (int j = 0; j < 32; ++j)
+              r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(prev_park + static_cast<size_t>(c * 32 + j) * kWM));
+          }
+          if (park) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcg(my_park + static_cast<size_t>(c * 32 + j) * kWM, __uint_as_float(r[j]));
+          } else if (row < C) {
+            float* dst = dW + static_cast<size_t>(row) * D + col0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (col0 + 4 * q + 4 <= D) {
+                float4 o;
+                o.x = __uint_as_float(r[4 * q + 0]) * scale;
+                o.y = __uint_as_float(r[4 * q + 1]) * scale;
+                o.z = __uint_as_float(r[4 * q + 2]) * scale;
+                o.w = __uint_as_float(r[4 * q + 3]) * scale;
+                *reinterpret_cast<float4*>(dst + 4 * q) = o;
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
+        if (park) {  // publish: every epilogue thread's stores, then the flag
+          __threadfence();
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 64) atomicExch(&flags[pair * 2 + crank], 1);
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&sm.acc_empty[acc]);
     }
   }
   tc_fence_before();
-  cluster_sync();  // the partner may still be multicasting into / arriving on this CTA's shared memory
+  cluster_sync();  // the partner may still be signalling this CTA's barriers / the leader reading its operands
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -236,7 +327,12 @@ __global__ void db_final_kernel(const float* __restrict__ partial, int C, int ld
 
 using namespace gg;
 
-extern "C" size_t gg_head_bwd_workspace_bytes(int C) { return static_cast<size_t>(kDbSlices) * C * sizeof(float); }
+// workspace: [flags: one int per CTA][parked stream-K partials: 128 x 256 fp32 per CTA][db column-sum slices]
+static size_t bwd_flag_bytes() { return ((static_cast<size_t>(device_sm_count()) * sizeof(int)) + 255) & ~size_t(255); }
+static size_t bwd_park_bytes() { return static_cast<size_t>(device_sm_count()) * kPartialFloats * sizeof(float); }
+extern "C" size_t gg_head_bwd_workspace_bytes(int C) {
+  return bwd_flag_bytes() + bwd_park_bytes() + static_cast<size_t>(kDbSlices) * C * sizeof(float);
+}
 
 extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
                            float scale, const float* grad_scale, float* dW, float* db, const float* db_partials,
@@ -245,7 +341,7 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   GG_CHECK(dlogits_bf16 && x_bf16 && dW, GG_ERR_ARG, "gg_head_bwd: null pointer");
   GG_CHECK(ldc >= C && ldc % 8 == 0, GG_ERR_ARG, "gg_head_bwd: ldc=%d must be >= C and a multiple of 8", ldc);
   GG_CHECK(D % 8 == 0 && x_ld >= D && x_ld % 8 == 0, GG_ERR_ARG, "gg_head_bwd: D=%d / x_ld=%d must be multiples of 8", D, x_ld);
-  GG_CHECK(!db || workspace || db_partials, GG_ERR_ARG, "gg_head_bwd: db needs the workspace or db_partials");
+  GG_CHECK(workspace, GG_ERR_ARG, "gg_head_bwd: workspace (gg_head_bwd_workspace_bytes) is required");
   GG_CHECK(!db_partials || (db_parts > 0 && db_ld >= C), GG_ERR_ARG, "gg_head_bwd: bad db_partials shape");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUtensorMap tm_g, tm_x;
@@ -257,14 +353,18 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   const int pairs = std::max(1, std::min(pair_tiles, device_sm_count() / 2));
   const size_t smem = sizeof(BwdSmem) + 1024;
   if (int e = set_max_dynamic_smem_once(head_bwd_kernel, smem)) return e;
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  int* flags = reinterpret_cast<int*>(wsb);
+  float* parked = reinterpret_cast<float*>(wsb + bwd_flag_bytes());
+  GG_CUDA(cudaMemsetAsync(flags, 0, bwd_flag_bytes(), s));
   // cluster shape (2,1,1) is compiled into the kernel
-  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale);
+  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale, parked, flags);
   GG_LAUNCH_CHECK();
   if (db && db_partials) {  // column sums already accumulated by the loss kernel (one row per CTA)
     db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(db_partials, C, db_ld, db_parts, scale, grad_scale, db);
     GG_LAUNCH_CHECK();
   } else if (db) {
-    float* partial = static_cast<float*>(workspace);
+    float* partial = reinterpret_cast<float*>(wsb + bwd_flag_bytes() + bwd_park_bytes());
     dim3 blk(32, 8), grd(ceil_div(ldc, 256), kDbSlices);
     db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);
     GG_LAUNCH_CHECK();

@@ -237,7 +237,7 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_p
             db = None
     c0, c1 = (0, C) if c_range is None else c_range
     assert 0 <= c0 < c1 <= C and c0 % 8 == 0, "geocell range must start at a multiple of 8"
-    ws = _u8(lib.gg_head_bwd_workspace_bytes(c1 - c0), dev) if (want_db and db_partials is None) else None
+    ws = _u8(lib.gg_head_bwd_workspace_bytes(c1 - c0), dev)
     if not want_db:
         db_partials = None
     if grad_scale is not None:

@@ -114,7 +114,9 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * x (B, x_ld) bf16 (first D columns used).  scale = 1/B (1/global batch under data parallelism);
  * grad_scale: optional DEVICE scalar (the upstream dL/dloss of autograd), multiplied in on the
  * device so that backward needs no host synchronisation.  db_partials (db_parts, db_ld): column
- * sums from gg_hav_ce_fwd_bwd; when null, db is computed from dlogits (needs workspace). */
+ * sums from gg_hav_ce_fwd_bwd; when null, db is computed from dlogits.  workspace
+ * (gg_head_bwd_workspace_bytes(C) bytes, required): parked partial accumulators + flags of the stream-K
+ * schedule, and the column-sum slices of the db pass. */
 int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
                 const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
                 void* workspace, gg_stream_t stream);

@@ -250,3 +250,42 @@ def test_data_parallel_gradient_average_gloo_world2():
     for p in procs:
         p.join(60)
     assert eW < 1e-7 and eb < 1e-7
+
+
+def _bwd_pair_schedule(pair, P, T, nk):
+    """Python mirror of PairSchedule (geoguessr_ai_b200/csrc/head_bwd.cu): whole rounds + stream-K tail."""
+    rounds = T // P
+    base = rounds * P
+    total = (T - base) * nk
+    u0, u1 = total * pair // P, total * (pair + 1) // P
+    segs = [(i * P + pair, 0, nk) for i in range(rounds)]
+    if u1 > u0:
+        for t in range((u1 - 1) // nk, u0 // nk - 1, -1):
+            b = t * nk
+            segs.append((base + t, max(u0, b) - b, min(u1, b + nk) - b))
+    lower = -1 if (u0 <= 0 or total <= 0) else (u0 * P + total - 1) // total - 1
+    return segs, lower
+
+
+@pytest.mark.parametrize("T,nk,P", [(200, 64, 74), (150, 2, 74), (12, 5, 12), (1, 1, 1), (7, 3, 4), (75, 1, 74),
+                                    (76, 9, 74), (3, 100, 2), (396, 64, 74)])
+def test_head_bwd_schedule_covers_every_unit_once(T, nk, P):
+    """dW schedule: every (pair-tile, k-block) unit is computed exactly once, and a pair that starts in the middle
+    of a tile finds that tile's first k-blocks parked by a LOWER pair (deadlock-free wait direction)."""
+    P = min(P, T)
+    cover, parks = {}, {}
+    scheds = [_bwd_pair_schedule(p, P, T, nk) for p in range(P)]
+    for p, (segs, _) in enumerate(scheds):
+        for t, k0, k1 in segs:
+            for kb in range(k0, k1):
+                cover[(t, kb)] = cover.get((t, kb), 0) + 1
+            if k1 < nk:
+                assert p not in parks  # one parking slot per pair
+                parks[p] = (t, k1)
+    assert len(cover) == T * nk and set(cover.values()) == {1}
+    for p, (segs, lower) in enumerate(scheds):
+        for t, k0, k1 in segs:
+            if k0 > 0:
+                assert 0 <= lower < p and parks[lower] == (t, k0)
+    work = [sum(k1 - k0 for _, k0, k1 in segs) for segs, _ in scheds]
+    assert max(work) - min(work) <= 1 + (0 if T % P else 0)  # balanced to one k-block

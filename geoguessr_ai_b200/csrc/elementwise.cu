@@ -57,8 +57,16 @@ __global__ void fuse_headings_kernel(const float* __restrict__ emb, bf16* __rest
 }
 
 // W (C,D) fp32 -> bf16 operand.  split = 0: (C,D).  split = 1: (C,3D) = [hi | lo | hi].
+// Blocks past the weight matrix zero-pad the bias (b (C) -> bias_pad (Cpad)); b == nullptr: weights only.
 template <int SPLIT>
-__global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, long long n4, int d4) {
+__global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, long long n4, int d4,
+                                   const float* __restrict__ b, float* __restrict__ bias_pad, int C, int Cpad,
+                                   int w_blocks) {
+  if (static_cast<int>(blockIdx.x) >= w_blocks) {
+    const int i = (blockIdx.x - w_blocks) * blockDim.x + threadIdx.x;
+    if (i < Cpad) bias_pad[i] = i < C ? b[i] : 0.f;
+    return;
+  }
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = __ldcs(reinterpret_cast<const float4*>(w) + i);
@@ -78,11 +86,6 @@ __global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict
     o[d4 + c] = lo;
     o[2 * d4 + c] = hi;
   }
-}
-
-__global__ void pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int C, int Cpad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Cpad) out[i] = i < C ? b[i] : 0.f;
 }
 
 // squared L2 norm of each bf16 row (prototype bank), one warp per row
@@ -132,21 +135,21 @@ extern "C" int gg_prepare_head_weights(const float* w, const float* b, void* w_b
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n4 = static_cast<long long>(C) * D / 4;
   const int blocks = static_cast<int>(ceil_div_ll(n4, 256));
-  if (split)
-    cast_weight_kernel<1><<<blocks, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4);
-  else
-    cast_weight_kernel<0><<<blocks, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4);
-  GG_LAUNCH_CHECK();
   const int Cpad = gg_head_bias_pad(C);
-  pad_bias_kernel<<<ceil_div(Cpad, 256), 256, 0, s>>>(b, bias_pad, C, Cpad);
+  const int grid = blocks + ceil_div(Cpad, 256);  // the last blocks pad the bias
+  if (split)
+    cast_weight_kernel<1><<<grid, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4, b, bias_pad, C, Cpad, blocks);
+  else
+    cast_weight_kernel<0><<<grid, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4, b, bias_pad, C, Cpad, blocks);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 extern "C" int gg_cast_bf16(const float* src, void* dst_bf16, long long n, gg_stream_t stream) {
   GG_CHECK(src && dst_bf16 && n > 0 && n % 4 == 0, GG_ERR_ARG, "gg_cast_bf16: n must be a positive multiple of 4");
-  cast_weight_kernel<0><<<static_cast<int>(ceil_div_ll(n / 4, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<bf16*>(dst_bf16), n / 4, 1);
+  const int blocks = static_cast<int>(ceil_div_ll(n / 4, 256));
+  cast_weight_kernel<0><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<bf16*>(dst_bf16), n / 4, 1,
+                                                                               nullptr, nullptr, 0, 0, blocks);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

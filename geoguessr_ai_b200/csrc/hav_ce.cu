@@ -455,9 +455,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
 constexpr int kStripWarps = 4;                       // consumer warps per CTA: a strip of 1024 classes
 constexpr int kStripCols = kStripWarps * kColsPerWarp;
 constexpr int kStageRows = 8;                        // rows per pipeline stage
-constexpr int kStreamStages = 4;
+constexpr int kStreamStages = 3;
 constexpr int kStreamThreads = 32 * (kStripWarps + 1);  // + one TMA producer warp
-constexpr int kStreamCtasPerSm = 3;
+constexpr int kStreamCtasPerSm = 4;
 constexpr uint32_t kSliceTileBytes = kStageRows * kColsPerWarp * 2;  // one TMA box: 8 rows x 512 B
 constexpr uint32_t kStageBytes = kStripWarps * kSliceTileBytes;      // 16 KB
 

@@ -87,7 +87,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
 head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, rows B
                 const __grid_constant__ CUtensorMap tm_x,  // x:       inner D, rows B
                 float* __restrict__ dW, int C, int D, int Bk, float scale_in,
-                const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags) {
+                const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags,
+                float* __restrict__ db, const float* __restrict__ db_partials, int db_parts, int db_ld) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,6 +250,18 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
+        // bias gradient: whoever finishes a geocell block's first column tile also sums that block's column-sum
+        // partials from the loss kernel (fixed order; 128 consecutive geocells per warp-quartet: coalesced)
+        if (db != nullptr && !park && n0 == 0 && row < C) {
+          float s0 = 0.f, s1 = 0.f;
+          int i = 0;
+          for (; i + 1 < db_parts; i += 2) {
+            s0 += __ldg(db_partials + static_cast<size_t>(i) * db_ld + row);
+            s1 += __ldg(db_partials + static_cast<size_t>(i + 1) * db_ld + row);
+          }
+          if (i < db_parts) s0 += __ldg(db_partials + static_cast<size_t>(i) * db_ld + row);
+          db[row] = (s0 + s1) * scale;
+        }
         if (park) {  // publish: every epilogue thread's stores, then the flag
           __threadfence();
           named_bar_sync(1, 128);
@@ -358,12 +371,12 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   float* parked = reinterpret_cast<float*>(wsb + bwd_flag_bytes());
   GG_CUDA(cudaMemsetAsync(flags, 0, bwd_flag_bytes(), s));
   // cluster shape (2,1,1) is compiled into the kernel
-  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale, parked, flags);
+  // with the loss kernel's column-sum partials at hand the GEMM's epilogue finishes db as well
+  const bool db_fused = db && db_partials;
+  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale, parked, flags,
+                                                       db_fused ? db : nullptr, db_partials, db_parts, db_ld);
   GG_LAUNCH_CHECK();
-  if (db && db_partials) {  // column sums already accumulated by the loss kernel (one row per CTA)
-    db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(db_partials, C, db_ld, db_parts, scale, grad_scale, db);
-    GG_LAUNCH_CHECK();
-  } else if (db) {
+  if (db && !db_fused) {
     float* partial = reinterpret_cast<float*>(wsb + bwd_flag_bytes() + bwd_park_bytes());
     dim3 blk(32, 8), grd(ceil_div(ldc, 256), kDbSlices);
     db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);

@@ -115,6 +115,32 @@ def test_cfg2_full_size_against_oracle(centroids):
     assert out2.loss.item() == out.loss.item()
 
 
+def test_cfg4_per_gpu_shape_against_oracle(centroids):
+    """BASELINE configs[3] at 8 GPUs: TinyViT D=576 head, 4096 samples per GPU (3 embedding-column tiles: the dW
+    schedule's last round is cut stream-K style, partial accumulators are parked and re-added)."""
+    B, D = 4096, 576
+    emb, W, b, labels = synth.head_inputs(B, D, C, seed=4, bf16_round=True)
+    m = make_model(D, centroids, W, b, "bf16", should_smooth_labels=True).train()
+    out = m(embedding=emb.to(DEV), labels=labels.to(DEV), labels_clf=torch.zeros(B, dtype=torch.int64, device=DEV))
+    out.loss.backward()
+    ref, gW, gb = sgo.forward_backward(emb, W, b, centroids, labels)
+    assert abs(out.loss.item() - ref.loss.item()) <= 1e-3 * ref.loss.item()
+    logits = torch.nn.functional.linear(emb.mean(1), W, b)
+    top8 = torch.topk(logits, 8, -1)
+    assert_topk_matches(out.top5_geocells.indices, top8.values.numpy(), top8.indices.numpy())
+    assert (m.cell_layer.weight.grad.cpu() - gW).abs().max().item() <= 2e-2 * gW.abs().max().item()
+    assert (m.cell_layer.bias.grad.cpu() - gb).abs().max().item() <= 2e-2 * gb.abs().max().item()
+    # the same gradient from the plain fp32 contraction of the kernel's own bf16 dlogits: isolates the GEMM
+    # (tile schedule, parked partials) from the loss arithmetic -- must agree to fp32 accumulation noise
+    x16 = ops.fuse_headings(emb.to(DEV))
+    w16, bp = ops.prepare_head_weights(W.to(DEV), b.to(DEV))
+    head = ops.head_forward(x16, w16, bp, C, 5, centroids.to(DEV), want_logits=True)
+    dl = ops.hav_ce(head["logits"], head["lse"], labels.to(DEV), ops.centroid_unit_vectors(centroids.to(DEV)), C)[0]
+    dW, _ = ops.head_backward(dl, x16, C, D, scale=1.0 / B)
+    ref_dW = (dl[:, :C].float().t() @ x16.float()) / B
+    assert (dW - ref_dW).abs().max().item() <= 1e-5 * ref_dW.abs().max().item() + 1e-9
+
+
 def test_loss_kernel_edge_cases(centroids):
     """Exact mode (far_km=inf) == default cut-off to fp32 noise; labels on a centroid, mid-ocean, at the
     poles / date line; non-finite labels give zero targets (utils.py:31 nan_to_num semantics)."""

@@ -81,6 +81,56 @@ def test_refiner_matches_oracle_on_bf16_inputs(B, D, P, topk, missing, centroids
     assert (haversine_m(llh.cpu()[agree], o_llh[agree]) <= 1.0).all()
 
 
+def test_cfg3_size_sharded_equals_unsharded_and_oracle_subsample(centroids):
+    """BASELINE configs[2] size: 1 M prototypes, 65 536 queries, top-5.  (a) two geocell shards on one device,
+    merged the way the all-gathered records are (gg_proto_refine with nranks=2), give bit-identical results to
+    the unsharded bank; (b) a 192-query subsample agrees with the oracle."""
+    from geoguessr_ai_b200 import ops, shard_cells
+
+    Cn, D, B, P, k = centroids.shape[0], 1024, 65536, 1_000_000, 5
+    sizes = synth.cell_sizes(Cn, P, seed=0, mode="skewed")
+    off = np.zeros(Cn + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    g = torch.Generator(device=DEV).manual_seed(3)
+    bank = torch.randn((P, D), device=DEV, generator=g).to(torch.bfloat16)
+    cell_of = torch.repeat_interleave(torch.arange(Cn, device=DEV), torch.from_numpy(sizes).to(DEV))
+    xy = centroids.to(DEV)[cell_of] + (torch.rand((P, 2), device=DEV, generator=g) - 0.5)
+    off32 = torch.from_numpy(off.astype(np.int32))
+    emb = torch.randn((B, D), device=DEV, generator=g).to(torch.bfloat16).float()
+    cand = torch.randint(0, Cn, (B, k), device=DEV, generator=g)
+    probs = torch.softmax(torch.randn((B, k), device=DEV, generator=g), -1).sort(-1, descending=True).values
+    initial = centroids.to(DEV)[cand[:, 0]]
+
+    full = gg.ProtoRefiner(topk=k, protos="bank", bank=(off32, bank, xy), device=DEV, report_changed=False)
+    _, llh, cells, guess, score, proto = full(emb, initial, cand, probs, return_debug=True)
+    recs = []
+    for r in range(2):
+        lo, hi = shard_cells(off, 2)[r]
+        sh = gg.ProtoRefiner(topk=k, protos="bank", bank=(off32, bank[off[lo]:off[hi]], xy[off[lo]:off[hi]]), shard=(r, 2),
+                             bank_is_local=True, device=DEV, report_changed=False)
+        recs.append(sh.retrieve(emb, cand))
+    llh2, cells2, guess2, score2, proto2 = ops.proto_refine(torch.stack(recs), 2, cand, probs, initial, k, 1.6, 1000.0,
+                                                            want_debug=True)
+    assert torch.equal(proto, proto2) and torch.equal(score, score2)
+    assert torch.equal(cells, cells2) and torch.equal(llh, llh2) and torch.equal(guess, guess2)
+
+    n = 192
+    e, c = emb[:n].cpu(), cand[:n].cpu()
+    protos, coords = [None] * Cn, [None] * Cn
+    for cell in set(c.flatten().tolist()):
+        if off[cell + 1] > off[cell]:
+            protos[cell] = bank[off[cell]:off[cell + 1]].float().cpu()
+            coords[cell] = xy[off[cell]:off[cell + 1]].cpu()
+    ref_score, ref_idx, second = pro.best_per_candidate(e, c, protos, k)
+    np.testing.assert_allclose(score[:n].cpu().numpy(), ref_score.numpy(), atol=2e-3)
+    ref_gidx = torch.where(ref_idx >= 0, ref_idx + torch.from_numpy(off)[c], ref_idx)
+    assert int(((proto[:n].cpu().long() != ref_gidx) & ((ref_score - second) > 1e-3)).sum()) == 0
+    _, o_llh, o_cell, _ = pro.forward(e, initial[:n].cpu(), c, probs[:n].cpu(), protos, coords, topk=k)
+    agree = cells[:n].cpu() == o_cell
+    assert agree.float().mean() >= 0.99
+    assert (haversine_m(llh[:n].cpu()[agree], o_llh[agree]) <= 1.0).all()
+
+
 def test_all_candidates_missing_and_default_probs(centroids):
     """Cells without prototypes score -100000 with coords (0,0) (proto_refiner.py:181-187); with every
     candidate missing the un-stabilised softmax is 0/0 = NaN and torch.argmax picks index 0 (:205-211)."""

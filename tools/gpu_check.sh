@@ -21,6 +21,12 @@ for w in $what; do
     ncufwd)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-^head_fwd}" -s 4 -c 2 -f -o gpurun_out/prof_k \
         python tools/kbench.py 2 > gpurun_out/ncu_k.log 2>&1; echo "ncuk rc=$?" ;;
+    infer)
+      timeout 300 python bench.py --workload infer --protos 1000000 --steps 10 --warmup 3 > gpurun_out/infer_1m.json 2> gpurun_out/infer_1m.err; echo "infer1m rc=$?"
+      timeout 300 python bench.py --workload infer --protos 10000000 --steps 5 --warmup 3 --no-cpu > gpurun_out/infer_10m.json 2> gpurun_out/infer_10m.err; echo "infer10m rc=$?" ;;
+    ncuinfer)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(proto_|head_fwd|head_merge|fuse_headings)" -s 27 -c 9 -f -o gpurun_out/prof_infer \
+        python bench.py --workload infer --protos 1000000 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_infer.log 2>&1; echo "ncuinfer rc=$?" ;;
     klaunch)
       timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -s 30 -c 60 --csv --log-file gpurun_out/klaunch.csv \
         python tools/kbench.py 3 > gpurun_out/klaunch.log 2>&1; echo "klaunch rc=$?" ;;
@@ -29,7 +35,7 @@ for w in $what; do
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on \
-        -k regex:"${NCU_KERNELS:-^(cast_weight|fuse_headings|hav_|head_|label_xyz|pad_bias|db_final)}" -s ${NCU_SKIP:-44} -c ${NCU_COUNT:-11} -f -o gpurun_out/prof_train \
+        -k regex:"${NCU_KERNELS:-^(cast_weight|fuse_headings|hav_|head_|label_xyz|pad_bias|db_final)}" -s ${NCU_SKIP:-36} -c ${NCU_COUNT:-9} -f -o gpurun_out/prof_train \
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
   esac
 done

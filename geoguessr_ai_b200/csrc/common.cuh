@@ -44,6 +44,8 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 // contiguously (box_inner * 2 bytes apart) in shared memory.
 int make_tmap_bf16_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                             uint32_t box_inner, uint32_t box_rows);
+int make_tmap_bf16_2d_sw64(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                            uint32_t box_inner, uint32_t box_rows);
 
 int device_sm_count();
 

@@ -22,18 +22,24 @@
 //  (A) gg_hav_row_stats, no B x C data: label unit vectors (fp64 trig, one thread per row), then one
 //      warp per row bounds every spatial group's distance from its cap, evaluates exact q only in
 //      the groups that can hold the nearest cell / a near cell, and emits {u, q_thr, dmin, 1/sum s}
-//      plus the bitmask of class groups that contain near cells (and argmin_c d as a by-product).
+//      plus the bitmask of exactly the 64-class groups that hold a near cell (and argmin_c d as a
+//      by-product).
 //  (B) hav_ce_stream_kernel, the HBM-bound pass.  A warp owns 256 adjacent classes (4 groups = one
-//      nibble of the near mask) and walks a block of rows; a lane owns one bf16 pair in each of the
-//      four groups (unit vectors and bias-gradient column sums in registers), so every warp-level
+//      nibble of the near mask), walks a block of rows and feeds itself through a private 3-stage TMA
+//      ring (no producer warp, no block-wide synchronisation); a lane owns one bf16 pair in each of
+//      the four groups (unit vectors and bias-gradient column sums in registers), so every warp-level
 //      load/store is one full 128-byte line and a near group costs every lane exactly two target
-//      evaluations -- no divergence.  Per row: p = exp(l - lse), minus t in the near groups, and
-//      the row's sum_c t*l.  No block-wide synchronisation, 4 rows of loads in flight per lane.
-//  (C) hav_loss_finish_kernel: loss_b = lse_b - sum_c t*l (fixed-order sum of the per-warp
-//      partials), and optionally the batch mean (deterministic two-level sum, last block finishes).
+//      evaluations -- no divergence.  Per 8-row stage: a branch-free pass p = exp(l - lse) over all
+//      rows, then the rows with a near group redo the flagged groups as p - t (packed fp32x2 math) and
+//      collect sum_c t*l, reduced once per stage and added to a per-row 2^-32 fixed-point accumulator
+//      (integer atomics commute exactly: deterministic).
+//  (C) tail of (B): the last strip CTA of a row block turns the accumulators into loss_b = lse_b -
+//      sum_c t*l; the last row block sums the block partials in block order (batch mean).  Tickets and
+//      accumulators live in the row-statistics buffer and are left zeroed for the next launch.
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -137,6 +143,29 @@ __device__ __forceinline__ float target_weight_narrow(float q, float q_thr, floa
 __device__ __forceinline__ float chord2(float ux, float uy, float uz, float x, float y, float z) {
   const float dx = ux - x, dy = uy - y, dz = uz - z;
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// Packed (fp32x2) forms for the streaming pass: every half goes through exactly the operations of the scalar
+// functions above (FADD2 / FMUL2 / FFMA2 round each half like FADD / FMUL / FFMA), so the bits are those (A) summed.
+__device__ __forceinline__ float2 chord2x2(float2 ux, float2 uy, float2 uz, float2 x, float2 y, float2 z) {
+  const float2 dx = __fadd2_rn(ux, make_float2(-x.x, -x.y)), dy = __fadd2_rn(uy, make_float2(-y.x, -y.y)),
+               dz = __fadd2_rn(uz, make_float2(-z.x, -z.y));
+  return __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+}
+__device__ __forceinline__ float2 asin_poly2(float2 r, float2 z) {
+  float2 p = make_float2(4.2163199048e-2f, 4.2163199048e-2f);
+  p = __ffma2_rn(p, z, make_float2(2.4181311049e-2f, 2.4181311049e-2f));
+  p = __ffma2_rn(p, z, make_float2(4.5470025998e-2f, 4.5470025998e-2f));
+  p = __ffma2_rn(p, z, make_float2(7.4953002686e-2f, 7.4953002686e-2f));
+  p = __ffma2_rn(p, z, make_float2(1.6666752422e-1f, 1.6666752422e-1f));
+  return __ffma2_rn(__fmul2_rn(p, z), r, r);
+}
+__device__ __forceinline__ float2 target_weight_narrow2(float2 q, float q_thr, float2 neg_rk2, float2 off) {
+  const float2 h4 = __fmul2_rn(make_float2(0.25f, 0.25f), q);
+  const float2 h = make_float2(fminf(h4.x, 1.0f), fminf(h4.y, 1.0f));
+  const float2 a = asin_poly2(make_float2(sqrt_approx(h.x), sqrt_approx(h.y)), h);
+  const float2 e = __ffma2_rn(neg_rk2, __fmul2_rn(make_float2(2.0f, 2.0f), a), off);
+  return make_float2(q.x < q_thr ? ex2_approx(e.x) : 0.f, q.y < q_thr ? ex2_approx(e.y) : 0.f);
 }
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -260,10 +289,12 @@ __global__ void table_group_kernel(float* __restrict__ table, int C) {
 // Unit vectors of the labels: (B,4) = {x, y, z, valid}.  Non-finite labels give valid = 0 (the
 // reference's nan_to_num turns such a row's targets into zeros, utils.py:31).
 __global__ void label_xyz_kernel(const float* __restrict__ labels, float4* __restrict__ out, int B,
-                                 unsigned int* __restrict__ counter) {
+                                 unsigned int* __restrict__ counters, int ncounters,
+                                 unsigned long long* __restrict__ row_acc) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) *counter = 0u;  // ticket of the finishing kernel
+  if (b < ncounters) counters[b] = 0u;  // tickets of the loss kernel's finishing steps (grid >= ncounters threads)
   if (b >= B) return;
+  row_acc[b] = 0ull;  // the loss kernel's per-row fixed-point accumulator of sum_c t*l
   const float lngf = labels[2 * b], latf = labels[2 * b + 1];
   float4 o = make_float4(0.f, 0.f, 1.f, 0.f);
   if (isfinite(lngf) && isfinite(latf)) {
@@ -285,9 +316,10 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
                      float* __restrict__ nearest_km) {
   __shared__ float s_f[4];
   __shared__ int s_i[4];
-  __shared__ uint32_t s_mask[4][kMaxMaskWords];
+  __shared__ uint32_t s_near[kMaxMaskWords];  // the row's near mask: bit = 64-class group holding a cell with q < q_thr
   const int row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kMaxMaskWords) s_near[threadIdx.x] = 0u;  // (ordered before phase 3 by the barriers of phases 1-2)
   const TableView tv = view_table(table, C);
   const float4 u = __ldg(lab_xyz + row);
   const float ux = u.x, uy = u.y, uz = u.z;
@@ -389,7 +421,6 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
   // phase 3: sum of the unnormalised targets over my near groups; lane w accumulates word w of the
   // class-group mask
   float ssum = 0.f;
-  uint32_t mask_word = 0u;
 #pragma unroll
   for (int k = 0; k < SLOTS; ++k) {
     uint32_t m = valid ? __ballot_sync(0xffffffffu, lo[k] < a_thr) : 0u;  // lo = inf for absent groups
@@ -414,20 +445,26 @@ hav_row_stats_kernel(const float4* __restrict__ lab_xyz, const float* __restrict
       s0 = ok0 ? s0 : 0.f;
       s1 = ok1 ? s1 : 0.f;
       ssum += s0 + s1;
-      if (__any_sync(0xffffffffu, (ok0 && q0 < q_thr) || (ok1 && q1 < q_thr))) {
-        if (lane < kMaxMaskWords) mask_word |= __ldg(tv.gmask + static_cast<size_t>(g) * kMaxMaskWords + lane);
+      // Exactly the class groups of the near cells (not every class group the spatial group touches: that
+      // doubled the (row, slice) pairs the streaming pass had to treat as near).
+      if (ok0 && q0 < q_thr) {
+        const int cls = __float_as_int(c0.w);
+        atomicOr(&s_near[cls >> 11], 1u << ((cls >> 6) & 31));
+      }
+      if (ok1 && q1 < q_thr) {
+        const int cls = __float_as_int(c1.w);
+        atomicOr(&s_near[cls >> 11], 1u << ((cls >> 6) & 31));
       }
     }
   }
   ssum = warp_sum(ssum);
   __syncthreads();  // every warp has read s_f / s_i
   if (lane == 0) s_f[warp] = ssum;
-  if (lane < kMaxMaskWords) s_mask[warp][lane] = mask_word;
   __syncthreads();
   if (warp != 0) return;
   if (lane < nwp)
     near[static_cast<size_t>(row) * nwp + lane] =
-        lane < kMaxMaskWords ? (s_mask[0][lane] | s_mask[1][lane] | s_mask[2][lane] | s_mask[3][lane]) : 0u;
+        lane < kMaxMaskWords ? s_near[lane] : 0u;
   if (lane == 0) {
     ssum = (s_f[0] + s_f[1]) + (s_f[2] + s_f[3]);
     RowRec r;
@@ -452,22 +489,22 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   return v;
 }
 
-constexpr int kStripWarps = 4;                       // consumer warps per CTA: a strip of 1024 classes
+constexpr int kStripWarps = 4;                       // warps per CTA: a strip of 1024 classes
 constexpr int kStripCols = kStripWarps * kColsPerWarp;
 constexpr int kStageRows = 8;                        // rows per pipeline stage
 constexpr int kStreamStages = 3;
-constexpr int kStreamThreads = 32 * (kStripWarps + 1);  // + one TMA producer warp
+constexpr int kStreamThreads = 32 * kStripWarps;
 constexpr int kStreamCtasPerSm = 4;
 constexpr uint32_t kSliceTileBytes = kStageRows * kColsPerWarp * 2;  // one TMA box: 8 rows x 512 B
 constexpr uint32_t kStageBytes = kStripWarps * kSliceTileBytes;      // 16 KB
 
 struct StreamSmem {
   uint8_t tile[kStreamStages][kStageBytes];
-  float4 rec[kStreamStages][kStageRows][2];   // the stage's row records (RowRec)
-  float lse2[kStreamStages][kStageRows];      // row log-sum-exp * log2(e)
-  uint32_t near[kStreamStages][kStageRows];   // the strip's word of the row's near mask (4 bits per consumer warp)
-  uint64_t full[kStreamStages];
-  uint64_t empty[kStreamStages];
+  float4 rec[kStripWarps][kStageRows][2];   // per warp: the current stage's row records (RowRec)
+  float lse2[kStripWarps][kStageRows];      // row log-sum-exp * log2(e)
+  uint32_t near[kStripWarps][kStageRows];   // the warp's 4 near bits of the row
+  float slp[kStripWarps][kStageRows][32];   // per lane partials of a near row's sum_c t*l (reduced once per stage)
+  uint64_t full[kStripWarps][kStreamStages];
 };
 
 __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
@@ -476,181 +513,225 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
   return v;
 }
 
-// CTA = (row block rb, strip of 4 warp slices).  The producer warp streams the strip's logits through a
-// 4-stage TMA -> shared-memory ring (8 rows x 1024 classes per stage, 64 KB in flight per CTA, three
-// CTAs per SM), so the depth of the memory pipeline does not depend on registers or occupancy; its
-// lanes 0..7 also stage the 8 rows' scalars (record, lse, near bits), fetched one stage ahead, so the
-// consumers never touch global memory for per-row data.
-// Consumer warp w owns classes [256 (4 strip + w), +256): lane l holds the bf16 pairs at 64 j + 2 l +
-// {0,1}, j = 0..3 -- one pair in each of the slice's four 64-class groups -- so a near group costs
-// every lane exactly two target evaluations (no divergence), shared-memory reads are conflict-free
-// and every global store is one full 128-byte line.  Rows are padded to a multiple of 256 columns
-// (ldc >= Cpad): nothing in the row loop is predicated; pad columns carry p only and are never read
+// CTA = (row block rb, strip of 4 warp slices); the four warps are independent pipelines.  Warp w owns classes
+// [256 (4 strip + w), +256) and streams its own slice of the logits through a private 3-stage TMA -> shared
+// memory ring (8 rows x 256 classes = 4 KB per stage; 48 KB in flight per CTA, four CTAs per SM): lane 0 refills
+// a stage as soon as the warp has consumed it, so there is no producer warp polling for free slots -- which
+// used to load one scheduler of every SM with four spinning warps (profiles/r01c) -- and no block-wide
+// synchronisation.  Lanes 0..7 fetch the 8 rows' scalars (record, lse, near bits) one stage ahead into
+// registers and publish them to the warp's own shared-memory slot, so the row loop reads them as broadcasts.
+// Lane l holds the bf16 pairs at 64 j + 2 l + {0,1}, j = 0..3 -- one pair in each of the slice's four 64-class
+// groups -- so a near group costs every lane exactly two target evaluations (no divergence), shared-memory
+// reads are conflict-free and every global store is one full 128-byte line.  Rows are padded to a multiple of
+// 256 columns (ldc >= Cpad): nothing in the row loop is predicated; pad columns carry p only and are never read
 // downstream.  Pairs are processed with the packed fp32x2 pipe (fma / add on both halves at once).
 template <bool WANT_DB>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, const float* __restrict__ lse,
                      const RowRec* __restrict__ rec, const uint32_t* __restrict__ near, int nwp,
                      const float* __restrict__ table, int B, int C, int rows_per_block, int nslices, int nstrips,
-                     float neg_rk2, bf16* __restrict__ dlogits, float* __restrict__ loss_part,
-                     float* __restrict__ db_part) {
+                     float neg_rk2, bf16* __restrict__ dlogits, unsigned long long* __restrict__ row_acc,
+                     float* __restrict__ db_part, unsigned int* __restrict__ counters, float* __restrict__ loss_rows,
+                     float* __restrict__ block_part, float mean_scale, float* __restrict__ loss_mean) {
   extern __shared__ uint8_t smem_raw[];
   StreamSmem& sm = *reinterpret_cast<StreamSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = blockIdx.x / nstrips, strip = blockIdx.x - rb * nstrips;
-  const int nactive = min(kStripWarps, nslices - strip * kStripWarps);  // consumer warps with a slice
+  const int nactive = min(kStripWarps, nslices - strip * kStripWarps);  // warps with a slice
   const int row0 = rb * rows_per_block, row1 = min(B, row0 + rows_per_block);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_logits);
-    for (int s = 0; s < kStreamStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], nactive);
-    }
+    for (int w = 0; w < kStripWarps; ++w)
+      for (int st = 0; st < kStreamStages; ++st) mbar_init(&sm.full[w][st], 1);
     fence_barrier_init();
   }
   __syncthreads();
-
-  if (warp == kStripWarps) {
-    // ===================== producer warp =====================
-    const int near_word = (strip * kStripWarps) >> 3;  // the strip's 16 bits live in one mask word
-    const int near_shift = 4 * ((strip * kStripWarps) & 7);
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    float l2 = 0.f;
-    uint32_t nw = 0u;
-    auto fetch = [&](int row) {  // lanes 0..7: one row each
-      r0 = make_float4(0.f, 0.f, 0.f, 0.f); r1 = r0; l2 = 0.f; nw = 0u;
-      if (lane < kStageRows && row + lane < row1) {
-        const float4* rp = reinterpret_cast<const float4*>(rec + row + lane);
-        r0 = __ldg(rp);
-        r1 = __ldg(rp + 1);
-        l2 = __ldg(lse + row + lane) * kLog2eF;
-        nw = (__ldg(near + static_cast<size_t>(row + lane) * nwp + near_word) >> near_shift) & 0xffffu;
-      }
-    };
-    fetch(row0);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int row = row0; row < row1; row += kStageRows) {
-      mbar_wait_relaxed(&sm.empty[s], ph ^ 1);
-      if (lane < kStageRows) {
-        sm.rec[s][lane][0] = r0;
-        sm.rec[s][lane][1] = r1;
-        sm.lse2[s][lane] = l2;
-        sm.near[s][lane] = nw;
-      }
-      __syncwarp();  // lanes' stores ordered before lane 0's releasing arrive
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&sm.full[s], nactive * kSliceTileBytes);
-        for (int w = 0; w < nactive; ++w)
-          tma_load_2d_hint(sm.tile[s] + w * kSliceTileBytes, &tm_logits, &sm.full[s],
-                           (strip * kStripWarps + w) * kColsPerWarp, row, kPolicyEvictFirst);
-      }
-      fetch(row + kStageRows);  // next stage's scalars: in flight while we wait for its slot
-      if (++s == kStreamStages) { s = 0; ph ^= 1; }
-    }
-    return;
-  }
   if (warp >= nactive) return;
 
-  // ===================== consumers =====================
   const int ws = strip * kStripWarps + warp;
   const int Cpad = table_cpad(C);
   const int cbase = ws * kColsPerWarp + 2 * lane;  // + 64 j
-  const uint32_t near_shift = 4 * warp;
+  const int near_word = ws >> 3;                   // the warp's 4 near bits: nibble (ws & 7) of this mask word
+  const uint32_t near_shift = 4 * (ws & 7);
 
-  float vx[8], vy[8], vz[8];
+  // this warp's ring: lane 0 arms the stage's barrier and issues the 4 KB box (rows past B are zero-filled)
+  uint8_t* const my_tiles = sm.tile[0] + warp * kSliceTileBytes;
+  auto issue = [&](int stage_idx, int row) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.full[warp][stage_idx], kSliceTileBytes);
+      tma_load_2d_hint(my_tiles + stage_idx * kStageBytes, &tm_logits, &sm.full[warp][stage_idx], ws * kColsPerWarp,
+                       row, kPolicyEvictFirst);
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < kStreamStages; ++st)
+    if (row0 + st * kStageRows < row1) issue(st, row0 + st * kStageRows);
+
+  // lanes 0..7: one row's scalars each, fetched a stage ahead
+  // (raw values only: any arithmetic on them here would stall the warp on the loads it has just issued)
+  float4 pr0 = make_float4(0.f, 0.f, 0.f, 0.f), pr1 = pr0;
+  float plse = 0.f;
+  uint32_t pnw = 0u;
+  auto fetch = [&](int row) {
+    pr0 = make_float4(0.f, 0.f, 0.f, 0.f); pr1 = pr0; plse = 0.f; pnw = 0u;
+    if (lane < kStageRows && row + lane < row1) {
+      const float4* rp = reinterpret_cast<const float4*>(rec + row + lane);
+      pr0 = __ldg(rp);
+      pr1 = __ldg(rp + 1);
+      plse = __ldg(lse + row + lane);
+      pnw = __ldg(near + static_cast<size_t>(row + lane) * nwp + near_word);
+    }
+  };
+  fetch(row0);
+
+  float2 vx[4], vy[4], vz[4];  // unit vectors of this lane's pair in each of the slice's four 64-class groups
   float2 db[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 a = __ldg(reinterpret_cast<const float2*>(table + cbase + 64 * j));
-    const float2 b = __ldg(reinterpret_cast<const float2*>(table + Cpad + cbase + 64 * j));
-    const float2 c = __ldg(reinterpret_cast<const float2*>(table + 2 * static_cast<size_t>(Cpad) + cbase + 64 * j));
-    vx[2 * j] = a.x; vx[2 * j + 1] = a.y;
-    vy[2 * j] = b.x; vy[2 * j + 1] = b.y;
-    vz[2 * j] = c.x; vz[2 * j + 1] = c.y;
+    vx[j] = __ldg(reinterpret_cast<const float2*>(table + cbase + 64 * j));
+    vy[j] = __ldg(reinterpret_cast<const float2*>(table + Cpad + cbase + 64 * j));
+    vz[j] = __ldg(reinterpret_cast<const float2*>(table + 2 * static_cast<size_t>(Cpad) + cbase + 64 * j));
     db[j] = make_float2(0.f, 0.f);
   }
-  // pad classes (column >= C, last slice only) carry no target mass even when q_thr = inf
-  uint32_t cell_ok = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) cell_ok |= (cbase + 64 * (i >> 1) + (i & 1) < C) ? (1u << i) : 0u;
+  // Pad classes (column >= C, last slice only) sit at 1e9 in the table (q ~ 3e18): capping the row's threshold
+  // below that keeps them without target mass even when q_thr = inf, and changes no decision on a real cell
+  // (q <= 4), so (A) and (B) still agree.
+  constexpr float kPadCut = 1.0e18f;
 
   const size_t pitch = static_cast<size_t>(ldc);
   uint32_t* gptr = reinterpret_cast<uint32_t*>(dlogits + static_cast<size_t>(row0) * pitch + cbase);
   const size_t pitch_w = pitch / 2;  // row pitch in 32-bit words (ldc is even)
-  const uint32_t tile0 = smem_u32(sm.tile[0]) + warp * kSliceTileBytes + 4 * lane;
-  const uint32_t rec0 = smem_u32(&sm.rec[0][0][0]), lse0 = smem_u32(&sm.lse2[0][0]), near0 = smem_u32(&sm.near[0][0]);
+  const uint32_t tile0 = smem_u32(my_tiles) + 4 * lane;
+  const uint32_t rec0 = smem_u32(&sm.rec[warp][0][0]), lse0 = smem_u32(&sm.lse2[warp][0]),
+                 near0 = smem_u32(&sm.near[warp][0]);
   const float2 log2e2 = make_float2(kLog2eF, kLog2eF);
   int stage = 0;
   uint32_t phase = 0;
 
   for (int rbase = row0; rbase < row1; rbase += kStageRows) {
     const int nr = min(kStageRows, row1 - rbase);
-    mbar_wait(&sm.full[stage], phase);
+    __syncwarp();  // every lane is done with the previous stage's scalars
+    if (lane < kStageRows) {
+      sm.rec[warp][lane][0] = pr0;
+      sm.rec[warp][lane][1] = pr1;
+      sm.lse2[warp][lane] = plse * kLog2eF;
+      sm.near[warp][lane] = (pnw >> near_shift) & 0xfu;
+    }
+    // rows of this stage with a near group among this warp's classes (bit r = row r; rows past the batch fetch 0)
+    const uint32_t near_rows = __ballot_sync(0xffffffffu, lane < kStageRows && ((pnw >> near_shift) & 0xfu) != 0u);
+    fetch(rbase + kStageRows);  // next stage's scalars: in flight while this stage is processed
+    __syncwarp();
+    mbar_wait(&sm.full[warp][stage], phase);
     const uint32_t tile = tile0 + stage * kStageBytes;
     float my_sl = 0.f;  // lane r keeps row r's sum_c t*l of this warp's classes
-#pragma unroll 2
-    for (int rr = 0; rr < kStageRows; ++rr) {
-      if (rr >= nr) break;  // warp-uniform
+
+    // ---- pass 1, branch-free: p = 2^(l log2e - lse log2e) for every row of the stage, stored and added to the
+    // bias-gradient column sums.  Nothing data dependent in here, so the rows' chains interleave freely.
+    auto row_probs = [&](int rr, float2 (&g)[4]) {
       uint32_t cur[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = lds_u32(tile + rr * (kColsPerWarp * 2) + 128 * j);
-      const float nlse2 = -__uint_as_float(lds_u32(lse0 + (stage * kStageRows + rr) * 4));
-      const uint32_t nb = (lds_u32(near0 + (stage * kStageRows + rr) * 4) >> near_shift) & 0xfu;
+      const float nlse2 = -__uint_as_float(lds_u32(lse0 + rr * 4));
       const float2 nl = make_float2(nlse2, nlse2);
-      float2 g[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {  // softmax probability 2^(l log2e - lse log2e), both halves of the pair at once
+      for (int j = 0; j < 4; ++j) {  // both halves of the pair at once
         const float2 a = __ffma2_rn(make_float2(__uint_as_float(cur[j] << 16), __uint_as_float(cur[j] & 0xffff0000u)),
                                     log2e2, nl);
         g[j] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
       }
-      if (nb != 0u) {  // some group of this warp's 256 classes holds a near cell (warp-uniform)
-        const uint4 ua = lds_u128(rec0 + (stage * kStageRows + rr) * 32);
-        const uint4 ub = lds_u128(rec0 + (stage * kStageRows + rr) * 32 + 16);
-        const float ux = __uint_as_float(ua.x), uy = __uint_as_float(ua.y), uz = __uint_as_float(ua.z);
-        const float q_thr = __uint_as_float(ua.w), off = __uint_as_float(ub.x), inv_s = __uint_as_float(ub.y);
-        float sl = 0.f;
-        auto near_groups = [&](auto narrow_tag) {
-          constexpr bool kNarrow = decltype(narrow_tag)::value;
+    };
+    if (nr == kStageRows) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if ((nb >> j) & 1u) {  // warp-uniform
-              float t[2];
+      for (int rr = 0; rr < kStageRows; ++rr) {
+        float2 g[4];
+        row_probs(rr, g);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int i = 2 * j + h;
-                const float q = chord2(ux, uy, uz, vx[i], vy[i], vz[i]);
-                // same bits either way (see target_weight_narrow); (A) summed exactly these values
-                const float w = kNarrow ? target_weight_narrow(q, q_thr, neg_rk2, off)
-                                        : target_weight(q, q_thr, neg_rk2, off);
-                t[h] = ((cell_ok >> i) & 1u) ? w * inv_s : 0.f;
-              }
-              g[j].x -= t[0];
-              g[j].y -= t[1];
-              sl = fmaf(t[0], __uint_as_float(cur[j] << 16), sl);
-              sl = fmaf(t[1], __uint_as_float(cur[j] & 0xffff0000u), sl);
-            }
-          }
-        };
-        // row-uniform: with q_thr <= 1 every near cell is on the first asin branch
-        if (q_thr <= 1.0f) near_groups(std::true_type{});
-        else near_groups(std::false_type{});
-        sl = warp_sum(sl);
-        if (lane == rr) my_sl = sl;
+        for (int j = 0; j < 4; ++j) __stcs(gptr + rr * pitch_w + 32 * j, pack_bf16x2(g[j].x, g[j].y));
+        if (WANT_DB) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) db[j] = __fadd2_rn(db[j], g[j]);
+        }
       }
+    } else {
+      for (int rr = 0; rr < nr; ++rr) {  // ragged last stage of the batch
+        float2 g[4];
+        row_probs(rr, g);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) __stcs(gptr + 32 * j, pack_bf16x2(g[j].x, g[j].y));
-      gptr += pitch_w;
-      if (WANT_DB) {
+        for (int j = 0; j < 4; ++j) __stcs(gptr + rr * pitch_w + 32 * j, pack_bf16x2(g[j].x, g[j].y));
+        if (WANT_DB) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) db[j] = __fadd2_rn(db[j], g[j]);
+          for (int j = 0; j < 4; ++j) db[j] = __fadd2_rn(db[j], g[j]);
+        }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[stage]);  // this warp is done with the stage
-    if (lane < nr) loss_part[static_cast<size_t>(ws) * B + rbase + lane] = my_sl;
+
+    // ---- pass 2, rows with a near group in this warp's 256 classes (about one in seven): the flagged groups
+    // are redone as p - t from the tile still in shared memory and stored over pass 1's lines (they merge in
+    // L2), t leaves the column sums, and the row's sum_c t*l is collected.
+    for (uint32_t rows = near_rows; rows != 0u; rows &= rows - 1u) {  // warp-uniform
+      const int rr = __ffs(rows) - 1;
+      const uint32_t nb = lds_u32(near0 + rr * 4);
+      const float nlse2 = -__uint_as_float(lds_u32(lse0 + rr * 4));
+      const float2 nl = make_float2(nlse2, nlse2);
+      const uint4 ua = lds_u128(rec0 + rr * 32);
+      const uint4 ub = lds_u128(rec0 + rr * 32 + 16);
+      const float ux = __uint_as_float(ua.x), uy = __uint_as_float(ua.y), uz = __uint_as_float(ua.z);
+      const float q_thr = __uint_as_float(ua.w), off = __uint_as_float(ub.x), inv_s = __uint_as_float(ub.y);
+      const float q_cut = fminf(q_thr, kPadCut);
+      const float2 ux2 = make_float2(ux, ux), uy2 = make_float2(uy, uy), uz2 = make_float2(uz, uz);
+      const float2 nrk = make_float2(neg_rk2, neg_rk2), off2 = make_float2(off, off), inv2 = make_float2(inv_s, inv_s);
+      float2 sl2 = make_float2(0.f, 0.f);
+      auto near_groups = [&](auto narrow_tag) {
+        constexpr bool kNarrow = decltype(narrow_tag)::value;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((nb >> j) & 1u) {  // warp-uniform
+            const uint32_t cur = lds_u32(tile + rr * (kColsPerWarp * 2) + 128 * j);
+            const float2 l2 = make_float2(__uint_as_float(cur << 16), __uint_as_float(cur & 0xffff0000u));
+            const float2 a = __ffma2_rn(l2, log2e2, nl);
+            const float2 pr = make_float2(ex2_approx(a.x), ex2_approx(a.y));  // the bits pass 1 computed
+            const float2 q = chord2x2(ux2, uy2, uz2, vx[j], vy[j], vz[j]);
+            // same bits either way (see target_weight_narrow); (A) summed exactly these values
+            const float2 w = kNarrow ? target_weight_narrow2(q, q_cut, nrk, off2)
+                                     : make_float2(target_weight(q.x, q_cut, neg_rk2, off),
+                                                   target_weight(q.y, q_cut, neg_rk2, off));
+            const float2 t = __fmul2_rn(w, inv2);
+            const float2 nt = make_float2(-t.x, -t.y);
+            const float2 gg2 = __fadd2_rn(pr, nt);
+            __stcs(gptr + rr * pitch_w + 32 * j, pack_bf16x2(gg2.x, gg2.y));
+            if (WANT_DB) db[j] = __fadd2_rn(db[j], nt);
+            sl2 = __ffma2_rn(t, l2, sl2);
+          }
+        }
+      };
+      // row-uniform: with q_thr <= 1 every near cell is on the first asin branch
+      if (q_thr <= 1.0f) near_groups(std::true_type{});
+      else near_groups(std::false_type{});
+      sm.slp[warp][rr][lane] = sl2.x + sl2.y;
+    }
+    if (near_rows != 0u) {  // warp-uniform
+      // one transposed reduction per stage instead of a shuffle tree per near row: lane l sums a quarter of
+      // row l / 4's partials, two shuffle rounds finish the row, and lane r fetches row r's total
+      __syncwarp();
+      float part = 0.f;
+      if ((near_rows >> (lane >> 2)) & 1u) {
+        const float4* sp = reinterpret_cast<const float4*>(&sm.slp[warp][lane >> 2][(lane & 3) * 8]);
+        const float4 a = sp[0], b = sp[1];
+        part = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      my_sl = __shfl_sync(0xffffffffu, part, (lane * 4) & 31);  // lanes >= 8 read rows that do not exist: unused
+    }
+    gptr += kStageRows * pitch_w;
+    __syncwarp();  // all lanes have read the stage's tile: lane 0 may hand the slot back to the TMA engine
+    if (rbase + kStreamStages * kStageRows < row1) issue(stage, rbase + kStreamStages * kStageRows);
+    // Row sums of t*l across the 50 warp slices: 2^-32 fixed point in a 64-bit integer (|sum| <= max |logit|),
+    // so the atomic adds commute exactly -- deterministic in any arrival order, and exact where an fp32 sum
+    // would round.  Most (row, slice) pairs hold no near cell and add nothing.
+    if (lane < nr && my_sl != 0.f)
+      atomicAdd(row_acc + rbase + lane, static_cast<unsigned long long>(__float2ll_rn(my_sl * 4294967296.0f)));
     if (++stage == kStreamStages) { stage = 0; phase ^= 1; }
   }
   if (WANT_DB) {
@@ -658,54 +739,50 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<float2*>(db_part + static_cast<size_t>(rb) * Cpad + cbase + 64 * j) = db[j];
   }
-}
 
-// ------------------------------------------------------------------ (C) per-row loss, batch mean
-// Block (32 rows x 8 slice lanes).  loss_b = lse_b - sum over warp slices of sum_c t*l, summed in a
-// fixed order; the batch mean is a fixed-order sum of block partials done by whichever block
-// finishes last (deterministic).
-__global__ void __launch_bounds__(256)
-hav_loss_finish_kernel(const float* __restrict__ loss_part, int nslices, const float* __restrict__ lse,
-                       const RowRec* __restrict__ rec, int B, float* __restrict__ loss_rows,
-                       float* __restrict__ block_part, unsigned int* __restrict__ counter, float mean_scale,
-                       float* __restrict__ loss_mean) {
-  __shared__ float red[8][33];
-  __shared__ bool last;
-  const int row = blockIdx.x * 32 + threadIdx.x;
-  float sl = 0.f;
-  if (row < B)
-    for (int s = threadIdx.y; s < nslices; s += 8) sl += loss_part[static_cast<size_t>(s) * B + row];
-  red[threadIdx.y][threadIdx.x] = sl;
-  __syncthreads();
-  if (threadIdx.y != 0) return;
-  float v = 0.f;
-  if (row < B) {
-    sl = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) sl += red[y][threadIdx.x];
-    v = rec[row].valid != 0.f ? lse[row] - sl : 0.f;
-    loss_rows[row] = v;
-  }
-  if (loss_mean == nullptr) return;
-  v = warp_sum(v);  // threadIdx.y == 0: exactly one warp
-  if (threadIdx.x == 0) {
-    block_part[blockIdx.x] = v;
-    __threadfence();
-    last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  }
+  // ---- (C) folded in: whichever strip CTA of this row block finishes last turns the rows' accumulators into
+  // loss_b = lse_b - sum_c t*l, and whichever row block finishes last sums the row-block partials in block
+  // order: deterministic, and no second launch.
+  __threadfence();  // my row_acc adds are performed device-wide before this CTA takes its ticket
   __syncwarp();
-  if (last) {  // block partials summed in block order whichever block is last
+  named_bar_sync(1, nactive * 32);  // consumer warps only (the producer and idle warps have returned)
+  if (warp != 0) return;
+  unsigned int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(counters + 1 + rb, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != static_cast<unsigned int>(nstrips - 1)) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int row = row0 + lane; row < row1; row += 32) {  // always warp 0, 32 lanes: the same order whoever is last
+    const float sl = static_cast<float>(static_cast<double>(static_cast<long long>(__ldcg(row_acc + row))) *
+                                        (1.0 / 4294967296.0));
+    row_acc[row] = 0ull;  // ready for the next launch on the same row statistics
+    const float v = __ldg(&rec[row].valid) != 0.f ? __ldg(lse + row) - sl : 0.f;
+    loss_rows[row] = v;
+    acc += v;
+  }
+  if (lane == 0) counters[1 + rb] = 0u;  // ready for the next launch on the same row statistics
+  if (loss_mean == nullptr) return;
+  acc = warp_sum(acc);
+  const int nrb = gridDim.x / nstrips;
+  unsigned int last = 0;
+  if (lane == 0) {
+    block_part[rb] = acc;
     __threadfence();
-    float s = 0.f;
-    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) s += __ldcg(block_part + i);
-    s = warp_sum(s);
-    if (threadIdx.x == 0) {
-      loss_mean[0] = s * mean_scale;
-      *counter = 0u;  // ready for the next launch on the same row statistics
-    }
+    last = atomicAdd(counters, 1u) == static_cast<unsigned int>(nrb - 1) ? 1u : 0u;
+  }
+  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
+  __threadfence();
+  float tot = 0.f;
+  for (int i = lane; i < nrb; i += 32) tot += __ldcg(block_part + i);
+  tot = warp_sum(tot);
+  if (lane == 0) {
+    loss_mean[0] = tot * mean_scale;
+    counters[0] = 0u;
   }
 }
 
+// ------------------------------------------------------------------ hard-label CE, batch mean
 // Hard-label cross entropy (super_guessr.py:383, nn.CrossEntropyLoss) and its gradient
 // p - onehot, for should_smooth_labels=False or labels=None.  One CTA per row.
 __global__ void hard_ce_kernel(const bf16* __restrict__ logits, int ldc, const float* __restrict__ lse,
@@ -754,28 +831,9 @@ __global__ void loss_mean_kernel(const float* __restrict__ loss_rows, int B, flo
 }
 
 // ------------------------------------------------------------------ host-side planning
-// Row statistics buffer (gg_hav_row_stats -> gg_hav_ce_fwd_bwd): rec[B] | near[B * nwp] | counter | lab_xyz[B]
-struct StatsPlan {
-  int nwp;
-  size_t off_rec, off_near, off_counter, off_lab, bytes;
-};
-static StatsPlan make_stats_plan(int B, int C) {
-  StatsPlan p;
-  const int Cpad = table_cpad(C);
-  const int class_groups = Cpad / kCellsPerGroup;
-  p.nwp = ceil_div(ceil_div(class_groups, 32), 4) * 4;
-  size_t o = 0;
-  auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~size_t(255); return r; };
-  p.off_rec = take(sizeof(RowRec) * static_cast<size_t>(B));
-  p.off_near = take(sizeof(uint32_t) * static_cast<size_t>(B) * p.nwp);
-  p.off_counter = take(sizeof(unsigned int));
-  p.off_lab = take(sizeof(float4) * static_cast<size_t>(B));
-  p.bytes = o;
-  return p;
-}
 struct HavPlan {
-  int Cpad, nslices, nstrips, rows_per_block, nrb, finish_blocks;
-  size_t off_loss_part, off_block_part, bytes;
+  int Cpad, nslices, nstrips, rows_per_block, nrb;
+  size_t off_block_part, bytes;
 };
 static HavPlan make_hav_plan(int B, int C) {
   HavPlan p;
@@ -783,14 +841,41 @@ static HavPlan make_hav_plan(int B, int C) {
   p.nslices = p.Cpad / kColsPerWarp;
   p.nstrips = ceil_div(p.nslices, kStripWarps);
   // one resident wave of CTAs: row blocks x strips <= SMs x CTAs per SM, row blocks of whole stages
-  const int capacity = std::max(1, device_sm_count() * kStreamCtasPerSm / p.nstrips);
+  // (GG_HAV_WAVES > 1: that many times more, smaller row blocks -- the hardware block scheduler then evens out
+  // the near-cell work, which differs by +-50 % between strips; tuning knob, read once)
+  static const int waves = [] {
+    const char* e = getenv("GG_HAV_WAVES");
+    const int w = e ? atoi(e) : 1;
+    return w >= 1 && w <= 16 ? w : 1;
+  }();
+  const int capacity = std::max(1, waves * device_sm_count() * kStreamCtasPerSm / p.nstrips);
   p.rows_per_block = ceil_div(std::max(kStageRows, ceil_div(B, capacity)), kStageRows) * kStageRows;
   p.nrb = ceil_div(B, p.rows_per_block);
-  p.finish_blocks = ceil_div(B, 32);
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~size_t(255); return r; };
-  p.off_loss_part = take(sizeof(float) * static_cast<size_t>(B) * p.nslices);
-  p.off_block_part = take(sizeof(float) * p.finish_blocks);
+  p.off_block_part = take(sizeof(float) * p.nrb);
+  p.bytes = o;
+  return p;
+}
+// Row statistics buffer (gg_hav_row_stats -> gg_hav_ce_fwd_bwd):
+//   rec[B] | near[B * nwp] | counters[1 + row blocks of the loss kernel] | lab_xyz[B] | row_acc[B] (u64)
+struct StatsPlan {
+  int nwp, ncounters;
+  size_t off_rec, off_near, off_counter, off_lab, off_acc, bytes;
+};
+static StatsPlan make_stats_plan(int B, int C) {
+  StatsPlan p;
+  const int Cpad = table_cpad(C);
+  const int class_groups = Cpad / kCellsPerGroup;
+  p.nwp = ceil_div(ceil_div(class_groups, 32), 4) * 4;
+  p.ncounters = 1 + make_hav_plan(B, C).nrb;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~size_t(255); return r; };
+  p.off_rec = take(sizeof(RowRec) * static_cast<size_t>(B));
+  p.off_near = take(sizeof(uint32_t) * static_cast<size_t>(B) * p.nwp);
+  p.off_counter = take(sizeof(unsigned int) * p.ncounters);
+  p.off_lab = take(sizeof(float4) * static_cast<size_t>(B));
+  p.off_acc = take(sizeof(unsigned long long) * static_cast<size_t>(B));
   p.bytes = o;
   return p;
 }
@@ -839,7 +924,8 @@ extern "C" int gg_hav_row_stats(const float* labels, const float* cent_table, in
   uint32_t* near = reinterpret_cast<uint32_t*>(base + p.off_near);
   unsigned int* counter = reinterpret_cast<unsigned int*>(base + p.off_counter);
   float4* lab = reinterpret_cast<float4*>(base + p.off_lab);
-  label_xyz_kernel<<<ceil_div(B, 128), 128, 0, s>>>(labels, lab, B, counter);
+  label_xyz_kernel<<<ceil_div(std::max(B, p.ncounters), 128), 128, 0, s>>>(
+      labels, lab, B, counter, p.ncounters, reinterpret_cast<unsigned long long*>(base + p.off_acc));
   GG_LAUNCH_CHECK();
   // phi = far / R; far = inf (skip disabled) or >= pi R  ->  cos(phi/2) <= 0  ->  everything is near
   double phi = static_cast<double>(far_km) / 6378.137;
@@ -880,7 +966,7 @@ extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* 
   const uint32_t* near = reinterpret_cast<const uint32_t*>(sb + sp.off_near);
   unsigned int* counter = reinterpret_cast<unsigned int*>(const_cast<uint8_t*>(sb) + sp.off_counter);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* loss_part = reinterpret_cast<float*>(ws + p.off_loss_part);
+  unsigned long long* row_acc = reinterpret_cast<unsigned long long*>(const_cast<uint8_t*>(sb) + sp.off_acc);
   float* block_part = reinterpret_cast<float*>(ws + p.off_block_part);
   const float neg_rk2 = -kEarthRadiusKm * (1.0f / tau) * kLog2eF;
 
@@ -895,17 +981,16 @@ extern "C" int gg_hav_ce_fwd_bwd(const void* logits_bf16, int ldc, const float* 
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
     kern<<<grid_b, kStreamThreads, smem, s>>>(tm_logits, ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
                                               p.nslices, p.nstrips, neg_rk2, static_cast<bf16*>(dlogits_bf16),
-                                              loss_part, db_partials);
+                                              row_acc, db_partials, counter, loss_rows, block_part, mean_scale,
+                                              loss_mean);
   } else {
     auto kern = hav_ce_stream_kernel<false>;
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
     kern<<<grid_b, kStreamThreads, smem, s>>>(tm_logits, ldc, lse, rec, near, sp.nwp, cent_table, B, C, p.rows_per_block,
                                               p.nslices, p.nstrips, neg_rk2, static_cast<bf16*>(dlogits_bf16),
-                                              loss_part, nullptr);
+                                              row_acc, nullptr, counter, loss_rows, block_part, mean_scale,
+                                              loss_mean);
   }
-  GG_LAUNCH_CHECK();
-  hav_loss_finish_kernel<<<p.finish_blocks, dim3(32, 8), 0, s>>>(loss_part, p.nslices, lse, rec, B, loss_rows,
-                                                                 block_part, counter, mean_scale, loss_mean);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

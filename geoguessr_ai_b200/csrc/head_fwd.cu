@@ -36,7 +36,10 @@ namespace gg {
 constexpr int kBM = 128;        // rows of x per tile (UMMA M)
 constexpr int kBN = 256;        // geocells per tile   (UMMA N)
 constexpr int kBK = 64;         // K elements per stage (128 B of bf16 = one swizzle span)
-constexpr int kStages = 4;      // 4 x (16 KB + 16 KB) = 128 KB per CTA (+ 64 KB of logits staging for the TMA stores)
+// Operand ring: 32 KB per stage and CTA.  The MMA warp was waiting on operands about half of the time with four
+// stages (profiles/r01c): the ring is latency bound, so it gets all the shared memory the epilogue can spare --
+// five stages next to 32 KB of logits staging in training, six in serving (no staging).
+template <bool WRITE_LOGITS> struct FwdCfg { static constexpr int kStages = WRITE_LOGITS ? 5 : 6; };
 constexpr int kEpiWarps = 16;
 constexpr int kColGroups = kEpiWarps / 4;       // column groups of a tile (one warp per TMEM lane quadrant each)
 constexpr int kColsPerEpiWarp = kBN / kColGroups;
@@ -48,10 +51,13 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kThrSlots = 8;    // shared top-k thresholds are kept per run, in a ring of run slots
 constexpr int kKeyMin = static_cast<int>(0x80000000u);
 
+template <bool WRITE_LOGITS>
 struct FwdSmem {
+  static constexpr int kStages = FwdCfg<WRITE_LOGITS>::kStages;
   uint8_t a[kStages][kStageBytesA];
   uint8_t b[kStages][kStageBytesB];
-  uint8_t out[kEpiWarps][32 * 128];  // per epilogue warp: 32 rows x 64 bf16 logits, 128-byte swizzled (TMA store box)
+  // per epilogue warp: 32 rows x 32 bf16 logits (one 32-column chunk), 64-byte swizzled (TMA store box)
+  uint8_t out[WRITE_LOGITS ? kEpiWarps : 1][32 * 64];
   int thr[kThrSlots][kBM];           // per row: best known lower bound of the run's k-th largest logit (ordered key)
   uint64_t full[kStages];
   uint64_t empty[kStages];
@@ -128,7 +134,9 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 float* __restrict__ pmax, float* __restrict__ psum, float* __restrict__ ptopv,
                 int* __restrict__ ptopi, int M, int N, int K, FwdSched sc) {
   extern __shared__ uint8_t smem_raw[];
-  FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Smem = FwdSmem<WRITE_LOGITS>;
+  constexpr int kStages = Smem::kStages;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -217,9 +225,9 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const int cg = (warp - 2) >> 2;   // which 64 columns of the 256-wide tile
     const int row_in_tile = quad * 32 + lane;
-    uint8_t* const my_out = sm.out[warp - 2];
+    uint8_t* const my_out = sm.out[WRITE_LOGITS ? warp - 2 : 0];
     const uint32_t leader_acc_empty = mapa_u32(smem_u32(&sm.acc_empty[0]), 0);
-    const uint32_t my_out_row = smem_u32(my_out) + lane * 128;
+    const uint32_t my_out_row = smem_u32(my_out) + lane * 64;
 
     float run_max = -INFINITY, run_sum = 0.f;
     float tv[KTOP];
@@ -236,15 +244,11 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int m0 = (2 * mb + crank) * kBM, n0 = nb * kBN + cg * kColsPerEpiWarp;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      int* const thr_slot = &sm.thr[run_id & (kThrSlots - 1)][row_in_tile];
+      const uint32_t thr_slot = smem_u32(&sm.thr[run_id & (kThrSlots - 1)][row_in_tile]);
       mbar_wait(&sm.acc_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + cg * kColsPerEpiWarp;
-      if (WRITE_LOGITS) {  // the previous tile's TMA store has finished reading the staging buffer
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-      }
 
 #pragma unroll 1
       for (int c = 0; c < kColsPerEpiWarp / 32; ++c) {
@@ -265,14 +269,24 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq[q].w;
         }
         if (WRITE_LOGITS) {
-          // 16-byte piece j of row r sits at piece j ^ (r & 7): the 128-byte TMA swizzle, and conflict-free
+          // One 2 KB staging buffer per warp: the previous chunk's TMA store was issued a whole chunk of
+          // soft-max / top-k work ago, so waiting for it to have READ the buffer costs nothing.
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          // 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3): the 64-byte TMA swizzle, and conflict-free
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t dst = my_out_row + (((4 * c + q) ^ (lane & 7)) << 4);
+            const uint32_t dst = my_out_row + ((q ^ ((lane >> 1) & 3)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
                          "r"(pack_bf16x2(v[8 * q + 0], v[8 * q + 1])), "r"(pack_bf16x2(v[8 * q + 2], v[8 * q + 3])),
                          "r"(pack_bf16x2(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16x2(v[8 * q + 6], v[8 * q + 7]))
                          : "memory");
+          }
+          fence_proxy_async_smem();  // staging writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm_out, my_out, col0, m0 + quad * 32);  // rows >= M / columns >= ldc are clipped
+            tma_store_commit();
           }
         }
         if (col0 + 32 > N) {  // tail tile: geocells >= C do not exist
@@ -302,7 +316,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // Top-k.  A logit can only matter if it beats a lower bound of the row's k-th best in this run:
         // this warp's own k-th best, or the one any of the three other warps of the row has published.
         // (Strict '>': a logit exactly equal to the bound may be dropped -- below the score-gap tolerance.)
-        const float thr = fmaxf(tv[KTOP - 1], key_to_float(*reinterpret_cast<volatile int*>(thr_slot)));
+        const float thr = fmaxf(tv[KTOP - 1], key_to_float(ld_volatile_s32_shared(thr_slot)));
         if (__any_sync(0xffffffffu, cmax > thr)) {
           uint32_t mask = 0;
 #pragma unroll
@@ -326,15 +340,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
               topk_insert<KTOP>(tv, ti, select32(v, i), col0 + i);
             }
           }
-          if (mine && tv[KTOP - 1] > -INFINITY) atomicMax(thr_slot, ordered_key(tv[KTOP - 1]));
-        }
-      }
-      if (WRITE_LOGITS) {
-        fence_proxy_async_smem();  // staging writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tm_out, my_out, n0, m0 + quad * 32);  // rows >= M / columns >= ldc are clipped
-          tma_store_commit();
+          if (mine && tv[KTOP - 1] > -INFINITY) red_max_s32_shared(thr_slot, ordered_key(tv[KTOP - 1]));
         }
       }
       // TMEM accumulator drained -> hand it back to the leader's MMA warp
@@ -376,19 +382,60 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   }
 }
 
-// One warp per row: merge the row's partials (one per (CTA run, column group)).
+// Merge of the per-(CTA run, column group) partials of every row.
 //   topk_val = softmax probabilities exp(l - max) / sum   (super_guessr.py:355,365)
 //   pred_cell = argmax (:358), pred_llh = centroids[pred_cell] (:359-361), lse = max + log(sum)
+// The partial arrays are [partial][value][row in the 128-row tile]: a block takes 32 consecutive rows (lane =
+// row, so every load is one full 128-byte line), its kMergeWarps warps split the row's partials, and warp 0
+// folds the warps' (max, sum, top-k) states in warp order.  Ties keep the lower geocell index first.
+constexpr int kMergeWarps = 8;
+
 template <int KTOP>
-__global__ void head_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum,
-                                  const float* __restrict__ ptopv, const int* __restrict__ ptopi, FwdSched sc, int M,
-                                  int k, const float* __restrict__ centroids, float* __restrict__ topk_val,
-                                  long long* __restrict__ topk_idx, long long* __restrict__ pred_cell,
-                                  float* __restrict__ pred_llh, float* __restrict__ lse) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const int mb = row / (2 * kBM), crank = (row / kBM) & 1, rit = row % kBM;  // pair row block, CTA of the pair
+__device__ __forceinline__ void merge_insert(float (&tv)[KTOP], int (&ti)[KTOP], float v, int id) {
+  if (v > tv[KTOP - 1] || (v == tv[KTOP - 1] && v > -INFINITY && id < ti[KTOP - 1])) {
+    tv[KTOP - 1] = v;
+    ti[KTOP - 1] = id;
+#pragma unroll
+    for (int q = KTOP - 1; q > 0; --q) {
+      if (tv[q] > tv[q - 1] || (tv[q] == tv[q - 1] && ti[q] < ti[q - 1])) {
+        float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+        int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void lse_merge(float& lmax, float& lsum, float m, float s) {
+  if (m > -INFINITY) {
+    if (m > lmax) { lsum = lsum * expf(lmax - m) + s; lmax = m; }
+    else lsum += s * expf(m - lmax);
+  }
+}
+
+// merge a descending list (pv, pi) into (tv, ti); stops at the first element that cannot enter
+template <int KTOP>
+__device__ __forceinline__ void merge_list(float (&tv)[KTOP], int (&ti)[KTOP], const float (&pv)[KTOP],
+                                           const int (&pi)[KTOP]) {
+#pragma unroll
+  for (int j = 0; j < KTOP; ++j) {
+    // lists are sorted: once the warp's lanes are all done with this list, skip the rest (warp-uniform exit)
+    const bool enters = pv[j] > tv[KTOP - 1] || (pv[j] == tv[KTOP - 1] && pv[j] > -INFINITY && pi[j] < ti[KTOP - 1]);
+    if (!__any_sync(0xffffffffu, enters)) break;
+    merge_insert<KTOP>(tv, ti, pv[j], pi[j]);
+  }
+}
+
+template <int KTOP>
+__global__ void __launch_bounds__(32 * kMergeWarps)
+head_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, const float* __restrict__ ptopv,
+                  const int* __restrict__ ptopi, FwdSched sc, int M, int k, const float* __restrict__ centroids,
+                  float* __restrict__ topk_val, long long* __restrict__ topk_idx, long long* __restrict__ pred_cell,
+                  float* __restrict__ pred_llh, float* __restrict__ lse) {
+  __shared__ float s_f[kMergeWarps][2 + KTOP][32];
+  __shared__ int s_i[kMergeWarps][KTOP][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * 32;  // 32 | kBM: the block's rows share pair row block, CTA and partial list
+  const int row = row0 + lane;
+  const int mb = row0 / (2 * kBM), crank = (row0 / kBM) & 1, rit = row % kBM;
   const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
   const int nparts = (c_hi - c_lo + 1) * kColGroups;
 
@@ -397,86 +444,77 @@ __global__ void head_merge_kernel(const float* __restrict__ pmax, const float* _
   int ti[KTOP];
 #pragma unroll
   for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  for (int i = lane; i < nparts; i += 32) {
+
+  // this warp's partials, the next one's loads in flight while the current one is merged
+  float m = -INFINITY, sum = 0.f, pv[KTOP];
+  int pi[KTOP];
+  auto load = [&](int i) {
     const int c = c_lo + i / kColGroups;
     const int run = mb - sc.start(c) / sc.num_n;
     const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + (i % kColGroups);
-    // all loads of this partial first (independent: one memory latency), then the merge
-    const float m = pmax[p * kBM + rit];
-    const float s = psum[p * kBM + rit];
-    float pv[KTOP];
-    int pi[KTOP];
+    m = pmax[p * kBM + rit];
+    sum = psum[p * kBM + rit];
 #pragma unroll
     for (int j = 0; j < KTOP; ++j) {
       pv[j] = ptopv[(p * KTOP + j) * kBM + rit];
       pi[j] = ptopi[(p * KTOP + j) * kBM + rit];
     }
-    if (m > -INFINITY) {
-      if (m > lmax) { lsum = lsum * expf(lmax - m) + s; lmax = m; }
-      else lsum += s * expf(m - lmax);
-    }
+  };
+  if (warp < nparts) load(warp);
+  for (int i = warp; i < nparts; i += kMergeWarps) {  // warp-uniform
+    const float cm = m, cs = sum;
+    float cv[KTOP];
+    int ci[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) { cv[j] = pv[j]; ci[j] = pi[j]; }
+    if (i + kMergeWarps < nparts) load(i + kMergeWarps);
+    lse_merge(lmax, lsum, cm, cs);
+    merge_list<KTOP>(tv, ti, cv, ci);
+  }
+  // tree over the warps: 4 <- 8, 2 <- 4, 1 <- 2 (fixed order: deterministic)
+  auto publish = [&]() {
+    s_f[warp][0][lane] = lmax;
+    s_f[warp][1][lane] = lsum;
 #pragma unroll
     for (int j = 0; j < KTOP; ++j) {
-      const float v = pv[j];
-      if (!(v > tv[KTOP - 1]) && !(v == tv[KTOP - 1] && v > -INFINITY)) break;  // lists are sorted descending
-      const int id = pi[j];
-      // equal values across partials: keep the lower geocell index first
-      if (v > tv[KTOP - 1] || id < ti[KTOP - 1]) {
-        tv[KTOP - 1] = v;
-        ti[KTOP - 1] = id;
+      s_f[warp][2 + j][lane] = tv[j];
+      s_i[warp][j][lane] = ti[j];
+    }
+  };
 #pragma unroll
-        for (int q = KTOP - 1; q > 0; --q) {
-          if (tv[q] > tv[q - 1] || (tv[q] == tv[q - 1] && ti[q] < ti[q - 1])) {
-            float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
-            int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
-          }
-        }
-      }
+  for (int half = kMergeWarps / 2; half >= 1; half >>= 1) {
+    if (warp >= half && warp < 2 * half) publish();
+    __syncthreads();
+    if (warp < half) {
+      const int w = warp + half;
+      lse_merge(lmax, lsum, s_f[w][0][lane], s_f[w][1][lane]);
+      float cv[KTOP];
+      int ci[KTOP];
+#pragma unroll
+      for (int j = 0; j < KTOP; ++j) { cv[j] = s_f[w][2 + j][lane]; ci[j] = s_i[w][j][lane]; }
+      merge_list<KTOP>(tv, ti, cv, ci);
     }
   }
-  // warp-wide log-sum-exp
-  float gmax = lmax;
+  if (warp != 0 || row >= M) return;
+  const float inv = 1.f / lsum;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-  float gsum = lmax > -INFINITY ? lsum * expf(lmax - gmax) : 0.f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-  const float inv = 1.f / gsum;
-  // k rounds: the best head among the lanes' sorted lists wins and is popped
-  int best0 = 0;
-  for (int j = 0; j < k; ++j) {
-    float bv = tv[0];
-    int bi = ti[0], bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bl = ol; }
-    }
-    if (lane == bl) {  // pop
-#pragma unroll
-      for (int q = 0; q < KTOP - 1; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
-      tv[KTOP - 1] = -INFINITY;
-      ti[KTOP - 1] = 0x7fffffff;
-    }
-    if (j == 0) best0 = bi;
-    if (lane == 0) {
-      topk_val[static_cast<size_t>(row) * k + j] = expf(bv - gmax) * inv;
-      topk_idx[static_cast<size_t>(row) * k + j] = bi;
+  for (int j = 0; j < KTOP; ++j) {
+    if (j < k) {
+      topk_val[static_cast<size_t>(row) * k + j] = expf(tv[j] - lmax) * inv;
+      topk_idx[static_cast<size_t>(row) * k + j] = ti[j];
     }
   }
-  if (lane == 0) {
-    if (pred_cell) pred_cell[row] = best0;
-    if (pred_llh) {
-      pred_llh[2 * row + 0] = centroids[2 * best0 + 0];
-      pred_llh[2 * row + 1] = centroids[2 * best0 + 1];
-    }
-    if (lse) lse[row] = gmax + logf(gsum);
+  const int best0 = ti[0];
+  if (pred_cell) pred_cell[row] = best0;
+  if (pred_llh) {
+    pred_llh[2 * row + 0] = centroids[2 * best0 + 0];
+    pred_llh[2 * row + 1] = centroids[2 * best0 + 1];
   }
+  if (lse) lse[row] = lmax + logf(lsum);
 }
 
-static size_t fwd_smem_bytes() { return sizeof(FwdSmem) + 1024; }
+template <bool WRITE_LOGITS>
+static size_t fwd_smem_bytes() { return sizeof(FwdSmem<WRITE_LOGITS>) + 1024; }
 
 static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(2 * sc.grid) * sc.runs * kColGroups; }
 
@@ -502,7 +540,7 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
   if (rc) return rc;
   CUtensorMap tm_out = tm_x;  // placeholder in serving (never dereferenced)
   if (logits) {
-    rc = make_tmap_bf16_2d(&tm_out, logits, ldc, B, static_cast<uint64_t>(ldc) * 2, 64, 32);
+    rc = make_tmap_bf16_2d_sw64(&tm_out, logits, ldc, B, static_cast<uint64_t>(ldc) * 2, 32, 32);
     if (rc) return rc;
   }
   const FwdSched sc = make_sched(B, C, device_sm_count());
@@ -511,21 +549,22 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
   float* psum = pmax + np;
   float* ptopv = psum + np;
   int* ptopi = reinterpret_cast<int*>(ptopv + np * KTOP);
-  const size_t smem = fwd_smem_bytes();
   // every (CTA, run, half) slot the merge reads is flushed by the CTA that owns those tiles
   if (logits) {
     auto kern = head_fwd_kernel<KTOP, true>;
+    const size_t smem = fwd_smem_bytes<true>();
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
     GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, pmax, psum, ptopv, ptopi, B, C, D,
                          sc));
   } else {
     auto kern = head_fwd_kernel<KTOP, false>;
+    const size_t smem = fwd_smem_bytes<false>();
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
     GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, pmax, psum, ptopv, ptopi, B, C, D,
                          sc));
   }
   GG_LAUNCH_CHECK();
-  head_merge_kernel<KTOP><<<ceil_div(B, 8), 256, 0, stream>>>(pmax, psum, ptopv, ptopi, sc, B, k, centroids,
+  head_merge_kernel<KTOP><<<ceil_div(B, 32), 32 * kMergeWarps, 0, stream>>>(pmax, psum, ptopv, ptopi, sc, B, k, centroids,
                                                               topk_val, topk_idx, pred_cell, pred_llh, lse);
   GG_LAUNCH_CHECK();
   return GG_OK;

@@ -140,9 +140,21 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier that may live in another CTA of the cluster (shared::cluster address)
+// arrive on an mbarrier that may live in another CTA of the cluster (shared::cluster address).
+// Default (.release.cta) form: a bare SYNCS.ARRIVE.  The .release.cluster form costs MEMBAR.ALL.GPU + ERRBAR per
+// arrive (20 % of the head_fwd epilogue warps' time, profiles/r01b); what these arrives order -- tcgen05.ld of
+// the accumulator -- is already ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// atomic max on a shared-memory word by its shared::cta address (a generic-pointer atomicMax compiles to ATOM.E...GPU)
+__device__ __forceinline__ int ld_volatile_s32_shared(uint32_t saddr) {
+  int v;
+  asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void red_max_s32_shared(uint32_t saddr, int v) {
+  asm volatile("red.shared::cta.max.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 // TMA load for CTA pairs (cta_group::2): data lands in THIS CTA's shared memory, completion bytes are
 // signalled on an mbarrier given by its shared::cluster address (normally the pair leader's).

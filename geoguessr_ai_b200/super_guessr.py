@@ -15,6 +15,8 @@ The vision encoder (base_model) stays PyTorch and is outside this path.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import Tensor, nn
 
@@ -29,15 +31,22 @@ class _GeocellHeadLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, embedding, weight, bias, module, labels, labels_clf, smooth):
         C, D = weight.shape
+        # The label-only half of the loss (nearest centroid, sum of smoothed targets, near-group mask) reads no
+        # logits and runs on a side stream.  Launched AFTER the persistent head GEMM (its small CTAs co-reside
+        # with the GEMM's one CTA per SM and fill its idle issue slots) but ordered only behind the work that
+        # precedes the GEMM, so the HBM-bound fusion / weight cast have the machine to themselves.
         stats = None
-        if smooth:
-            # the label-only half of the loss (nearest centroid, sum of smoothed targets, near-group
-            # mask) reads no logits: it runs on a side stream next to the head GEMM
+        under_gemm = smooth and module._stats_under_gemm
+        if smooth and not under_gemm:
             stats = module._row_stats_async(labels, C)
         st = module._operands(weight, bias)
         x16 = ops.fuse_headings(embedding, split=st["split"])
+        if under_gemm:
+            fork = module._row_stats_prepare(labels, C)
         head = ops.head_forward(x16, st["w16"], st["bias_pad"], C, module.num_candidates,
                                 module.geocell_centroid_coords.data, want_logits=True)
+        if under_gemm:
+            stats = module._row_stats_launch(fork)
         dbp = None
         if smooth:
             torch.cuda.current_stream().wait_stream(module._side_stream)
@@ -166,6 +175,7 @@ class SuperGuessr(nn.Module):
         self._op_cache = None
         self._xyz_cache = None
         self._side_stream = None
+        self._stats_under_gemm = os.environ.get("GG_STATS_UNDER_GEMM", "1") != "0"
         self._dp = None
         print(f"Initialized SuperGuessr classification model with {self.num_cells} geocells.")
 
@@ -213,21 +223,32 @@ class SuperGuessr(nn.Module):
             self._op_cache = dict(key=key, w16=w16, bias_pad=bias_pad, split=split)
         return self._op_cache
 
-    def _row_stats_async(self, labels, C):
-        """gg_hav_row_stats on a side stream (joined by the caller before the loss kernel)."""
+    def _row_stats_prepare(self, labels, C):
+        """Buffers for gg_hav_row_stats, made on the current stream, and the fork point (an event on the
+        current stream) the side-stream launch is ordered behind."""
         cur = torch.cuda.current_stream()
         table = self._centroid_xyz()
         if self._side_stream is None or self._side_stream.device != labels.device:
             self._side_stream = torch.cuda.Stream(device=labels.device)
-        side = self._side_stream
         # the buffer belongs to the main stream (which joins the side stream before the loss kernel reads
         # it and before anything later could reuse it); labels are made fp32-contiguous there as well
         labels = labels.detach().float().contiguous()
         stats = ops.row_stats_buffer(labels.shape[0], C, labels.device)
-        side.wait_stream(cur)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        return labels, table, C, stats, ev
+
+    def _row_stats_launch(self, fork):
+        """gg_hav_row_stats on the side stream behind the fork point (joined by the caller before the loss kernel)."""
+        labels, table, C, stats, ev = fork
+        side = self._side_stream
+        side.wait_event(ev)
         with torch.cuda.stream(side):
             ops.hav_row_stats(labels, table, C, tau=self.label_smoothing_tau, far_km=self.far_km, out=stats)
         return stats
+
+    def _row_stats_async(self, labels, C):
+        return self._row_stats_launch(self._row_stats_prepare(labels, C))
 
     def _centroid_xyz(self):
         c = self.geocell_centroid_coords

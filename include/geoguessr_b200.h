@@ -96,7 +96,9 @@ int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, i
  * -sum_c t log_softmax; loss_mean (optional, 1 float) = mean_scale * sum_b loss_rows, summed in a fixed
  * order (deterministic) -- the `.mean()` of super_guessr.py:380 with mean_scale = 1/B.  db_partials
  * (optional, (gg_hav_ce_db_parts(B,C), gg_hav_cpad(C)) fp32) = per-row-block column sums of dlogits,
- * finished by gg_head_bwd (saves a second pass over dlogits for the bias gradient). */
+ * finished by gg_head_bwd (saves a second pass over dlogits for the bias gradient).
+ * row_stats also carries the kernel's finishing tickets and per-row fixed-point accumulators (zeroed by
+ * gg_hav_row_stats, left zeroed by every launch): one gg_hav_ce_fwd_bwd at a time per row_stats buffer. */
 int gg_centroid_unit_vectors(const float* centroids, float* cent_table, int C, void* workspace, gg_stream_t stream);
 int gg_hav_row_stats(const float* labels, const float* cent_table, int B, int C, float tau, float far_km,
                      void* row_stats, long long* nearest_cell, float* nearest_km, gg_stream_t stream);

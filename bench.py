@@ -205,7 +205,8 @@ def run_b200_train(args):
     model.train()
     if world > 1:  # gradients are averaged inside backward(), range by range, overlapped with the dW GEMM
         model.enable_data_parallel(chunks=args.dp_chunks,
-                                   comm_dtype=torch.bfloat16 if args.dp_bf16 else None)
+                                   comm_dtype=torch.bfloat16 if args.dp_bf16 else None,
+                                   comm="nccl" if args.dp_bf16 or args.dp_chunks > 1 else args.dp_comm)
     params = [model.cell_layer.weight, model.cell_layer.bias]
     use_graph = not args.no_graph
     opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=use_graph)
@@ -380,14 +381,23 @@ def run_b200_train(args):
                "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
                          "reference forward + autograd backward + AdamW)"}
 
-    launches_per_step = 1 + 2 + 2 + 2 + 2 + 2  # fuse, prepare(cast+bias), head_fwd(+merge), row_stats(labels+stats), hav(stream+finish), bwd(+db)
+    grad_comm = None
+    if world > 1:
+        if model._dp["symm"] is not None:
+            grad_comm = (("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if model._dp["symm"]["kind"] == "nvls"
+                          else "peer load/store two-shot (rank-order sums)")
+                         + " all-reduce (avg, fp32) of [dW | db] in symmetric memory over NVLink, one kernel per rank "
+                           "between two symmetric-memory barriers")
+        else:
+            grad_comm = (f"nccl avg, {'bf16' if args.dp_bf16 else 'fp32'}, {args.dp_chunks} geocell ranges overlapped "
+                         "with the dW GEMM")
+    # fuse, weight cast, head_fwd + merge, label vectors + row statistics, loss stream kernel, dW GEMM [, gradient exchange]
+    launches_per_step = 1 + 1 + 2 + 2 + 1 + 1 + (1 if world > 1 and model._dp["symm"] is not None else 0)
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": dict(train_config(world, cfg), cuda_graph=use_graph,
-                                            grad_allreduce=(None if world == 1 else
-                                                            f"nccl avg, {'bf16' if args.dp_bf16 else 'fp32'}, {args.dp_chunks} "
-                                                            "geocell ranges overlapped with the dW GEMM")), "clocks": clocks,
+                                            grad_allreduce=grad_comm), "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "steps": Ke},
         "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
@@ -652,6 +662,9 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="infer: queries per batch over all GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
     ap.add_argument("--dp-chunks", type=int, default=1, help="geocell ranges of the overlapped dW GEMM + all-reduce (N > 1)")
+    ap.add_argument("--dp-comm", default="auto", choices=["auto", "nvls", "p2p", "nccl"],
+                    help="gradient exchange for N > 1: own kernel over symmetric memory (NVSwitch multicast or peer "
+                         "loads/stores) or NCCL all-reduce")
     ap.add_argument("--dp-bf16", action="store_true", help="all-reduce the gradients in bf16 (opt-in, N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()

@@ -1,0 +1,181 @@
+// Gradient averaging for data-parallel head training over NVLink / NVSwitch peer memory.
+//
+// The reference leaves this step to DDP / Accelerate (an NCCL ring all-reduce of dW (C,D) and db (C) after
+// loss.backward(), main_coordinator_idun_s3.py:423-424).  Here every rank keeps its [dW | db] gradient in a
+// symmetric-memory buffer mapped into all peers, and ONE kernel per rank does a two-shot all-reduce in place:
+//   shot 1  rank r reads slice r of every rank's buffer over NVLink (16-byte loads, many in flight per thread)
+//           and sums them in rank order -- the same order on every rank and for every element, so the result
+//           is deterministic and identical everywhere -- times 1 / world;
+//   shot 2  it writes the averaged slice r back into every rank's buffer (posted 16-byte peer stores).
+// Slice r is read and written by rank r only, so the exchange needs no staging copy.  Per rank (N - 1) / N of
+// the buffer crosses NVLink in each direction, once: 26 MB each way for the 51.8 MB head gradient at N = 2,
+// 45 MB at N = 8, against the 2 (N - 1) / N a ring moves in 2 (N - 1) latency-bound steps.  The caller brackets
+// the launch with symmetric-memory barriers (all gradients written / all slices delivered).
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int kP2PMaxWorld = 8;
+constexpr int kP2PThreads = 512;
+
+struct PeerPtrs {
+  float4* p[kP2PMaxWorld];
+};
+
+// L2-only accesses (no L1 allocation): the lines are written by other GPUs between launches
+__device__ __forceinline__ float4 ld_peer(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_peer(float4* p, const float4& v) { __stcg(p, v); }
+
+// Scheduling fence: the value is "produced" by an (empty) volatile asm, and volatile asms keep their program
+// order.  Placed after a batch of loads it stops the compiler from sinking arithmetic in between them, where the
+// in-order issue would stall on the first NVLink round trip with most of the batch still unissued.
+__device__ __forceinline__ void pin(float4& v) { asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)); }
+
+template <int WORLD>
+__global__ void __launch_bounds__(kP2PThreads)
+p2p_allreduce_avg_kernel(const __grid_constant__ PeerPtrs peers, size_t lo, size_t hi, float inv_world) {
+  constexpr int kUnroll = WORLD >= 4 ? 2 : 4;  // WORLD x unroll 16-byte loads in flight per thread
+  const size_t stride = static_cast<size_t>(gridDim.x) * kP2PThreads;
+  size_t base = lo + static_cast<size_t>(blockIdx.x) * kP2PThreads + threadIdx.x;
+  // whole rounds: every load of the round first, then the sums (rank order: identical on every rank), then the stores
+  for (; base + (kUnroll - 1) * stride < hi; base += stride * kUnroll) {
+    float4 v[kUnroll][WORLD];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) v[u][r] = ld_peer(peers.p[r] + base + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) pin(v[u][r]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float4 acc = v[u][0];
+#pragma unroll
+      for (int r = 1; r < WORLD; ++r) {
+        acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w;
+      }
+      acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) st_peer(peers.p[r] + base + u * stride, acc);
+    }
+  }
+  for (; base < hi; base += stride) {  // ragged end of the slice
+    float4 acc = ld_peer(peers.p[0] + base);
+#pragma unroll
+    for (int r = 1; r < WORLD; ++r) {
+      const float4 t = ld_peer(peers.p[r] + base);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) st_peer(peers.p[r] + base, acc);
+  }
+}
+
+// Same exchange through the NVSwitch's multicast object (NVLS): one multimem.ld_reduce pulls slice r from every
+// GPU and adds the copies INSIDE the switch, one multimem.st broadcasts the averaged slice to every GPU.  Each
+// GPU then sends and receives about one buffer's worth of bytes whatever the number of ranks (the two-shot
+// peer version moves 2 (N - 1) / N of it per direction), and the reduced value is computed once -- by the
+// switch, in its fixed port order -- so every rank still ends up with identical bits.
+__device__ __forceinline__ float4 multimem_ld_add(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kP2PThreads)
+nvls_allreduce_avg_kernel(float4* __restrict__ mc, size_t lo, size_t hi, float inv_world) {
+  constexpr int kUnroll = 8;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kP2PThreads;
+  size_t base = lo + static_cast<size_t>(blockIdx.x) * kP2PThreads + threadIdx.x;
+  for (; base + (kUnroll - 1) * stride < hi; base += stride * kUnroll) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = multimem_ld_add(mc + base + u * stride);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) pin(v[u]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      v[u].x *= inv_world; v[u].y *= inv_world; v[u].z *= inv_world; v[u].w *= inv_world;
+      multimem_st(mc + base + u * stride, v[u]);
+    }
+  }
+  for (; base < hi; base += stride) {
+    float4 v = multimem_ld_add(mc + base);
+    v.x *= inv_world; v.y *= inv_world; v.z *= inv_world; v.w *= inv_world;
+    multimem_st(mc + base, v);
+  }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+// Slice of rank r, in 16-byte units: equal parts of ceil(n4 / world), the last one short.
+extern "C" void gg_p2p_slice(size_t n_floats, int world, int rank, size_t* lo4, size_t* hi4) {
+  const size_t n4 = n_floats / 4;
+  const size_t per = (n4 + world - 1) / world;
+  const size_t lo = std::min(n4, per * static_cast<size_t>(rank));
+  *lo4 = lo;
+  *hi4 = std::min(n4, lo + per);
+}
+
+extern "C" int gg_p2p_allreduce_avg(const unsigned long long* peer_ptrs, int world, int rank, size_t n_floats,
+                                    gg_stream_t stream) {
+  GG_CHECK(peer_ptrs && world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, GG_ERR_ARG,
+           "gg_p2p_allreduce_avg: world=%d rank=%d (1 <= world <= %d)", world, rank, kP2PMaxWorld);
+  GG_CHECK(world == 1 || world == 2 || world == 4 || world == 8, GG_ERR_UNSUPPORTED,
+           "gg_p2p_allreduce_avg: world=%d (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
+  GG_CHECK(n_floats % 4 == 0, GG_ERR_ARG, "gg_p2p_allreduce_avg: n_floats=%zu must be a multiple of 4", n_floats);
+  PeerPtrs peers = {};
+  for (int r = 0; r < world; ++r) {
+    GG_CHECK(peer_ptrs[r] != 0 && (peer_ptrs[r] & 15) == 0, GG_ERR_ARG, "gg_p2p_allreduce_avg: peer buffer %d (%p) missing or not 16-byte aligned",
+             r, reinterpret_cast<void*>(peer_ptrs[r]));
+    peers.p[r] = reinterpret_cast<float4*>(peer_ptrs[r]);
+  }
+  if (world == 1 || n_floats == 0) return GG_OK;
+  size_t lo, hi;
+  gg_p2p_slice(n_floats, world, rank, &lo, &hi);
+  if (hi <= lo) return GG_OK;
+  const size_t work = hi - lo;
+  const int sms = device_sm_count();
+  const size_t per_cta = static_cast<size_t>(kP2PThreads) * (world >= 4 ? 2 : 4);
+  const int grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(2 * sms), (work + per_cta - 1) / per_cta));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float inv = 1.0f / static_cast<float>(world);
+  if (world == 2) p2p_allreduce_avg_kernel<2><<<grid, kP2PThreads, 0, s>>>(peers, lo, hi, inv);
+  else if (world == 4) p2p_allreduce_avg_kernel<4><<<grid, kP2PThreads, 0, s>>>(peers, lo, hi, inv);
+  else p2p_allreduce_avg_kernel<8><<<grid, kP2PThreads, 0, s>>>(peers, lo, hi, inv);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_floats, gg_stream_t stream) {
+  GG_CHECK(multicast_ptr && (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) == 0, GG_ERR_ARG,
+           "gg_nvls_allreduce_avg: multicast address %p missing or not 16-byte aligned", multicast_ptr);
+  GG_CHECK(world >= 1 && rank >= 0 && rank < world, GG_ERR_ARG, "gg_nvls_allreduce_avg: world=%d rank=%d", world, rank);
+  GG_CHECK(n_floats % 4 == 0, GG_ERR_ARG, "gg_nvls_allreduce_avg: n_floats=%zu must be a multiple of 4", n_floats);
+  if (n_floats == 0) return GG_OK;
+  size_t lo, hi;
+  gg_p2p_slice(n_floats, world, rank, &lo, &hi);
+  if (hi <= lo) return GG_OK;
+  const size_t per_cta = static_cast<size_t>(kP2PThreads) * 8;
+  const int grid = static_cast<int>(
+      std::min<size_t>(static_cast<size_t>(2 * device_sm_count()), (hi - lo + per_cta - 1) / per_cta));
+  nvls_allreduce_avg_kernel<<<grid, kP2PThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float4*>(multicast_ptr), lo, hi, 1.0f / static_cast<float>(world));
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}

@@ -250,6 +250,33 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_p
     return dW, db
 
 
+def p2p_allreduce_avg(peer_ptrs, rank, n_floats):
+    """In-place two-shot average of a symmetric-memory fp32 buffer over the ranks (gg_p2p_allreduce_avg) on the
+    current stream.  peer_ptrs: every rank's buffer address as mapped on this device (rank order).  The caller
+    puts a symmetric-memory barrier on either side."""
+    import ctypes
+
+    world = len(peer_ptrs)
+    arr = (ctypes.c_ulonglong * world)(*[int(p) for p in peer_ptrs])
+    _call("gg_p2p_allreduce_avg", _lib.load().gg_p2p_allreduce_avg, ctypes.cast(arr, ctypes.c_void_p), world, int(rank),
+          int(n_floats), _stream())
+
+
+def nvls_allreduce_avg(multicast_ptr, world, rank, n_floats):
+    """The same average through the NVSwitch multicast mapping of the buffer (gg_nvls_allreduce_avg)."""
+    _call("gg_nvls_allreduce_avg", _lib.load().gg_nvls_allreduce_avg, int(multicast_ptr), int(world), int(rank),
+          int(n_floats), _stream())
+
+
+def p2p_slice(n_floats, world, rank):
+    """[lo, hi) of rank's slice of the gradient buffer, in floats (gg_p2p_slice)."""
+    import ctypes
+
+    lo, hi = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.load().gg_p2p_slice(int(n_floats), int(world), int(rank), ctypes.byref(lo), ctypes.byref(hi))
+    return 4 * lo.value, 4 * hi.value
+
+
 # --------------------------------------------------------------------------- a10-a15
 def proto_retrieve(q16, q_sqnorm, cand, topk, bank16, bank_sqnorm, bank_coords, cell_off, cell_lo, cell_hi,
                    proto_base=0):

@@ -258,28 +258,96 @@ class SuperGuessr(nn.Module):
         return self._xyz_cache[1]
 
     # ---- data-parallel head training --------------------------------------------
-    def enable_data_parallel(self, process_group=None, chunks: int = 1, comm_dtype=None):
+    def enable_data_parallel(self, process_group=None, chunks: int = 1, comm_dtype=None, comm: str = "auto"):
         """Average the head gradients over the ranks of ``process_group`` INSIDE ``backward()`` (what the
-        reference leaves to DDP / Accelerate): NCCL all-reduce (AVG) of dW and db on a communication stream.
-        With ``chunks`` > 1 the dW GEMM runs in that many geocell ranges (dp_chunk_bounds) and every range is
-        all-reduced while the next one is computed.  Measured on 2 x B200 (r01) this does NOT pay with NCCL:
-        its kernels cannot co-reside with the persistent 148-CTA GEMM (registers), so the ranges serialise and
-        three small all-reduces cost more than one large one -- hence the default of 1; the knob stays for
-        communication back-ends that do not need SMs.  ``comm_dtype=torch.bfloat16`` halves the bytes on
-        NVLink by rounding each rank's gradient before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
-        After this call ``.grad`` is already the global average: do not wrap the module in DDP as well."""
+        reference leaves to DDP / Accelerate).  After this call ``.grad`` is already the global average: do not
+        wrap the module in DDP as well.
+
+        comm="nvls" / "p2p": [dW | db] live in a symmetric-memory buffer mapped into every peer over NVLink,
+        and one kernel per rank averages its slice in place between two symmetric-memory barriers -- "nvls"
+        through the NVSwitch multicast mapping (gg_nvls_allreduce_avg: the switch adds the copies, about one
+        buffer of traffic per GPU whatever the rank count), "p2p" with peer loads / stores (gg_p2p_allreduce_avg:
+        two-shot, rank-order sums; 1, 2, 4 or 8 ranks).
+        comm="nccl": NCCL all-reduce (AVG) of dW and db on a communication stream.  With ``chunks`` > 1 the dW
+        GEMM runs in that many geocell ranges (dp_chunk_bounds) and every range is all-reduced while the next
+        one is computed; measured on 2 x B200 (r01) this does NOT pay with NCCL -- its kernels cannot co-reside
+        with the persistent 148-CTA GEMM (registers), so the ranges serialise -- hence the default of 1.
+        ``comm_dtype=torch.bfloat16`` (NCCL only) halves the bytes on NVLink by rounding each rank's gradient
+        before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
+        comm="auto": what measured fastest on B200 NVSwitch boxes for the 51.9 MB head gradient (r01,
+        tools/p2p_check.py): "p2p" up to 4 ranks (2 GPUs: 105 us against NCCL's 122 us and 175 us through the
+        switch), "nvls" from 8 ranks (176 us against 186 us peer-to-peer and NCCL's 210 us); "nccl" if the
+        symmetric-memory rendezvous fails (and for CPU / gloo groups, where the path uses whatever all_reduce
+        the group's backend provides)."""
         import torch.distributed as dist
 
         if not dist.is_initialized():
             raise RuntimeError("enable_data_parallel needs an initialised torch.distributed process group")
-        self._dp = dict(group=process_group, chunks=int(chunks), comm_dtype=comm_dtype, stream=None)
+        if comm not in ("auto", "nvls", "p2p", "nccl"):
+            raise ValueError("comm must be 'auto', 'nvls', 'p2p' or 'nccl'")
+        self._dp = dict(group=process_group, chunks=int(chunks), comm_dtype=comm_dtype, stream=None, comm=comm,
+                        symm=None)
         return self
+
+    def _symm_gradient_buffer(self, C, D, dev):
+        """The symmetric-memory [dW | db | pad] buffer and its peer addresses (allocated and exchanged once)."""
+        import torch.distributed as dist
+
+        dp = self._dp
+        if dp["symm"] is not None and dp["symm"]["key"] == (C, D, dev):
+            return dp["symm"]
+        import torch.distributed._symmetric_memory as symm
+
+        group = dp["group"] if dp["group"] is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = C * D + C
+        n_pad = -(-n // (4 * world)) * (4 * world)
+        buf = symm.empty(n_pad, dtype=torch.float32, device=dev)
+        handle = symm.rendezvous(buf, group.group_name)
+        mc = int(getattr(handle, "multicast_ptr", 0) or 0)
+        if dp["comm"] == "nvls" and mc == 0:
+            raise RuntimeError("comm='nvls': this group has no NVSwitch multicast mapping (multicast_ptr == 0)")
+        dp["symm"] = dict(key=(C, D, dev), buf=buf, handle=handle, ptrs=[int(p) for p in handle.buffer_ptrs],
+                          world=world, rank=rank, n=n_pad, multicast=mc,
+                          kind="nvls" if mc != 0 and (dp["comm"] == "nvls" or (dp["comm"] == "auto" and world >= 8))
+                          else "p2p")
+        return dp["symm"]
+
+    def _backward_data_parallel_p2p(self, dlogits, x16, C, D, B, gloss, want_b, dbp):
+        sm = self._symm_gradient_buffer(C, D, dlogits.device)
+        buf, h = sm["buf"], sm["handle"]
+        dW = buf[: C * D].view(C, D)
+        db = buf[C * D: C * D + C]
+        # gradient accumulation without zero_grad(): .grad may still alias this buffer -- move it out first
+        for prm, view in ((self.cell_layer.weight, dW), (self.cell_layer.bias, db)):
+            if prm.grad is not None and prm.grad.data_ptr() == view.data_ptr():
+                prm.grad = prm.grad.clone()
+        ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=True, db_partials=dbp,
+                          out=(dW, db))
+        h.barrier(channel=0)  # every rank's gradient is written
+        if sm["kind"] == "nvls":
+            ops.nvls_allreduce_avg(sm["multicast"], sm["world"], sm["rank"], sm["n"])
+        else:
+            ops.p2p_allreduce_avg(sm["ptrs"], sm["rank"], sm["n"])
+        h.barrier(channel=1)  # every rank's slice has landed everywhere (and nobody still reads my copy)
+        return dW, (db if want_b else None)
 
     def _backward_data_parallel(self, dlogits, x16, C, D, B, gloss, want_b, dbp):
         import torch.distributed as dist
 
         dp = self._dp
         dev = dlogits.device
+        if dp["comm"] in ("auto", "nvls", "p2p") and dlogits.is_cuda:
+            try:
+                return self._backward_data_parallel_p2p(dlogits, x16, C, D, B, gloss, want_b, dbp)
+            except Exception as e:  # noqa: BLE001
+                if dp["comm"] != "auto" or dp["symm"] is not None:
+                    raise
+                import sys
+
+                print(f"[geoguessr_ai_b200] symmetric-memory gradient exchange unavailable ({type(e).__name__}: {e}); "
+                      "using NCCL all-reduce", file=sys.stderr)
+                dp["comm"] = "nccl"
         if dp["stream"] is None or dp["stream"].device != dev:
             dp["stream"] = torch.cuda.Stream(device=dev)
         comm, cur = dp["stream"], torch.cuda.current_stream()

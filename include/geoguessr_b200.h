@@ -148,6 +148,23 @@ int gg_proto_refine(const void* rec, int nranks, long long rank_stride, const fl
                     float max_refinement_km, float* out_llh, long long* out_cell, int* out_guess, float* out_score,
                     int* out_proto, gg_stream_t stream);
 
+/* ---- a8 across GPUs: gradient averaging for data-parallel head training -------------------------
+ * The reference leaves this to DDP / Accelerate after loss.backward() (main_coordinator_idun_s3.py:423-424;
+ * SURVEY 8e).  peer_ptrs[r] = device address, valid on THIS device, of rank r's copy of the gradient buffer
+ * (n_floats fp32, e.g. [dW | db | pad], n_floats % 4 == 0), all mapped over NVLink (symmetric memory).  Two-shot
+ * all-reduce in place: this rank sums slice `rank` of every copy in rank order (deterministic, identical on all
+ * ranks), scales by 1 / world and writes the slice into every copy.  world in {1, 2, 4, 8}.  The caller must
+ * order the launch after every rank has written its buffer and must not read any copy before every rank's launch
+ * has completed (a symmetric-memory barrier on either side).  gg_p2p_slice: the [lo, hi) range of rank's slice
+ * in 16-byte units. */
+void gg_p2p_slice(size_t n_floats, int world, int rank, size_t* lo4, size_t* hi4);
+int gg_p2p_allreduce_avg(const unsigned long long* peer_ptrs, int world, int rank, size_t n_floats, gg_stream_t stream);
+/* The same exchange through the NVSwitch multicast mapping of the buffer (NVLS): multimem.ld_reduce adds the
+ * copies of slice `rank` inside the switch, multimem.st broadcasts the average to every copy; about one buffer
+ * of traffic per GPU and direction for any number of ranks.  multicast_ptr: the symmetric-memory handle's
+ * multicast address of the buffer on this device.  Same ordering contract as gg_p2p_allreduce_avg. */
+int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_floats, gg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

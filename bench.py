@@ -206,7 +206,7 @@ def run_b200_train(args):
     if world > 1:  # gradients are averaged inside backward(), range by range, overlapped with the dW GEMM
         model.enable_data_parallel(chunks=args.dp_chunks,
                                    comm_dtype=torch.bfloat16 if args.dp_bf16 else None,
-                                   comm="nccl" if args.dp_bf16 or args.dp_chunks > 1 else args.dp_comm)
+                                   comm="nccl" if args.dp_bf16 else args.dp_comm)
     params = [model.cell_layer.weight, model.cell_layer.bias]
     use_graph = not args.no_graph
     opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=use_graph)
@@ -387,12 +387,13 @@ def run_b200_train(args):
             grad_comm = (("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if model._dp["symm"]["kind"] == "nvls"
                           else "peer load/store two-shot (rank-order sums)")
                          + " all-reduce (avg, fp32) of [dW | db] in symmetric memory over NVLink, one kernel per rank "
-                           "between two symmetric-memory barriers")
+                           f"and geocell range between two symmetric-memory barriers; {args.dp_chunks} range(s), each "
+                           "exchanged while the next one's dW GEMM runs")
         else:
             grad_comm = (f"nccl avg, {'bf16' if args.dp_bf16 else 'fp32'}, {args.dp_chunks} geocell ranges overlapped "
                          "with the dW GEMM")
     # fuse, weight cast, head_fwd + merge, label vectors + row statistics, loss stream kernel, dW GEMM [, gradient exchange]
-    launches_per_step = 1 + 1 + 2 + 2 + 1 + 1 + (1 if world > 1 and model._dp["symm"] is not None else 0)
+    launches_per_step = 1 + 1 + 2 + 2 + 1 + 1 + (args.dp_chunks - 1 + args.dp_chunks if world > 1 and model._dp["symm"] is not None else 0)
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -322,14 +322,37 @@ class SuperGuessr(nn.Module):
         for prm, view in ((self.cell_layer.weight, dW), (self.cell_layer.bias, db)):
             if prm.grad is not None and prm.grad.data_ptr() == view.data_ptr():
                 prm.grad = prm.grad.clone()
-        ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=True, db_partials=dbp,
-                          out=(dW, db))
-        h.barrier(channel=0)  # every rank's gradient is written
-        if sm["kind"] == "nvls":
-            ops.nvls_allreduce_avg(sm["multicast"], sm["world"], sm["rank"], sm["n"])
-        else:
-            ops.p2p_allreduce_avg(sm["ptrs"], sm["rank"], sm["n"])
-        h.barrier(channel=1)  # every rank's slice has landed everywhere (and nobody still reads my copy)
+        dp = self._dp
+        dev = dlogits.device
+        if dp["stream"] is None or dp["stream"].device != dev:
+            dp["stream"] = torch.cuda.Stream(device=dev)
+        comm, cur = dp["stream"], torch.cuda.current_stream()
+
+        def exchange(off, n):  # floats [off, off + n) of the buffer, on the current (= communication) stream
+            h.barrier(channel=0)  # every rank's part of the gradient is written
+            if sm["kind"] == "nvls":
+                ops.nvls_allreduce_avg(sm["multicast"] + 4 * off, sm["world"], sm["rank"], n)
+            else:
+                ops.p2p_allreduce_avg([p + 4 * off for p in sm["ptrs"]], sm["rank"], n)
+            h.barrier(channel=1)  # every rank's slice has landed everywhere (and nobody still reads my copy)
+
+        # The dW GEMM runs in `chunks` geocell ranges; each range is exchanged on the communication stream while
+        # the next one is computed (the exchange kernel's small CTAs co-reside with the persistent GEMM), so only
+        # the last range's exchange -- which also carries db -- is exposed.
+        bounds = dp_chunk_bounds(C, dp["chunks"])
+        comm.wait_stream(cur)
+        for i, (c0, c1) in enumerate(bounds):
+            ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=True, db_partials=dbp,
+                              c_range=(c0, c1), out=(dW, db))
+            done = torch.cuda.Event()
+            done.record(cur)
+            comm.wait_event(done)
+            with torch.cuda.stream(comm):
+                if i + 1 < len(bounds):
+                    exchange(c0 * D, (c1 - c0) * D)
+                else:  # last range: its dW rows, db and the padding in one launch
+                    exchange(c0 * D, sm["n"] - c0 * D)
+        cur.wait_stream(comm)
         return dW, (db if want_b else None)
 
     def _backward_data_parallel(self, dlogits, x16, C, D, B, gloss, want_b, dbp):

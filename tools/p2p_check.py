@@ -72,7 +72,7 @@ if mc:
 
 
 # ---- 2. a data-parallel training step, p2p vs nccl
-def train_step(comm):
+def train_step(comm, chunks=1):
     import contextlib
     import io
 
@@ -85,7 +85,7 @@ def train_step(comm):
         m.cell_layer.weight.copy_(W)
         m.cell_layer.bias.copy_(b)
     m.train()
-    m.enable_data_parallel(comm=comm)
+    m.enable_data_parallel(comm=comm, chunks=chunks)
     sl = slice(rank * B, (rank + 1) * B)
     out = m(embedding=emb[sl].to(dev), labels=labels[sl].to(dev), labels_clf=torch.zeros(B, dtype=torch.int64, device=dev))
     out.loss.backward()
@@ -94,12 +94,12 @@ def train_step(comm):
 
 
 gw_n, gb_n, _ = train_step("nccl")
-for kind in (["nvls"] if mc else []) + ["p2p"]:
-    gw_p, gb_p, used = train_step(kind)
+for kind, chunks in ([("nvls", 1), ("nvls", 3)] if mc else []) + [("p2p", 1), ("p2p", 3)]:
+    gw_p, gb_p, used = train_step(kind, chunks)
     assert used, f"{kind} path did not run"
     ew = (gw_p - gw_n).abs().max().item() / gw_n.abs().max().item()
     eb = (gb_p - gb_n).abs().max().item() / gb_n.abs().max().item()
-    say(f"DP step {kind} vs nccl: dW rel diff {ew:.2e}, db rel diff {eb:.2e}")
+    say(f"DP step {kind} x{chunks} vs nccl: dW rel diff {ew:.2e}, db rel diff {eb:.2e}")
     assert ew < 1e-6 and eb < 1e-6
 
 

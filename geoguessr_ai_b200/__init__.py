@@ -10,7 +10,7 @@ CUDA: TMA + tcgen05/TMEM GEMMs, fused bandwidth-bound kernels) behind the C ABI 
 from .utils import ModelOutput, TopK  # noqa: F401
 from .super_guessr import SuperGuessr, dp_chunk_bounds  # noqa: F401
 from .proto_refiner import ProtoRefiner, shard_cells  # noqa: F401
-from . import embedding_store, ops, synth  # noqa: F401
+from . import embedding_store, ops, proto_builder, synth  # noqa: F401
 
 __all__ = ["SuperGuessr", "ProtoRefiner", "ModelOutput", "TopK", "ops", "synth", "shard_cells", "dp_chunk_bounds",
-           "embedding_store"]
+           "embedding_store", "proto_builder"]

@@ -44,6 +44,7 @@ SIGNATURES = {
     "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P]),
     "gg_proto_retrieve": (I, [P, P, I, I, P, I, I, P, P, P, L, P, I, I, I, P, P, P]),
     "gg_proto_refine": (I, [P, I, L, P, I, P, I, P, I, I, F, F, P, P, P, P, P, P]),
+    "gg_build_prototypes": (I, [P, L, I, I, P, P, P, L, P, P, P, P]),
     "gg_p2p_slice": (None, [c_size_t, I, I, P, P]),
     "gg_p2p_allreduce_avg": (I, [P, I, I, c_size_t, P]),
     "gg_nvls_allreduce_avg": (I, [P, I, I, c_size_t, P]),

@@ -109,6 +109,55 @@ __global__ void row_sqnorm_bf16_kernel(const bf16* __restrict__ m, long long row
   if ((threadIdx.x & 31) == 0) out[row] = acc;
 }
 
+
+// Prototype bank builder: one prototype per cluster = mean over the cluster's member locations of
+// the location's mean over its V headings -- the reference's Embeddings.generate_embeddings
+// (models/proto_refiner.py:461-517: per member `vec.mean(dim=0)`, running fp32 sum in member order,
+// `sum / count`; members out of range or without finite coordinates are skipped (:467-472); no valid member ->
+// zero vector (:499-515)), with the encoder replaced by the stored embeddings.  One CTA per cluster, threads
+// across D (16-byte loads), members walked in list order so the fp32 sum has the reference's order.
+__global__ void __launch_bounds__(256)
+build_prototypes_kernel(const float* __restrict__ emb, long long L, int V, int D, const long long* __restrict__ member_off,
+                        const int* __restrict__ members, const unsigned char* __restrict__ valid,
+                        bf16* __restrict__ bank, float* __restrict__ bank_f32, int* __restrict__ count_out) {
+  const long long p = blockIdx.x;
+  const long long m0 = member_off[p], m1 = member_off[p + 1];
+  const int d4 = D >> 2;
+  const float inv_v = 1.0f / static_cast<float>(V);
+  int count = 0;
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) {
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = 0;
+    for (long long m = m0; m < m1; ++m) {
+      const long long idx = members[m];
+      if (idx < 0 || idx >= L || (valid && !valid[idx])) continue;  // block-uniform
+      const float4* src = reinterpret_cast<const float4*>(emb + idx * static_cast<long long>(V) * D) + i;
+      float4 acc = __ldg(src);
+      for (int v = 1; v < V; ++v) {
+        const float4 t = __ldg(src + static_cast<size_t>(v) * d4);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      if (V > 1) { acc.x *= inv_v; acc.y *= inv_v; acc.z *= inv_v; acc.w *= inv_v; }
+      sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += acc.w;
+      ++n;
+    }
+    if (n > 0) {
+      const float c = static_cast<float>(n);
+      sum.x /= c; sum.y /= c; sum.z /= c; sum.w /= c;
+    }
+    count = n;
+    uint2 o;
+    o.x = pack_bf16x2(sum.x, sum.y);
+    o.y = pack_bf16x2(sum.z, sum.w);
+    *reinterpret_cast<uint2*>(bank + p * D + 4 * i) = o;
+    if (bank_f32) *reinterpret_cast<float4*>(bank_f32 + p * D + 4 * i) = sum;
+  }
+  if (count_out && threadIdx.x == 0) {
+    if (d4 == 0) count = 0;
+    count_out[p] = count;
+  }
+}
+
 }  // namespace gg
 
 using namespace gg;
@@ -158,6 +207,20 @@ extern "C" int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, flo
   GG_CHECK(m_bf16 && out && rows > 0 && D > 0 && D % 8 == 0, GG_ERR_ARG, "gg_row_sqnorm_bf16: bad arguments");
   row_sqnorm_bf16_kernel<<<static_cast<int>(ceil_div_ll(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(m_bf16), rows, D, out);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_build_prototypes(const float* emb, long long L, int V, int D, const long long* member_off,
+                                   const int* members, const unsigned char* valid, long long P, void* bank_bf16,
+                                   float* bank_f32, int* count, gg_stream_t stream) {
+  GG_CHECK(emb && member_off && members && bank_bf16, GG_ERR_ARG, "gg_build_prototypes: null pointer");
+  GG_CHECK(L > 0 && V >= 1 && D > 0 && D % 4 == 0, GG_ERR_ARG, "gg_build_prototypes: L=%lld V=%d D=%d (D a multiple of 4)", L,
+           V, D);
+  GG_CHECK(P >= 0 && P <= 0x7fffffffLL, GG_ERR_ARG, "gg_build_prototypes: P=%lld clusters", P);
+  if (P == 0) return GG_OK;
+  build_prototypes_kernel<<<static_cast<unsigned int>(P), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      emb, L, V, D, member_off, members, valid, static_cast<bf16*>(bank_bf16), bank_f32, count);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

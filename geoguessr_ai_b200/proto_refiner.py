@@ -107,8 +107,9 @@ class ProtoRefiner(nn.Module):
         else:
             raise NotImplementedError(
                 "protos=None asks the reference to BUILD prototypes from images (embedders + S3, "
-                "proto_refiner.py:89-103); that offline job is outside this package. Pass protos='load', "
-                "protos=[...]+coords=[...], or bank=(cell_off, bank, coords).")
+                "proto_refiner.py:89-103).  With stored embeddings that job is "
+                "geoguessr_ai_b200.proto_builder.build_prototype_bank(embeddings, proto_df, num_cells) -> pass its "
+                "result as bank=(cell_off, bank, coords); or pass protos='load' / protos=[...]+coords=[...].")
         self._install_bank(cell_off, mat, xy, shard, device, bank_is_local)
 
     # ---- bank construction ------------------------------------------------------------------

@@ -148,6 +148,17 @@ int gg_proto_refine(const void* rec, int nranks, long long rank_stride, const fl
                     float max_refinement_km, float* out_llh, long long* out_cell, int* out_guess, float* out_score,
                     int* out_proto, gg_stream_t stream);
 
+/* ---- next row f-3: prototype bank builder --------------------------------------------------------
+ * models/proto_refiner.py:391-406 + :461-517 (Embeddings.generate_embeddings) with the encoder replaced by stored
+ * embeddings: prototype p = mean over the members of cluster p (members[member_off[p] .. member_off[p+1]), location
+ * indices into emb (L,V,D) fp32, walked in list order) of the member's mean over its V headings; members < 0, >= L
+ * or with valid[idx] == 0 (non-finite coordinates, :470-472) are skipped; a cluster without valid members gives
+ * the zero vector (:499-515).  bank_bf16 (P,D) is the retrieval operand; bank_f32 (optional) the unrounded mean;
+ * count (optional, P) the members used. */
+int gg_build_prototypes(const float* emb, long long L, int V, int D, const long long* member_off, const int* members,
+                        const unsigned char* valid, long long P, void* bank_bf16, float* bank_f32, int* count,
+                        gg_stream_t stream);
+
 /* ---- a8 across GPUs: gradient averaging for data-parallel head training -------------------------
  * The reference leaves this to DDP / Accelerate after loss.backward() (main_coordinator_idun_s3.py:423-424;
  * SURVEY 8e).  peer_ptrs[r] = device address, valid on THIS device, of rank r's copy of the gradient buffer

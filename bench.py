@@ -296,12 +296,13 @@ def run_b200_train(args):
     # ahead, so the events bracket device time only (no launch gaps inside the brackets).
     ops.enable_timing(True)
     barrier()
-    for i in range(min(K, 20)):
+    n_timed = min(K, 20)
+    for i in range(n_timed):
         torch.cuda._sleep(2_000_000)
         step(*resident[i % 3])
     tms = ops.timing_ms()
     ops.enable_timing(False)
-    per = {k: sum(v) / len(v) for k, v in tms.items()}
+    per = {k: sum(v) / n_timed for k, v in tms.items()}  # per step (a launcher may run more than once: --dp-chunks)
 
     # ---------------- end to end from host buffers (`e2e`): H2D of the batch + D2H of the loss every step
     copy_stream = torch.cuda.Stream()

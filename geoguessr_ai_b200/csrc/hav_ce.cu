@@ -17,8 +17,7 @@
 //
 // Kernels:
 //  (T) centroid table (once per table): unit vectors in class order, plus a copy sorted along a
-//      Morton curve in 64-cell spatial groups with one bounding cap (centre, angular radius) each and,
-//      per spatial group, the bitmask of the 64-column class groups its members fall in.
+//      Morton curve in 64-cell spatial groups with one bounding cap (centre, angular radius) each.
 //  (A) gg_hav_row_stats, no B x C data: label unit vectors (fp64 trig, one thread per row), then one
 //      warp per row bounds every spatial group's distance from its cap, evaluates exact q only in
 //      the groups that can hold the nearest cell / a near cell, and emits {u, q_thr, dmin, 1/sum s}
@@ -64,19 +63,17 @@ struct RowRec {  // 32 bytes per row, written by (A), read by (B)/(C)
 //   x[Cpad] y[Cpad] z[Cpad]                       class order, Cpad = C rounded up to 256
 //   scell[Cs] = {x, y, z, class index (int bits)}  Morton order, Cs = C rounded up to 64 (pad: 1e9, INT_MAX)
 //   caps[Cs/64] = {cx, cy, cz, radius}             radius 4 = anywhere, < 0 = empty group
-//   gmask[kMaxMaskWords * Cs/64] (uint)            class groups touched by each spatial group
 struct TableView {
   int Cpad, Cs, ngroups;
   const float *x, *y, *z;
   const float4* scell;
   const float4* caps;
-  const uint32_t* gmask;
 };
 __host__ __device__ inline int table_cpad(int C) { return (C + 255) / 256 * 256; }
 __host__ __device__ inline int table_cs(int C) { return (C + 63) / 64 * 64; }
 __host__ __device__ inline size_t table_words(int C) {
   const size_t Cpad = table_cpad(C), Cs = table_cs(C);
-  return 3 * Cpad + 4 * Cs + (4 + kMaxMaskWords) * (Cs / kCellsPerGroup);
+  return 3 * Cpad + 4 * Cs + 4 * (Cs / kCellsPerGroup);
 }
 __host__ __device__ inline TableView view_table(const float* t, int C) {
   TableView v;
@@ -88,7 +85,6 @@ __host__ __device__ inline TableView view_table(const float* t, int C) {
   v.z = v.y + v.Cpad;
   v.scell = reinterpret_cast<const float4*>(v.z + v.Cpad);  // 3 * Cpad words: 16-byte aligned (Cpad % 256 == 0)
   v.caps = v.scell + v.Cs;
-  v.gmask = reinterpret_cast<const uint32_t*>(v.caps + v.ngroups);
   return v;
 }
 
@@ -236,7 +232,7 @@ __global__ void table_rank_kernel(const uint32_t* __restrict__ keys, int C, floa
   if (c < C) scell[rank].w = __int_as_float(c);
 }
 // sorted copy, one warp per spatial group (2 cells per lane): centre = normalised mean of the
-// members, radius = largest member angle + margin; class-group bitmask of the members
+// members, radius = largest member angle + margin
 __global__ void table_group_kernel(float* __restrict__ table, int C) {
   const TableView tv = view_table(table, C);
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -274,15 +270,6 @@ __global__ void table_group_kernel(float* __restrict__ table, int C) {
     rad = warp_max(a) * (1.0f + 1.0e-6f) + kCapMargin;
   }
   if (lane == 0) const_cast<float4*>(tv.caps)[g] = make_float4(mx, my, mz, rad);
-  uint32_t* gm = const_cast<uint32_t*>(tv.gmask) + static_cast<size_t>(g) * kMaxMaskWords;
-  for (int w = 0; w < kMaxMaskWords; ++w) {
-    uint32_t bits = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-      if (idx[h] != 0x7fffffff && (idx[h] >> 11) == w) bits |= 1u << ((idx[h] >> 6) & 31);
-    bits = __reduce_or_sync(0xffffffffu, bits);
-    if (lane == 0) gm[w] = bits;
-  }
 }
 
 // ------------------------------------------------------------------ (A) per-row statistics

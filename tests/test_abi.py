@@ -32,7 +32,7 @@ def test_layout_helpers():
     assert lib.gg_head_logits_ld(12647) == 12800 and lib.gg_head_logits_ld(64) == 256
     assert lib.gg_head_bias_pad(12647) == 12800
     assert lib.gg_hav_cpad(12647) == 12800
-    assert lib.gg_centroid_table_floats(12647) == 3 * 12800 + 4 * 12672 + 12 * 198
+    assert lib.gg_centroid_table_floats(12647) == 3 * 12800 + 4 * 12672 + 4 * 198
     assert lib.gg_head_fwd_workspace_bytes(4096, 12647, 5) >= 148 * 2 * 128 * 12 * 4
     assert lib.gg_proto_retrieve_workspace_bytes(64, 5, 1024, 12647) > 64 * 5 * 1024 * 2
 

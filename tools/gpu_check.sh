@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box pass: parity tests, bench (both arms), ncu launch list + full capture of the three hot kernels.
-# Usage (from the repo root, under gpurun): bash tools/gpu_check.sh [tests] [bench] [launches] [ncu]
+# Usage (from the repo root, under gpurun): bash tools/gpu_check.sh [tests] [smoke] [bench] [kbench] [launches] [ncu] [infer] [p2p]
 set -u
 mkdir -p gpurun_out
 what="${*:-tests bench launches ncu}"
@@ -27,6 +27,11 @@ for w in $what; do
     ncuinfer)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(proto_|head_fwd|head_merge|fuse_headings)" -s 27 -c 9 -f -o gpurun_out/prof_infer \
         python bench.py --workload infer --protos 1000000 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_infer.log 2>&1; echo "ncuinfer rc=$?" ;;
+    p2p)  # needs gpurun --gpus N (N = 2, 4 or 8): gradient exchange kernels against NCCL + data-parallel bench
+      N=$(nvidia-smi -L | wc -l)
+      T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29540"
+      timeout 200 $T tools/p2p_check.py > gpurun_out/p2p_check_${N}gpu.log 2>&1; tail -9 gpurun_out/p2p_check_${N}gpu.log
+      timeout 200 $T bench.py --gpus $N --no-cpu > gpurun_out/scale${N}_train.json 2> gpurun_out/scale${N}_train.err; echo "bench$N rc=$?" ;;
     klaunch)
       timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -s 30 -c 60 --csv --log-file gpurun_out/klaunch.csv \
         python tools/kbench.py 3 > gpurun_out/klaunch.log 2>&1; echo "klaunch rc=$?" ;;

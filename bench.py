@@ -402,8 +402,12 @@ def run_b200_train(args):
                                             grad_allreduce=grad_comm), "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "steps": Ke},
-        "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-        "loss": final_loss,
+        "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels,
+        "kernels_timing": "CUDA events around every launcher in a second, eager pass over the same steps with nothing "
+                          "running beside the timed launcher (the label statistics, which the timed region runs "
+                          "underneath the head GEMM on a side stream, run serially there); a launcher may hold a small "
+                          "helper kernel (gg_head_fwd: GEMM + merge)",
+        "cpu_baseline": cpu, "loss": final_loss,
     }
     print(json.dumps(line), flush=True)
     finish(world)

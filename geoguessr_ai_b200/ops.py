@@ -26,6 +26,10 @@ def enable_timing(on: bool = True):
     _events = {} if on else None
 
 
+def timing_enabled() -> bool:
+    return _events is not None
+
+
 def timing_ms():
     """Synchronises and returns {launcher: [ms per call, ...]} for the calls since enable_timing()."""
     torch.cuda.synchronize()

@@ -357,6 +357,7 @@ def run_b200_train(args):
         "gg_hav_ce_fwd_bwd": ("hbm", B * C * (2 + 2) + 8 * B + 12 * C, "GB/s"),
         "gg_fuse_headings": ("hbm", B * D * (4 * V + 2), "GB/s"),
         "gg_prepare_head_weights": ("hbm", C * D * (4 + 2) + 8 * C, "GB/s"),
+        "gg_fuse_and_prepare": ("hbm", B * D * (4 * V + 2) + C * D * (4 + 2) + 8 * C, "GB/s"),
     }
     kernels = {}
     for name, ms in per.items():
@@ -393,8 +394,8 @@ def run_b200_train(args):
         else:
             grad_comm = (f"nccl avg, {'bf16' if args.dp_bf16 else 'fp32'}, {args.dp_chunks} geocell ranges overlapped "
                          "with the dW GEMM")
-    # fuse, weight cast, head_fwd + merge, label vectors + row statistics, loss stream kernel, dW GEMM [, gradient exchange]
-    launches_per_step = 1 + 1 + 2 + 2 + 1 + 1 + (args.dp_chunks - 1 + args.dp_chunks if world > 1 and model._dp["symm"] is not None else 0)
+    # fusion + weight cast, head_fwd + merge, label vectors + row statistics, loss stream kernel, dW GEMM [, gradient exchange]
+    launches_per_step = 1 + 2 + 2 + 1 + 1 + (args.dp_chunks - 1 + args.dp_chunks if world > 1 and model._dp["symm"] is not None else 0)
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

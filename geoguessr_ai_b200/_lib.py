@@ -33,6 +33,7 @@ SIGNATURES = {
     "gg_proto_retrieve_workspace_bytes": (c_size_t, [I, I, I, I]),
     "gg_fuse_headings": (I, [P, P, I, I, I, I, P, P]),
     "gg_prepare_head_weights": (I, [P, P, P, P, I, I, I, P]),
+    "gg_fuse_and_prepare": (I, [P, P, I, I, I, P, P, P, P, I, I, P]),
     "gg_cast_bf16": (I, [P, P, L, P]),
     "gg_row_sqnorm_bf16": (I, [P, L, I, P, P]),
     "gg_head_fwd": (I, [P, P, P, I, I, I, P, I, I, P, P, P, P, P, P, P, P]),

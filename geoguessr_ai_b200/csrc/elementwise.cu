@@ -11,9 +11,8 @@ namespace gg {
 // contracted against W' = [hi | lo | hi] so that x.W ~= hi.hi + hi.lo + lo.hi.
 // Optionally also writes ||hi||^2 per row (prototype retrieval needs the query norms).
 template <int SPLIT>
-__global__ void fuse_headings_kernel(const float* __restrict__ emb, bf16* __restrict__ x, int B, int V, int D, int ld,
-                                     float* __restrict__ sqnorm) {
-  const int row = blockIdx.x;
+__device__ __forceinline__ void fuse_headings_row(const float* __restrict__ emb, bf16* __restrict__ x, int row, int V,
+                                                  int D, int ld, float* __restrict__ sqnorm) {
   const float inv = 1.0f / static_cast<float>(V);
   const float4* src = reinterpret_cast<const float4*>(emb + static_cast<size_t>(row) * V * D);
   const int d4 = D >> 2;
@@ -55,19 +54,24 @@ __global__ void fuse_headings_kernel(const float* __restrict__ emb, bf16* __rest
     }
   }
 }
+template <int SPLIT>
+__global__ void fuse_headings_kernel(const float* __restrict__ emb, bf16* __restrict__ x, int B, int V, int D, int ld,
+                                     float* __restrict__ sqnorm) {
+  fuse_headings_row<SPLIT>(emb, x, blockIdx.x, V, D, ld, sqnorm);
+}
 
 // W (C,D) fp32 -> bf16 operand.  split = 0: (C,D).  split = 1: (C,3D) = [hi | lo | hi].
 // Blocks past the weight matrix zero-pad the bias (b (C) -> bias_pad (Cpad)); b == nullptr: weights only.
 template <int SPLIT>
-__global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, long long n4, int d4,
-                                   const float* __restrict__ b, float* __restrict__ bias_pad, int C, int Cpad,
-                                   int w_blocks) {
-  if (static_cast<int>(blockIdx.x) >= w_blocks) {
-    const int i = (blockIdx.x - w_blocks) * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void cast_weight_block(int block, const float* __restrict__ w, bf16* __restrict__ out,
+                                                  long long n4, int d4, const float* __restrict__ b,
+                                                  float* __restrict__ bias_pad, int C, int Cpad, int w_blocks) {
+  if (block >= w_blocks) {
+    const int i = (block - w_blocks) * blockDim.x + threadIdx.x;
     if (i < Cpad) bias_pad[i] = i < C ? b[i] : 0.f;
     return;
   }
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long i = static_cast<long long>(block) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = __ldcs(reinterpret_cast<const float4*>(w) + i);
   uint2 hi;
@@ -86,6 +90,24 @@ __global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict
     o[d4 + c] = lo;
     o[2 * d4 + c] = hi;
   }
+}
+template <int SPLIT>
+__global__ void cast_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, long long n4, int d4,
+                                   const float* __restrict__ b, float* __restrict__ bias_pad, int C, int Cpad,
+                                   int w_blocks) {
+  cast_weight_block<SPLIT>(blockIdx.x, w, out, n4, d4, b, bias_pad, C, Cpad, w_blocks);
+}
+
+// Heading fusion and weight cast of one training step in ONE launch: two short HBM-bound kernels back to back
+// each pay their own ramp and tail (37 us for 153 MB, profiles/r01g); as one grid the cast blocks fill in behind
+// the fusion blocks.  Blocks [0, B) fuse one row each, the rest cast 256 float4 of W each / pad the bias.
+template <int SPLIT>
+__global__ void __launch_bounds__(256)
+fuse_and_cast_kernel(const float* __restrict__ emb, bf16* __restrict__ x, int B, int V, int D, int ld,
+                     const float* __restrict__ w, bf16* __restrict__ w16, long long n4, const float* __restrict__ b,
+                     float* __restrict__ bias_pad, int C, int Cpad, int w_blocks) {
+  if (static_cast<int>(blockIdx.x) < B) fuse_headings_row<SPLIT>(emb, x, blockIdx.x, V, D, ld, nullptr);
+  else cast_weight_block<SPLIT>(blockIdx.x - B, w, w16, n4, D / 4, b, bias_pad, C, Cpad, w_blocks);
 }
 
 // squared L2 norm of each bf16 row (prototype bank), one warp per row
@@ -190,6 +212,27 @@ extern "C" int gg_prepare_head_weights(const float* w, const float* b, void* w_b
     cast_weight_kernel<1><<<grid, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4, b, bias_pad, C, Cpad, blocks);
   else
     cast_weight_kernel<0><<<grid, 256, 0, s>>>(w, static_cast<bf16*>(w_bf16), n4, D / 4, b, bias_pad, C, Cpad, blocks);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_fuse_and_prepare(const float* emb, void* x_bf16, int B, int V, int D, const float* w, const float* b,
+                                   void* w_bf16, float* bias_pad, int C, int split, gg_stream_t stream) {
+  GG_CHECK(emb && x_bf16 && w && b && w_bf16 && bias_pad && B > 0 && V > 0 && C > 0 && D > 0, GG_ERR_ARG,
+           "gg_fuse_and_prepare: bad arguments");
+  GG_CHECK(D % 8 == 0, GG_ERR_ARG, "gg_fuse_and_prepare: D=%d must be a multiple of 8", D);
+  GG_CHECK((reinterpret_cast<uintptr_t>(emb) & 15) == 0, GG_ERR_ARG, "gg_fuse_and_prepare: emb must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n4 = static_cast<long long>(C) * D / 4;
+  const int w_blocks = static_cast<int>(ceil_div_ll(n4, 256));
+  const int Cpad = gg_head_bias_pad(C);
+  const int grid = B + w_blocks + ceil_div(Cpad, 256);
+  if (split)
+    fuse_and_cast_kernel<1><<<grid, 256, 0, s>>>(emb, static_cast<bf16*>(x_bf16), B, V, D, 3 * D, w,
+                                                 static_cast<bf16*>(w_bf16), n4, b, bias_pad, C, Cpad, w_blocks);
+  else
+    fuse_and_cast_kernel<0><<<grid, 256, 0, s>>>(emb, static_cast<bf16*>(x_bf16), B, V, D, D, w,
+                                                 static_cast<bf16*>(w_bf16), n4, b, bias_pad, C, Cpad, w_blocks);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -107,6 +107,28 @@ def prepare_head_weights(weight: torch.Tensor, bias: torch.Tensor, split: bool =
     return w16, bp
 
 
+def fuse_and_prepare(emb: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, split: bool = False):
+    """fuse_headings + prepare_head_weights of one training step in a single launch (gg_fuse_and_prepare).
+    Returns (x bf16, w16 bf16, bias_pad fp32)."""
+    _need_cuda(emb, weight, bias)
+    emb = emb.float().contiguous() if emb.dtype != torch.float32 else emb.contiguous()
+    if emb.dim() == 2:
+        B, D = emb.shape
+        V = 1
+    else:
+        B, V, D = emb.shape
+    C = weight.shape[0]
+    assert weight.shape[1] == D, "embedding dim of the batch and of the head differ"
+    w = weight.detach().float().contiguous()
+    b = bias.detach().float().contiguous()
+    x = torch.empty((B, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
+    w16 = torch.empty((C, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
+    bp = torch.empty((bias_pad_len(C),), dtype=torch.float32, device=emb.device)
+    _call("gg_fuse_and_prepare", _lib.load().gg_fuse_and_prepare, _ptr(emb), _ptr(x), B, V, D, _ptr(w), _ptr(b), _ptr(w16),
+          _ptr(bp), C, int(split), _stream())
+    return x, w16, bp
+
+
 def row_sqnorm_bf16(m: torch.Tensor) -> torch.Tensor:
     _need_cuda(m)
     assert m.dtype == torch.bfloat16 and m.dim() == 2 and m.is_contiguous()

@@ -44,8 +44,15 @@ class _GeocellHeadLoss(torch.autograd.Function):
                               tau=module.label_smoothing_tau, far_km=module.far_km, out=stats)
         elif smooth and not under_gemm:
             stats = module._row_stats_async(labels, C)
-        st = module._operands(weight, bias)
-        x16 = ops.fuse_headings(embedding, split=st["split"])
+        if module.training:
+            # the weights move every step: their bf16 operand is rebuilt in the same launch as the fusion
+            split = module.precision == "bf16x3"
+            x16, w16, bias_pad = ops.fuse_and_prepare(embedding, weight, bias, split=split)
+            module._op_cache = None  # the eval-mode cache must not outlive a training step
+            st = dict(w16=w16, bias_pad=bias_pad, split=split)
+        else:
+            st = module._operands(weight, bias)
+            x16 = ops.fuse_headings(embedding, split=st["split"])
         if under_gemm:
             fork = module._row_stats_prepare(labels, C)
         head = ops.head_forward(x16, st["w16"], st["bias_pad"], C, module.num_candidates,

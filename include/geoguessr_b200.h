@@ -58,6 +58,10 @@ int gg_fuse_headings(const float* emb, void* x_bf16, int B, int V, int D, int sp
  * (C,3D) = [hi|lo|hi] when split=1; b (C) -> zero-padded fp32 (gg_head_bias_pad(C)). */
 int gg_prepare_head_weights(const float* w, const float* b, void* w_bf16, float* bias_pad, int C, int D, int split,
                             gg_stream_t stream);
+/* Both of the above for one training step in a single launch (the weights move every step, so their bf16
+ * operand is rebuilt next to the fusion of that step's batch): same arguments and results, no sqnorm. */
+int gg_fuse_and_prepare(const float* emb, void* x_bf16, int B, int V, int D, const float* w, const float* b,
+                        void* w_bf16, float* bias_pad, int C, int split, gg_stream_t stream);
 int gg_cast_bf16(const float* src, void* dst_bf16, long long n, gg_stream_t stream);
 int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, float* out, gg_stream_t stream);
 

@@ -40,7 +40,7 @@ for w in $what; do
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on \
-        -k regex:"${NCU_KERNELS:-^(cast_weight|fuse_headings|hav_|head_|label_xyz|pad_bias|db_final)}" -s ${NCU_SKIP:-36} -c ${NCU_COUNT:-9} -f -o gpurun_out/prof_train \
+        -k regex:"${NCU_KERNELS:-^(cast_weight|fuse_|hav_|head_|label_xyz)}" -s ${NCU_SKIP:-28} -c ${NCU_COUNT:-7} -f -o gpurun_out/prof_train \
         python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
   esac
 done

@@ -48,6 +48,7 @@ dl = ops.hav_ce(head["logits"], head["lse"], None, table, C, want_db=True, want_
 flops = 2.0 * B * C * D
 timed("fuse_headings", lambda: ops.fuse_headings(emb), B * D * 18, "TB/s*1e3")
 timed("prepare_head_weights", lambda: ops.prepare_head_weights(W, b), C * D * 6, "TB/s*1e3")
+timed("fuse_and_prepare", lambda: ops.fuse_and_prepare(emb, W, b), B * D * 18 + C * D * 6, "TB/s*1e3")
 timed("head_fwd train", lambda: ops.head_forward(x16, w16, bp, C, k, cent, want_logits=True), flops, "PF/s*1e3")
 timed("head_fwd serve", lambda: ops.head_forward(x16, w16, bp, C, k, cent, want_logits=False), flops, "PF/s*1e3")
 timed("hav_row_stats", lambda: ops.hav_row_stats(labels, table, C, out=stats))

@@ -16,11 +16,16 @@ ATen call), of
 * ``models/utils.py:20-57``           (``smooth_labels``, ``haversine_matrix``)
 * ``models/proto_refiner.py:129-237,364-389`` and
   ``preprocessing/geo_utils.py:39-54`` (refiner forward) -> ``proto_refiner_oracle``
+* ``models/proto_refiner.py:461-517`` (cluster prototypes from member embeddings; the
+  encoder call replaced by stored embeddings)         -> ``proto_builder_oracle``
 
 Pinning: the reference's own tests hold no vector for this path (its only
 collected test is ``assert True``), so the oracle is pinned against the
 reference ITSELF, imported and executed in the build container by
 ``oracle/make_golden.py`` (which needs ``/root/reference``); the resulting
 vectors are committed under ``tests/golden/`` and ``tests/test_oracle.py``
-re-checks the oracle against them on every run.
+re-checks the oracle against them on every run.  The same holds for the two
+host-side formats next to the path: ``make_golden_sqlite.py`` executes the
+reference's panorama grouping (``training/load_sqlite_dataset.py:104-150``) and
+``make_golden_protos.py`` its ``ProtoDataManager`` (``models/utils.py:98-181``).
 """

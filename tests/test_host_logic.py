@@ -289,3 +289,17 @@ def test_head_bwd_schedule_covers_every_unit_once(T, nk, P):
                 assert 0 <= lower < p and parks[lower] == (t, k0)
     work = [sum(k1 - k0 for _, k0, k1 in segs) for segs, _ in scheds]
     assert max(work) - min(work) <= 1 + (0 if T % P else 0)  # balanced to one k-block
+
+
+@pytest.mark.parametrize("n,world", [(12647 * 1024 + 12648, 2), (12647 * 576 + 12648, 8), (16, 8), (4, 4), (40, 1), (1000, 4)])
+def test_gradient_exchange_slices_cover_the_buffer_once(n, world):
+    """gg_p2p_slice (host side of the two-shot all-reduce): the ranks' slices tile the 16-byte units of the buffer."""
+    from geoguessr_ai_b200 import ops
+
+    n -= n % 4
+    edges = [ops.p2p_slice(n, world, r) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+        assert lo <= hi == lo2 and lo % 4 == 0
+    sizes = [hi - lo for lo, hi in edges]
+    assert max(sizes) - min(s for s in sizes[:-1] or sizes) <= 4 * world or world == 1

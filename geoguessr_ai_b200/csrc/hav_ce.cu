@@ -477,7 +477,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
 }
 
 constexpr int kStripWarps = 4;                       // warps per CTA: a strip of 1024 classes
-constexpr int kStripCols = kStripWarps * kColsPerWarp;
 constexpr int kStageRows = 8;                        // rows per pipeline stage
 constexpr int kStreamStages = 3;
 constexpr int kStreamThreads = 32 * kStripWarps;
@@ -732,7 +731,7 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
   // order: deterministic, and no second launch.
   __threadfence();  // my row_acc adds are performed device-wide before this CTA takes its ticket
   __syncwarp();
-  named_bar_sync(1, nactive * 32);  // consumer warps only (the producer and idle warps have returned)
+  named_bar_sync(1, nactive * 32);  // the warps that own a slice (idle warps of the last strip have returned)
   if (warp != 0) return;
   unsigned int ticket = 0;
   if (lane == 0) ticket = atomicAdd(counters + 1 + rb, 1u);

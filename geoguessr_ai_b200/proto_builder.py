@@ -15,7 +15,7 @@ takes.  The host side only parses and orders the table; no arithmetic of the pat
 from __future__ import annotations
 
 import ast
-from typing import Iterable, List, Sequence, Tuple
+from typing import Iterable, List, Sequence
 
 import numpy as np
 import torch

@@ -3,7 +3,6 @@
 all-reduce cost through NCCL and through torch's multimem op?"""
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist

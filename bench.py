@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the post-encoder geolocation hot path (BASELINE.json contract).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|retrieve]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload all|train|infer]
 
-Default workload = BASELINE.json configs[1]: geocell-head training step with the haversine
-label-smoothed CE, batch 4096 per GPU, D = 1024, C = 12 647, bf16 operands, 1 x B200.  A "step" is
-what the reference's trainer does per batch (main_coordinator_idun_s3.py:393-424): zero_grad ->
-SuperGuessr.forward (fusion, head, top-5, smoothed CE) -> loss.backward() (dW, db) -> [N > 1:
-NCCL all-reduce of the gradients] -> AdamW step.  Prints ONE JSON line on rank 0.
+ONE JSON line on rank 0.  Its top level is BASELINE.json configs[1] -- the geocell-head training step with the
+haversine label-smoothed CE, batch 4096 per GPU, D = 1024, C = 12 647, bf16 operands: a "step" is what the
+reference's trainer does per batch (main_coordinator_idun_s3.py:393-424): zero_grad -> SuperGuessr.forward
+(fusion, head, top-5, smoothed CE) -> loss.backward() (dW, db) -> [N > 1: gradient exchange] -> AdamW step.
+The serving half of the metric (geolocation queries/s: SuperGuessr serving forward -> ProtoRefiner retrieval on a
+geocell-sharded prototype bank, BASELINE configs[2] = 1 M and configs[4] = 10 M prototypes, 65 536 queries per
+batch) is measured in the same run and reported under the "infer" key of that line, each entry with its own
+value / ms_per_step / roofline / cpu_baseline / e2e.  --workload train|infer runs one half only (profiler runs).
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -27,6 +32,8 @@ sys.path.insert(0, REPO)
 
 C_CELLS = 12647
 TRAIN = dict(B=4096, D=1024, V=4, k=5)
+INFER = dict(B=65536, D=1024, V=4, k=5)
+INFER_CONFIGS = (("cfg2_1m", 1_000_000), ("cfg4_10m", 10_000_000))
 
 
 def env_int(name, default):
@@ -84,7 +91,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -93,17 +100,49 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        top = sorted(sm)[len(sm) // 2:] if sm else []  # samples under load = upper half
+        # samples under load = the upper half by power draw (idle samples bracket the timed region)
+        order = sorted(range(len(sm)), key=lambda i: pw[i])
+        top = [sm[i] for i in order[len(order) // 2:]] if sm else []
         return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------
+class Ctx:
+    """Rank / device / process group of this bench process (one process per GPU)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = torch.tensor([ms], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
 def make_batches(n, B, D, V, seed0):
     from geoguessr_ai_b200 import synth
 
@@ -142,12 +181,45 @@ def cpu_reference_train(steps, warmup, B, D, V, threads=None):
     return B / (ms / 1e3), ms, torch.get_num_threads()
 
 
+def cpu_reference_infer_host(P, nq, D=1024, V=4, k=5, seed=5):
+    """Reference arm of the serving workload with no GPU involved: the oracle's eager CPU head + the reference's
+    Python (query x candidate) ProtoRefiner loop on `nq` queries; the prototypes of the cells those queries touch
+    are generated on the host with the bench's cell-size distribution.  Returns (queries/s, cores)."""
+    from geoguessr_ai_b200 import synth
+    from geoguessr_ai_b200.geocells import load_packaged_centroids
+    from oracle import proto_refiner_oracle as pro
+    from oracle import super_guessr_oracle as sgo
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cent = load_packaged_centroids()
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn((nq, V, D), generator=g)
+    W = (torch.rand((C_CELLS, D), generator=g) * 2 - 1) / D ** 0.5
+    b = (torch.rand((C_CELLS,), generator=g) * 2 - 1) / D ** 0.5
+    sizes = synth.cell_sizes(C_CELLS, P, seed=0, mode="skewed")
+    dummy = torch.zeros(nq, dtype=torch.int64)
+    out = sgo.forward(e, W, b, cent, None, dummy)  # warm-up + the candidate cells
+    protos, coords = [None] * C_CELLS, [None] * C_CELLS
+    for c in sorted(set(out.top5_geocells.indices.flatten().tolist())):
+        n = int(sizes[c])
+        if n > 0:
+            protos[c] = torch.randn((n, D), generator=g)
+            coords[c] = cent[c].unsqueeze(0).expand(n, 2) + (torch.rand((n, 2), generator=g) - 0.5)
+    t0 = time.perf_counter()
+    out = sgo.forward(e, W, b, cent, None, dummy)
+    pro.forward(e, out.preds_LLH, out.top5_geocells.indices, out.top5_geocells.values.detach(), protos, coords, topk=k)
+    dt = time.perf_counter() - t0
+    return nq / dt, torch.get_num_threads()
+
+
 def run_reference(args):
-    rank = env_int("RANK", 0)
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the oracle port:
+    the reference is pure Python/PyTorch and its modules need packages absent from the image).
+    Rank 0 only; the other ranks exit without work."""
+    if env_int("RANK", 0) != 0:
         return
     cfg = TRAIN
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    steps, warmup = max(1, min(args.steps, 5)), min(args.warmup, 1)
     val, ms, cores = cpu_reference_train(steps, warmup, cfg["B"], cfg["D"], cfg["V"])
     line = {
         "impl": "reference", "metric": "head-train samples/s", "value": val, "unit": "samples/s",
@@ -159,6 +231,16 @@ def run_reference(args):
                                    "models/super_guessr.py forward + autograd backward + AdamW)"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.workload in ("all", "infer"):
+        inf = {}
+        for key, P in INFER_CONFIGS:
+            nq = 64
+            qps, cores = cpu_reference_infer_host(P, nq)
+            inf[key] = {"metric": "geolocation queries/s", "value": qps, "unit": "queries/s", "cores": cores,
+                        "kind": "port", "prototypes": P,
+                        "sample": f"{nq} queries: eager CPU head + the reference's Python (query x candidate) refiner "
+                                  "loop (oracle port), prototypes of the touched cells generated on the host"}
+        line["infer"] = inf
     print(json.dumps(line), flush=True)
 
 
@@ -172,29 +254,50 @@ def train_config(n_gpus, cfg):
                   "L2; input batches rotate over 3 resident buffers"}
 
 
-def run_b200_train(args):
-    import torch.distributed as dist
+def kernel_table(per, calls, algo, peaks):
+    """{launcher: {ms, [calls_per_step], bound, achieved, peak, unit, frac}}: tensor-bound launchers against the
+    BURST cuBLAS figure (each launcher is event-timed alone in a short region), HBM-bound ones against the copy."""
+    kernels = {}
+    for name, ms in per.items():
+        entry = {"ms": ms}
+        if calls is not None:
+            entry["calls_per_step"] = max(1, calls.get(name, 1))
+        if name in algo:
+            bound, work, unit = algo[name]
+            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+            peak = peaks["tf_burst"] if bound == "tensor" else peaks["hbm"]
+            entry.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak})
+            if bound == "tensor":
+                entry["frac_of_sustained"] = ach / peaks["tf_sustained"]
+        kernels[name] = entry
+    return kernels
 
+
+def dominant_roofline(kernels, peaks, extra=None):
+    dom = max((k for k in kernels if "frac" in kernels[k]),
+              key=lambda k: kernels[k]["ms"] * kernels[k].get("calls_per_step", 1))
+    roof = {k: v for k, v in kernels[dom].items() if k not in ("ms", "calls_per_step")}
+    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom),
+                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; "
+                                + ("bf16_tflops, the burst figure: the launcher is timed alone with CUDA events"
+                                   if roof["bound"] == "tensor" else "hbm_gbs") + ")"})
+    if extra:
+        roof.update(extra.get(dom, {}))
+    return roof
+
+
+# ------------------------------------------------------------------------------------------------ training
+def run_b200_train(args, ctx):
     import geoguessr_ai_b200 as gg
     from geoguessr_ai_b200 import ops
     from geoguessr_ai_b200.geocells import load_packaged_centroids
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    dist, rank, world, local, dev = ctx.dist, ctx.rank, ctx.world, ctx.local, ctx.dev
     cfg = TRAIN
     B, D, V = cfg["B"], cfg["D"], cfg["V"]
     K, Wm = args.steps, max(args.warmup, 3)
 
     cent = load_packaged_centroids()
-    import contextlib
-    import io
-
     with contextlib.redirect_stdout(io.StringIO()):
         model = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, embed_dim=D, centroids=cent,
                                num_candidates=cfg["k"]).to(dev)
@@ -203,7 +306,7 @@ def run_b200_train(args):
         model.cell_layer.weight.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
         model.cell_layer.bias.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
     model.train()
-    if world > 1:  # gradients are averaged inside backward(), range by range, overlapped with the dW GEMM
+    if world > 1:  # gradients are averaged inside backward()
         model.enable_data_parallel(chunks=args.dp_chunks,
                                    comm_dtype=torch.bfloat16 if args.dp_bf16 else None,
                                    comm="nccl" if args.dp_bf16 else args.dp_comm)
@@ -223,20 +326,10 @@ def run_b200_train(args):
         opt.step()
         return out.loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
-    # One CUDA graph per input buffer: the ~25 launches of a step (ours, the fused AdamW, the NCCL
-    # all-reduce) replay without host work in between.  Falls back to eager launches if capture fails.
+    # One CUDA graph per input buffer: the launches of a step (ours, the fused AdamW, the gradient exchange)
+    # replay without host work in between.  Falls back to eager launches if capture fails.
     graphs = {}
 
     def capture(key, emb, labels):
@@ -291,6 +384,24 @@ def run_b200_train(args):
     value = world * B / (ms_step / 1e3)
     final_loss = loss.item()
 
+    # ---------------- the same loop run back to back for >= 2 s: what the step does under the power cap
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = int(max(K, min(200000, args.sustained_s * 1e3 / ms_step)))
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0.record()
+        for i in range(n_sus):
+            run(("res", i % 3), *resident[i % 3])
+        e1.record()
+        barrier()
+        ms_sus = max_over_ranks(e0.elapsed_time(e1)) / n_sus
+        sus_clocks = sampler.stop() if rank == 0 else None
+        sustained = {"steps": n_sus, "seconds": ms_sus * n_sus / 1e3, "ms_per_step": ms_sus,
+                     "value": world * B / (ms_sus / 1e3), "unit": "samples/s", "clocks": sus_clocks}
+
     # ---------------- per-launcher CUDA-event timing over a second identical timed region
     # Eager launches; a ~1 ms device-side spin queued ahead of every step lets the host run a whole step
     # ahead, so the events bracket device time only (no launch gaps inside the brackets).
@@ -303,6 +414,11 @@ def run_b200_train(args):
     tms = ops.timing_ms()
     ops.enable_timing(False)
     per = {k: sum(v) / n_timed for k, v in tms.items()}  # per step (a launcher may run more than once: --dp-chunks)
+
+    # ---------------- N > 1: the averaged gradient of one step against NCCL (all ranks take part)
+    dp_check = None
+    if world > 1:
+        dp_check = check_dp_gradient(model, resident[0], dummy_clf, dist)
 
     # ---------------- end to end from host buffers (`e2e`): H2D of the batch + D2H of the loss every step
     copy_stream = torch.cuda.Stream()
@@ -343,9 +459,12 @@ def run_b200_train(args):
     e2e_val = world * B / (ms_e2e / 1e3)
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
 
+    grad_comm = None
+    if world > 1:
+        grad_comm = model.describe_data_parallel()
+    del graphs
     if rank != 0:
-        finish(world)
-        return
+        return None
 
     # ---------------- roofline of the dominant launcher
     peaks = measured_peaks()
@@ -359,22 +478,8 @@ def run_b200_train(args):
         "gg_prepare_head_weights": ("hbm", C * D * (4 + 2) + 8 * C, "GB/s"),
         "gg_fuse_and_prepare": ("hbm", B * D * (4 * V + 2) + C * D * (4 + 2) + 8 * C, "GB/s"),
     }
-    kernels = {}
-    for name, ms in per.items():
-        if name in algo:
-            bound, work, unit = algo[name]
-            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
-            peak = peaks["tf_sustained"] if bound == "tensor" else peaks["hbm"]
-            kernels[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
-        else:
-            kernels[name] = {"ms": ms}
-    dom = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms"])
-    roof = dict(kernels[dom])
-    roof.pop("ms")
-    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom),
-                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; "
-                                + ("bf16_tflops_sustained: kernel timed inside the step" if roof["bound"] == "tensor"
-                                   else "hbm_gbs") + ")"})
+    kernels = kernel_table(per, None, algo, peaks)
+    roof = dominant_roofline(kernels, peaks)
 
     cpu = None
     if not args.no_cpu:
@@ -383,19 +488,11 @@ def run_b200_train(args):
                "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
                          "reference forward + autograd backward + AdamW)"}
 
-    grad_comm = None
-    if world > 1:
-        if model._dp["symm"] is not None:
-            grad_comm = (("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if model._dp["symm"]["kind"] == "nvls"
-                          else "peer load/store two-shot (rank-order sums)")
-                         + " all-reduce (avg, fp32) of [dW | db] in symmetric memory over NVLink, one kernel per rank "
-                           f"and geocell range between two symmetric-memory barriers; {args.dp_chunks} range(s), each "
-                           "exchanged while the next one's dW GEMM runs")
-        else:
-            grad_comm = (f"nccl avg, {'bf16' if args.dp_bf16 else 'fp32'}, {args.dp_chunks} geocell ranges overlapped "
-                         "with the dW GEMM")
-    # fusion + weight cast, head_fwd + merge, label vectors + row statistics, loss stream kernel, dW GEMM [, gradient exchange]
-    launches_per_step = 1 + 2 + 2 + 1 + 1 + (args.dp_chunks - 1 + args.dp_chunks if world > 1 and model._dp["symm"] is not None else 0)
+    launches_per_step = sum(1 for _ in per)  # launcher calls; kernels per launcher below
+    kernels_per_launcher = {"gg_fuse_and_prepare": 1, "gg_head_fwd": 1, "gg_hav_row_stats": 2, "gg_hav_ce_fwd_bwd": 1,
+                            "gg_head_bwd": 1, "gg_grad_exchange": 1, "gg_p2p_allreduce_avg": 1,
+                            "gg_nvls_allreduce_avg": 1}
+    launches_per_step = sum(kernels_per_launcher.get(n, 1) * max(1, round(len(tms[n]) / n_timed)) for n in tms)
     line = {
         "metric": "head-train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -406,20 +503,40 @@ def run_b200_train(args):
         "gpu_launches": launches_per_step * K, "roofline": roof, "kernels": kernels,
         "kernels_timing": "CUDA events around every launcher in a second, eager pass over the same steps with nothing "
                           "running beside the timed launcher (the label statistics, which the timed region runs "
-                          "underneath the head GEMM on a side stream, run serially there); a launcher may hold a small "
-                          "helper kernel (gg_head_fwd: GEMM + merge)",
-        "cpu_baseline": cpu, "loss": final_loss,
+                          "underneath the head GEMM on a side stream, run serially there)",
+        "sustained": sustained, "cpu_baseline": cpu, "loss": final_loss,
     }
-    print(json.dumps(line), flush=True)
-    finish(world)
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    return line
 
 
-# ------------------------------------------------------------------------------------------------
-# Serving workload (BASELINE configs[2] / [4]): SuperGuessr serving forward -> ProtoRefiner on a geocell-sharded
-# prototype bank.  Not the default bench line (configs[1] is); run with --workload infer.
-INFER = dict(B=65536, D=1024, V=4, k=5)
+def check_dp_gradient(model, batch, dummy_clf, dist):
+    """One eager data-parallel step's averaged head gradient against NCCL's all_reduce(AVG) of the per-rank
+    gradients (computed with the exchange switched off)."""
+    emb, labels = batch
+    dp = model._dp
+    model._dp = None
+    model.zero_grad(set_to_none=True)
+    model(embedding=emb, labels=labels, labels_clf=dummy_clf).loss.backward()
+    world = dist.get_world_size()
+    want_w = model.cell_layer.weight.grad.detach().clone() / world  # local 1/B_local scaling -> global mean
+    want_b = model.cell_layer.bias.grad.detach().clone() / world
+    dist.all_reduce(want_w, op=dist.ReduceOp.SUM)
+    dist.all_reduce(want_b, op=dist.ReduceOp.SUM)
+    model._dp = dp
+    model.zero_grad(set_to_none=True)
+    model(embedding=emb, labels=labels, labels_clf=dummy_clf).loss.backward()
+    torch.cuda.synchronize()
+    gw, gb = model.cell_layer.weight.grad, model.cell_layer.bias.grad
+    err = torch.stack([(gw - want_w).abs().max(), (gb - want_b).abs().max(), want_w.abs().max()])
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    err = err.tolist()
+    return {"against": "NCCL all_reduce(SUM) / world of the per-rank gradients", "max_abs_diff_dW": err[0],
+            "max_abs_diff_db": err[1], "max_abs_dW": err[2], "ok": bool(err[0] <= 1e-6 * max(err[2], 1e-30) + 1e-12)}
 
 
+# ------------------------------------------------------------------------------------------------ serving
 def infer_config(n_gpus, cfg, P, B):
     return {"workload": f"BASELINE configs[{2 if P <= 1_000_000 else 4}]: SuperGuessr serving + ProtoRefiner retrieval vs "
                         f"{P} synthetic prototypes sharded by geocell, top-{cfg['k']} cells",
@@ -452,7 +569,7 @@ def make_local_bank(P, D, rank, world, dev, cent):
 def cpu_reference_infer(model_w, model_b, cent, emb, refiner, nq):
     """The reference's serving path restated by the oracle on `nq` queries: eager CPU head + the Python
     (query x candidate) loop of ProtoRefiner.forward.  Prototypes of the cells those queries touch are copied
-    back from the device bank.  Returns (queries/s, cores)."""
+    back from the device bank.  Returns (queries/s, cores, oracle outputs)."""
     from oracle import proto_refiner_oracle as pro
     from oracle import super_guessr_oracle as sgo
 
@@ -471,35 +588,23 @@ def cpu_reference_infer(model_w, model_b, cent, emb, refiner, nq):
                 coords[c] = refiner.bank_coords[a:z].cpu()
     t0 = time.perf_counter()
     out = sgo.forward(e, W, b, cent, None, torch.zeros(nq, dtype=torch.int64))
-    pro.forward(e, out.preds_LLH, out.top5_geocells.indices, out.top5_geocells.values.detach(), protos, coords, topk=5)
+    res = pro.forward(e, out.preds_LLH, out.top5_geocells.indices, out.top5_geocells.values.detach(), protos, coords,
+                      topk=5)
     dt = time.perf_counter() - t0
-    return nq / dt, torch.get_num_threads()
+    return nq / dt, torch.get_num_threads(), (out, res)
 
 
-def run_b200_infer(args):
-    import contextlib
-    import io
-
-    import torch.distributed as dist
-
+def run_b200_infer(args, ctx, P, B, K):
     import geoguessr_ai_b200 as gg
     from geoguessr_ai_b200 import ops
     from geoguessr_ai_b200.geocells import load_packaged_centroids
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    dist, rank, world, local, dev = ctx.dist, ctx.rank, ctx.world, ctx.local, ctx.dev
     cfg = INFER
     D, V, k = cfg["D"], cfg["V"], cfg["k"]
-    B, P = args.batch, args.protos
     assert B % world == 0
     Bl = B // world
-    K, Wm = args.steps, max(args.warmup, 3)
+    Wm = max(min(args.warmup, 5), 3)
 
     cent = load_packaged_centroids()
     with contextlib.redirect_stdout(io.StringIO()):
@@ -517,25 +622,14 @@ def run_b200_infer(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(77 + rank)
     resident = [torch.randn((Bl, V, D), device=dev, generator=gen) for _ in range(2)]
-    host = [r.cpu().pin_memory() for r in resident[:1]]
+    host = [resident[0].cpu().pin_memory()]
 
     def step(emb):
         llh, topk, _ = model(embedding=emb)
         _, r_llh, r_cell = refiner(emb, llh, topk.indices, topk.values)
         return r_llh, r_cell
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
+    barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
     for i in range(Wm):
         step(resident[i % 2])
     barrier()
@@ -553,15 +647,17 @@ def run_b200_infer(args):
     clocks = sampler.stop() if rank == 0 else None
     value = B / (ms_step / 1e3)
 
+    nt = min(K, 5)
     ops.enable_timing(True)
     barrier()
-    for i in range(min(K, 5)):
+    for i in range(nt):
         torch.cuda._sleep(40_000_000)
         step(resident[i % 2])
     tms = ops.timing_ms()
     ops.enable_timing(False)
     per = {kk: sum(v) / len(v) for kk, v in tms.items()}
-    calls = {kk: len(v) // min(K, 5) for kk, v in tms.items()}
+    calls = {kk: len(v) // nt for kk, v in tms.items()}
+    stats = refiner.last_retrieve_stats()  # work items / accumulation units / operand bytes of the last batch
 
     # end to end: the batch crosses PCIe from pinned memory, results come back to the host
     copy_stream = torch.cuda.Stream()
@@ -595,53 +691,63 @@ def run_b200_infer(args):
     h2d = host[0].numel() * 4
     d2h = Bl * (8 + 8)
 
-    if rank != 0:
-        finish(world)
-        return
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        P_local = p1 - p0
+        npair_local = stats["pairs"] if stats else B * k / world
+        # retrieval: the bank shard once + the gathered query rows once (algorithmic); executed = what the
+        # launcher's kernels move: the operand boxes the TMA engine loads, the query gather (read + write) and the
+        # records
+        algo_retr = P_local * D * 2.0 + npair_local * D * 2.0
+        algo = {
+            "gg_head_fwd": ("tensor", 2.0 * Bl * C_CELLS * D, "TFLOP/s"),
+            "gg_proto_retrieve": ("hbm", algo_retr, "GB/s"),
+            "gg_fuse_headings": ("hbm", Bl * D * (4 * V + 2.0), "GB/s"),
+            "gg_proto_refine": ("hbm", (world * k * 16 + k * 12 + 24.0) * Bl, "GB/s"),
+        }
+        kernels = kernel_table(per, calls, algo, peaks)
+        extra = {}
+        if stats and "gg_proto_retrieve" in kernels:
+            ex = {"algorithmic_bytes": algo_retr, "executed_bytes": stats["executed_bytes"],
+                  "executed_flop": stats["executed_flop"], "algorithmic_flop": stats["algorithmic_flop"],
+                  "work_items": stats["work_items"], "units": stats["units"]}
+            kernels["gg_proto_retrieve"].update(ex)
+            extra["gg_proto_retrieve"] = ex
+        roof = dominant_roofline(kernels, peaks, extra)
+        cpu = agree = None
+        if not args.no_cpu:
+            nq = 256
+            cval, cores, (o_head, o_ref) = cpu_reference_infer(model.cell_layer.weight, model.cell_layer.bias, cent,
+                                                               resident[0], refiner, nq)
+            cpu = {"value": cval, "unit": "queries/s", "cores": cores, "kind": "port",
+                   "sample": f"{nq} queries of the same batch through the oracle (eager CPU head + the reference's Python "
+                             "(query x candidate) refiner loop); prototypes of the touched cells copied from the device bank"
+                             + ("" if world == 1 else "; cells owned by other ranks count as missing")}
+            if world == 1:  # the same 256 queries through the CUDA path against the oracle's outputs
+                from oracle import proto_refiner_oracle as pro
 
-    peaks = measured_peaks()
-    P_local = p1 - p0
-    algo = {
-        "gg_head_fwd": ("tensor", 2.0 * Bl * C_CELLS * D, "TFLOP/s"),
-        # bank shard read once + grouped queries written and read + records
-        "gg_proto_retrieve": ("hbm", P_local * D * 2.0 + 3.0 * B * k * D * 2 + B * k * 16, "GB/s"),
-        "gg_fuse_headings": ("hbm", Bl * D * (4 * V + 2.0), "GB/s"),
-        "gg_proto_refine": ("hbm", (world * k * 16 + k * 12 + 24.0) * Bl, "GB/s"),
-    }
-    kernels = {}
-    for name, ms in per.items():
-        n = max(1, calls.get(name, 1))
-        if name in algo:
-            bound, work, unit = algo[name]
-            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
-            peak = peaks["tf_sustained"] if bound == "tensor" else peaks["hbm"]
-            kernels[name] = {"ms": ms, "calls_per_step": n, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                             "frac": ach / peak}
-        else:
-            kernels[name] = {"ms": ms, "calls_per_step": n}
-    dom = max((kk for kk in kernels if "frac" in kernels[kk]), key=lambda kk: kernels[kk]["ms"] * kernels[kk]["calls_per_step"])
-    roof = {kk: v for kk, v in kernels[dom].items() if kk not in ("ms", "calls_per_step")}
-    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom),
-                 "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})"})
-    cpu = None
-    if not args.no_cpu:
-        nq = 256
-        cval, cores = cpu_reference_infer(model.cell_layer.weight, model.cell_layer.bias, cent, resident[0], refiner, nq)
-        cpu = {"value": cval, "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"{nq} queries of the same batch through the oracle (eager CPU head + the reference's Python "
-                         "(query x candidate) refiner loop); prototypes of the touched cells copied from the device bank"
-                         + ("" if world == 1 else "; cells owned by other ranks count as missing")}
-    launches = 2 + 2 + 1 + 6 + 1  # fuse, head (GEMM + merge), refiner fuse, retrieval (memset + 5 kernels), refine
-    line = {
-        "metric": "geolocation queries/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": infer_config(world, cfg, P, B), "clocks": clocks,
-        "e2e": {"value": B / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": Ke},
-        "gpu_launches": launches * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-    }
-    print(json.dumps(line), flush=True)
-    finish(world)
+                r_llh, r_cell = step(resident[0][:nq].contiguous())
+                same = (r_cell.cpu() == o_ref[2])
+                d = pro.haversine(r_llh.cpu()[same].double(), o_ref[1][same].double()) * 1000.0
+                agree = {"queries": nq, "refined_cells_equal": float(same.float().mean()),
+                         "max_coord_err_m_where_equal": float(d.max()) if d.numel() else 0.0,
+                         "note": "oracle runs the head in fp32, the CUDA path in bf16: candidate lists can differ on "
+                                 "near-tied logits (parity proper is tests/, on identical bf16 inputs)"}
+        launches = sum(calls.values())
+        line = {
+            "metric": "geolocation queries/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": infer_config(world, cfg, P, B), "clocks": clocks,
+            "e2e": {"value": B / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke},
+            "launcher_calls": launches * K, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+        }
+        if agree is not None:
+            line["oracle_agreement"] = agree
+    del refiner, model, resident, bufs, host
+    torch.cuda.empty_cache()
+    return line
 
 
 def finish(world):
@@ -663,24 +769,47 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "infer"],
-                    help="train = BASELINE configs[1] (the bench line); infer = serving + sharded prototype retrieval")
-    ap.add_argument("--protos", type=int, default=1_000_000, help="infer: total prototypes (configs[2]: 1e6, configs[4]: 1e7)")
+    ap.add_argument("--workload", default="all", choices=["all", "train", "infer"],
+                    help="all = BASELINE configs[1] training line with the serving workloads (configs[2], configs[4]) "
+                         "under its 'infer' key; train / infer = one half only")
+    ap.add_argument("--protos", type=int, default=0,
+                    help="infer: total prototypes (configs[2]: 1e6, configs[4]: 1e7); 0 = both, under the 'infer' key")
     ap.add_argument("--batch", type=int, default=65536, help="infer: queries per batch over all GPUs")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs only)")
-    ap.add_argument("--dp-chunks", type=int, default=1, help="geocell ranges of the overlapped dW GEMM + all-reduce (N > 1)")
-    ap.add_argument("--dp-comm", default="auto", choices=["auto", "nvls", "p2p", "nccl"],
-                    help="gradient exchange for N > 1: own kernel over symmetric memory (NVSwitch multicast or peer "
-                         "loads/stores) or NCCL all-reduce")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (profiler runs only)")
+    ap.add_argument("--sustained-s", type=float, default=2.0,
+                    help="train: seconds of back-to-back steps for the 'sustained' key (0 = skip)")
+    ap.add_argument("--dp-chunks", type=int, default=1, help="comm=nccl: geocell ranges of the dW GEMM + all-reduce (N > 1)")
+    ap.add_argument("--dp-comm", default="auto", choices=["auto", "fused", "nvls", "p2p", "nccl"],
+                    help="gradient exchange for N > 1: fused = progressive exchange under the dW GEMM (own kernels over "
+                         "symmetric memory), nvls / p2p = one exchange kernel after the GEMM, nccl = NCCL all-reduce")
     ap.add_argument("--dp-bf16", action="store_true", help="all-reduce the gradients in bf16 (opt-in, N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "infer":
-        run_b200_infer(args)
-    else:
-        run_b200_train(args)
+        return
+    ctx = Ctx()
+    line = None
+    if args.workload in ("all", "train"):
+        line = run_b200_train(args, ctx)
+        torch.cuda.empty_cache()
+    if args.workload in ("all", "infer"):
+        configs = INFER_CONFIGS if args.protos == 0 else ((f"protos_{args.protos}", args.protos),)
+        inf = {}
+        for key, P in configs:
+            K = max(3, min(args.steps, 20 if P <= 2_000_000 else 10))
+            inf[key] = run_b200_infer(args, ctx, P, args.batch, K)
+        if ctx.rank == 0:
+            if line is None:  # --workload infer: the (first) serving line on its own
+                first = next(iter(inf.values()))
+                line = dict(first)
+                if len(inf) > 1:
+                    line["infer"] = inf
+            else:
+                line["infer"] = inf
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    finish(ctx.world)
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgeoguessr_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
@@ -27,28 +27,32 @@ SIGNATURES = {
     "gg_centroid_table_workspace_bytes": (c_size_t, [I]),
     "gg_hav_row_stats_bytes": (c_size_t, [I, I]),
     "gg_head_fwd_workspace_bytes": (c_size_t, [I, I, I]),
+    "gg_head_fwd_ticket_bytes": (c_size_t, [I]),
     "gg_head_bwd_workspace_bytes": (c_size_t, [I]),
     "gg_hav_ce_workspace_bytes": (c_size_t, [I, I]),
     "gg_hav_ce_db_parts": (I, [I, I]),
     "gg_proto_retrieve_workspace_bytes": (c_size_t, [I, I, I, I]),
-    "gg_fuse_headings": (I, [P, P, I, I, I, I, P, P]),
+    "gg_fuse_headings": (I, [P, I, P, I, I, I, I, P, P]),
     "gg_prepare_head_weights": (I, [P, P, P, P, I, I, I, P]),
-    "gg_fuse_and_prepare": (I, [P, P, I, I, I, P, P, P, P, I, I, P]),
-    "gg_cast_bf16": (I, [P, P, L, P]),
-    "gg_row_sqnorm_bf16": (I, [P, L, I, P, P]),
-    "gg_head_fwd": (I, [P, P, P, I, I, I, P, I, I, P, P, P, P, P, P, P, P]),
+    "gg_fuse_and_prepare": (I, [P, I, P, I, I, I, P, P, P, P, I, I, P]),
+    "gg_cast_bf16": (I, [P, P, L, I, I, P]),
+    "gg_row_sqnorm_bf16": (I, [P, L, I, I, P, P]),
+    "gg_head_fwd": (I, [P, P, P, I, I, I, P, I, I, P, P, P, P, P, P, P, P, P]),
     "gg_centroid_unit_vectors": (I, [P, P, I, P, P]),
     "gg_hav_row_stats": (I, [P, P, I, I, F, F, P, P, P, P]),
     "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, P, P, P, P, P, F, P]),
     "gg_hard_ce_fwd_bwd": (I, [P, I, P, P, I, I, P, P, P]),
     "gg_loss_mean": (I, [P, I, F, P, P]),
-    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P]),
-    "gg_proto_retrieve": (I, [P, P, I, I, P, I, I, P, P, P, L, P, I, I, I, P, P, P]),
+    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P, I, P]),
+    "gg_proto_group_cells": (I, [P, I, P]),
+    "gg_proto_retrieve": (I, [P, P, I, I, P, I, I, P, P, P, L, P, I, I, P, I, I, I, I, P, P, P]),
     "gg_proto_refine": (I, [P, I, L, P, I, P, I, P, I, I, F, F, P, P, P, P, P, P]),
     "gg_build_prototypes": (I, [P, L, I, I, P, P, P, L, P, P, P, P]),
     "gg_p2p_slice": (None, [c_size_t, I, I, P, P]),
     "gg_p2p_allreduce_avg": (I, [P, I, I, c_size_t, P]),
     "gg_nvls_allreduce_avg": (I, [P, I, I, c_size_t, P]),
+    "gg_grad_ctrl_bytes": (c_size_t, []),
+    "gg_grad_exchange": (I, [P, P, P, P, I, I, I, I, I, P]),
 }
 
 _lib = None

@@ -119,6 +119,31 @@ int make_tmap_bf16_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, 
   return GG_OK;
 }
 
+int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return GG_ERR_CUDA;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    GG_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
+  GG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, GG_ERR_ARG, "TMA base %p is not 16-byte aligned", base);
+  GG_CHECK(pitch_bytes % 16 == 0, GG_ERR_ARG, "TMA row pitch %llu is not a multiple of 16 bytes",
+           (unsigned long long)pitch_bytes);
+  GG_CHECK(box_rows >= 1 && box_rows <= 256, GG_ERR_ARG, "bad TMA box 32 x %u", box_rows);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GG_CHECK(r == CUDA_SUCCESS, GG_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed with CUresult %d (inner=%llu outer=%llu pitch=%llu)",
+           (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes);
+  return GG_OK;
+}
+
 int set_max_dynamic_smem_once_impl(const void* kernel, size_t bytes) {
   struct Entry { const void* fn; unsigned long long devs; };
   static Entry table[64];

@@ -47,6 +47,10 @@ int make_tmap_bf16_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, 
 int make_tmap_bf16_2d_sw64(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                             uint32_t box_inner, uint32_t box_rows);
 
+// fp32 row-major tensor map, 128-byte swizzle: box = {32 floats (= 128 B), box_rows} (TMA stores of fp32 tiles)
+int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                     uint32_t box_rows);
+
 int device_sm_count();
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): keeps the launch path free

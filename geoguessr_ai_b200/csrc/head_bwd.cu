@@ -38,10 +38,12 @@ constexpr uint32_t kAtomBytes = kWK * 128;                 // 64 k-rows x 128 B
 constexpr uint32_t kWStageA = (kWM / 64) * kAtomBytes;     // 16 KB: my 128 geocells
 constexpr uint32_t kWStageB = (kWN / 128) * kAtomBytes;    // 16 KB: my half of the embedding columns
 constexpr size_t kPartialFloats = static_cast<size_t>(kWM) * kWN;  // one CTA's parked accumulator half
+constexpr int kGradMaxWorld = 8;
 
 struct BwdSmem {
   uint8_t a[kWStages][kWStageA];
   uint8_t b[kWStages][kWStageB];
+  uint8_t out[4][2][32 * 128];  // per epilogue warp: two 32 x 32 fp32 staging tiles (128-byte swizzled TMA store boxes)
   uint64_t full[kWStages];
   uint64_t empty[kWStages];
   uint64_t acc_full[2];
@@ -83,10 +85,23 @@ struct PairSchedule {
   }
 };
 
+// Data-parallel training (gg_grad_exchange): when the last column tile of a 128-geocell block of dW (and its db
+// rows) has been written, the block is announced to the rank that reduces it -- a system-scope release add on
+// that rank's `ready` counter in symmetric memory -- so the exchange proceeds block by block underneath the GEMM.
+struct GradSignal {
+  unsigned int* blk_count;             // local: finished column tiles per 128-geocell block (self-resetting)
+  unsigned int* ready[kGradMaxWorld];  // every rank's `ready` counters (peer-mapped); block b belongs to rank b % world
+  int world;                           // 0 / 1: no signalling
+};
+__device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
-head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, rows B
-                const __grid_constant__ CUtensorMap tm_x,  // x:       inner D, rows B
-                float* __restrict__ dW, int C, int D, int Bk, float scale_in,
+head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C, rows B
+                const __grid_constant__ CUtensorMap tm_x,   // x:       inner D, rows B
+                const __grid_constant__ CUtensorMap tm_dw,  // dW (C, D) fp32: 32 x 32 store boxes
+                const __grid_constant__ GradSignal sig, int C, int D, int Bk, float scale_in,
                 const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags,
                 float* __restrict__ db, const float* __restrict__ db_partials, int db_parts, int db_ld) {
   extern __shared__ uint8_t smem_raw[];
@@ -105,6 +120,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_g);
     tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_dw);
     for (int s = 0; s < kWStages; ++s) {
       mbar_init(&sm.full[s], 1);   // leader's: its own arrive.expect_tx, bytes from both CTAs' loads
       mbar_init(&sm.empty[s], 1);  // one multicast commit per round
@@ -195,6 +211,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
       const int lower = ps.lower_neighbour();  // whose parked partial a straddling first tile continues
       const float* const prev_park = parked + (static_cast<size_t>(lower < 0 ? 0 : lower) * 2 + crank) * kPartialFloats + rit;
       int it = 0;
+      int obuf = 0;  // staging buffer of the next dW store (alternates per store)
       for (; it < nseg; ++it) {
         int t, k0, k1;
         ps.get(it, t, k0, k1);
@@ -232,18 +249,27 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
           if (park) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) __stcg(my_park + static_cast<size_t>(c * 32 + j) * kWM, __uint_as_float(r[j]));
-          } else if (row < C) {
-            float* dst = dW + static_cast<size_t>(row) * D + col0;
+          } else if (col0 < D) {  // (warp-uniform)
+            // 32 geocells x 32 columns through a swizzled staging tile and one TMA store: full 128-byte lines
+            // instead of 32 row-strided 16-byte pieces per store instruction; rows >= C / columns >= D are clipped.
+            uint8_t* const buf = sm.out[quad][obuf];
+            obuf ^= 1;
+            if (lane == 0) tma_store_wait_read<1>();  // the store issued two stores ago has read this buffer
+            __syncwarp();
+            const uint32_t dst_row = smem_u32(buf) + lane * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              if (col0 + 4 * q + 4 <= D) {
-                float4 o;
-                o.x = __uint_as_float(r[4 * q + 0]) * scale;
-                o.y = __uint_as_float(r[4 * q + 1]) * scale;
-                o.z = __uint_as_float(r[4 * q + 2]) * scale;
-                o.w = __uint_as_float(r[4 * q + 3]) * scale;
-                *reinterpret_cast<float4*>(dst + 4 * q) = o;
-              }
+              const uint32_t dst = dst_row + ((q ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(__uint_as_float(r[4 * q + 0]) * scale),
+                           "f"(__uint_as_float(r[4 * q + 1]) * scale), "f"(__uint_as_float(r[4 * q + 2]) * scale),
+                           "f"(__uint_as_float(r[4 * q + 3]) * scale)
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tm_dw, buf, col0, m0 + quad * 32);
+              tma_store_commit();
             }
           }
         }
@@ -266,8 +292,26 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,  // dlogits: inner C, 
           __threadfence();
           named_bar_sync(1, 128);
           if (threadIdx.x == 64) atomicExch(&flags[pair * 2 + crank], 1);
+        } else if (sig.world > 1 && m0 < C) {
+          // this CTA's 128 geocells x 256 columns of dW (and, with the first column tile, the block's db rows) are
+          // final on this rank: count the block's column tiles, the last one announces the block to its reducer
+          if (lane == 0) {
+            tma_store_wait_all<0>();  // the bulk stores have been performed, not merely read from shared memory
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 64) {
+            __threadfence_system();
+            const int blk = m0 / kWM;
+            const unsigned int old = atomicAdd(sig.blk_count + blk, 1u);
+            if (old + 1u == static_cast<unsigned int>(num_n)) {
+              sig.blk_count[blk] = 0u;  // left zeroed for the next step
+              red_release_sys_add(sig.ready[blk % sig.world] + blk, 1u);
+            }
+          }
         }
       }
+      if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last bulk store
     }
   }
   tc_fence_before();
@@ -286,7 +330,9 @@ __global__ void db_partial_kernel(const bf16* __restrict__ g, int ldc, int B, in
   __shared__ float red[8][32][8];
   const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (c0 < ldc) {
+  // columns bounded by C rounded up to 8 (<= ldc): with a geocell range (dlogits advanced by c0 columns) the rows'
+  // 16-byte loads stay inside the allocation
+  if (c0 < ((C + 7) & ~7)) {
     for (int r = blockIdx.y * 8 + threadIdx.y; r < B; r += 8 * gridDim.y) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ldc + c0));
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -349,19 +395,34 @@ extern "C" size_t gg_head_bwd_workspace_bytes(int C) {
 
 extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
                            float scale, const float* grad_scale, float* dW, float* db, const float* db_partials,
-                           int db_parts, int db_ld, void* workspace, gg_stream_t stream) {
+                           int db_parts, int db_ld, void* workspace, const unsigned long long* signal_ptrs,
+                           int signal_world, gg_stream_t stream) {
   GG_CHECK(B > 0 && C > 0 && D > 0, GG_ERR_ARG, "gg_head_bwd: empty problem B=%d C=%d D=%d", B, C, D);
   GG_CHECK(dlogits_bf16 && x_bf16 && dW, GG_ERR_ARG, "gg_head_bwd: null pointer");
   GG_CHECK(ldc >= C && ldc % 8 == 0, GG_ERR_ARG, "gg_head_bwd: ldc=%d must be >= C and a multiple of 8", ldc);
   GG_CHECK(D % 8 == 0 && x_ld >= D && x_ld % 8 == 0, GG_ERR_ARG, "gg_head_bwd: D=%d / x_ld=%d must be multiples of 8", D, x_ld);
   GG_CHECK(workspace, GG_ERR_ARG, "gg_head_bwd: workspace (gg_head_bwd_workspace_bytes) is required");
   GG_CHECK(!db_partials || (db_parts > 0 && db_ld >= C), GG_ERR_ARG, "gg_head_bwd: bad db_partials shape");
+  GG_CHECK(signal_world >= 0 && signal_world <= kGradMaxWorld && (signal_world <= 1 || signal_ptrs), GG_ERR_ARG,
+           "gg_head_bwd: signal_world=%d (<= %d) needs signal_ptrs", signal_world, kGradMaxWorld);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CUtensorMap tm_g, tm_x;
+  CUtensorMap tm_g, tm_x, tm_dw;
   int rc = make_tmap_bf16_2d(&tm_g, dlogits_bf16, C, B, static_cast<uint64_t>(ldc) * 2, 64, kWK);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_x, x_bf16, D, B, static_cast<uint64_t>(x_ld) * 2, 64, kWK);
   if (rc) return rc;
+  rc = make_tmap_f32_2d(&tm_dw, dW, D, C, static_cast<uint64_t>(D) * 4, 32);
+  if (rc) return rc;
+  GradSignal sig = {};
+  if (signal_world > 1) {
+    sig.world = signal_world;
+    sig.blk_count = reinterpret_cast<unsigned int*>(signal_ptrs[0]);
+    for (int r = 0; r < signal_world; ++r) {
+      GG_CHECK(signal_ptrs[1 + r] != 0, GG_ERR_ARG, "gg_head_bwd: ready counters of rank %d missing", r);
+      sig.ready[r] = reinterpret_cast<unsigned int*>(signal_ptrs[1 + r]);
+    }
+    GG_CHECK(sig.blk_count, GG_ERR_ARG, "gg_head_bwd: block counters missing");
+  }
   const int pair_tiles = ceil_div(C, 2 * kWM) * ceil_div(D, kWN);
   const int pairs = std::max(1, std::min(pair_tiles, device_sm_count() / 2));
   const size_t smem = sizeof(BwdSmem) + 1024;
@@ -369,20 +430,26 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
   int* flags = reinterpret_cast<int*>(wsb);
   float* parked = reinterpret_cast<float*>(wsb + bwd_flag_bytes());
-  GG_CUDA(cudaMemsetAsync(flags, 0, bwd_flag_bytes(), s));
-  // cluster shape (2,1,1) is compiled into the kernel
   // with the loss kernel's column-sum partials at hand the GEMM's epilogue finishes db as well
   const bool db_fused = db && db_partials;
-  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, dW, C, D, B, scale, grad_scale, parked, flags,
-                                                       db_fused ? db : nullptr, db_partials, db_parts, db_ld);
-  GG_LAUNCH_CHECK();
-  if (db && !db_fused) {
+  auto db_from_dlogits = [&]() -> int {
     float* partial = reinterpret_cast<float*>(wsb + bwd_flag_bytes() + bwd_park_bytes());
-    dim3 blk(32, 8), grd(ceil_div(ldc, 256), kDbSlices);
+    dim3 blk(32, 8), grd(ceil_div(C, 256), kDbSlices);
     db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);
     GG_LAUNCH_CHECK();
     db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(partial, C, C, kDbSlices, scale, grad_scale, db);
     GG_LAUNCH_CHECK();
-  }
+    return GG_OK;
+  };
+  // announced blocks carry their db rows: without the partials db is finished BEFORE the GEMM then
+  if (db && !db_fused && sig.world > 1)
+    if (int e = db_from_dlogits()) return e;
+  GG_CUDA(cudaMemsetAsync(flags, 0, bwd_flag_bytes(), s));
+  // cluster shape (2,1,1) is compiled into the kernel
+  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, tm_dw, sig, C, D, B, scale, grad_scale, parked, flags,
+                                                       db_fused ? db : nullptr, db_partials, db_parts, db_ld);
+  GG_LAUNCH_CHECK();
+  if (db && !db_fused && sig.world <= 1)
+    if (int e = db_from_dlogits()) return e;
   return GG_OK;
 }

@@ -21,8 +21,12 @@
 // The per-row state therefore stays in registers across tiles ("run") and is flushed once per
 // (CTA, row block): after the first tile the running 5th-best logit rejects almost every 32-column
 // chunk by its maximum alone (which the softmax needs anyway), so the top-k costs ~1 compare per
-// chunk.  A warp-per-row merge kernel combines the few partials of a row into top-k probabilities
-// and indices, argmax, predicted centroid and the row log-sum-exp.
+// chunk.  The few partials of a row are combined into top-k probabilities and indices, argmax, predicted
+// centroid and the row log-sum-exp by whichever CTA flushes the LAST partial of a 128-row block (tickets in the
+// workspace): no second launch, and only that block's short merge trails the GEMM.
+// num_candidates > 8 (torch.topk has no limit, super_guessr.py:365): the GEMM is run again per further 8
+// ranks with a per-row "ceiling" (the previous pass's last entry): only logits ordered after it compete, so
+// every pass is exact on the same fp32 accumulators.
 //
 // Layout: x (M=B, K=D) bf16 row-major; W (N=C, K=D) bf16 row-major (both K-major operands, 128 B
 // swizzled TMA boxes of 64 K-elements); logits (B, ldc) bf16, ldc >= C padded to a multiple of 64.
@@ -59,14 +63,16 @@ struct FwdSmem {
   // per epilogue warp: 32 rows x 32 bf16 logits (one 32-column chunk), 64-byte swizzled (TMA store box)
   uint8_t out[WRITE_LOGITS ? kEpiWarps : 1][32 * 64];
   int thr[kThrSlots][kBM];           // per row: best known lower bound of the run's k-th largest logit (ordered key)
+  float mrg[8][2 + 2 * 8][32];       // merge tree scratch: 8 publishing warps x (max, sum, 8 values, 8 indices) x lane
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  uint32_t is_last;
 };
 
-// Static schedule shared by the kernel, the merge kernel and the host.  Units are CTA PAIRS and
+// Static schedule shared by the kernel, its merge step and the host.  Units are CTA PAIRS and
 // pair-tiles: num_m = 256-row blocks, grid = number of pairs (clusters); CTA 2c + r of pair c works on
 // row block 2 * mb + r.
 struct FwdSched {
@@ -127,12 +133,173 @@ __device__ __forceinline__ int ordered_key(float f) {
 }
 __device__ __forceinline__ float key_to_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 
-template <int KTOP, bool WRITE_LOGITS>
+// ------------------------------------------------------------------ merge of a 128-row block's partials
+//   topk_val = softmax probabilities exp(l - max) / sum   (super_guessr.py:355,365)
+//   pred_cell = argmax (:358), pred_llh = centroids[pred_cell] (:359-361), lse = max + log(sum)
+// The partial arrays are [partial][value][row in the 128-row tile] (lane = row: every load is one full
+// 128-byte line).  Ties keep the lower geocell index first.
+struct FwdOut {
+  const float* centroids;
+  float* topk_val;
+  long long* topk_idx;
+  long long* pred_cell;
+  float* pred_llh;
+  float* lse;
+  int k;      // row pitch of topk_val / topk_idx
+  int k_off;  // first rank this pass writes
+  int k_cnt;  // ranks this pass writes (<= KTOP)
+  float* ceil_v;        // (B) last (value, index) of this pass = ceiling of the next one; null when this is the last
+  int* ceil_i;
+  const float* lse_in;  // ceiling passes: the row log-sum-exp of pass 0
+};
+
+template <int KTOP>
+__device__ __forceinline__ void merge_insert(float (&tv)[KTOP], int (&ti)[KTOP], float v, int id) {
+  if (v > tv[KTOP - 1] || (v == tv[KTOP - 1] && v > -INFINITY && id < ti[KTOP - 1])) {
+    tv[KTOP - 1] = v;
+    ti[KTOP - 1] = id;
+#pragma unroll
+    for (int q = KTOP - 1; q > 0; --q) {
+      if (tv[q] > tv[q - 1] || (tv[q] == tv[q - 1] && ti[q] < ti[q - 1])) {
+        float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+        int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void lse_merge(float& lmax, float& lsum, float m, float s) {
+  if (m > -INFINITY) {
+    if (m > lmax) { lsum = lsum * expf(lmax - m) + s; lmax = m; }
+    else lsum += s * expf(m - lmax);
+  }
+}
+// merge a descending list (pv, pi) into (tv, ti); stops at the first element that cannot enter
+template <int KTOP>
+__device__ __forceinline__ void merge_list(float (&tv)[KTOP], int (&ti)[KTOP], const float (&pv)[KTOP],
+                                           const int (&pi)[KTOP]) {
+#pragma unroll
+  for (int j = 0; j < KTOP; ++j) {
+    // lists are sorted: once the warp's lanes are all done with this list, skip the rest (warp-uniform exit)
+    const bool enters = pv[j] > tv[KTOP - 1] || (pv[j] == tv[KTOP - 1] && pv[j] > -INFINITY && pi[j] < ti[KTOP - 1]);
+    if (!__any_sync(0xffffffffu, enters)) break;
+    merge_insert<KTOP>(tv, ti, pv[j], pi[j]);
+  }
+}
+
+constexpr uint32_t kEpiBarrier = 1;  // named barrier of the 16 epilogue warps
+
+// Called by all epilogue warps of the CTA that flushed the last partial of row block (mb, crank).  Warp (quad, cg)
+// folds partials cg, cg + 4, ... of rows quad * 32 + lane; the four column-group warps of a quadrant are then
+// combined through shared memory in a fixed order (deterministic), and cg 0 writes the rows' results.
+template <int KTOP, bool HAS_CEIL, typename Smem>
+__device__ __forceinline__ void merge_block(Smem& sm, const float* __restrict__ pmax, const float* __restrict__ psum,
+                                            const float* __restrict__ ptopv, const int* __restrict__ ptopi,
+                                            const FwdSched& sc, int mb, int crank, int quad, int cg, int lane, int M,
+                                            const FwdOut& o) {
+  const int rit = quad * 32 + lane;
+  const int row = (2 * mb + crank) * kBM + rit;
+  const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
+  const int nparts = (c_hi - c_lo + 1) * kColGroups;
+
+  float lmax = -INFINITY, lsum = 0.f;
+  float tv[KTOP];
+  int ti[KTOP];
+#pragma unroll
+  for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+
+  // this warp's partials, the next one's loads in flight while the current one is merged (L2 loads: the
+  // partials were written by other SMs during this launch)
+  float m = -INFINITY, sum = 0.f, pv[KTOP];
+  int pi[KTOP];
+  auto load = [&](int i) {
+    const int c = c_lo + i / kColGroups;
+    const int run = mb - sc.start(c) / sc.num_n;
+    const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + (i % kColGroups);
+    if (!HAS_CEIL) {
+      m = __ldcg(pmax + p * kBM + rit);
+      sum = __ldcg(psum + p * kBM + rit);
+    }
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) {
+      pv[j] = __ldcg(ptopv + (p * KTOP + j) * kBM + rit);
+      pi[j] = __ldcg(ptopi + (p * KTOP + j) * kBM + rit);
+    }
+  };
+  if (cg < nparts) load(cg);
+  for (int i = cg; i < nparts; i += kColGroups) {  // warp-uniform
+    const float cm = m, cs = sum;
+    float cv[KTOP];
+    int ci[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) { cv[j] = pv[j]; ci[j] = pi[j]; }
+    if (i + kColGroups < nparts) load(i + kColGroups);
+    if (!HAS_CEIL) lse_merge(lmax, lsum, cm, cs);
+    merge_list<KTOP>(tv, ti, cv, ci);
+  }
+  auto publish = [&](int slot) {
+    float(*dst)[32] = sm.mrg[slot];
+    dst[0][lane] = lmax;
+    dst[1][lane] = lsum;
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) {
+      dst[2 + j][lane] = tv[j];
+      dst[2 + 8 + j][lane] = __int_as_float(ti[j]);
+    }
+  };
+  auto absorb = [&](int slot) {
+    float(*src)[32] = sm.mrg[slot];
+    if (!HAS_CEIL) lse_merge(lmax, lsum, src[0][lane], src[1][lane]);
+    float cv[KTOP];
+    int ci[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) { cv[j] = src[2 + j][lane]; ci[j] = __float_as_int(src[2 + 8 + j][lane]); }
+    merge_list<KTOP>(tv, ti, cv, ci);
+  };
+  if (cg >= 2) publish((cg - 2) * 4 + quad);
+  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
+  if (cg < 2) absorb(cg * 4 + quad);  // 0 <- 2, 1 <- 3
+  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
+  if (cg == 1) publish(quad);
+  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
+  if (cg != 0) return;
+  absorb(quad);
+  if (row >= M) return;
+  float lse_row, inv = 1.f;
+  if (!HAS_CEIL) {
+    inv = 1.f / lsum;
+    lse_row = lmax + logf(lsum);
+  } else {
+    lse_row = o.lse_in[row];
+    lmax = lse_row;
+  }
+#pragma unroll
+  for (int j = 0; j < KTOP; ++j) {
+    if (j < o.k_cnt) {
+      o.topk_val[static_cast<size_t>(row) * o.k + o.k_off + j] = expf(tv[j] - lmax) * inv;
+      o.topk_idx[static_cast<size_t>(row) * o.k + o.k_off + j] = ti[j];
+    }
+  }
+  if (o.ceil_v) {
+    o.ceil_v[row] = tv[KTOP - 1];
+    o.ceil_i[row] = ti[KTOP - 1];
+  }
+  if (HAS_CEIL) return;
+  const int best0 = ti[0];
+  if (o.pred_cell) o.pred_cell[row] = best0;
+  if (o.pred_llh) {
+    o.pred_llh[2 * row + 0] = o.centroids[2 * best0 + 0];
+    o.pred_llh[2 * row + 1] = o.centroids[2 * best0 + 1];
+  }
+  if (o.lse) o.lse[row] = lse_row;
+}
+
+template <int KTOP, bool WRITE_LOGITS, bool HAS_CEIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias_pad,
                 float* __restrict__ pmax, float* __restrict__ psum, float* __restrict__ ptopv,
-                int* __restrict__ ptopi, int M, int N, int K, FwdSched sc) {
+                int* __restrict__ ptopi, unsigned int* __restrict__ tickets, const float* __restrict__ ceil_in_v,
+                const int* __restrict__ ceil_in_i, int M, int N, int K, FwdSched sc, FwdOut out) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = FwdSmem<WRITE_LOGITS>;
   constexpr int kStages = Smem::kStages;
@@ -237,6 +404,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int mb_first = t_begin / sc.num_n;
     int run_id = 0;
     sm.thr[4][row_in_tile] = kKeyMin;  // slot of run 4 (see the flush below); slots 0..3 start clean
+    // ceiling passes: only logits ordered after (ceil_v, ceil_i) -- lower value, or equal value and higher index
+    float ceil_v = INFINITY;
+    int ceil_i = -1;
+    int ceil_mb = -1;
 
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -245,6 +416,12 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const uint32_t thr_slot = smem_u32(&sm.thr[run_id & (kThrSlots - 1)][row_in_tile]);
+      if (HAS_CEIL && mb != ceil_mb) {
+        const int row = m0 + row_in_tile;
+        ceil_v = row < M ? __ldg(ceil_in_v + row) : -INFINITY;
+        ceil_i = row < M ? __ldg(ceil_in_i + row) : 0x7fffffff;
+        ceil_mb = mb;
+      }
       mbar_wait(&sm.acc_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr =
@@ -294,24 +471,31 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           for (int i = 0; i < 32; ++i)
             if (col0 + i >= N) v[i] = -INFINITY;
         }
+        if (HAS_CEIL) {  // the softmax statistics are pass 0's; entries at or before the ceiling are out
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = (v[i] < ceil_v || (v[i] == ceil_v && col0 + i > ceil_i)) ? v[i] : -INFINITY;
+        }
         float cmax = v[0];
 #pragma unroll
         for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
-        if (cmax > run_max) {
-          run_sum *= ex2_approx((run_max - cmax) * kLog2e);  // run_max = -inf -> 0 * 0
-          run_max = cmax;
-        }
-        if (run_max > -INFINITY) {
-          const float ms = run_max * kLog2e;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            s0 += ex2_approx(fmaf(v[i + 0], kLog2e, -ms));
-            s1 += ex2_approx(fmaf(v[i + 1], kLog2e, -ms));
-            s2 += ex2_approx(fmaf(v[i + 2], kLog2e, -ms));
-            s3 += ex2_approx(fmaf(v[i + 3], kLog2e, -ms));
+        if (!HAS_CEIL) {
+          if (cmax > run_max) {
+            run_sum *= ex2_approx((run_max - cmax) * kLog2e);  // run_max = -inf -> 0 * 0
+            run_max = cmax;
           }
-          run_sum += (s0 + s1) + (s2 + s3);
+          if (run_max > -INFINITY) {
+            const float ms = run_max * kLog2e;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              s0 += ex2_approx(fmaf(v[i + 0], kLog2e, -ms));
+              s1 += ex2_approx(fmaf(v[i + 1], kLog2e, -ms));
+              s2 += ex2_approx(fmaf(v[i + 2], kLog2e, -ms));
+              s3 += ex2_approx(fmaf(v[i + 3], kLog2e, -ms));
+            }
+            run_sum += (s0 + s1) + (s2 + s3);
+          }
         }
         // Top-k.  A logit can only matter if it beats a lower bound of the row's k-th best in this run:
         // this warp's own k-th best, or the one any of the three other warps of the row has published.
@@ -351,12 +535,14 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       // end of this CTA's run over row block mb: flush the row state
       if (nb == sc.num_n - 1 || t == t_end - 1) {
         const size_t p = (static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first)) * kColGroups + cg;
-        pmax[p * kBM + row_in_tile] = run_max;
-        psum[p * kBM + row_in_tile] = run_sum;
+        if (!HAS_CEIL) {
+          __stcg(&pmax[p * kBM + row_in_tile], run_max);
+          __stcg(&psum[p * kBM + row_in_tile], run_sum);
+        }
 #pragma unroll
         for (int j = 0; j < KTOP; ++j) {
-          ptopv[(p * KTOP + j) * kBM + row_in_tile] = tv[j];
-          ptopi[(p * KTOP + j) * kBM + row_in_tile] = ti[j];
+          __stcg(&ptopv[(p * KTOP + j) * kBM + row_in_tile], tv[j]);
+          __stcg(&ptopi[(p * KTOP + j) * kBM + row_in_tile], ti[j]);
         }
         run_max = -INFINITY;
         run_sum = 0.f;
@@ -367,6 +553,23 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // r-2 .. r+2 (mod 8); slot r+4 is free and is cleaned here, long before anyone enters run r+4.
         ++run_id;
         sm.thr[(run_id + 4) & (kThrSlots - 1)][row_in_tile] = kKeyMin;
+
+        // Ticket of row block (mb, crank): one per contributing CTA.  Whoever draws the last one finds every
+        // partial of these 128 rows in L2 and merges them (the other CTAs go on with their next run).
+        __threadfence();
+        named_bar_sync(kEpiBarrier, 32 * kEpiWarps);  // all 16 epilogue warps have flushed (and fenced)
+        if (threadIdx.x == 64) {
+          const int contrib = sc.owner((mb + 1) * sc.num_n - 1) - sc.owner(mb * sc.num_n) + 1;
+          const unsigned int old = atomicAdd(&tickets[2 * mb + crank], 1u);
+          const bool last = old + 1u == static_cast<unsigned int>(contrib);
+          if (last) tickets[2 * mb + crank] = 0u;  // left zeroed for the next launch
+          sm.is_last = last ? 1u : 0u;
+        }
+        named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
+        if (sm.is_last != 0u) {
+          __threadfence();
+          merge_block<KTOP, HAS_CEIL>(sm, pmax, psum, ptopv, ptopi, sc, mb, crank, quad, cg, lane, M, out);
+        }
       }
     }
     if (WRITE_LOGITS) {
@@ -380,137 +583,6 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
-}
-
-// Merge of the per-(CTA run, column group) partials of every row.
-//   topk_val = softmax probabilities exp(l - max) / sum   (super_guessr.py:355,365)
-//   pred_cell = argmax (:358), pred_llh = centroids[pred_cell] (:359-361), lse = max + log(sum)
-// The partial arrays are [partial][value][row in the 128-row tile]: a block takes 32 consecutive rows (lane =
-// row, so every load is one full 128-byte line), its kMergeWarps warps split the row's partials, and warp 0
-// folds the warps' (max, sum, top-k) states in warp order.  Ties keep the lower geocell index first.
-constexpr int kMergeWarps = 8;
-
-template <int KTOP>
-__device__ __forceinline__ void merge_insert(float (&tv)[KTOP], int (&ti)[KTOP], float v, int id) {
-  if (v > tv[KTOP - 1] || (v == tv[KTOP - 1] && v > -INFINITY && id < ti[KTOP - 1])) {
-    tv[KTOP - 1] = v;
-    ti[KTOP - 1] = id;
-#pragma unroll
-    for (int q = KTOP - 1; q > 0; --q) {
-      if (tv[q] > tv[q - 1] || (tv[q] == tv[q - 1] && ti[q] < ti[q - 1])) {
-        float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
-        int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void lse_merge(float& lmax, float& lsum, float m, float s) {
-  if (m > -INFINITY) {
-    if (m > lmax) { lsum = lsum * expf(lmax - m) + s; lmax = m; }
-    else lsum += s * expf(m - lmax);
-  }
-}
-
-// merge a descending list (pv, pi) into (tv, ti); stops at the first element that cannot enter
-template <int KTOP>
-__device__ __forceinline__ void merge_list(float (&tv)[KTOP], int (&ti)[KTOP], const float (&pv)[KTOP],
-                                           const int (&pi)[KTOP]) {
-#pragma unroll
-  for (int j = 0; j < KTOP; ++j) {
-    // lists are sorted: once the warp's lanes are all done with this list, skip the rest (warp-uniform exit)
-    const bool enters = pv[j] > tv[KTOP - 1] || (pv[j] == tv[KTOP - 1] && pv[j] > -INFINITY && pi[j] < ti[KTOP - 1]);
-    if (!__any_sync(0xffffffffu, enters)) break;
-    merge_insert<KTOP>(tv, ti, pv[j], pi[j]);
-  }
-}
-
-template <int KTOP>
-__global__ void __launch_bounds__(32 * kMergeWarps)
-head_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, const float* __restrict__ ptopv,
-                  const int* __restrict__ ptopi, FwdSched sc, int M, int k, const float* __restrict__ centroids,
-                  float* __restrict__ topk_val, long long* __restrict__ topk_idx, long long* __restrict__ pred_cell,
-                  float* __restrict__ pred_llh, float* __restrict__ lse) {
-  __shared__ float s_f[kMergeWarps][2 + KTOP][32];
-  __shared__ int s_i[kMergeWarps][KTOP][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = blockIdx.x * 32;  // 32 | kBM: the block's rows share pair row block, CTA and partial list
-  const int row = row0 + lane;
-  const int mb = row0 / (2 * kBM), crank = (row0 / kBM) & 1, rit = row % kBM;
-  const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
-  const int nparts = (c_hi - c_lo + 1) * kColGroups;
-
-  float lmax = -INFINITY, lsum = 0.f;
-  float tv[KTOP];
-  int ti[KTOP];
-#pragma unroll
-  for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-
-  // this warp's partials, the next one's loads in flight while the current one is merged
-  float m = -INFINITY, sum = 0.f, pv[KTOP];
-  int pi[KTOP];
-  auto load = [&](int i) {
-    const int c = c_lo + i / kColGroups;
-    const int run = mb - sc.start(c) / sc.num_n;
-    const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + (i % kColGroups);
-    m = pmax[p * kBM + rit];
-    sum = psum[p * kBM + rit];
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) {
-      pv[j] = ptopv[(p * KTOP + j) * kBM + rit];
-      pi[j] = ptopi[(p * KTOP + j) * kBM + rit];
-    }
-  };
-  if (warp < nparts) load(warp);
-  for (int i = warp; i < nparts; i += kMergeWarps) {  // warp-uniform
-    const float cm = m, cs = sum;
-    float cv[KTOP];
-    int ci[KTOP];
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) { cv[j] = pv[j]; ci[j] = pi[j]; }
-    if (i + kMergeWarps < nparts) load(i + kMergeWarps);
-    lse_merge(lmax, lsum, cm, cs);
-    merge_list<KTOP>(tv, ti, cv, ci);
-  }
-  // tree over the warps: 4 <- 8, 2 <- 4, 1 <- 2 (fixed order: deterministic)
-  auto publish = [&]() {
-    s_f[warp][0][lane] = lmax;
-    s_f[warp][1][lane] = lsum;
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) {
-      s_f[warp][2 + j][lane] = tv[j];
-      s_i[warp][j][lane] = ti[j];
-    }
-  };
-#pragma unroll
-  for (int half = kMergeWarps / 2; half >= 1; half >>= 1) {
-    if (warp >= half && warp < 2 * half) publish();
-    __syncthreads();
-    if (warp < half) {
-      const int w = warp + half;
-      lse_merge(lmax, lsum, s_f[w][0][lane], s_f[w][1][lane]);
-      float cv[KTOP];
-      int ci[KTOP];
-#pragma unroll
-      for (int j = 0; j < KTOP; ++j) { cv[j] = s_f[w][2 + j][lane]; ci[j] = s_i[w][j][lane]; }
-      merge_list<KTOP>(tv, ti, cv, ci);
-    }
-  }
-  if (warp != 0 || row >= M) return;
-  const float inv = 1.f / lsum;
-#pragma unroll
-  for (int j = 0; j < KTOP; ++j) {
-    if (j < k) {
-      topk_val[static_cast<size_t>(row) * k + j] = expf(tv[j] - lmax) * inv;
-      topk_idx[static_cast<size_t>(row) * k + j] = ti[j];
-    }
-  }
-  const int best0 = ti[0];
-  if (pred_cell) pred_cell[row] = best0;
-  if (pred_llh) {
-    pred_llh[2 * row + 0] = centroids[2 * best0 + 0];
-    pred_llh[2 * row + 1] = centroids[2 * best0 + 1];
-  }
-  if (lse) lse[row] = lmax + logf(lsum);
 }
 
 template <bool WRITE_LOGITS>
@@ -528,44 +600,46 @@ static cudaError_t launch_pairs(Kern kern, int pairs, size_t smem, cudaStream_t 
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-template <int KTOP>
-static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, int B, int C, int D, void* logits,
-                           int ldc, int k, void* workspace, const float* centroids, float* topk_val,
-                           long long* topk_idx, long long* pred_cell, float* pred_llh, float* lse,
-                           cudaStream_t stream) {
-  CUtensorMap tm_x, tm_w;
-  int rc = make_tmap_bf16_2d(&tm_x, x, D, B, static_cast<uint64_t>(D) * 2, kBK, kBM);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_w, W, D, C, static_cast<uint64_t>(D) * 2, kBK, kBN / 2);  // one CTA's half
-  if (rc) return rc;
-  CUtensorMap tm_out = tm_x;  // placeholder in serving (never dereferenced)
-  if (logits) {
-    rc = make_tmap_bf16_2d_sw64(&tm_out, logits, ldc, B, static_cast<uint64_t>(ldc) * 2, 32, 32);
-    if (rc) return rc;
-  }
-  const FwdSched sc = make_sched(B, C, device_sm_count());
+// workspace: [partials: pmax | psum | ptopv | ptopi][ceil_v (B) | ceil_i (B) | lse (B): passes beyond the first]
+struct FwdWs {
+  float *pmax, *psum, *ptopv;
+  int* ptopi;
+  float* ceil_v[2];
+  int* ceil_i[2];
+  float* lse;
+  size_t bytes;
+};
+static FwdWs carve_fwd_ws(void* base, const FwdSched& sc, int B, int ktop, bool multipass) {
+  FwdWs w;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  auto take = [&](size_t nbytes) {
+    uint8_t* r = p;
+    p += (nbytes + 255) & ~size_t(255);
+    return r;
+  };
   const size_t np = fwd_partials(sc) * kBM;
-  float* pmax = static_cast<float*>(workspace);
-  float* psum = pmax + np;
-  float* ptopv = psum + np;
-  int* ptopi = reinterpret_cast<int*>(ptopv + np * KTOP);
-  // every (CTA, run, half) slot the merge reads is flushed by the CTA that owns those tiles
-  if (logits) {
-    auto kern = head_fwd_kernel<KTOP, true>;
-    const size_t smem = fwd_smem_bytes<true>();
-    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
-    GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, pmax, psum, ptopv, ptopi, B, C, D,
-                         sc));
-  } else {
-    auto kern = head_fwd_kernel<KTOP, false>;
-    const size_t smem = fwd_smem_bytes<false>();
-    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
-    GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, pmax, psum, ptopv, ptopi, B, C, D,
-                         sc));
+  w.pmax = reinterpret_cast<float*>(take(np * sizeof(float)));
+  w.psum = reinterpret_cast<float*>(take(np * sizeof(float)));
+  w.ptopv = reinterpret_cast<float*>(take(np * ktop * sizeof(float)));
+  w.ptopi = reinterpret_cast<int*>(take(np * ktop * sizeof(int)));
+  for (int i = 0; i < 2; ++i) {
+    w.ceil_v[i] = reinterpret_cast<float*>(take(multipass ? sizeof(float) * B : 0));
+    w.ceil_i[i] = reinterpret_cast<int*>(take(multipass ? sizeof(int) * B : 0));
   }
-  GG_LAUNCH_CHECK();
-  head_merge_kernel<KTOP><<<ceil_div(B, 32), 32 * kMergeWarps, 0, stream>>>(pmax, psum, ptopv, ptopi, sc, B, k, centroids,
-                                                              topk_val, topk_idx, pred_cell, pred_llh, lse);
+  w.lse = reinterpret_cast<float*>(take(multipass ? sizeof(float) * B : 0));
+  w.bytes = static_cast<size_t>(p - static_cast<uint8_t*>(base));
+  return w;
+}
+
+template <int KTOP, bool WRITE_LOGITS, bool HAS_CEIL>
+static int launch_one(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_out, const float* bias_pad,
+                      const FwdWs& w, unsigned int* tickets, const float* ceil_in_v, const int* ceil_in_i, int B, int C,
+                      int D, const FwdSched& sc, const FwdOut& out, cudaStream_t stream) {
+  auto kern = head_fwd_kernel<KTOP, WRITE_LOGITS, HAS_CEIL>;
+  const size_t smem = fwd_smem_bytes<WRITE_LOGITS>();
+  if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
+  GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, w.pmax, w.psum, w.ptopv, w.ptopi,
+                       tickets, ceil_in_v, ceil_in_i, B, C, D, sc, out));
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -574,29 +648,77 @@ static int launch_head_fwd(const void* x, const void* W, const float* bias_pad, 
 
 using namespace gg;
 
+static int fwd_ktop(int k) { return k <= 5 ? 5 : 8; }
+
 extern "C" size_t gg_head_fwd_workspace_bytes(int B, int C, int k) {
-  const int ktop = k <= 5 ? 5 : 8;
   const FwdSched sc = make_sched(B, C, device_sm_count());
-  return fwd_partials(sc) * kBM * (2 + 2 * ktop) * sizeof(float);
+  return carve_fwd_ws(nullptr, sc, B, fwd_ktop(k), k > 8).bytes;
 }
+extern "C" size_t gg_head_fwd_ticket_bytes(int B) { return sizeof(unsigned int) * 2 * ceil_div(B, 2 * kBM); }
 
 extern "C" int gg_head_logits_ld(int C) { return ceil_div(C, 256) * 256; }
 extern "C" int gg_head_bias_pad(int C) { return ceil_div(C, kBN) * kBN; }
 
 extern "C" int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, int B, int C, int D,
-                           void* logits_bf16, int ldc, int k, void* workspace, const float* centroids,
+                           void* logits_bf16, int ldc, int k, void* workspace, void* tickets, const float* centroids,
                            float* topk_val, long long* topk_idx, long long* pred_cell, float* pred_llh, float* lse,
                            gg_stream_t stream) {
   GG_CHECK(B > 0 && C > 0 && D > 0, GG_ERR_ARG, "gg_head_fwd: empty problem B=%d C=%d D=%d", B, C, D);
   GG_CHECK(D % 8 == 0, GG_ERR_ARG, "gg_head_fwd: embed dim D=%d must be a multiple of 8 (16-byte TMA pitch)", D);
-  GG_CHECK(k >= 1 && k <= 8 && k <= C, GG_ERR_ARG, "gg_head_fwd: num_candidates k=%d must be in [1, min(8, C)]", k);
+  GG_CHECK(k >= 1 && k <= C, GG_ERR_ARG, "gg_head_fwd: num_candidates k=%d must be in [1, C=%d]", k, C);
   GG_CHECK(!logits_bf16 || (ldc >= C && ldc % 8 == 0), GG_ERR_ARG, "gg_head_fwd: ldc=%d must be >= C and a multiple of 8", ldc);
-  GG_CHECK(x_bf16 && w_bf16 && bias_pad && workspace && topk_val && topk_idx, GG_ERR_ARG, "gg_head_fwd: null pointer");
+  GG_CHECK(x_bf16 && w_bf16 && bias_pad && workspace && tickets && topk_val && topk_idx, GG_ERR_ARG,
+           "gg_head_fwd: null pointer");
   GG_CHECK(!pred_llh || centroids, GG_ERR_ARG, "gg_head_fwd: pred_llh needs the centroid table");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (k <= 5)
-    return launch_head_fwd<5>(x_bf16, w_bf16, bias_pad, B, C, D, logits_bf16, ldc, k, workspace, centroids, topk_val,
-                              topk_idx, pred_cell, pred_llh, lse, s);
-  return launch_head_fwd<8>(x_bf16, w_bf16, bias_pad, B, C, D, logits_bf16, ldc, k, workspace, centroids, topk_val,
-                            topk_idx, pred_cell, pred_llh, lse, s);
+  CUtensorMap tm_x, tm_w;
+  int rc = make_tmap_bf16_2d(&tm_x, x_bf16, D, B, static_cast<uint64_t>(D) * 2, kBK, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tm_w, w_bf16, D, C, static_cast<uint64_t>(D) * 2, kBK, kBN / 2);  // one CTA's half
+  if (rc) return rc;
+  CUtensorMap tm_out = tm_x;  // placeholder in serving (never dereferenced)
+  if (logits_bf16) {
+    rc = make_tmap_bf16_2d_sw64(&tm_out, logits_bf16, ldc, B, static_cast<uint64_t>(ldc) * 2, 32, 32);
+    if (rc) return rc;
+  }
+  const FwdSched sc = make_sched(B, C, device_sm_count());
+  const int ktop = fwd_ktop(k);
+  const bool multipass = k > 8;
+  const FwdWs w = carve_fwd_ws(workspace, sc, B, ktop, multipass);
+  unsigned int* tk = static_cast<unsigned int*>(tickets);
+  FwdOut o;
+  o.centroids = centroids;
+  o.topk_val = topk_val;
+  o.topk_idx = topk_idx;
+  o.pred_cell = pred_cell;
+  o.pred_llh = pred_llh;
+  o.lse = multipass && !lse ? w.lse : lse;
+  o.k = k;
+  o.k_off = 0;
+  o.k_cnt = k < ktop ? k : ktop;
+  o.ceil_v = multipass ? w.ceil_v[0] : nullptr;
+  o.ceil_i = multipass ? w.ceil_i[0] : nullptr;
+  o.lse_in = nullptr;
+  if (ktop == 5) {
+    rc = logits_bf16 ? launch_one<5, true, false>(tm_x, tm_w, tm_out, bias_pad, w, tk, nullptr, nullptr, B, C, D, sc, o, s)
+                     : launch_one<5, false, false>(tm_x, tm_w, tm_out, bias_pad, w, tk, nullptr, nullptr, B, C, D, sc, o, s);
+    return rc;
+  }
+  rc = logits_bf16 ? launch_one<8, true, false>(tm_x, tm_w, tm_out, bias_pad, w, tk, nullptr, nullptr, B, C, D, sc, o, s)
+                   : launch_one<8, false, false>(tm_x, tm_w, tm_out, bias_pad, w, tk, nullptr, nullptr, B, C, D, sc, o, s);
+  if (rc) return rc;
+  // ranks 8, 9, ...: the GEMM again per 8 ranks, each pass below the previous pass's last entry
+  const float* lse0 = o.lse;
+  for (int off = 8, pass = 1; off < k; off += 8, ++pass) {
+    FwdOut p = o;
+    p.k_off = off;
+    p.k_cnt = k - off < 8 ? k - off : 8;
+    const int in = (pass - 1) & 1, outb = pass & 1;
+    p.ceil_v = off + 8 < k ? w.ceil_v[outb] : nullptr;
+    p.ceil_i = off + 8 < k ? w.ceil_i[outb] : nullptr;
+    p.lse_in = lse0;
+    rc = launch_one<8, false, true>(tm_x, tm_w, tm_out, bias_pad, w, tk, w.ceil_v[in], w.ceil_i[in], B, C, D, sc, p, s);
+    if (rc) return rc;
+  }
+  return GG_OK;
 }

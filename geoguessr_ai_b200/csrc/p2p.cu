@@ -11,6 +11,10 @@
 // the buffer crosses NVLink in each direction, once: 26 MB each way for the 51.8 MB head gradient at N = 2,
 // 45 MB at N = 8, against the 2 (N - 1) / N a ring moves in 2 (N - 1) latency-bound steps.  The caller brackets
 // the launch with symmetric-memory barriers (all gradients written / all slices delivered).
+#include <stdio.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gg {
@@ -119,6 +123,169 @@ nvls_allreduce_avg_kernel(float4* __restrict__ mc, size_t lo, size_t hi, float i
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Progressive exchange underneath the dW GEMM (gg_grad_exchange).  The two kernels above run AFTER the GEMM, between
+// two host-issued barriers: the whole exchange is exposed.  Here the exchange kernel is launched NEXT TO gg_head_bwd
+// (another stream; its few small CTAs co-reside with the GEMM's one CTA per SM) and works block by block: dW is cut
+// into blocks of 128 geocells (+ the block's 128 db entries), block b is reduced by rank b % world.  The GEMM
+// announces a finished block with a system-scope release add on the reducer's `ready[b]` counter; the reducer waits
+// for all ranks' announcements, averages the block (multimem.ld_reduce through the NVSwitch, or peer loads in rank
+// order), writes the average into every rank's copy (multimem.st / peer stores) and adds to every rank's `done`
+// counter; each rank's kernel ends when every block of every reducer has landed in its copy.  Only the blocks the
+// GEMM finishes last are exchanged after it.  No host barrier: counters only ever grow (the expected values are
+// multiples of a per-launch epoch kept in the control region), nothing is reset while a peer could still add.
+//
+// Control region (symmetric memory, GG_GRAD_CTRL_BYTES per rank, zeroed once): u32 words
+//   [0, 1024)     blk_count  finished column tiles per block (gg_head_bwd, local, self-resetting)
+//   [1024, 2048)  ready      announcements per block (remote adds by every rank's gg_head_bwd)
+//   [2048]        done       exchanged units landed in this rank's copy (remote adds by the reducers)
+//   [2049]        exit ticket, [2050] epoch (local)
+constexpr int kCtrlReady = 1024, kCtrlDone = 2048, kCtrlExit = 2049, kCtrlEpoch = 2050;
+constexpr int kGradBlockRows = 128;
+constexpr int kGradParts = 4;      // CTAs that share one block
+constexpr int kGradThreads = 256;   // <= 154 registers per thread leaves room next to the GEMM CTA of an SM
+constexpr int kGradMaxCtas = 64;
+
+struct GradPeers {
+  float4* grad[kP2PMaxWorld];        // every rank's [dW | db | pad] buffer
+  unsigned int* ctrl[kP2PMaxWorld];  // every rank's control region
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_red_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until *p has reached `target` (wrap-safe); traps instead of hanging the GPU if a peer never arrives
+__device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target, const char* what, int a, int b) {
+  const long long t0 = clock64();
+  while (static_cast<int>(ld_acquire_sys(p) - target) < 0) {
+    __nanosleep(200);
+    if (clock64() - t0 > 10000000000LL) {
+      printf("gg: grad exchange timeout waiting for %s (rank %d, index %d): have %u want %u\n", what, a, b,
+             ld_acquire_sys(p), target);
+      __trap();
+    }
+  }
+}
+
+// average float4 [lo, hi) of every copy (this CTA's threads stride over it)
+template <int WORLD, bool NVLS>
+__device__ __forceinline__ void exchange_range(const GradPeers& peers, float4* mc, size_t lo, size_t hi, float inv_world) {
+  // <= 64 registers: the kernel's CTAs share SMs with the dW GEMM's
+  constexpr int kUnroll = NVLS ? 4 : (WORLD >= 8 ? 1 : (WORLD >= 4 ? 2 : 4));
+  size_t base = lo + threadIdx.x;
+  const size_t stride = kGradThreads;
+  if (NVLS) {
+    for (; base + (kUnroll - 1) * stride < hi; base += stride * kUnroll) {
+      float4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = multimem_ld_add(mc + base + u * stride);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) pin(v[u]);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        v[u].x *= inv_world; v[u].y *= inv_world; v[u].z *= inv_world; v[u].w *= inv_world;
+        multimem_st(mc + base + u * stride, v[u]);
+      }
+    }
+    for (; base < hi; base += stride) {
+      float4 v = multimem_ld_add(mc + base);
+      v.x *= inv_world; v.y *= inv_world; v.z *= inv_world; v.w *= inv_world;
+      multimem_st(mc + base, v);
+    }
+  } else {
+    for (; base + (kUnroll - 1) * stride < hi; base += stride * kUnroll) {
+      float4 v[kUnroll][WORLD];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) v[u][r] = ld_peer(peers.grad[r] + base + u * stride);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) pin(v[u][r]);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float4 acc = v[u][0];
+#pragma unroll
+        for (int r = 1; r < WORLD; ++r) {  // rank order: identical on every rank
+          acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w;
+        }
+        acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) st_peer(peers.grad[r] + base + u * stride, acc);
+      }
+    }
+    for (; base < hi; base += stride) {
+      float4 acc = ld_peer(peers.grad[0] + base);
+#pragma unroll
+      for (int r = 1; r < WORLD; ++r) {
+        const float4 t = ld_peer(peers.grad[r] + base);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) st_peer(peers.grad[r] + base, acc);
+    }
+  }
+}
+
+template <int WORLD, bool NVLS>
+__global__ void __launch_bounds__(kGradThreads, 1)
+grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict__ mc_grad,
+                     unsigned int* __restrict__ mc_ctrl, int rank, int C, int D, int nblk, float inv_world, int no_wait) {
+  unsigned int* const ctrl = peers.ctrl[rank];
+  __shared__ unsigned int s_epoch;
+  if (threadIdx.x == 0) s_epoch = ld_acquire_sys(ctrl + kCtrlEpoch);
+  __syncthreads();
+  const unsigned int epoch = s_epoch + 1u;  // announcements / landed units expected so far = epoch x (per-launch count)
+  const int own = nblk > rank ? (nblk - rank + WORLD - 1) / WORLD : 0;  // blocks rank, rank + WORLD, ...
+  const size_t row4 = static_cast<size_t>(D) / 4;                       // float4 per geocell row
+  const size_t db4 = static_cast<size_t>(C) * row4;                     // float4 offset of db
+  for (int u = blockIdx.x; u < own * kGradParts; u += gridDim.x) {
+    const int b = rank + (u / kGradParts) * WORLD, part = u % kGradParts;
+    if (threadIdx.x == 0) spin_until(ctrl + kCtrlReady + b, epoch * static_cast<unsigned int>(WORLD), "block", rank, b);
+    __syncthreads();
+    const int r0 = b * kGradBlockRows, r1 = min(C, r0 + kGradBlockRows);
+    const size_t lo = static_cast<size_t>(r0) * row4, n4 = static_cast<size_t>(r1 - r0) * row4;
+    exchange_range<WORLD, NVLS>(peers, mc_grad, lo + n4 * part / kGradParts, lo + n4 * (part + 1) / kGradParts, inv_world);
+    if (part == 0)  // the block's db entries (128 floats; the last block's ragged end runs into the zero pad)
+      exchange_range<WORLD, NVLS>(peers, mc_grad, db4 + static_cast<size_t>(r0) / 4,
+                                  db4 + (static_cast<size_t>(r1) + 3) / 4, inv_world);
+    __syncthreads();  // every thread's stores are issued
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (NVLS) {
+        multimem_red_release_sys(mc_ctrl + kCtrlDone, 1u);
+      } else {
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) red_release_sys(peers.ctrl[r] + kCtrlDone, 1u);
+      }
+    }
+  }
+  // every unit of every reducer has landed in this rank's copy
+  if (threadIdx.x == 0) {
+    if (!no_wait)
+      spin_until(ctrl + kCtrlDone, epoch * static_cast<unsigned int>(nblk * kGradParts), "landed units", rank, -1);
+    __threadfence_system();
+    if (atomicAdd(ctrl + kCtrlExit, 1u) == gridDim.x - 1) {  // last CTA out: next launch's epoch
+      ctrl[kCtrlExit] = 0u;
+      __threadfence();
+      atomicExch(ctrl + kCtrlEpoch, epoch);
+    }
+  }
+}
+
 }  // namespace gg
 
 using namespace gg;
@@ -176,6 +343,46 @@ extern "C" int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, s
       std::min<size_t>(static_cast<size_t>(2 * device_sm_count()), (hi - lo + per_cta - 1) / per_cta));
   nvls_allreduce_avg_kernel<<<grid, kP2PThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<float4*>(multicast_ptr), lo, hi, 1.0f / static_cast<float>(world));
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" size_t gg_grad_ctrl_bytes(void) { return GG_GRAD_CTRL_BYTES; }
+
+extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsigned long long* ctrl_ptrs, void* grad_mc,
+                                void* ctrl_mc, int world, int rank, int C, int D, int flags, gg_stream_t stream) {
+  GG_CHECK(grad_ptrs && ctrl_ptrs && world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, GG_ERR_ARG,
+           "gg_grad_exchange: world=%d rank=%d (1 <= world <= %d)", world, rank, kP2PMaxWorld);
+  GG_CHECK(world == 1 || world == 2 || world == 4 || world == 8, GG_ERR_UNSUPPORTED,
+           "gg_grad_exchange: world=%d (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
+  GG_CHECK(C > 0 && D > 0 && D % 4 == 0, GG_ERR_ARG, "gg_grad_exchange: C=%d D=%d (D a multiple of 4)", C, D);
+  const int nblk = (C + kGradBlockRows - 1) / kGradBlockRows;
+  GG_CHECK(nblk <= kCtrlReady, GG_ERR_UNSUPPORTED, "gg_grad_exchange: C=%d exceeds %d geocells", C, kCtrlReady * kGradBlockRows);
+  GG_CHECK((grad_mc == nullptr) == (ctrl_mc == nullptr), GG_ERR_ARG, "gg_grad_exchange: both multicast addresses or none");
+  if (world == 1) return GG_OK;
+  GradPeers peers = {};
+  for (int r = 0; r < world; ++r) {
+    GG_CHECK(grad_ptrs[r] != 0 && (grad_ptrs[r] & 15) == 0 && ctrl_ptrs[r] != 0 && (ctrl_ptrs[r] & 15) == 0, GG_ERR_ARG,
+             "gg_grad_exchange: buffers of rank %d missing or not 16-byte aligned", r);
+    peers.grad[r] = reinterpret_cast<float4*>(grad_ptrs[r]);
+    peers.ctrl[r] = reinterpret_cast<unsigned int*>(ctrl_ptrs[r]);
+  }
+  const int own = nblk > rank ? (nblk - rank + world - 1) / world : 0;
+  const int grid = std::max(1, std::min(kGradMaxCtas, own * kGradParts));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float inv = 1.0f / static_cast<float>(world);
+  float4* mg = static_cast<float4*>(grad_mc);
+  unsigned int* mcc = static_cast<unsigned int*>(ctrl_mc);
+  const int nw = (flags & GG_GRAD_NO_WAIT) ? 1 : 0;
+#define GG_GX(W)                                                                                              \
+  do {                                                                                                        \
+    if (mg) grad_exchange_kernel<W, true><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, rank, C, D, nblk, inv, nw);  \
+    else grad_exchange_kernel<W, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, rank, C, D, nblk, inv, nw);    \
+  } while (0)
+  if (world == 2) GG_GX(2);
+  else if (world == 4) GG_GX(4);
+  else GG_GX(8);
+#undef GG_GX
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

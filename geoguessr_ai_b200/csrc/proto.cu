@@ -36,6 +36,13 @@ constexpr uint32_t kPStageB = kPN * kPK * 2;
 constexpr float kMissingScore = -100000.0f;  // proto_refiner.py:185
 
 // ------------------------------------------------------------------ stage 0: grouping
+// Geocells are packed into GROUPS when the bank is installed (gg_proto_group_cells): consecutive cells whose
+// prototypes fit one 256-row accumulation unit share it (a mean cell of the 1 M bank has 79 prototypes: alone it
+// would fill a third of the unit and its neighbours' rows would be loaded -- and thrown away -- with it); a cell
+// with more than 256 prototypes is a group of its own.  A work item is (group, chunk of <= 128 pairs); the pairs of
+// a group are contiguous because pairs are sorted by cell, and every pair carries its own cell's prototype range,
+// which masks the unit's columns in the epilogue.
+//
 // rec[p] initialised to "missing" (owned cell) or "not mine" (-inf); counts per owned cell.
 __global__ void proto_count_kernel(const long long* __restrict__ cand, int cand_ld, int B, int topk, int cell_lo,
                                    int cell_hi, int* __restrict__ cnt, float4* __restrict__ rec) {
@@ -47,76 +54,109 @@ __global__ void proto_count_kernel(const long long* __restrict__ cand, int cand_
   if (mine) atomicAdd(&cnt[c - cell_lo], 1);
 }
 
-// Single CTA: exclusive scans over the owned cells -> pair_off (C+1), and the work list
-// (cell, chunk) for every cell that has both pairs and prototypes.  meta[0] = #work items.
+// Single CTA.  Pass 1: exclusive scan of the pair counts over the owned cells -> pair_off (ncell+1).  Pass 2: scan
+// over the groups -> work list (group, chunk) for every group that has both pairs and prototypes.
+// meta = {work items, pairs, accumulation units (work items x 256-prototype blocks of the group), 0}.
 __global__ void proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off, int ncell,
-                                  int* __restrict__ pair_off, int* __restrict__ cursor, int* __restrict__ work_cell,
-                                  int* __restrict__ work_chunk, int* __restrict__ meta) {
-  __shared__ int s_pairs[1024], s_tiles[1024];
+                                  const int* __restrict__ group_off, int ngroups, int* __restrict__ pair_off,
+                                  int* __restrict__ cursor, int* __restrict__ work_group, int* __restrict__ work_chunk,
+                                  int* __restrict__ meta) {
+  __shared__ int s_a[1024], s_b[1024];
   const int tid = threadIdx.x;
-  const int per = (ncell + 1023) / 1024;
-  const int c0 = tid * per, c1 = min(ncell, c0 + per);
-  int np = 0, nt = 0;
-  for (int c = c0; c < c1; ++c) {
-    const int n = cnt[c];
-    np += n;
-    if (cell_off[c + 1] > cell_off[c]) nt += (n + kPM - 1) / kPM;
+  {
+    const int per = (ncell + 1023) / 1024;
+    const int c0 = min(ncell, tid * per), c1 = min(ncell, c0 + per);
+    int np = 0;
+    for (int c = c0; c < c1; ++c) np += cnt[c];
+    s_a[tid] = np;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+      const int a = tid >= o ? s_a[tid - o] : 0;
+      __syncthreads();
+      s_a[tid] += a;
+      __syncthreads();
+    }
+    int pbase = s_a[tid] - np;
+    for (int c = c0; c < c1; ++c) {
+      pair_off[c] = pbase;
+      cursor[c] = 0;
+      pbase += cnt[c];
+    }
+    if (tid == 1023) {
+      pair_off[ncell] = s_a[1023];
+      meta[1] = s_a[1023];
+    }
+    __syncthreads();  // pair_off complete (block-scope visibility of the global writes)
   }
-  s_pairs[tid] = np;
-  s_tiles[tid] = nt;
+  const int per = (ngroups + 1023) / 1024;
+  const int g0 = min(ngroups, tid * per), g1 = min(ngroups, g0 + per);
+  int nt = 0, nu = 0;
+  for (int g = g0; g < g1; ++g) {
+    const int c0 = group_off[g], c1 = group_off[g + 1];
+    const int n = pair_off[c1] - pair_off[c0], np = cell_off[c1] - cell_off[c0];
+    if (n > 0 && np > 0) {
+      const int chunks = (n + kPM - 1) / kPM;
+      nt += chunks;
+      nu += chunks * ((np + kPN - 1) / kPN);
+    }
+  }
+  s_a[tid] = nt;
+  s_b[tid] = nu;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+  for (int o = 1; o < 1024; o <<= 1) {
     int a = 0, b = 0;
-    if (tid >= o) { a = s_pairs[tid - o]; b = s_tiles[tid - o]; }
+    if (tid >= o) { a = s_a[tid - o]; b = s_b[tid - o]; }
     __syncthreads();
-    s_pairs[tid] += a;
-    s_tiles[tid] += b;
+    s_a[tid] += a;
+    s_b[tid] += b;
     __syncthreads();
   }
-  int pbase = s_pairs[tid] - np, tbase = s_tiles[tid] - nt;
-  for (int c = c0; c < c1; ++c) {
-    const int n = cnt[c];
-    pair_off[c] = pbase;
-    cursor[c] = 0;
-    if (cell_off[c + 1] > cell_off[c]) {
+  int tbase = s_a[tid] - nt;
+  for (int g = g0; g < g1; ++g) {
+    const int c0 = group_off[g], c1 = group_off[g + 1];
+    const int n = pair_off[c1] - pair_off[c0], np = cell_off[c1] - cell_off[c0];
+    if (n > 0 && np > 0) {
       const int chunks = (n + kPM - 1) / kPM;
       for (int m = 0; m < chunks; ++m) {
-        work_cell[tbase + m] = c;
+        work_group[tbase + m] = g;
         work_chunk[tbase + m] = m;
       }
       tbase += chunks;
     }
-    pbase += n;
   }
   if (tid == 1023) {
-    pair_off[ncell] = s_pairs[1023];
-    meta[0] = s_tiles[1023];
-    meta[1] = s_pairs[1023];
+    meta[0] = s_a[1023];
+    meta[2] = s_b[1023];
+    meta[3] = 0;
   }
 }
 
+// slot = position of the pair in cell order: its pair id, its query row and its cell's prototype range
 __global__ void proto_scatter_kernel(const long long* __restrict__ cand, int cand_ld, int B, int topk, int cell_lo,
                                      int cell_hi, const int* __restrict__ pair_off, int* __restrict__ cursor,
-                                     int* __restrict__ pair_ids) {
+                                     const int* __restrict__ cell_off, int* __restrict__ pair_ids,
+                                     int* __restrict__ slot_q, int2* __restrict__ slot_range) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= B * topk) return;
   const long long c = cand[static_cast<size_t>(p / topk) * cand_ld + (p % topk)];
   if (c < cell_lo || c >= cell_hi) return;
   const int lc = static_cast<int>(c - cell_lo);
-  pair_ids[pair_off[lc] + atomicAdd(&cursor[lc], 1)] = p;
+  const int slot = pair_off[lc] + atomicAdd(&cursor[lc], 1);
+  pair_ids[slot] = p;
+  slot_q[slot] = p / topk;
+  slot_range[slot] = make_int2(cell_off[lc], cell_off[lc + 1]);
 }
 
-// One warp per grouped slot: copy the query row (bf16, D) and its squared norm into cell order.
-__global__ void proto_gather_kernel(const bf16* __restrict__ q, const float* __restrict__ qn,
-                                    const int* __restrict__ pair_ids, const int* __restrict__ meta, int topk, int D,
-                                    bf16* __restrict__ qs, float* __restrict__ qs_n) {
+// One warp per grouped slot: copy the query row (bf16, D) into cell order (only when the retrieval kernel does
+// not gather the rows itself).
+__global__ void proto_gather_kernel(const bf16* __restrict__ q, const int* __restrict__ slot_q,
+                                    const int* __restrict__ meta, int D, bf16* __restrict__ qs) {
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (slot >= meta[1]) return;
-  const int qi = pair_ids[slot] / topk;
+  const int qi = slot_q[slot];
   const uint4* src = reinterpret_cast<const uint4*>(q + static_cast<size_t>(qi) * D);
   uint4* dst = reinterpret_cast<uint4*>(qs + static_cast<size_t>(slot) * D);
   for (int i = threadIdx.x & 31; i < (D >> 3); i += 32) dst[i] = __ldg(src + i);
-  if ((threadIdx.x & 31) == 0) qs_n[slot] = qn[qi];
 }
 
 // ------------------------------------------------------------------ stage 1: retrieval
@@ -131,14 +171,31 @@ struct ProtoSmem {
   uint32_t tmem_base;
 };
 
+// 4 rows of a 2-D bf16 tensor, picked by index, into 4 consecutive 128-byte rows of a swizzled tile
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0, int r1, int r2,
+                                            int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, "
+      "%6}], [%7];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// GATHER4: the A operand (a work item's <= 128 query rows) is gathered straight from the query matrix by the TMA
+// engine, four rows per instruction, one instruction per producer lane and k-block -- the rows never make the
+// round trip through a cell-ordered copy in HBM.  Otherwise tm_q maps that copy (proto_gather_kernel).
+// COSINE: score = q.p / (|q| |p|) (models/proto_refiner.py:347-362) instead of -|q - p| (:364-376).
+template <bool GATHER4, bool COSINE>
 __global__ void __launch_bounds__(kProtoThreads, 1)
-proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // Qs   (slots, D)
+proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: q (B, D), 1-row boxes; else Qs (slots, D)
                       const __grid_constant__ CUtensorMap tm_bank,  // bank (P_local, D)
-                      const int* __restrict__ meta, const int* __restrict__ work_cell,
-                      const int* __restrict__ work_chunk, const int* __restrict__ pair_off,
-                      const int* __restrict__ pair_ids, const int* __restrict__ cell_off,
-                      const float* __restrict__ qs_n, const float* __restrict__ pnorm,
-                      const float* __restrict__ pcoords, int proto_base, int D, float4* __restrict__ rec) {
+                      const int* __restrict__ meta, const int* __restrict__ work_group,
+                      const int* __restrict__ work_chunk, const int* __restrict__ group_off,
+                      const int* __restrict__ pair_off, const int* __restrict__ pair_ids,
+                      const int* __restrict__ slot_q, const int2* __restrict__ slot_range,
+                      const int* __restrict__ cell_off, const float* __restrict__ q_n,
+                      const float* __restrict__ pnorm, const float* __restrict__ pcoords, int proto_base, int D,
+                      float4* __restrict__ rec) {
   extern __shared__ uint8_t smem_raw[];
   ProtoSmem& sm = *reinterpret_cast<ProtoSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,21 +225,35 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // Qs   (slo
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int c = work_cell[w];
-        const int a_row0 = pair_off[c] + work_chunk[w] * kPM;
-        const int p0 = cell_off[c], p1 = cell_off[c + 1];
-        for (int n0 = p0; n0 < p1; n0 += kPN) {
-          for (int kb = 0; kb < num_k; ++kb) {
-            mbar_wait(&sm.empty[s], ph ^ 1);
+    // ===== producer (whole warp: with GATHER4 every lane issues one 4-row gather per k-block) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int g = work_group[w];
+      const int c0 = group_off[g], c1 = group_off[g + 1];
+      const int a_row0 = pair_off[c0] + work_chunk[w] * kPM;
+      const int a_last = pair_off[c1] - 1;  // last slot of the group: rows past it repeat this one (results unused)
+      const int p0 = cell_off[c0], p1 = cell_off[c1];
+      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      if (GATHER4) {
+        r0 = __ldg(slot_q + min(a_row0 + 4 * lane + 0, a_last));
+        r1 = __ldg(slot_q + min(a_row0 + 4 * lane + 1, a_last));
+        r2 = __ldg(slot_q + min(a_row0 + 4 * lane + 2, a_last));
+        r3 = __ldg(slot_q + min(a_row0 + 4 * lane + 3, a_last));
+      }
+      for (int n0 = p0; n0 < p1; n0 += kPN) {
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&sm.empty[s], ph ^ 1);
+          if (lane == 0) {
             mbar_arrive_expect_tx(&sm.full[s], kPStageA + kPStageB);
-            tma_load_2d(sm.a[s], &tm_q, &sm.full[s], kb * kPK, a_row0);
             tma_load_2d_hint(sm.b[s], &tm_bank, &sm.full[s], kb * kPK, n0, kPolicyEvictFirst);
-            if (++s == kPStages) { s = 0; ph ^= 1; }
+            if (!GATHER4) tma_load_2d(sm.a[s], &tm_q, &sm.full[s], kb * kPK, a_row0);
           }
+          if (GATHER4) {
+            __syncwarp();  // the barrier is armed before any lane's bytes can land
+            tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
+          }
+          if (++s == kPStages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -193,8 +264,8 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // Qs   (slo
       uint32_t ph = 0;
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int c = work_cell[w];
-        const int p0 = cell_off[c], p1 = cell_off[c + 1];
+        const int g = work_group[w];
+        const int p0 = cell_off[group_off[g]], p1 = cell_off[group_off[g + 1]];
         for (int n0 = p0; n0 < p1; n0 += kPN, ++it) {
           const int acc = it & 1;
           const uint32_t acc_ph = (it >> 1) & 1;
@@ -224,24 +295,39 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // Qs   (slo
     const int et = threadIdx.x - 64;       // 0..127 among the epilogue threads
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int c = work_cell[w];
-      const int a_row0 = pair_off[c] + work_chunk[w] * kPM;
-      const int nq = min(kPM, pair_off[c + 1] - a_row0);
-      const int p0 = cell_off[c], p1 = cell_off[c + 1];
+      const int g = work_group[w];
+      const int c0 = group_off[g], c1 = group_off[g + 1];
+      const int a_row0 = pair_off[c0] + work_chunk[w] * kPM;
+      const int nq = min(kPM, pair_off[c1] - a_row0);
+      const int p0 = cell_off[c0], p1 = cell_off[c1];
+      // this pair's cell: only its prototypes [lo, hi) of the unit's columns compete
+      int2 rng = make_int2(0, 0);
+      if (r < nq) rng = __ldg(slot_range + a_row0 + r);
       float best = CUDART_INF_F;
       int best_i = -1;
       for (int n0 = p0; n0 < p1; n0 += kPN, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
-        // prototype norms of this unit -> smem (pad with +inf: prototypes of the next cell / past the bank)
-        for (int i = et; i < kPN; i += 128) sm.pn[acc][i] = (n0 + i < p1) ? __ldg(pnorm + n0 + i) : CUDART_INF_F;
+        // prototype norms of this unit -> smem (pad with +inf: prototypes past the group / the bank);
+        // cosine: 1 / |p| (0 for the pad and for zero vectors: their score is 0, never NaN)
+        for (int i = et; i < kPN; i += 128) {
+          float v = CUDART_INF_F;
+          if (n0 + i < p1) v = __ldg(pnorm + n0 + i);
+          if (COSINE) v = (n0 + i < p1 && v > 0.f) ? rsqrtf(v) : 0.f;
+          sm.pn[acc][i] = v;
+        }
         named_bar_sync(1, 128);
         mbar_wait(&sm.acc_full[acc], acc_ph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kPN;
 #pragma unroll 1
         for (int cc = 0; cc < kPN / 32; ++cc) {
-          if (n0 + cc * 32 >= p1) break;  // uniform across the CTA
+          const int base = n0 + cc * 32;
+          if (base >= p1) break;  // uniform across the CTA
+          // columns of this chunk inside my cell's range (bit i = column base + i)
+          const int lo = max(rng.x - base, 0), hi = min(rng.y - base, 32);
+          const uint32_t msk = lo < hi ? ((hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo)) : 0u;
+          if (!__any_sync(0xffffffffu, msk != 0u)) continue;  // (pairs are sorted by cell: most chunks are one warp's)
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + cc * 32, v);
           tmem_ld_wait();
@@ -249,24 +335,36 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // Qs   (slo
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 pn = pn4[q4];
-            const float d0 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 0]), pn.x);
-            const float d1 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 1]), pn.y);
-            const float d2 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 2]), pn.z);
-            const float d3 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 3]), pn.w);
-            const int j = n0 + cc * 32 + 4 * q4;
-            if (d0 < best) { best = d0; best_i = j; }
-            if (d1 < best) { best = d1; best_i = j + 1; }
-            if (d2 < best) { best = d2; best_i = j + 2; }
-            if (d3 < best) { best = d3; best_i = j + 3; }
+            float d0, d1, d2, d3;
+            if (COSINE) {  // minimise -cos |q|
+              d0 = -__uint_as_float(v[4 * q4 + 0]) * pn.x;
+              d1 = -__uint_as_float(v[4 * q4 + 1]) * pn.y;
+              d2 = -__uint_as_float(v[4 * q4 + 2]) * pn.z;
+              d3 = -__uint_as_float(v[4 * q4 + 3]) * pn.w;
+            } else {       // minimise |p|^2 - 2 q.p
+              d0 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 0]), pn.x);
+              d1 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 1]), pn.y);
+              d2 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 2]), pn.z);
+              d3 = fmaf(-2.f, __uint_as_float(v[4 * q4 + 3]), pn.w);
+            }
+            const int j = base + 4 * q4;
+            const uint32_t m4 = msk >> (4 * q4);
+            if ((m4 & 1u) && d0 < best) { best = d0; best_i = j; }
+            if ((m4 & 2u) && d1 < best) { best = d1; best_i = j + 1; }
+            if ((m4 & 4u) && d2 < best) { best = d2; best_i = j + 2; }
+            if ((m4 & 8u) && d3 < best) { best = d3; best_i = j + 3; }
           }
         }
         tc_fence_before();
         mbar_arrive(&sm.acc_empty[acc]);
       }
       if (r < nq && best_i >= 0) {
-        const float d2 = fmaxf(best + __ldg(qs_n + a_row0 + r), 0.f);
+        const float qn = __ldg(q_n + __ldg(slot_q + a_row0 + r));
+        float score;
+        if (COSINE) score = qn > 0.f ? -best * rsqrtf(qn) : 0.f;
+        else score = -sqrtf(fmaxf(best + qn, 0.f));
         const int p = __ldg(pair_ids + a_row0 + r);
-        rec[p] = make_float4(-sqrtf(d2), __ldg(pcoords + 2 * static_cast<size_t>(best_i)),
+        rec[p] = make_float4(score, __ldg(pcoords + 2 * static_cast<size_t>(best_i)),
                              __ldg(pcoords + 2 * static_cast<size_t>(best_i) + 1),
                              __int_as_float(proto_base + best_i));
       }
@@ -349,11 +447,11 @@ __global__ void proto_refine_kernel(const float4* __restrict__ rec, int nranks, 
 using namespace gg;
 
 // workspace layout (ints unless noted), ncell = cell_hi - cell_lo, npair = B * topk:
-//   cnt[ncell] | pair_off[ncell+1] | cursor[ncell] | work_cell[ncell + npair/128 + 1] | work_chunk[same] |
-//   meta[4] | pair_ids[npair] | qs_n[npair] (float) | pad to 256 B | Qs[npair * D] (bf16)
+//   cnt[ncell] | pair_off[ncell+1] | cursor[ncell] | work_group[ncell + npair/128 + 1] | work_chunk[same] |
+//   meta[4] | pair_ids[npair] | slot_q[npair] | slot_range[npair] (int2) | pad to 256 B | Qs[(npair + 128) * D] (bf16)
 struct ProtoWs {
-  int *cnt, *pair_off, *cursor, *work_cell, *work_chunk, *meta, *pair_ids;
-  float* qs_n;
+  int *cnt, *pair_off, *cursor, *work_group, *work_chunk, *meta, *pair_ids, *slot_q;
+  int2* slot_range;
   bf16* qs;
   size_t bytes;
 };
@@ -366,14 +464,15 @@ static ProtoWs carve_proto_ws(void* base, int ncell, long long npair, int D) {
     return r;
   };
   const size_t nwork = static_cast<size_t>(ncell) + npair / kPM + 1;
+  w.meta = reinterpret_cast<int*>(take(sizeof(int) * 4));  // first: gg_proto_retrieve_meta reads it back
   w.cnt = reinterpret_cast<int*>(take(sizeof(int) * ncell));
   w.pair_off = reinterpret_cast<int*>(take(sizeof(int) * (ncell + 1)));
   w.cursor = reinterpret_cast<int*>(take(sizeof(int) * ncell));
-  w.work_cell = reinterpret_cast<int*>(take(sizeof(int) * nwork));
+  w.work_group = reinterpret_cast<int*>(take(sizeof(int) * nwork));
   w.work_chunk = reinterpret_cast<int*>(take(sizeof(int) * nwork));
-  w.meta = reinterpret_cast<int*>(take(sizeof(int) * 4));
   w.pair_ids = reinterpret_cast<int*>(take(sizeof(int) * npair));
-  w.qs_n = reinterpret_cast<float*>(take(sizeof(float) * npair));
+  w.slot_q = reinterpret_cast<int*>(take(sizeof(int) * npair));
+  w.slot_range = reinterpret_cast<int2*>(take(sizeof(int2) * npair));
   w.qs = reinterpret_cast<bf16*>(take(sizeof(bf16) * static_cast<size_t>(npair + kPM) * D));
   w.bytes = static_cast<size_t>(p - static_cast<uint8_t*>(base));
   return w;
@@ -383,10 +482,25 @@ extern "C" size_t gg_proto_retrieve_workspace_bytes(int B, int topk, int D, int 
   return carve_proto_ws(nullptr, ncell, static_cast<long long>(B) * topk, D).bytes;
 }
 
+// HOST: pack consecutive geocells into groups of <= 256 prototypes (a larger cell is its own group).
+// cell_off: (ncell+1) host ints; group_off: (ncell+1) host ints to fill; returns the number of groups.
+extern "C" int gg_proto_group_cells(const int* cell_off, int ncell, int* group_off) {
+  int ng = 0, c = 0;
+  group_off[0] = 0;
+  while (c < ncell) {
+    int e = c + 1;
+    while (e < ncell && cell_off[e + 1] - cell_off[c] <= kPN) ++e;
+    group_off[++ng] = e;
+    c = e;
+  }
+  return ng;
+}
+
 extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int B, int D, const long long* cand,
                                  int cand_ld, int topk, const void* bank_bf16, const float* bank_sqnorm,
                                  const float* bank_coords, long long n_protos, const int* cell_off, int cell_lo,
-                                 int cell_hi, int proto_base, void* rec_out, void* workspace, gg_stream_t stream) {
+                                 int cell_hi, const int* group_off, int ngroups, int proto_base, int metric, int flags,
+                                 void* rec_out, void* workspace, gg_stream_t stream) {
   GG_CHECK(B > 0 && D > 0 && topk >= 1 && topk <= kMaxTopk, GG_ERR_ARG,
            "gg_proto_retrieve: bad sizes B=%d D=%d topk=%d (topk <= %d)", B, D, topk, kMaxTopk);
   GG_CHECK(D % 8 == 0, GG_ERR_ARG, "gg_proto_retrieve: D=%d must be a multiple of 8", D);
@@ -395,36 +509,63 @@ extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int 
   GG_CHECK(q_bf16 && q_sqnorm && cand && cell_off && rec_out && workspace, GG_ERR_ARG, "gg_proto_retrieve: null pointer");
   GG_CHECK(n_protos >= 0 && n_protos < (1ll << 31), GG_ERR_ARG, "gg_proto_retrieve: n_protos out of range");
   GG_CHECK(n_protos == 0 || (bank_bf16 && bank_sqnorm && bank_coords), GG_ERR_ARG, "gg_proto_retrieve: null bank pointer");
+  GG_CHECK(n_protos == 0 || (group_off && ngroups >= 1 && ngroups <= cell_hi - cell_lo), GG_ERR_ARG,
+           "gg_proto_retrieve: group table missing (gg_proto_group_cells)");
+  GG_CHECK(metric == GG_METRIC_L2 || metric == GG_METRIC_COSINE, GG_ERR_ARG, "gg_proto_retrieve: metric=%d", metric);
   GG_CHECK(static_cast<long long>(B) * topk < (1ll << 31), GG_ERR_ARG, "gg_proto_retrieve: B*topk overflows int32");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int ncell = cell_hi - cell_lo;
   const long long npair = static_cast<long long>(B) * topk;
   ProtoWs w = carve_proto_ws(workspace, ncell, npair, D);
   float4* rec = static_cast<float4*>(rec_out);
+  const bool gather4 = (flags & GG_RETRIEVE_NO_GATHER4) == 0;
 
   GG_CUDA(cudaMemsetAsync(w.cnt, 0, sizeof(int) * ncell, s));
   const int pb = static_cast<int>(ceil_div_ll(npair, 256));
   proto_count_kernel<<<pb, 256, 0, s>>>(cand, cand_ld, B, topk, cell_lo, cell_hi, w.cnt, rec);
   GG_LAUNCH_CHECK();
-  if (n_protos == 0) return GG_OK;  // this rank owns cells but no prototypes: every owned pair stays "missing"
-  proto_scan_kernel<<<1, 1024, 0, s>>>(w.cnt, cell_off, ncell, w.pair_off, w.cursor, w.work_cell, w.work_chunk, w.meta);
+  if (n_protos == 0) {  // this rank owns cells but no prototypes: every owned pair stays "missing"
+    GG_CUDA(cudaMemsetAsync(w.meta, 0, sizeof(int) * 4, s));
+    return GG_OK;
+  }
+  proto_scan_kernel<<<1, 1024, 0, s>>>(w.cnt, cell_off, ncell, group_off, ngroups, w.pair_off, w.cursor, w.work_group,
+                                        w.work_chunk, w.meta);
   GG_LAUNCH_CHECK();
-  proto_scatter_kernel<<<pb, 256, 0, s>>>(cand, cand_ld, B, topk, cell_lo, cell_hi, w.pair_off, w.cursor, w.pair_ids);
-  GG_LAUNCH_CHECK();
-  proto_gather_kernel<<<static_cast<int>(ceil_div_ll(npair, 8)), 256, 0, s>>>(
-      static_cast<const bf16*>(q_bf16), q_sqnorm, w.pair_ids, w.meta, topk, D, w.qs, w.qs_n);
+  proto_scatter_kernel<<<pb, 256, 0, s>>>(cand, cand_ld, B, topk, cell_lo, cell_hi, w.pair_off, w.cursor, cell_off,
+                                          w.pair_ids, w.slot_q, w.slot_range);
   GG_LAUNCH_CHECK();
 
   CUtensorMap tm_q, tm_bank;
-  int rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, kPM);
+  int rc;
+  if (gather4) {
+    rc = make_tmap_bf16_2d(&tm_q, q_bf16, D, static_cast<uint64_t>(B), static_cast<uint64_t>(D) * 2, kPK, 1);
+  } else {
+    proto_gather_kernel<<<static_cast<int>(ceil_div_ll(npair, 8)), 256, 0, s>>>(static_cast<const bf16*>(q_bf16), w.slot_q,
+                                                                             w.meta, D, w.qs);
+    GG_LAUNCH_CHECK();
+    rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, kPM);
+  }
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPN);
   if (rc) return rc;
   const size_t smem = sizeof(ProtoSmem) + 1024;
-  if (int e = set_max_dynamic_smem_once(proto_retrieve_kernel, smem)) return e;
-  proto_retrieve_kernel<<<device_sm_count(), kProtoThreads, smem, s>>>(tm_q, tm_bank, w.meta, w.work_cell, w.work_chunk,
-                                                                      w.pair_off, w.pair_ids, cell_off, w.qs_n,
-                                                                      bank_sqnorm, bank_coords, proto_base, D, rec);
+  const int grid = device_sm_count();
+#define GG_RETRIEVE(G4, COS)                                                                                       \
+  do {                                                                                                             \
+    auto kern = proto_retrieve_kernel<G4, COS>;                                                                    \
+    if (int e = set_max_dynamic_smem_once(kern, smem)) return e;                                                   \
+    kern<<<grid, kProtoThreads, smem, s>>>(tm_q, tm_bank, w.meta, w.work_group, w.work_chunk, group_off, w.pair_off, \
+                                           w.pair_ids, w.slot_q, w.slot_range, cell_off, q_sqnorm, bank_sqnorm,    \
+                                           bank_coords, proto_base, D, rec);                                       \
+  } while (0)
+  if (gather4) {
+    if (metric == GG_METRIC_COSINE) GG_RETRIEVE(true, true);
+    else GG_RETRIEVE(true, false);
+  } else {
+    if (metric == GG_METRIC_COSINE) GG_RETRIEVE(false, true);
+    else GG_RETRIEVE(false, false);
+  }
+#undef GG_RETRIEVE
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -36,14 +36,20 @@ def timing_ms():
     return {k: [a.elapsed_time(b) for a, b in v] for k, v in (_events or {}).items()}
 
 
-def _call(name, fn, *args):
+def _call(name, fn, dev, *args):
+    """One launcher call on device ``dev``: every launcher works on the CURRENT CUDA device (its stream argument,
+    cudaFuncSetAttribute, the SM count), so the tensors' device is made current around the call -- a module on
+    cuda:1 while cuda:0 is current would otherwise launch on GPU 0 with GPU-1 pointers."""
+    if dev is not None and dev.index is not None and torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            return _call(name, fn, None, *args)
     if _events is None:
         _lib.check(fn(*args), name)
         return
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    a.record(torch.cuda.current_stream())
     _lib.check(fn(*args), name)
-    b.record()
+    b.record(torch.cuda.current_stream())
     _events.setdefault(name, []).append((a, b))
 
 
@@ -51,15 +57,59 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None):
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def _need_cuda(*tensors):
+    """All given tensors (None entries skipped) must live on ONE CUDA device; returns it."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.GeoguessrB200Error(
                 "geoguessr_ai_b200 kernels need CUDA tensors (sm_100a); got a CPU tensor and there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.GeoguessrB200Error(
+                f"geoguessr_ai_b200 kernels need all tensors of a call on one device; got {dev} and {t.device}")
+    return dev
+
+
+_IN_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}  # GG_IN_F32 / GG_IN_BF16 / GG_IN_F16
+
+
+def _as_embedding(t):
+    """Embeddings are read by the fusion kernel in their own dtype: fp32 (the reference's storage format,
+    backend/s3bucket.py:848-859) or, opt-in, bf16 / fp16 (half the bytes over PCIe).  Anything else is rejected
+    rather than cast by an eager torch op: no arithmetic of the path runs in PyTorch."""
+    code = _IN_DTYPES.get(t.dtype)
+    if code is None:
+        raise _lib.GeoguessrB200Error(f"embeddings must be float32, bfloat16 or float16 (got {t.dtype})")
+    return (t if t.is_contiguous() else t.contiguous()), code
+
+
+_ticket_cache = {}
+
+
+def _tickets(nbytes, device):
+    """Zero-initialised ticket words of a launcher that counts its own CTAs' arrivals (gg_head_fwd): zeroed once,
+    left zeroed by every launch, one launch at a time -- so one buffer per (device, stream).  During CUDA-graph
+    capture a fresh zeroed buffer is taken instead (its memset is captured with the launch)."""
+    nbytes = max(int(nbytes), 16)
+    if torch.cuda.is_current_stream_capturing():
+        key = None
+    else:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        t = _ticket_cache.get(key)
+        if t is not None and t.numel() >= nbytes:
+            return t
+    t = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=device)
+    if key is not None:
+        _ticket_cache[key] = t
+    return t
 
 
 def _u8(nbytes, device):
@@ -77,11 +127,10 @@ def bias_pad_len(C: int) -> int:
 
 # --------------------------------------------------------------------------- a1
 def fuse_headings(emb: torch.Tensor, split: bool = False, want_sqnorm: bool = False):
-    """(B,V,D) or (B,D) fp32 -> bf16 (B,D) [or (B,3D) hi|hi|lo]; optional ||x||^2 (B) fp32."""
-    _need_cuda(emb)
-    if emb.dtype != torch.float32:
-        emb = emb.float()
-    emb = emb.contiguous()
+    """(B,V,D) or (B,D) fp32 (opt-in: bf16 / fp16, read directly) -> bf16 (B,D) [or (B,3D) hi|hi|lo]; optional
+    ||x||^2 (B) fp32."""
+    dev = _need_cuda(emb)
+    emb, in_dtype = _as_embedding(emb)
     if emb.dim() == 2:
         B, D = emb.shape
         V = 1
@@ -90,28 +139,29 @@ def fuse_headings(emb: torch.Tensor, split: bool = False, want_sqnorm: bool = Fa
     x = torch.empty((B, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
     sq = torch.empty((B,), dtype=torch.float32, device=emb.device) if want_sqnorm else None
     lib = _lib.load()
-    _call("gg_fuse_headings", lib.gg_fuse_headings, _ptr(emb), _ptr(x), B, V, D, int(split), _ptr(sq), _stream())
+    _call("gg_fuse_headings", lib.gg_fuse_headings, dev, _ptr(emb), in_dtype, _ptr(x), B, V, D, int(split), _ptr(sq),
+          _stream(dev))
     return (x, sq) if want_sqnorm else x
 
 
 def prepare_head_weights(weight: torch.Tensor, bias: torch.Tensor, split: bool = False):
     """fp32 nn.Linear parameters -> (bf16 operand (C,D) or (C,3D), zero-padded fp32 bias)."""
-    _need_cuda(weight, bias)
+    dev = _need_cuda(weight, bias)
     C, D = weight.shape
     w = weight.detach().float().contiguous()
     b = bias.detach().float().contiguous()
     w16 = torch.empty((C, 3 * D if split else D), dtype=torch.bfloat16, device=w.device)
     bp = torch.empty((bias_pad_len(C),), dtype=torch.float32, device=w.device)
     lib = _lib.load()
-    _call("gg_prepare_head_weights", lib.gg_prepare_head_weights, _ptr(w), _ptr(b), _ptr(w16), _ptr(bp), C, D, int(split), _stream())
+    _call("gg_prepare_head_weights", lib.gg_prepare_head_weights, dev, _ptr(w), _ptr(b), _ptr(w16), _ptr(bp), C, D, int(split), _stream(dev))
     return w16, bp
 
 
 def fuse_and_prepare(emb: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, split: bool = False):
     """fuse_headings + prepare_head_weights of one training step in a single launch (gg_fuse_and_prepare).
     Returns (x bf16, w16 bf16, bias_pad fp32)."""
-    _need_cuda(emb, weight, bias)
-    emb = emb.float().contiguous() if emb.dtype != torch.float32 else emb.contiguous()
+    dev = _need_cuda(emb, weight, bias)
+    emb, in_dtype = _as_embedding(emb)
     if emb.dim() == 2:
         B, D = emb.shape
         V = 1
@@ -124,25 +174,54 @@ def fuse_and_prepare(emb: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor
     x = torch.empty((B, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
     w16 = torch.empty((C, 3 * D if split else D), dtype=torch.bfloat16, device=emb.device)
     bp = torch.empty((bias_pad_len(C),), dtype=torch.float32, device=emb.device)
-    _call("gg_fuse_and_prepare", _lib.load().gg_fuse_and_prepare, _ptr(emb), _ptr(x), B, V, D, _ptr(w), _ptr(b), _ptr(w16),
-          _ptr(bp), C, int(split), _stream())
+    _call("gg_fuse_and_prepare", _lib.load().gg_fuse_and_prepare, dev, _ptr(emb), in_dtype, _ptr(x), B, V, D, _ptr(w), _ptr(b),
+          _ptr(w16), _ptr(bp), C, int(split), _stream(dev))
     return x, w16, bp
 
 
-def row_sqnorm_bf16(m: torch.Tensor) -> torch.Tensor:
-    _need_cuda(m)
+def row_sqnorm_bf16(m: torch.Tensor, split: bool = False) -> torch.Tensor:
+    """||row||^2 of a bf16 matrix; split: rows are [hi | lo | hi] (3D entries) and stand for hi + lo."""
+    dev = _need_cuda(m)
     assert m.dtype == torch.bfloat16 and m.dim() == 2 and m.is_contiguous()
+    D = m.shape[1] // 3 if split else m.shape[1]
     out = torch.empty((m.shape[0],), dtype=torch.float32, device=m.device)
     if m.shape[0]:
-        _call("gg_row_sqnorm_bf16", _lib.load().gg_row_sqnorm_bf16, _ptr(m), m.shape[0], m.shape[1], _ptr(out), _stream())
+        _call("gg_row_sqnorm_bf16", _lib.load().gg_row_sqnorm_bf16, dev, _ptr(m), m.shape[0], D, int(split), _ptr(out),
+              _stream(dev))
     return out
+
+
+def cast_bank_bf16(m: torch.Tensor, split: bool = False) -> torch.Tensor:
+    """(rows, D) fp32 -> bf16 (rows, D), or the hi/lo split operand (rows, 3D) = [hi | lo | hi] (gg_cast_bf16)."""
+    dev = _need_cuda(m)
+    assert m.dtype == torch.float32 and m.dim() == 2
+    m = m.contiguous()
+    rows, D = m.shape
+    out = torch.empty((rows, 3 * D if split else D), dtype=torch.bfloat16, device=m.device)
+    if rows:
+        _call("gg_cast_bf16", _lib.load().gg_cast_bf16, dev, _ptr(m), _ptr(out), rows, D, int(split), _stream(dev))
+    return out
+
+
+def proto_group_cells(cell_off_cpu):
+    """Geocells packed into accumulation groups of <= 256 prototypes (gg_proto_group_cells, host): returns the
+    (ngroups + 1) int32 group boundaries in cell indices."""
+    import ctypes
+
+    import numpy as np
+
+    off = np.ascontiguousarray(np.asarray(cell_off_cpu, dtype=np.int32))
+    ncell = len(off) - 1
+    out = np.zeros(ncell + 1, dtype=np.int32)
+    ng = _lib.load().gg_proto_group_cells(off.ctypes.data_as(ctypes.c_void_p), ncell, out.ctypes.data_as(ctypes.c_void_p))
+    return out[: ng + 1].copy()
 
 
 # --------------------------------------------------------------------------- a2-a4
 def head_forward(x16, w16, bias_pad, C, k, centroids, want_logits: bool):
     """Returns dict(topk_val (B,k), topk_idx (B,k) i64, pred_cell (B) i64, pred_llh (B,2), lse (B),
     logits (B,ldc) bf16 or None)."""
-    _need_cuda(x16, w16, bias_pad, centroids)
+    dev = _need_cuda(x16, w16, bias_pad, centroids)
     B, K = x16.shape
     assert w16.shape == (C, K), (w16.shape, C, K)
     dev = x16.device
@@ -150,27 +229,28 @@ def head_forward(x16, w16, bias_pad, C, k, centroids, want_logits: bool):
     ldc = logits_ld(C)
     logits = torch.empty((B, ldc), dtype=torch.bfloat16, device=dev) if want_logits else None
     ws = _u8(lib.gg_head_fwd_workspace_bytes(B, C, k), dev)
+    tickets = _tickets(lib.gg_head_fwd_ticket_bytes(B), dev)
     topk_val = torch.empty((B, k), dtype=torch.float32, device=dev)
     topk_idx = torch.empty((B, k), dtype=torch.int64, device=dev)
     pred_cell = torch.empty((B,), dtype=torch.int64, device=dev)
     pred_llh = torch.empty((B, 2), dtype=torch.float32, device=dev)
     lse = torch.empty((B,), dtype=torch.float32, device=dev)
-    _call("gg_head_fwd", lib.gg_head_fwd, _ptr(x16), _ptr(w16), _ptr(bias_pad), B, C, K, _ptr(logits), ldc, k, _ptr(ws),
-                        _ptr(centroids), _ptr(topk_val), _ptr(topk_idx), _ptr(pred_cell), _ptr(pred_llh), _ptr(lse),
-                        _stream())
+    _call("gg_head_fwd", lib.gg_head_fwd, dev, _ptr(x16), _ptr(w16), _ptr(bias_pad), B, C, K, _ptr(logits), ldc, k, _ptr(ws),
+                        _ptr(tickets), _ptr(centroids), _ptr(topk_val), _ptr(topk_idx), _ptr(pred_cell), _ptr(pred_llh), _ptr(lse),
+                        _stream(dev))
     return dict(topk_val=topk_val, topk_idx=topk_idx, pred_cell=pred_cell, pred_llh=pred_llh, lse=lse, logits=logits)
 
 
 # --------------------------------------------------------------------------- a5-a8
 def centroid_unit_vectors(centroids: torch.Tensor) -> torch.Tensor:
     """(C,2) (lng,lat) -> the loss kernels' centroid table (unit vectors + spatial index)."""
-    _need_cuda(centroids)
+    dev = _need_cuda(centroids)
     c = centroids.detach().float().contiguous()
     C = c.shape[0]
     lib = _lib.load()
     table = torch.empty((lib.gg_centroid_table_floats(C),), dtype=torch.float32, device=c.device)
     ws = _u8(lib.gg_centroid_table_workspace_bytes(C), c.device)
-    _call("gg_centroid_unit_vectors", lib.gg_centroid_unit_vectors, _ptr(c), _ptr(table), C, _ptr(ws), _stream())
+    _call("gg_centroid_unit_vectors", lib.gg_centroid_unit_vectors, dev, _ptr(c), _ptr(table), C, _ptr(ws), _stream(dev))
     return table
 
 
@@ -181,7 +261,7 @@ def row_stats_buffer(B, C, device):
 def hav_row_stats(labels, cent_table, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_nearest=False, out=None):
     """Label-only half of the smoothed loss.  Returns (row_stats buffer, nearest_cell (B) i64 | None,
     nearest_km (B) | None).  out: a buffer from row_stats_buffer() (e.g. allocated on another stream)."""
-    _need_cuda(labels, cent_table)
+    dev = _need_cuda(labels, cent_table)
     labels = labels.detach().float().contiguous()
     B = labels.shape[0]
     assert labels.shape == (B, 2), "labels must be (B, 2) (lng, lat)"
@@ -190,8 +270,8 @@ def hav_row_stats(labels, cent_table, C, tau=65.0, far_km=FAR_KM_DEFAULT, want_n
     stats = out if out is not None else row_stats_buffer(B, C, dev)
     ncell = torch.empty((B,), dtype=torch.int64, device=dev) if want_nearest else None
     nkm = torch.empty((B,), dtype=torch.float32, device=dev) if want_nearest else None
-    _call("gg_hav_row_stats", lib.gg_hav_row_stats, _ptr(labels), _ptr(cent_table), B, C, float(tau), float(far_km),
-          _ptr(stats), _ptr(ncell), _ptr(nkm), _stream())
+    _call("gg_hav_row_stats", lib.gg_hav_row_stats, dev, _ptr(labels), _ptr(cent_table), B, C, float(tau), float(far_km),
+          _ptr(stats), _ptr(ncell), _ptr(nkm), _stream(dev))
     return stats, ncell, nkm
 
 
@@ -201,7 +281,7 @@ def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, wa
     nearest_cell (B) i64 | None, nearest_km (B) | None[, db_partials (parts, Cpad) fp32 if want_db]
     [, loss_mean () fp32 if want_mean]).  row_stats: result of hav_row_stats() when it was computed
     ahead (then labels / far_km / want_nearest are not used here)."""
-    _need_cuda(logits, lse, cent_xyz)
+    dev = _need_cuda(logits, lse, cent_xyz)
     B, ldc = logits.shape
     dev = logits.device
     lib = _lib.load()
@@ -214,8 +294,8 @@ def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, wa
     dbp = (torch.empty((lib.gg_hav_ce_db_parts(B, C), lib.gg_hav_cpad(C)), dtype=torch.float32, device=dev)
            if want_db else None)
     mean = torch.empty((), dtype=torch.float32, device=dev) if want_mean else None
-    _call("gg_hav_ce_fwd_bwd", lib.gg_hav_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(row_stats), _ptr(cent_xyz), B, C,
-          float(tau), _ptr(dlogits), _ptr(loss_rows), _ptr(dbp), _ptr(ws), _ptr(mean), 1.0 / B, _stream())
+    _call("gg_hav_ce_fwd_bwd", lib.gg_hav_ce_fwd_bwd, dev, _ptr(logits), ldc, _ptr(lse), _ptr(row_stats), _ptr(cent_xyz), B, C,
+          float(tau), _ptr(dlogits), _ptr(loss_rows), _ptr(dbp), _ptr(ws), _ptr(mean), 1.0 / B, _stream(dev))
     out = (dlogits, loss_rows, ncell, nkm)
     if want_db:
         out += (dbp,)
@@ -225,32 +305,36 @@ def hav_ce(logits, lse, labels, cent_xyz, C, tau=65.0, far_km=FAR_KM_DEFAULT, wa
 
 
 def hard_ce(logits, lse, labels_clf, C):
-    _need_cuda(logits, lse, labels_clf)
+    dev = _need_cuda(logits, lse, labels_clf)
     B, ldc = logits.shape
     y = labels_clf.detach().to(torch.int64).contiguous()
     assert y.shape == (B,), "labels_clf must be (B,)"
     dlogits = torch.empty_like(logits)
     loss_rows = torch.zeros((B,), dtype=torch.float32, device=logits.device)
-    _call("gg_hard_ce_fwd_bwd", _lib.load().gg_hard_ce_fwd_bwd, _ptr(logits), ldc, _ptr(lse), _ptr(y), B, C, _ptr(dlogits), _ptr(loss_rows),
-                                       _stream())
+    _call("gg_hard_ce_fwd_bwd", _lib.load().gg_hard_ce_fwd_bwd, dev, _ptr(logits), ldc, _ptr(lse), _ptr(y), B, C, _ptr(dlogits), _ptr(loss_rows),
+                                       _stream(dev))
     return dlogits, loss_rows
 
 
 def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tensor:
+    dev = _need_cuda(loss_rows)
     B = loss_rows.shape[0]
     out = torch.empty((), dtype=torch.float32, device=loss_rows.device)
-    _call("gg_loss_mean", _lib.load().gg_loss_mean, _ptr(loss_rows), B, float(1.0 / B if scale is None else scale), _ptr(out),
-                                        _stream())
+    _call("gg_loss_mean", _lib.load().gg_loss_mean, dev, _ptr(loss_rows), B, float(1.0 / B if scale is None else scale), _ptr(out),
+                                        _stream(dev))
     return out
 
 
-def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None, c_range=None, out=None):
+def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None, c_range=None, out=None,
+                  signal=None):
     """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C) (from the loss kernel's column-sum
     partials when given, else from a pass over dlogits).
 
     c_range=(c0, c1) computes only geocells [c0, c1) (c0 a multiple of 8) into rows c0..c1 of ``out=(dW, db)``:
-    the data-parallel path runs the GEMM range by range and all-reduces each range while the next one runs."""
-    _need_cuda(dlogits, x16, grad_scale)
+    the NCCL data-parallel path runs the GEMM range by range and all-reduces each range while the next one runs.
+    signal=(blk_count_ptr, [ready_ptr of rank 0, 1, ...]): announce finished 128-geocell blocks to their reducers
+    (gg_grad_exchange runs next to this launch); whole range only."""
+    dev = _need_cuda(dlogits, x16, grad_scale)
     B, ldc = dlogits.shape
     dev = dlogits.device
     lib = _lib.load()
@@ -269,11 +353,39 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_p
     if grad_scale is not None:
         grad_scale = grad_scale.detach().float().contiguous()
     esz = dlogits.element_size()
-    _call("gg_head_bwd", lib.gg_head_bwd, _ptr(dlogits) + c0 * esz, ldc, _ptr(x16), x16.shape[1], B, c1 - c0, D, float(scale),
+    sig_arr, sig_world = None, 0
+    if signal is not None:
+        import ctypes
+
+        assert (c0, c1) == (0, C) and db is not None, "block announcements need the whole geocell range and db"
+        blk_count, ready = signal
+        sig_world = len(ready)
+        sig_arr = (ctypes.c_ulonglong * (1 + sig_world))(int(blk_count), *[int(p) for p in ready])
+    _call("gg_head_bwd", lib.gg_head_bwd, dev, _ptr(dlogits) + c0 * esz, ldc, _ptr(x16), x16.shape[1], B, c1 - c0, D, float(scale),
           _ptr(grad_scale), _ptr(dW) + c0 * D * 4, 0 if db is None else _ptr(db) + c0 * 4,
           0 if db_partials is None else _ptr(db_partials) + c0 * 4, 0 if db_partials is None else db_partials.shape[0],
-          0 if db_partials is None else db_partials.shape[1], _ptr(ws), _stream())
+          0 if db_partials is None else db_partials.shape[1], _ptr(ws),
+          0 if sig_arr is None else ctypes.cast(sig_arr, ctypes.c_void_p), sig_world, _stream(dev))
     return dW, db
+
+
+GRAD_CTRL_BYTES = 16384  # GG_GRAD_CTRL_BYTES
+GRAD_CTRL_READY_OFF = 4096  # GG_GRAD_CTRL_READY_OFF
+
+
+def grad_exchange(grad_ptrs, ctrl_ptrs, grad_mc, ctrl_mc, rank, C, D, no_wait=False):
+    """Block-by-block average of the symmetric-memory gradient buffers next to the dW GEMM (gg_grad_exchange), on
+    the current stream.  grad_ptrs / ctrl_ptrs: every rank's buffer / control region as mapped on this device;
+    grad_mc / ctrl_mc: their multicast addresses (0 = peer loads / stores).  no_wait: GG_GRAD_NO_WAIT (emulation)."""
+    import ctypes
+
+    world = len(grad_ptrs)
+    g = (ctypes.c_ulonglong * world)(*[int(p) for p in grad_ptrs])
+    c = (ctypes.c_ulonglong * world)(*[int(p) for p in ctrl_ptrs])
+    dev = None  # raw addresses: the caller's current device / stream
+    _call("gg_grad_exchange", _lib.load().gg_grad_exchange, dev, ctypes.cast(g, ctypes.c_void_p),
+          ctypes.cast(c, ctypes.c_void_p), int(grad_mc), int(ctrl_mc), world, int(rank), int(C), int(D), int(bool(no_wait)),
+          _stream(dev))
 
 
 def p2p_allreduce_avg(peer_ptrs, rank, n_floats):
@@ -284,14 +396,16 @@ def p2p_allreduce_avg(peer_ptrs, rank, n_floats):
 
     world = len(peer_ptrs)
     arr = (ctypes.c_ulonglong * world)(*[int(p) for p in peer_ptrs])
-    _call("gg_p2p_allreduce_avg", _lib.load().gg_p2p_allreduce_avg, ctypes.cast(arr, ctypes.c_void_p), world, int(rank),
-          int(n_floats), _stream())
+    dev = None  # raw addresses: the caller's current device / stream
+    _call("gg_p2p_allreduce_avg", _lib.load().gg_p2p_allreduce_avg, dev, ctypes.cast(arr, ctypes.c_void_p), world, int(rank),
+          int(n_floats), _stream(dev))
 
 
 def nvls_allreduce_avg(multicast_ptr, world, rank, n_floats):
     """The same average through the NVSwitch multicast mapping of the buffer (gg_nvls_allreduce_avg)."""
-    _call("gg_nvls_allreduce_avg", _lib.load().gg_nvls_allreduce_avg, int(multicast_ptr), int(world), int(rank),
-          int(n_floats), _stream())
+    dev = None  # raw address: the caller's current device / stream
+    _call("gg_nvls_allreduce_avg", _lib.load().gg_nvls_allreduce_avg, dev, int(multicast_ptr), int(world), int(rank),
+          int(n_floats), _stream(dev))
 
 
 def p2p_slice(n_floats, world, rank):
@@ -304,27 +418,35 @@ def p2p_slice(n_floats, world, rank):
 
 
 # --------------------------------------------------------------------------- a10-a15
+METRICS = {"l2": 0, "cosine": 1}  # GG_METRIC_L2 / GG_METRIC_COSINE
+
+
 def proto_retrieve(q16, q_sqnorm, cand, topk, bank16, bank_sqnorm, bank_coords, cell_off, cell_lo, cell_hi,
-                   proto_base=0):
-    """Stage 0+1.  Returns the (B*topk, 4) fp32 record array {score, lng, lat, proto id bits}."""
-    _need_cuda(q16, q_sqnorm, cand, cell_off)
+                   proto_base=0, group_off=None, metric="l2", gather4=True, want_meta=False):
+    """Stage 0+1.  Returns the (B*topk, 4) fp32 record array {score, lng, lat, proto id bits} [and the launcher's
+    meta words (int32 x 4, device): work items, pairs, accumulation units].  group_off: device int32 group
+    boundaries (proto_group_cells); None = one group per cell."""
+    dev = _need_cuda(q16, q_sqnorm, cand, cell_off, bank16, group_off)
     B, D = q16.shape
-    dev = q16.device
     lib = _lib.load()
     cand = cand.detach().to(torch.int64).contiguous()
     n_protos = 0 if bank16 is None else bank16.shape[0]
+    if group_off is None:
+        group_off = torch.arange(cell_hi - cell_lo + 1, dtype=torch.int32, device=dev)
     rec = torch.empty((B * topk, 4), dtype=torch.float32, device=dev)
     ws = _u8(lib.gg_proto_retrieve_workspace_bytes(B, topk, D, cell_hi - cell_lo), dev)
-    _call("gg_proto_retrieve", lib.gg_proto_retrieve, _ptr(q16), _ptr(q_sqnorm), B, D, _ptr(cand), cand.shape[1], topk, _ptr(bank16),
-                              _ptr(bank_sqnorm), _ptr(bank_coords), n_protos, _ptr(cell_off), cell_lo, cell_hi,
-                              proto_base, _ptr(rec), _ptr(ws), _stream())
+    _call("gg_proto_retrieve", lib.gg_proto_retrieve, dev, _ptr(q16), _ptr(q_sqnorm), B, D, _ptr(cand), cand.shape[1], topk,
+          _ptr(bank16), _ptr(bank_sqnorm), _ptr(bank_coords), n_protos, _ptr(cell_off), cell_lo, cell_hi, _ptr(group_off),
+          group_off.numel() - 1, proto_base, METRICS[metric], 0 if gather4 else 1, _ptr(rec), _ptr(ws), _stream(dev))
+    if want_meta:
+        return rec, ws[:16].view(torch.int32)
     return rec
 
 
 def proto_refine(rec, nranks, cand, cand_probs, initial, topk, temperature, max_refinement, want_debug=False):
     """Stage 2.  rec: (nranks, B*topk, 4) or (B*topk, 4).  Returns (preds_LLH (B,2) f32, preds_geocell (B) i64,
     guess_index (B) i32[, score (B,topk), proto (B,topk) i32])."""
-    _need_cuda(rec, cand, initial)
+    dev = _need_cuda(rec, cand, initial)
     dev = rec.device
     cand = cand.detach().to(torch.int64).contiguous()
     B = cand.shape[0]
@@ -338,10 +460,10 @@ def proto_refine(rec, nranks, cand, cand_probs, initial, topk, temperature, max_
     out_guess = torch.empty((B,), dtype=torch.int32, device=dev)
     out_score = torch.empty((B, topk), dtype=torch.float32, device=dev) if want_debug else None
     out_proto = torch.empty((B, topk), dtype=torch.int32, device=dev) if want_debug else None
-    _call("gg_proto_refine", _lib.load().gg_proto_refine, _ptr(rec), nranks, B * topk, _ptr(cand_probs),
+    _call("gg_proto_refine", _lib.load().gg_proto_refine, dev, _ptr(rec), nranks, B * topk, _ptr(cand_probs),
                                     0 if cand_probs is None else cand_probs.shape[1], _ptr(cand), cand.shape[1],
                                     _ptr(initial), B, topk, float(temperature), float(max_refinement), _ptr(out_llh),
-                                    _ptr(out_cell), _ptr(out_guess), _ptr(out_score), _ptr(out_proto), _stream())
+                                    _ptr(out_cell), _ptr(out_guess), _ptr(out_score), _ptr(out_proto), _stream(dev))
     if want_debug:
         return out_llh, out_cell, out_guess, out_score, out_proto
     return out_llh, out_cell, out_guess

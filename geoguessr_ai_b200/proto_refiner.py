@@ -67,6 +67,8 @@ class ProtoRefiner(nn.Module):
         split_queries: bool = False,
         bank_is_local: bool = False,
         report_changed: bool = True,
+        precision: str = "bf16",
+        metric: str = "l2",
         device="cuda",
     ):
         """Reference arguments (proto_refiner.py:33-62) plus keyword-only ways to hand over a bank:
@@ -84,8 +86,18 @@ class ProtoRefiner(nn.Module):
             the records of its own queries with one all-to-all.  False: every rank passes the same batch
             (records merged with one all-gather).
         bank_is_local: ``bank`` / ``coords`` already hold only this rank's rows (``cell_off`` stays global).
+        precision: "bf16" (prototypes and queries rounded to bf16, fp32 accumulate) or "bf16x3" (hi/lo split
+            operands, three products: fp32-faithful scores for fp32 banks such as the reference's CLIP prototypes;
+            3x the bank bytes).
+        metric: "l2" = the executable reference (``-cdist``, :190); "cosine" = the reference's unused
+            ``_cosine_similarity`` (:347-362), opt-in.
         """
         super().__init__()
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        if metric not in ops.METRICS:
+            raise ValueError("metric must be 'l2' or 'cosine'")
+        self.precision, self.metric = precision, metric
         self.topk = topk
         self.max_refinement = max_refinement
         self.verbose = verbose
@@ -171,14 +183,38 @@ class ProtoRefiner(nn.Module):
             assert mat.shape[0] == p1 - p0 and len(xy) == p1 - p0, "local bank does not match this rank's geocell range"
         else:
             mat, xy = mat[p0:p1], xy[p0:p1]
-        bank16 = mat.to(device=dev, dtype=torch.bfloat16).contiguous()
+        self._split = self.precision == "bf16x3"
+        mat = torch.as_tensor(mat)
+        if dev.type == "cuda" and mat.dtype == torch.float32:
+            bank16 = ops.cast_bank_bf16(mat.to(dev), split=self._split)  # gg_cast_bf16: no torch arithmetic
+        elif self._split:
+            hi = mat.to(torch.bfloat16)
+            lo = (mat.float() - hi.float()).to(torch.bfloat16)
+            bank16 = torch.cat([hi, lo, hi], 1).to(dev).contiguous()
+        else:
+            bank16 = mat.to(device=dev, dtype=torch.bfloat16).contiguous()
         self.register_buffer("bank", bank16, persistent=False)
         self.register_buffer("bank_coords", torch.as_tensor(xy, dtype=torch.float32).to(dev).contiguous(),
                              persistent=False)
         self.register_buffer("cell_off", local_off.to(dev), persistent=False)
-        self.register_buffer("bank_sqnorm",
-                             ops.row_sqnorm_bf16(bank16) if dev.type == "cuda" else torch.zeros(p1 - p0),
-                             persistent=False)
+        groups = ops.proto_group_cells(local_off.numpy())
+        self.num_groups = len(groups) - 1
+        self.register_buffer("group_off", torch.from_numpy(groups).to(dev), persistent=False)
+        # ||p||^2 needs the CUDA library: computed now on a CUDA device, else on the first forward after .to("cuda")
+        self.register_buffer("bank_sqnorm", torch.empty(0, dtype=torch.float32, device=dev), persistent=False)
+        self._sqnorm_for = None
+        self._last_meta = None
+        if dev.type == "cuda":
+            self._ensure_sqnorm()
+
+    def _ensure_sqnorm(self):
+        """``bank_sqnorm`` of the bank where it lives NOW (the reference idiom is ``ProtoRefiner(...).to(device)``,
+        inference.py:177: a bank installed on the CPU has no norms until it reaches the GPU)."""
+        key = (self.bank.data_ptr(), self.bank.device)
+        if self._sqnorm_for != key:
+            self.bank_sqnorm = (ops.row_sqnorm_bf16(self.bank, split=self._split) if self.bank.shape[0]
+                                else torch.empty(0, dtype=torch.float32, device=self.bank.device))
+            self._sqnorm_for = key
 
     def __str__(self):
         rep = "ProtoRefiner(\n"
@@ -191,15 +227,42 @@ class ProtoRefiner(nn.Module):
 
     # ---- forward (proto_refiner.py:129-237) -------------------------------------------------
     def _fuse(self, embedding: Tensor):
-        q16, qn = ops.fuse_headings(embedding, split=False, want_sqnorm=True)  # :150-151 mean over headings
-        if q16.shape[1] != self.embed_dim:
-            raise ValueError(f"embedding dim {q16.shape[1]} != prototype dim {self.embed_dim}")
+        q16, qn = ops.fuse_headings(embedding, split=self._split, want_sqnorm=True)  # :150-151 mean over headings
+        if q16.shape[1] != self.embed_dim * (3 if self._split else 1):
+            raise ValueError(f"embedding dim {q16.shape[1] // (3 if self._split else 1)} != prototype dim {self.embed_dim}")
         return q16, qn
 
     def _retrieve(self, q16, qn, candidate_cells):
+        self._ensure_sqnorm()
         bank = self.bank if self.bank.shape[0] > 0 else None
-        return ops.proto_retrieve(q16, qn, candidate_cells, self.topk, bank, self.bank_sqnorm, self.bank_coords,
-                                  self.cell_off, self.cell_lo, self.cell_hi, self.proto_base)
+        rec, meta = ops.proto_retrieve(q16, qn, candidate_cells, self.topk, bank, self.bank_sqnorm, self.bank_coords,
+                                       self.cell_off, self.cell_lo, self.cell_hi, self.proto_base,
+                                       group_off=self.group_off, metric=self.metric, gather4=self.gather4,
+                                       want_meta=True)
+        self._last_meta = (meta, q16.shape[0], q16.shape[1], candidate_cells)
+        return rec
+
+    gather4 = os.environ.get("GG_RETRIEVE_GATHER4", "1") != "0"  # query rows gathered by the TMA engine (tile::gather4)
+
+    def last_retrieve_stats(self):
+        """Work of the last retrieval on this rank (reads 16 bytes back: synchronises): work items, accumulation
+        units and the operand bytes / FLOP they stand for (the launcher's executed traffic, next to the
+        algorithmic P*D*2 + pairs*D*2)."""
+        if self._last_meta is None:
+            return None
+        meta, nq, K, cand = self._last_meta
+        items, pairs, units, _ = (int(v) for v in meta.cpu().tolist())
+        sizes = (self.cell_off[1:] - self.cell_off[:-1]).to(torch.int64)
+        c = cand[:, :self.topk].to(torch.int64) - self.cell_lo
+        mine = (c >= 0) & (c < sizes.numel())
+        algo_flop = 2.0 * K * float(sizes[c.clamp(0, max(sizes.numel() - 1, 0))][mine].sum().item()) if sizes.numel() else 0.0
+        row = K * 2
+        executed = units * (256 + 128) * row + pairs * 16 + nq * self.topk * 16
+        if not self.gather4:
+            executed += 2 * pairs * row
+        return dict(work_items=items, pairs=pairs, units=units, executed_bytes=float(executed),
+                    executed_flop=float(units) * 2 * 128 * 256 * K,
+                    algorithmic_flop=algo_flop, query_rows=nq)
 
     def retrieve(self, embedding: Tensor, candidate_cells: Tensor) -> Tensor:
         """Stage 0+1 on this rank's shard: (B*topk, 4) records."""

@@ -22,7 +22,7 @@ from torch import Tensor, nn
 
 from . import ops
 from .geocells import resolve_centroids
-from .utils import CLIP_EMBED_DIM, LABEL_SMOOTHING_CONSTANT, ModelOutput, TopK
+from .utils import CLIP_EMBED_DIM, CLIP_PRETRAINED_HEAD, LABEL_SMOOTHING_CONSTANT, ModelOutput, TopK
 
 
 class _GeocellHeadLoss(torch.autograd.Function):
@@ -202,9 +202,28 @@ class SuperGuessr(nn.Module):
                 self.mode = "convnext"
 
     def _freeze_params(self):
-        if self.base_model is not None and self.freeze_base:
+        """Same three branches as the reference (super_guessr.py:127-153): ``freeze_base`` freezes the whole
+        encoder; a CLIP backbone in training loads the pretrained head (if the file exists) and freezes every
+        encoder layer but the last; a TinyViT backbone in training freezes all but its last stage."""
+        if self.base_model is None:
+            return
+        if self.freeze_base:
             for p in self.base_model.parameters():
                 p.requires_grad = False
+            return
+        name = str(getattr(getattr(self.base_model, "config", None), "_name_or_path", ""))
+        if "clip-vit" in name and not self.serving:
+            head = CLIP_PRETRAINED_HEAD
+            if os.path.exists(head):
+                self.load_state(head)
+                print(f"Initialized model parameters from model: {head}")
+                for p in self.base_model.vision_model.encoder.layers[:-1].parameters():
+                    p.requires_grad = False
+            else:
+                print(f"Warning: pretrained head not found at '{head}'. "
+                      "Proceeding without loading and without freezing base layers.")
+        elif "tiny" in name and not self.serving:
+            self.base_model.freeze_all_but_last_stage()
 
     def _move_to_cuda(self, pixel_values=None, embedding=None, labels=None, labels_clf=None):
         # the reference only moves inputs in eval mode (:187-199)
@@ -275,114 +294,157 @@ class SuperGuessr(nn.Module):
         reference leaves to DDP / Accelerate).  After this call ``.grad`` is already the global average: do not
         wrap the module in DDP as well.
 
-        comm="nvls" / "p2p": [dW | db] live in a symmetric-memory buffer mapped into every peer over NVLink,
-        and one kernel per rank averages its slice in place between two symmetric-memory barriers -- "nvls"
-        through the NVSwitch multicast mapping (gg_nvls_allreduce_avg: the switch adds the copies, about one
-        buffer of traffic per GPU whatever the rank count), "p2p" with peer loads / stores (gg_p2p_allreduce_avg:
-        two-shot, rank-order sums; 1, 2, 4 or 8 ranks).
-        comm="nccl": NCCL all-reduce (AVG) of dW and db on a communication stream.  With ``chunks`` > 1 the dW
-        GEMM runs in that many geocell ranges (dp_chunk_bounds) and every range is all-reduced while the next
-        one is computed; measured on 2 x B200 (r01) this does NOT pay with NCCL -- its kernels cannot co-reside
-        with the persistent 148-CTA GEMM (registers), so the ranges serialise -- hence the default of 1.
+        comm="fused": [dW | db] live in a symmetric-memory buffer mapped into every peer over NVLink; the dW GEMM
+        announces every finished block of 128 geocells to the rank that reduces it and gg_grad_exchange, launched
+        next to the GEMM on a second stream, averages the blocks as they arrive (NVSwitch multicast from 8 ranks,
+        peer loads / stores below) -- only the blocks the GEMM finishes last are exchanged after it; no host barrier.
+        comm="nvls" / "p2p": the same buffer, ONE exchange kernel after the GEMM between two symmetric-memory
+        barriers -- "nvls" through the NVSwitch multicast mapping (gg_nvls_allreduce_avg), "p2p" with peer loads /
+        stores (gg_p2p_allreduce_avg: two-shot, rank-order sums).
+        comm="nccl": NCCL all-reduce (AVG) of dW and db on a communication stream; with ``chunks`` > 1 the dW GEMM
+        runs in that many geocell ranges (dp_chunk_bounds), each all-reduced while the next one is computed.
         ``comm_dtype=torch.bfloat16`` (NCCL only) halves the bytes on NVLink by rounding each rank's gradient
         before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
-        comm="auto": what measured fastest on B200 NVSwitch boxes for the 51.9 MB head gradient (r01,
-        tools/p2p_check.py): "p2p" up to 4 ranks (2 GPUs: 105 us against NCCL's 122 us and 175 us through the
-        switch), "nvls" from 8 ranks (176 us against 186 us peer-to-peer and NCCL's 210 us); "nccl" if the
-        symmetric-memory rendezvous fails (and for CPU / gloo groups, where the path uses whatever all_reduce
-        the group's backend provides)."""
+        comm="auto": "fused" for 2, 4 or 8 ranks when symmetric memory can be set up, else "nccl" (also for
+        CPU / gloo groups, where the path uses whatever all_reduce the group's backend provides).  The transport
+        is decided when the buffer is set up, before any kernel runs."""
         import torch.distributed as dist
 
         if not dist.is_initialized():
             raise RuntimeError("enable_data_parallel needs an initialised torch.distributed process group")
-        if comm not in ("auto", "nvls", "p2p", "nccl"):
-            raise ValueError("comm must be 'auto', 'nvls', 'p2p' or 'nccl'")
+        if comm not in ("auto", "fused", "nvls", "p2p", "nccl"):
+            raise ValueError("comm must be 'auto', 'fused', 'nvls', 'p2p' or 'nccl'")
         self._dp = dict(group=process_group, chunks=int(chunks), comm_dtype=comm_dtype, stream=None, comm=comm,
                         symm=None)
         return self
 
+    @staticmethod
+    def _dp_transport(comm: str, world: int, is_cuda: bool, comm_dtype=None) -> str:
+        """Which gradient exchange a group gets (pure function; host-tested): own kernels only cover 2, 4 or 8
+        ranks of one NVSwitch domain, anything else is NCCL -- decided before the first kernel runs."""
+        if comm == "nccl" or not is_cuda or comm_dtype is not None:
+            return "nccl"
+        if world in (2, 4, 8):
+            return "fused" if comm == "auto" else comm
+        if comm == "auto":
+            return "nccl"
+        raise ValueError(f"comm='{comm}' covers 2, 4 or 8 ranks; this group has {world} (use comm='auto' or 'nccl')")
+
     def _symm_gradient_buffer(self, C, D, dev):
-        """The symmetric-memory [dW | db | pad] buffer and its peer addresses (allocated and exchanged once)."""
+        """The symmetric-memory [control | dW | db | pad] buffer and its peer addresses (allocated, zeroed and
+        exchanged once).  Returns None when the group gets NCCL instead."""
         import torch.distributed as dist
 
         dp = self._dp
         if dp["symm"] is not None and dp["symm"]["key"] == (C, D, dev):
             return dp["symm"]
-        import torch.distributed._symmetric_memory as symm
-
+        if dp["comm"] == "nccl":
+            return None
         group = dp["group"] if dp["group"] is not None else dist.group.WORLD
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        n = C * D + C
-        n_pad = -(-n // (4 * world)) * (4 * world)
-        buf = symm.empty(n_pad, dtype=torch.float32, device=dev)
-        handle = symm.rendezvous(buf, group.group_name)
+        kind = self._dp_transport(dp["comm"], world, dev.type == "cuda", dp["comm_dtype"])
+        if kind == "nccl":
+            dp["comm"] = "nccl"
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            n = C * D + C
+            n_pad = -(-n // (4 * world)) * (4 * world)
+            ctrl_words = ops.GRAD_CTRL_BYTES // 4
+            buf = symm.empty(ctrl_words + n_pad, dtype=torch.float32, device=dev)
+            handle = symm.rendezvous(buf, group.group_name)
+        except Exception as e:  # noqa: BLE001
+            if dp["comm"] != "auto":
+                raise
+            import sys
+
+            print(f"[geoguessr_ai_b200] symmetric-memory gradient exchange unavailable ({type(e).__name__}: {e}); "
+                  "using NCCL all-reduce", file=sys.stderr)
+            dp["comm"] = "nccl"
+            return None
         mc = int(getattr(handle, "multicast_ptr", 0) or 0)
-        if dp["comm"] == "nvls" and mc == 0:
+        if kind == "nvls" and mc == 0:
             raise RuntimeError("comm='nvls': this group has no NVSwitch multicast mapping (multicast_ptr == 0)")
-        dp["symm"] = dict(key=(C, D, dev), buf=buf, handle=handle, ptrs=[int(p) for p in handle.buffer_ptrs],
-                          world=world, rank=rank, n=n_pad, multicast=mc,
-                          kind="nvls" if mc != 0 and (dp["comm"] == "nvls" or (dp["comm"] == "auto" and world >= 8))
-                          else "p2p")
+        buf.zero_()  # control words + pad start at zero on every rank ...
+        torch.cuda.current_stream(dev).synchronize()
+        handle.barrier(channel=0)  # ... before any peer can add to them
+        base = [int(p) for p in handle.buffer_ptrs]
+        off = ops.GRAD_CTRL_BYTES
+        use_mc = mc != 0 and (kind == "nvls" or (kind == "fused" and world >= 8))
+        dp["symm"] = dict(key=(C, D, dev), buf=buf, handle=handle, ctrl_ptrs=base, ptrs=[p + off for p in base],
+                          world=world, rank=rank, n=n_pad, multicast=(mc + off) if mc else 0,
+                          ctrl_multicast=mc, kind=kind, use_mc=use_mc, grad_off=ctrl_words)
         return dp["symm"]
 
-    def _backward_data_parallel_p2p(self, dlogits, x16, C, D, B, gloss, want_b, dbp):
-        sm = self._symm_gradient_buffer(C, D, dlogits.device)
-        buf, h = sm["buf"], sm["handle"]
-        dW = buf[: C * D].view(C, D)
-        db = buf[C * D: C * D + C]
+    def describe_data_parallel(self):
+        """One line for logs / the bench record: which exchange runs."""
+        dp = self._dp
+        if dp is None:
+            return None
+        sm = dp.get("symm")
+        if sm is None:
+            return (f"nccl avg, {'bf16' if dp['comm_dtype'] is not None else 'fp32'}, {dp['chunks']} geocell range(s) "
+                    "overlapped with the dW GEMM")
+        path = ("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if sm["use_mc"]
+                else "peer loads in rank order + peer stores")
+        if sm["kind"] == "fused":
+            return (f"fused: gg_head_bwd announces finished 128-geocell blocks of [dW | db] (symmetric memory, fp32) and "
+                    f"gg_grad_exchange averages them block by block next to the GEMM via {path}; no host barrier")
+        return (f"{sm['kind']}: one exchange kernel ({path}) over [dW | db] in symmetric memory after the dW GEMM, "
+                "between two symmetric-memory barriers")
+
+    def _grad_views(self, sm, C, D):
+        g0 = sm["grad_off"]
+        buf = sm["buf"]
+        dW = buf[g0: g0 + C * D].view(C, D)
+        db = buf[g0 + C * D: g0 + C * D + C]
         # gradient accumulation without zero_grad(): .grad may still alias this buffer -- move it out first
         for prm, view in ((self.cell_layer.weight, dW), (self.cell_layer.bias, db)):
             if prm.grad is not None and prm.grad.data_ptr() == view.data_ptr():
                 prm.grad = prm.grad.clone()
+        return dW, db
+
+    def _backward_data_parallel_symm(self, sm, dlogits, x16, C, D, B, gloss, want_b, dbp):
+        dW, db = self._grad_views(sm, C, D)
         dp = self._dp
         dev = dlogits.device
         if dp["stream"] is None or dp["stream"].device != dev:
             dp["stream"] = torch.cuda.Stream(device=dev)
-        comm, cur = dp["stream"], torch.cuda.current_stream()
-
-        def exchange(off, n):  # floats [off, off + n) of the buffer, on the current (= communication) stream
-            h.barrier(channel=0)  # every rank's part of the gradient is written
-            if sm["kind"] == "nvls":
-                ops.nvls_allreduce_avg(sm["multicast"] + 4 * off, sm["world"], sm["rank"], n)
-            else:
-                ops.p2p_allreduce_avg([p + 4 * off for p in sm["ptrs"]], sm["rank"], n)
-            h.barrier(channel=1)  # every rank's slice has landed everywhere (and nobody still reads my copy)
-
-        # The dW GEMM runs in `chunks` geocell ranges; each range is exchanged on the communication stream while
-        # the next one is computed (the exchange kernel's small CTAs co-reside with the persistent GEMM), so only
-        # the last range's exchange -- which also carries db -- is exposed.
-        bounds = dp_chunk_bounds(C, dp["chunks"])
-        comm.wait_stream(cur)
-        for i, (c0, c1) in enumerate(bounds):
+        comm, cur = dp["stream"], torch.cuda.current_stream(dev)
+        if sm["kind"] == "fused":
+            # the exchange kernel is ordered only behind what precedes the GEMM: it runs NEXT TO it, waiting block
+            # by block for every rank's announcement
+            comm.wait_stream(cur)
+            ready = [p + ops.GRAD_CTRL_READY_OFF for p in sm["ctrl_ptrs"]]
             ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=True, db_partials=dbp,
-                              c_range=(c0, c1), out=(dW, db))
-            done = torch.cuda.Event()
-            done.record(cur)
-            comm.wait_event(done)
+                              out=(dW, db), signal=(sm["ctrl_ptrs"][sm["rank"]], ready))
             with torch.cuda.stream(comm):
-                if i + 1 < len(bounds):
-                    exchange(c0 * D, (c1 - c0) * D)
-                else:  # last range: its dW rows, db and the padding in one launch
-                    exchange(c0 * D, sm["n"] - c0 * D)
+                ops.grad_exchange(sm["ptrs"], sm["ctrl_ptrs"], sm["multicast"] if sm["use_mc"] else 0,
+                                  sm["ctrl_multicast"] if sm["use_mc"] else 0, sm["rank"], C, D)
+            cur.wait_stream(comm)
+            return dW, (db if want_b else None)
+
+        h = sm["handle"]
+        ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=True, db_partials=dbp,
+                          out=(dW, db))
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            h.barrier(channel=0)  # every rank's gradient is written
+            if sm["use_mc"]:
+                ops.nvls_allreduce_avg(sm["multicast"], sm["world"], sm["rank"], sm["n"])
+            else:
+                ops.p2p_allreduce_avg(sm["ptrs"], sm["rank"], sm["n"])
+            h.barrier(channel=1)  # every rank's slice has landed everywhere (and nobody still reads my copy)
         cur.wait_stream(comm)
         return dW, (db if want_b else None)
 
     def _backward_data_parallel(self, dlogits, x16, C, D, B, gloss, want_b, dbp):
-        import torch.distributed as dist
-
         dp = self._dp
         dev = dlogits.device
-        if dp["comm"] in ("auto", "nvls", "p2p") and dlogits.is_cuda:
-            try:
-                return self._backward_data_parallel_p2p(dlogits, x16, C, D, B, gloss, want_b, dbp)
-            except Exception as e:  # noqa: BLE001
-                if dp["comm"] != "auto" or dp["symm"] is not None:
-                    raise
-                import sys
-
-                print(f"[geoguessr_ai_b200] symmetric-memory gradient exchange unavailable ({type(e).__name__}: {e}); "
-                      "using NCCL all-reduce", file=sys.stderr)
-                dp["comm"] = "nccl"
+        sm = self._symm_gradient_buffer(C, D, dev) if dlogits.is_cuda else None
+        if sm is not None:
+            return self._backward_data_parallel_symm(sm, dlogits, x16, C, D, B, gloss, want_b, dbp)
         if dp["stream"] is None or dp["stream"].device != dev:
             dp["stream"] = torch.cuda.Stream(device=dev)
         comm, cur = dp["stream"], torch.cuda.current_stream()

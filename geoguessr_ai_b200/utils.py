@@ -10,3 +10,4 @@ TopK = namedtuple("topk", ["values", "indices"])
 
 LABEL_SMOOTHING_CONSTANT = 65  # config.py:52 (PIGEOTTO)
 CLIP_EMBED_DIM = 1024  # config.py
+CLIP_PRETRAINED_HEAD = "saved_models/New_Base_smooth_avg_MT_Geo_SV.model"  # config.py:60

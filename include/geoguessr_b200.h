@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 2
+#define GG_ABI_VERSION 3
 
 #define GG_OK 0
 #define GG_ERR_ARG 1         /* bad shape / alignment / null pointer */
@@ -41,6 +41,7 @@ size_t gg_centroid_table_floats(int C); /* 4-byte words in the table gg_centroid
 size_t gg_centroid_table_workspace_bytes(int C);
 size_t gg_hav_row_stats_bytes(int B, int C);
 size_t gg_head_fwd_workspace_bytes(int B, int C, int k);
+size_t gg_head_fwd_ticket_bytes(int B); /* merge tickets of gg_head_fwd (one word per 128-row block) */
 size_t gg_head_bwd_workspace_bytes(int C);
 size_t gg_hav_ce_workspace_bytes(int B, int C);
 int gg_hav_ce_db_parts(int B, int C); /* rows of the loss kernel's bias-gradient partial sums (one per row block) */
@@ -49,9 +50,14 @@ size_t gg_proto_retrieve_workspace_bytes(int B, int topk, int D, int ncell);
 /* ---- a1: heading fusion -------------------------------------------------------------------
  * models/super_guessr.py:347  `output = layer_input.mean(dim=1)`  ((N,4,C) -> (N,C));
  * models/proto_refiner.py:150-151 (same mean for the refiner's queries).
- * emb (B,V,D) fp32 -> x (B, D) bf16 [split=0] or (B, 3D) = [hi|hi|lo] [split=1, fp32-faithful
- * "bf16x3" operands].  V=1 is the single-image pass-through (:351).  sqnorm (B) optional: ||x||^2. */
-int gg_fuse_headings(const float* emb, void* x_bf16, int B, int V, int D, int split, float* sqnorm,
+ * emb (B,V,D) -> x (B, D) bf16 [split=0] or (B, 3D) = [hi|hi|lo] [split=1, fp32-faithful
+ * "bf16x3" operands].  V=1 is the single-image pass-through (:351).  sqnorm (B) optional: ||x||^2.
+ * in_dtype: element type of emb -- GG_IN_F32 (the reference's storage format, backend/s3bucket.py:848-859), or,
+ * opt-in, GG_IN_BF16 / GG_IN_F16 embeddings read directly (half the bytes over PCIe; the mean is taken in fp32). */
+#define GG_IN_F32 0
+#define GG_IN_BF16 1
+#define GG_IN_F16 2
+int gg_fuse_headings(const void* emb, int in_dtype, void* x_bf16, int B, int V, int D, int split, float* sqnorm,
                      gg_stream_t stream);
 
 /* Operand preparation for nn.Linear(D, C) (super_guessr.py:102): W (C,D) fp32 -> bf16 (C,D), or
@@ -60,10 +66,13 @@ int gg_prepare_head_weights(const float* w, const float* b, void* w_bf16, float*
                             gg_stream_t stream);
 /* Both of the above for one training step in a single launch (the weights move every step, so their bf16
  * operand is rebuilt next to the fusion of that step's batch): same arguments and results, no sqnorm. */
-int gg_fuse_and_prepare(const float* emb, void* x_bf16, int B, int V, int D, const float* w, const float* b,
-                        void* w_bf16, float* bias_pad, int C, int split, gg_stream_t stream);
-int gg_cast_bf16(const float* src, void* dst_bf16, long long n, gg_stream_t stream);
-int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, float* out, gg_stream_t stream);
+int gg_fuse_and_prepare(const void* emb, int in_dtype, void* x_bf16, int B, int V, int D, const float* w,
+                        const float* b, void* w_bf16, float* bias_pad, int C, int split, gg_stream_t stream);
+/* Prototype-bank operand: (rows, D) fp32 -> bf16 (rows, D), or the hi/lo split (rows, 3D) = [hi | lo | hi] that,
+ * contracted against queries [hi | hi | lo], keeps fp32-faithful dot products ("bf16x3" retrieval). */
+int gg_cast_bf16(const float* src, void* dst_bf16, long long rows, int D, int split, gg_stream_t stream);
+/* ||row||^2 of a bf16 matrix (split: rows are [hi | lo | hi] and stand for hi + lo). */
+int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, int split, float* out, gg_stream_t stream);
 
 /* ---- a2-a4: geocell head ------------------------------------------------------------------
  * super_guessr.py:354 logits = cell_layer(output); :355 softmax; :358-361 argmax + centroid gather;
@@ -72,10 +81,16 @@ int gg_row_sqnorm_bf16(const void* m_bf16, long long rows, int D, float* out, gg
  * logits_bf16: (B, ldc) written only when non-null (training); serving never materialises them.
  * Outputs: topk_val (B,k) fp32 probabilities, sorted descending; topk_idx (B,k) int64; pred_cell (B)
  * int64 = argmax; pred_llh (B,2) fp32 = centroids[pred_cell] ((lng,lat)); lse (B) fp32 row
- * log-sum-exp (consumed by the loss).  pred_cell / pred_llh / lse may be null.  1 <= k <= 8. */
+ * log-sum-exp (consumed by the loss).  pred_cell / pred_llh / lse may be null.  Any 1 <= k <= C, as
+ * torch.topk: up to 8 candidates come out of the GEMM's epilogue in one pass; beyond that the GEMM runs once more
+ * per further 8 ranks, each pass restricted to the logits ordered after the previous pass's last entry (exact:
+ * every pass sees the same fp32 accumulators).
+ * One launch: the CTA that flushes the last partial of a 128-row block merges that block's partials (softmax
+ * denominators, top-k lists) -- `tickets` (gg_head_fwd_ticket_bytes(B) bytes) counts the flushes; the caller
+ * zero-initialises it ONCE, every launch leaves it zeroed, and it serves one launch at a time (a stream). */
 int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, int B, int C, int D, void* logits_bf16,
-                int ldc, int k, void* workspace, const float* centroids, float* topk_val, long long* topk_idx,
-                long long* pred_cell, float* pred_llh, float* lse, gg_stream_t stream);
+                int ldc, int k, void* workspace, void* tickets, const float* centroids, float* topk_val,
+                long long* topk_idx, long long* pred_cell, float* pred_llh, float* lse, gg_stream_t stream);
 
 /* ---- a5-a8: haversine label-smoothed cross-entropy, forward + gradient ---------------------
  * models/utils.py:39-57 haversine_matrix; :20-32 smooth_labels (tau = config.py:52 = 65 km);
@@ -122,10 +137,15 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * device so that backward needs no host synchronisation.  db_partials (db_parts, db_ld): column
  * sums from gg_hav_ce_fwd_bwd; when null, db is computed from dlogits.  workspace
  * (gg_head_bwd_workspace_bytes(C) bytes, required): parked partial accumulators + flags of the stream-K
- * schedule, and the column-sum slices of the db pass. */
+ * schedule, and the column-sum slices of the db pass.
+ * Data parallelism (gg_grad_exchange below): with signal_world > 1, dW / db are this rank's gradient buffer in
+ * symmetric memory and signal_ptrs (HOST array of 1 + signal_world device addresses) = {this rank's block counters,
+ * rank 0's `ready` counters, rank 1's, ...} (gg_grad_ctrl_layout): as soon as all column tiles of a 128-geocell
+ * block are written the kernel announces the block to the rank that reduces it (block b -> rank b % world), so
+ * the exchange runs block by block underneath this GEMM.  signal_world <= 1: no signalling, signal_ptrs unused. */
 int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
                 const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
-                void* workspace, gg_stream_t stream);
+                void* workspace, const unsigned long long* signal_ptrs, int signal_world, gg_stream_t stream);
 
 /* ---- a10-a15: ProtoRefiner ----------------------------------------------------------------
  * models/proto_refiner.py:165-203 (retrieval) -- for every (query i, candidate j < topk):
@@ -136,11 +156,23 @@ int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld,
  * (n_protos) fp32 from gg_row_sqnorm_bf16, bank_coords (n_protos,2) fp32 (lng,lat).  q (B,D) bf16 and
  * q_sqnorm (B) from gg_fuse_headings.  cand (B, cand_ld) int64.  rec_out: (B*topk) 16-byte records
  * {score f32, lng f32, lat f32, prototype id i32 (proto_base + local row, -1 if none)}; pairs whose
- * cell lies outside [cell_lo, cell_hi) get score = -inf (another rank owns them). */
+ * cell lies outside [cell_lo, cell_hi) get score = -inf (another rank owns them).
+ * group_off (ngroups+1 ints, DEVICE; local cell indices): geocells packed into accumulation groups of <= 256
+ * prototypes, built once per bank by gg_proto_group_cells (HOST arrays in, returns ngroups): small neighbouring
+ * cells share one 256-prototype unit, each pair masked to its own cell's columns.
+ * metric: GG_METRIC_L2 = the executable reference (-cdist, :190, :364-376); GG_METRIC_COSINE = the reference's unused
+ * _cosine_similarity (:347-362), opt-in: score = q.p / (|q| |p|), arg-max per cell.
+ * flags: GG_RETRIEVE_NO_GATHER4 = copy the query rows into cell order first (workspace) instead of letting the
+ * TMA engine gather them four rows at a time (tile::gather4). */
+#define GG_METRIC_L2 0
+#define GG_METRIC_COSINE 1
+#define GG_RETRIEVE_NO_GATHER4 1
+int gg_proto_group_cells(const int* cell_off_host, int ncell, int* group_off_host);
 int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int B, int D, const long long* cand, int cand_ld,
                       int topk, const void* bank_bf16, const float* bank_sqnorm, const float* bank_coords,
-                      long long n_protos, const int* cell_off, int cell_lo, int cell_hi, int proto_base, void* rec_out,
-                      void* workspace, gg_stream_t stream);
+                      long long n_protos, const int* cell_off, int cell_lo, int cell_hi, const int* group_off,
+                      int ngroups, int proto_base, int metric, int flags, void* rec_out, void* workspace,
+                      gg_stream_t stream);
 /* models/proto_refiner.py:205-228: temperature softmax (:378-389), x candidate probs (:210), argmax
  * (:211), max-refinement guard with preprocessing/geo_utils.py:39-54 haversine (:216-223), outputs
  * (:225-228).  rec: nranks record arrays rank_stride records apart (all-gather layout); cand_probs
@@ -179,6 +211,27 @@ int gg_p2p_allreduce_avg(const unsigned long long* peer_ptrs, int world, int ran
  * of traffic per GPU and direction for any number of ranks.  multicast_ptr: the symmetric-memory handle's
  * multicast address of the buffer on this device.  Same ordering contract as gg_p2p_allreduce_avg. */
 int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_floats, gg_stream_t stream);
+
+/* The same average, block by block UNDERNEATH the dW GEMM (no host barrier, only the last blocks are exposed).
+ * Every rank owns, in symmetric memory, a control region of GG_GRAD_CTRL_BYTES (zeroed once, before the first step)
+ * and its gradient buffer [dW (C,D) | db (C) | pad to a multiple of 4 floats].  gg_head_bwd (signal_ptrs = {ctrl +
+ * GG_GRAD_CTRL_BLKCOUNT_OFF of this rank, ctrl + GG_GRAD_CTRL_READY_OFF of rank 0, 1, ...}) announces every finished
+ * block of 128 geocells to rank (block % world); gg_grad_exchange, launched on ANOTHER stream next to that GEMM,
+ * waits per owned block for all ranks' announcements, averages the block -- multimem.ld_reduce / multimem.st through
+ * the NVSwitch when the multicast addresses are given, else peer loads in rank order + peer stores (deterministic,
+ * identical on all ranks) -- and tells every rank; it returns when every block of every owner has landed in this
+ * rank's copy.  grad_ptrs / ctrl_ptrs: HOST arrays of `world` device addresses (rank order, as mapped on this
+ * device); grad_mc / ctrl_mc: multicast addresses of the same buffers or both null.  world in {1, 2, 4, 8}.
+ * flags: GG_GRAD_NO_WAIT = return once this rank's own blocks are exchanged, without waiting for the other reducers'
+ * blocks to land (the caller orders the gradient's consumer behind every rank's exchange by other means; used by
+ * the single-process emulation of the tests, where the "ranks" share one GPU's launch queues). */
+#define GG_GRAD_CTRL_BYTES 16384
+#define GG_GRAD_CTRL_BLKCOUNT_OFF 0
+#define GG_GRAD_CTRL_READY_OFF 4096
+#define GG_GRAD_NO_WAIT 1
+size_t gg_grad_ctrl_bytes(void);
+int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsigned long long* ctrl_ptrs, void* grad_mc,
+                     void* ctrl_mc, int world, int rank, int C, int D, int flags, gg_stream_t stream);
 
 #ifdef __cplusplus
 }

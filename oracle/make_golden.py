@@ -217,8 +217,44 @@ def run_refiner_case(pr, name, B, D, P, seed, centroids, topk, with_probs, jitte
     finally:
         pr.torch = torch
     assert loss is None
+    # Margins of the reference's own decisions, from the reference's own helpers on the same inputs
+    # (proto_refiner.py:189-211, :216-219): per (query, candidate) the best and second-best score and the arg-best
+    # prototype, the final probabilities and the guard distance -- so that a parity test can demand that every
+    # disagreement sits on a tie of the reference (score gap / probability gap below the tolerance).
+    q = emb.mean(dim=1)
+    score = np.full((B, topk), -100000.0, np.float32)
+    second = np.full((B, topk), -np.inf, np.float32)
+    pidx = np.full((B, topk), -1, np.int64)
+    cos_score = np.full((B, topk), -100000.0, np.float32)
+    cos_second = np.full((B, topk), -np.inf, np.float32)
+    cos_pidx = np.full((B, topk), -1, np.int64)
+    final = np.zeros((B, topk), np.float32)
+    guard_km = np.zeros((B,), np.float32)
+    from preprocessing.geo_utils import haversine as ref_haversine
+    with torch.no_grad():
+        for i in range(B):
+            for j in range(topk):
+                c = int(cand[i, j])
+                if protos[c] is None:
+                    continue
+                for arr_s, arr_2, arr_i, fn in ((score, second, pidx, lambda m, v: -ref._euclidean_distance(m, v)),
+                                                (cos_score, cos_second, cos_pidx, ref._cosine_similarity)):
+                    lg = fn(protos[c], q[i])
+                    arr_s[i, j] = lg.max().item()
+                    arr_i[i, j] = lg.argmax().item()
+                    if lg.numel() > 1:
+                        arr_2[i, j] = torch.topk(lg, 2).values[1].item()
+            probs = ref._temperature_softmax(torch.from_numpy(score[i]))
+            cp = cprobs[i, :topk] if with_probs else torch.nn.functional.one_hot(torch.tensor(0), topk).float()
+            final[i] = (cp * probs).numpy()
+            gidx = int(torch.argmax(torch.from_numpy(final[i])))
+            c = int(cand[i, gidx])
+            xy_g = torch.zeros(1, 2) if protos[c] is None else coords[c][pidx[i, gidx]].unsqueeze(0)
+            guard_km[i] = ref_haversine(initial[i].unsqueeze(0), xy_g.float())[0].item()
     np.savez_compressed(
         os.path.join(GOLD, f"refiner_{name}.npz"),
+        score=score, second=second, proto_idx=pidx, final_probs=final, guard_km=guard_km,
+        cos_score=cos_score, cos_second=cos_second, cos_proto_idx=cos_pidx,
         B=B, D=D, P=P, seed=seed, topk=topk, with_probs=int(with_probs), jitter=jitter,
         missing=missing, far_frac=far_frac,
         preds_LLH=llh.numpy(), preds_geocell=cells.numpy(),

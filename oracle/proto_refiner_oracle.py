@@ -35,6 +35,20 @@ def euclidean_distance(matrix: Tensor, vector: Tensor) -> Tensor:
     return torch.cdist(matrix, vector.unsqueeze(0)).flatten()
 
 
+def cosine_similarity(matrix: Tensor, vector: Tensor) -> Tensor:
+    """proto_refiner.py:347-362 (defined by the reference, never called by it; the opt-in ``metric="cosine"``)."""
+    dot_product = torch.mm(matrix, vector.unsqueeze(1))
+    matrix_norm = torch.norm(matrix, dim=1).unsqueeze(1)
+    vector_norm = torch.norm(vector)
+    return (dot_product / (matrix_norm * vector_norm)).flatten()
+
+
+def similarity(matrix: Tensor, vector: Tensor, metric: str = "l2") -> Tensor:
+    """The per-cell logits of proto_refiner.py:190: ``-_euclidean_distance`` as executed ("l2"), or the cosine
+    alternative the file defines."""
+    return -euclidean_distance(matrix, vector) if metric == "l2" else cosine_similarity(matrix, vector)
+
+
 def temperature_softmax(x: Tensor, temperature: float | Tensor) -> Tensor:
     """proto_refiner.py:378-389 -- no max-subtraction, on purpose."""
     ex = torch.exp(x / temperature)
@@ -53,6 +67,7 @@ def forward(
     max_refinement: float = 1000,
     temperature: float = 1.6,
     device="cpu",
+    metric: str = "l2",
 ):
     """ProtoRefiner.forward, proto_refiner.py:129-237.  Returns
     (None, preds_LLH (B,2) fp32, preds_geocell (B,) int64, guess_index (B,))."""
@@ -76,7 +91,7 @@ def forward(
                 top_distances.append(torch.tensor(-100000, device=device))
                 top_preds.append([0.0, 0.0])
                 continue
-            logits = -euclidean_distance(cell_emb.to(device), emb)  # :189-190
+            logits = similarity(cell_emb.to(device), emb, metric)  # :189-190
             top_distances.append(torch.max(logits).item())  # :193
             j = torch.argmax(logits, dim=-1).item()  # :194
             lng, lat = coords[cell_id][j, 0].item(), coords[cell_id][j, 1].item()  # :251-252
@@ -100,7 +115,7 @@ def forward(
     return None, preds_llh, preds_geocell, guess_index
 
 
-def best_per_candidate(embedding: Tensor, candidate_cells: Tensor, protos: list, topk: int = 5):
+def best_per_candidate(embedding: Tensor, candidate_cells: Tensor, protos: list, topk: int = 5, metric: str = "l2"):
     """Stage-1 result only: per (query, candidate) the best score
     (max_p -||proto - q||, :190-193) and the arg-best prototype index within the
     cell (:194); missing cell -> (-100000, -1).  Used to check the retrieval
@@ -116,7 +131,7 @@ def best_per_candidate(embedding: Tensor, candidate_cells: Tensor, protos: list,
             c = int(candidate_cells[i, j])
             if protos[c] is None:
                 continue
-            logits = -euclidean_distance(protos[c], embedding[i])
+            logits = similarity(protos[c], embedding[i], metric)
             score[i, j] = logits.max()
             idx[i, j] = logits.argmax()
             if logits.numel() > 1:

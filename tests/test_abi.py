@@ -39,7 +39,7 @@ def test_layout_helpers():
 
 def test_argument_errors_are_reported_not_crashed():
     lib = _lib.load()
-    rc = lib.gg_head_fwd(0, 0, 0, 16, 100, 12, 0, 0, 5, 0, 0, 0, 0, 0, 0, 0, 0)  # D % 8 != 0
+    rc = lib.gg_head_fwd(0, 0, 0, 16, 100, 12, 0, 0, 5, 0, 0, 0, 0, 0, 0, 0, 0, 0)  # D % 8 != 0
     assert rc == 1 and b"multiple of 8" in lib.gg_last_error()
     rc = lib.gg_hav_ce_fwd_bwd(0, 0, 0, 0, 0, 0, 10, 65.0, 0, 0, 0, 0, 0, 1.0, 0)
     assert rc == 1

@@ -303,3 +303,20 @@ def test_gradient_exchange_slices_cover_the_buffer_once(n, world):
         assert lo <= hi == lo2 and lo % 4 == 0
     sizes = [hi - lo for lo, hi in edges]
     assert max(sizes) - min(s for s in sizes[:-1] or sizes) <= 4 * world or world == 1
+
+
+def test_gradient_transport_is_decided_before_any_kernel_runs():
+    """comm="auto" with a rank count the own exchange kernels do not cover (3, 5, 6, 7, > 8) must fall back to NCCL
+    when the buffer is set up -- not crash in the first backward; an explicit kernel choice there is an error."""
+    T = gg.SuperGuessr._dp_transport
+    for world in (2, 4, 8):
+        assert T("auto", world, True) == "fused"
+        assert T("p2p", world, True) == "p2p" and T("nvls", world, True) == "nvls" and T("fused", world, True) == "fused"
+    for world in (3, 5, 6, 7, 16):
+        assert T("auto", world, True) == "nccl"
+        for comm in ("fused", "p2p", "nvls"):
+            with pytest.raises(ValueError):
+                T(comm, world, True)
+    assert T("auto", 2, False) == "nccl"  # CPU / gloo groups
+    assert T("auto", 2, True, torch.bfloat16) == "nccl"  # rounded communication is an NCCL option
+    assert T("nccl", 8, True) == "nccl"

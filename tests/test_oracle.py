@@ -103,3 +103,17 @@ def test_refiner_oracle_matches_reference(name, centroids):
     np.testing.assert_array_equal(cells.numpy(), g["preds_geocell"])
     np.testing.assert_array_equal(llh.numpy(), g["preds_LLH"])
     assert llh.dtype == torch.float32 and cells.dtype == torch.int64
+
+
+@pytest.mark.parametrize("name", ["cfg1", "jitter_missing", "top3_noprobs"])
+def test_refiner_oracle_stage1_matches_reference_helpers(name, centroids):
+    """Per-(query, candidate) best score / arg-best prototype of the oracle against the reference's own
+    _euclidean_distance and _cosine_similarity executed on the same inputs (stored with the golden)."""
+    g, offsets, bank, xy, emb, cand, cprobs, initial = _refiner_case(name, centroids)
+    protos, _ = synth.bank_as_lists(offsets, bank, xy)
+    k = int(g["topk"])
+    for metric, ks, ki, k2 in (("l2", "score", "proto_idx", "second"), ("cosine", "cos_score", "cos_proto_idx", "cos_second")):
+        score, idx, second = pro.best_per_candidate(emb, cand, protos, k, metric=metric)
+        np.testing.assert_array_equal(score.numpy(), g[ks])
+        np.testing.assert_array_equal(idx.numpy(), g[ki])
+        np.testing.assert_array_equal(second.numpy(), g[k2])

@@ -136,7 +136,15 @@ def test_refiner_on_built_bank_matches_reference_restatement():
     protos, coords = pbo.build(emb, cells, lists, lng, lat, C)
     protos = [None if p is None else p.bfloat16().float() for p in protos]
     _, o_llh, o_cell, _ = pro.forward(q, init, cand, probs, protos, coords, topk=5)
-    agree = (cell.cpu() == o_cell).float().mean().item()
-    assert agree >= 0.98, agree  # a prototype one bf16 ulp apart can flip a near-tie
+    # The kernel rounds the fused query to bf16, the oracle keeps the fp32 mean, and a prototype may sit one bf16 ulp
+    # apart: scores move by ~2e-3 rms.  No percentage gate: every row whose refined cell differs must sit on a tie of
+    # the oracle -- two prototypes of a candidate within 0.02, or the two best final probabilities within 0.01.
+    score, _, second = pro.best_per_candidate(q, cand, protos, 5)
+    fp = probs * torch.softmax(score.double() / 1.6, -1).float()
+    srt = fp.sort(-1, descending=True).values
+    tie = ((score - second) < 0.02).any(-1) | ((srt[:, 0] - srt[:, 1]) < 0.01)
     same = cell.cpu() == o_cell
-    assert np.allclose(llh.cpu().numpy()[same.numpy()], o_llh.numpy()[same.numpy()], atol=1e-5)
+    assert int((~same & ~tie).sum()) == 0, "refined cells differ without a tie in the oracle"
+    assert same.float().mean().item() >= 0.9
+    clean = same & ~((score - second) < 0.02).any(-1)
+    assert np.allclose(llh.cpu().numpy()[clean.numpy()], o_llh.numpy()[clean.numpy()], atol=1e-5)

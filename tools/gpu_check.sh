@@ -11,10 +11,17 @@ for w in $what; do
     tests)
       timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
       echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log ;;
+    probe)  # hardware questions answered by tiny stand-alone programs (tools/probes)
+      timeout 60 tools/probes/gather4_probe > gpurun_out/gather4_probe.log 2>&1; echo "gather4 probe rc=$?"; cat gpurun_out/gather4_probe.log ;;
+    tests_split)  # one pytest process per file: a trapped kernel only takes its own file down
+      for f in tests/test_*.py; do
+        n=$(basename $f .py)
+        timeout 900 python -m pytest $f -m gpu -q -x > gpurun_out/pt_$n.log 2>&1; echo "$n rc=$?" | tee -a gpurun_out/pt_$n.log; tail -2 gpurun_out/pt_$n.log | head -1
+      done ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log ;;
     bench)
-      timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json
+      timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
       timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
     kbench)
       timeout 300 python tools/kbench.py 30 > gpurun_out/kbench.log 2>&1; cat gpurun_out/kbench.log ;;

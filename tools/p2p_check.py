@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""torchrun job (2, 4 or 8 GPUs): the symmetric-memory two-shot gradient exchange against NCCL.
+"""torchrun job (2, 4 or 8 GPUs): the symmetric-memory gradient exchanges against NCCL.
 
-  1. gg_p2p_allreduce_avg on a random [dW | db]-sized buffer == NCCL all_reduce(AVG)  (bit-exact at N = 2)
-  2. one data-parallel SuperGuessr training step with comm="p2p" == the same step with comm="nccl"
-  3. timing of both exchanges for the 51.8 MB head gradient (CUDA events, max over ranks)
+  1. gg_p2p_allreduce_avg / gg_nvls_allreduce_avg on a random [dW | db]-sized buffer == NCCL all_reduce(AVG)
+     (bit-exact at N = 2)
+  2. three consecutive data-parallel SuperGuessr training steps with comm="fused" (gg_head_bwd announcing blocks +
+     gg_grad_exchange next to it), "nvls", "p2p" == the same steps with comm="nccl"
+  3. timing of the exchanges for the 51.8 MB head gradient (CUDA events, max over ranks)
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/p2p_check.py [--quick]
 """
@@ -71,36 +73,47 @@ if mc:
     assert same and err < 1e-6
 
 
-# ---- 2. a data-parallel training step, p2p vs nccl
-def train_step(comm, chunks=1):
+# ---- 2. data-parallel training steps, own exchanges vs nccl
+def train_steps(comm, D=256, B=512, steps=3):
     import contextlib
     import io
 
     cent = load_packaged_centroids()
-    Dm, B = 256, 512
     with contextlib.redirect_stdout(io.StringIO()):
-        m = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, embed_dim=Dm, centroids=cent).to(dev)
-    emb, W, b, labels = synth.head_inputs(B * world, Dm, cent.shape[0], seed=7, bf16_round=True)
+        m = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, embed_dim=D, centroids=cent).to(dev)
+    emb, W, b, labels = synth.head_inputs(B * world, D, cent.shape[0], seed=7, bf16_round=True)
     with torch.no_grad():
         m.cell_layer.weight.copy_(W)
         m.cell_layer.bias.copy_(b)
     m.train()
-    m.enable_data_parallel(comm=comm, chunks=chunks)
+    m.enable_data_parallel(comm=comm)
+    opt = torch.optim.SGD(m.cell_layer.parameters(), lr=0.5)
     sl = slice(rank * B, (rank + 1) * B)
-    out = m(embedding=emb[sl].to(dev), labels=labels[sl].to(dev), labels_clf=torch.zeros(B, dtype=torch.int64, device=dev))
-    out.loss.backward()
-    torch.cuda.synchronize()
-    return m.cell_layer.weight.grad.clone(), m.cell_layer.bias.grad.clone(), m._dp["symm"] is not None
+    grads = []
+    for _ in range(steps):  # the weights move between the steps: every step exchanges a different gradient
+        opt.zero_grad(set_to_none=True)
+        out = m(embedding=emb[sl].to(dev), labels=labels[sl].to(dev), labels_clf=torch.zeros(B, dtype=torch.int64, device=dev))
+        out.loss.backward()
+        torch.cuda.synchronize()
+        grads.append((m.cell_layer.weight.grad.clone(), m.cell_layer.bias.grad.clone()))
+        opt.step()
+    return grads, m.describe_data_parallel()
 
 
-gw_n, gb_n, _ = train_step("nccl")
-for kind, chunks in ([("nvls", 1), ("nvls", 3)] if mc else []) + [("p2p", 1), ("p2p", 3)]:
-    gw_p, gb_p, used = train_step(kind, chunks)
-    assert used, f"{kind} path did not run"
-    ew = (gw_p - gw_n).abs().max().item() / gw_n.abs().max().item()
-    eb = (gb_p - gb_n).abs().max().item() / gb_n.abs().max().item()
-    say(f"DP step {kind} x{chunks} vs nccl: dW rel diff {ew:.2e}, db rel diff {eb:.2e}")
-    assert ew < 1e-6 and eb < 1e-6
+for D, B in ((256, 512), (576, 256)):
+    ref_grads, _ = train_steps("nccl", D, B)
+    for kind in ["fused"] + (["nvls"] if mc else []) + ["p2p"]:
+        got, what = train_steps(kind, D, B)
+        assert what.startswith(kind), what
+        worst_w = worst_b = 0.0
+        for (gw_p, gb_p), (gw_n, gb_n) in zip(got, ref_grads):
+            worst_w = max(worst_w, (gw_p - gw_n).abs().max().item() / gw_n.abs().max().item())
+            worst_b = max(worst_b, (gb_p - gb_n).abs().max().item() / gb_n.abs().max().item())
+        say(f"DP steps D={D} {kind} vs nccl ({len(got)} steps): dW rel diff {worst_w:.2e}, db rel diff {worst_b:.2e}")
+        assert worst_w < 1e-6 and worst_b < 1e-6
+        gathered_w = [torch.empty_like(got[-1][0]) for _ in range(world)]
+        dist.all_gather(gathered_w, got[-1][0])
+        assert all(torch.equal(gathered_w[0], g) for g in gathered_w), f"{kind}: ranks hold different gradients"
 
 
 # ---- 3. timing

@@ -44,6 +44,13 @@ SIGNATURES = {
     "gg_hard_ce_fwd_bwd": (I, [P, I, P, P, I, I, P, P, P]),
     "gg_loss_mean": (I, [P, I, F, P, P]),
     "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P, I, P]),
+    "gg_head_dx": (I, [P, I, P, I, I, I, I, F, P, I, P, P]),
+    "gg_topk_accuracy": (I, [P, I, P, I, P, P]),
+    "gg_split3_bf16": (I, [P, L, I, I, P, I, P, P]),
+    "gg_linear_bf16": (I, [P, I, P, I, P, I, I, I, P, I, P]),
+    "gg_hier_attention": (I, [P, I, I, I, I, P, P]),
+    "gg_proto_take_image_coords": (I, [P, P, L, P]),
+    "gg_proto_record_ids": (I, [P, L, P, P]),
     "gg_proto_group_cells": (I, [P, I, P]),
     "gg_proto_retrieve": (I, [P, P, I, I, P, I, I, P, P, P, L, P, I, I, P, I, I, I, I, P, P, P]),
     "gg_proto_refine": (I, [P, I, L, P, I, P, I, P, I, I, F, F, P, P, P, P, P, P]),

@@ -404,6 +404,49 @@ __device__ __forceinline__ int argmax_nan_first(const float* v, int k) {
 
 constexpr int kMaxTopk = 16;
 
+__global__ void proto_take_image_coords_kernel(float4* __restrict__ rec, const float4* __restrict__ rec_img, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 im = rec_img[i];
+  if (__float_as_int(im.w) >= 0) {
+    float4 r = rec[i];
+    r.y = im.y;
+    r.z = im.z;
+    rec[i] = r;
+  }
+}
+__global__ void proto_record_ids_kernel(const float4* __restrict__ rec, long long n, long long* __restrict__ ids) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = __float_as_int(rec[i].w);
+}
+
+// main_coordinator_idun_s3.py:399-408, one CTA, fixed summation order
+__global__ void topk_accuracy_kernel(const long long* __restrict__ topk_idx, int k, const long long* __restrict__ targets,
+                                     int B, float* __restrict__ acc) {
+  __shared__ int s1[32], sk[32];
+  int c1 = 0, ck = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const long long t = targets[i];
+    c1 += topk_idx[static_cast<size_t>(i) * k] == t ? 1 : 0;
+    bool any = false;
+    for (int j = 0; j < k; ++j) any |= topk_idx[static_cast<size_t>(i) * k + j] == t;
+    ck += any ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    ck += __shfl_xor_sync(0xffffffffu, ck, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = c1; sk[threadIdx.x >> 5] = ck; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t1 = 0, tk = 0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { t1 += s1[w]; tk += sk[w]; }
+    acc[0] = static_cast<float>(t1) / static_cast<float>(B);
+    acc[1] = static_cast<float>(tk) / static_cast<float>(B);
+  }
+}
+
 __global__ void proto_refine_kernel(const float4* __restrict__ rec, int nranks, long long rank_stride,
                                     const float* __restrict__ cprobs, int cprobs_ld,
                                     const long long* __restrict__ cand, int cand_ld,
@@ -581,6 +624,30 @@ extern "C" int gg_proto_refine(const void* rec, int nranks, long long rank_strid
   proto_refine_kernel<<<ceil_div(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float4*>(rec), nranks, rank_stride, cand_probs, cand_probs_ld, cand, cand_ld, initial_llh, B,
       topk, temperature, max_refinement_km, out_llh, out_cell, out_guess, out_score, out_proto);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_proto_take_image_coords(void* rec, const void* rec_img, long long n, gg_stream_t stream) {
+  GG_CHECK(rec && rec_img && n > 0, GG_ERR_ARG, "gg_proto_take_image_coords: bad arguments");
+  proto_take_image_coords_kernel<<<static_cast<unsigned int>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float4*>(rec), static_cast<const float4*>(rec_img), n);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_proto_record_ids(const void* rec, long long n, long long* ids, gg_stream_t stream) {
+  GG_CHECK(rec && ids && n > 0, GG_ERR_ARG, "gg_proto_record_ids: bad arguments");
+  proto_record_ids_kernel<<<static_cast<unsigned int>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float4*>(rec), n, ids);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_topk_accuracy(const long long* topk_idx, int k, const long long* targets, int B, float* acc,
+                                gg_stream_t stream) {
+  GG_CHECK(topk_idx && targets && acc && B > 0 && k >= 1, GG_ERR_ARG, "gg_topk_accuracy: bad arguments");
+  topk_accuracy_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(topk_idx, k, targets, B, acc);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -105,8 +105,9 @@ def build_prototype_bank(embedding: torch.Tensor, proto_df, num_cells: int, vali
     val = None if valid is None else torch.as_tensor(valid).to(dev, torch.uint8).contiguous()
     if val is not None and val.numel() != L:
         raise ValueError("valid must have one entry per location")
-    ops._call("gg_build_prototypes", _lib.load().gg_build_prototypes, emb.data_ptr(), L, V, D, moff.data_ptr(), mem.data_ptr(),
+    dev = ops._need_cuda(emb, moff, mem)
+    ops._call("gg_build_prototypes", _lib.load().gg_build_prototypes, dev, emb.data_ptr(), L, V, D, moff.data_ptr(), mem.data_ptr(),
               0 if val is None else val.data_ptr(), P, bank.data_ptr(), 0 if f32 is None else f32.data_ptr(),
-              0 if cnt is None else cnt.data_ptr(), ops._stream())
+              0 if cnt is None else cnt.data_ptr(), ops._stream(dev))
     out = (torch.from_numpy(cell_off), bank, torch.from_numpy(coords))
     return out + (f32, cnt) if return_f32 else out

@@ -69,6 +69,7 @@ class ProtoRefiner(nn.Module):
         report_changed: bool = True,
         precision: str = "bf16",
         metric: str = "l2",
+        images: tuple | None = None,
         device="cuda",
     ):
         """Reference arguments (proto_refiner.py:33-62) plus keyword-only ways to hand over a bank:
@@ -91,6 +92,12 @@ class ProtoRefiner(nn.Module):
             3x the bank bytes).
         metric: "l2" = the executable reference (``-cdist``, :190); "cosine" = the reference's unused
             ``_cosine_similarity`` (:347-362), opt-in.
+        images=(member_off, image_bank, image_coords): opt-in within-cluster refinement: the member
+            images of every prototype, sorted by prototype -- ``member_off`` (P+1) over the GLOBAL prototype order of
+            ``bank``, ``image_bank`` (L, D), ``image_coords`` (L, 2).  After the nearest prototype of a candidate cell
+            is found, the nearest member image of that cluster supplies the coordinates (a cluster without images keeps
+            its own: the ``count == 0`` branch, :251-252).  This is what ``_within_cluster_refinement`` (:239-269) is
+            meant to do; as written it cannot run (``self.dataset`` is never assigned) and takes the farthest member.
         """
         super().__init__()
         if precision not in ("bf16", "bf16x3"):
@@ -123,6 +130,7 @@ class ProtoRefiner(nn.Module):
                 "geoguessr_ai_b200.proto_builder.build_prototype_bank(embeddings, proto_df, num_cells) -> pass its "
                 "result as bank=(cell_off, bank, coords); or pass protos='load' / protos=[...]+coords=[...].")
         self._install_bank(cell_off, mat, xy, shard, device, bank_is_local)
+        self._install_images(images, device)
 
     # ---- bank construction ------------------------------------------------------------------
     @classmethod
@@ -207,6 +215,36 @@ class ProtoRefiner(nn.Module):
         if dev.type == "cuda":
             self._ensure_sqnorm()
 
+    def _install_images(self, images, device):
+        """Second-stage bank: member images sorted by prototype; this rank keeps those of its own prototypes."""
+        self.has_images = images is not None
+        if not self.has_images:
+            return
+        member_off, img, img_xy = images
+        moff = torch.as_tensor(member_off).to(torch.int64).cpu().numpy()
+        assert len(moff) == self.num_protos_total + 1, "member_off must have one entry per prototype of the whole bank + 1"
+        p0 = self.proto_base
+        p1 = p0 + int(self.bank.shape[0])
+        i0, i1 = int(moff[p0]), int(moff[p1])
+        self.img_base = i0
+        dev = torch.device(device)
+        local = torch.from_numpy((moff[p0:p1 + 1] - i0).astype(np.int32))
+        img = torch.as_tensor(img)[i0:i1]
+        if dev.type == "cuda" and img.dtype == torch.float32:
+            img16 = ops.cast_bank_bf16(img.to(dev), split=self._split)
+        elif self._split:
+            hi = img.to(torch.bfloat16)
+            img16 = torch.cat([hi, (img.float() - hi.float()).to(torch.bfloat16), hi], 1).to(dev).contiguous()
+        else:
+            img16 = img.to(device=dev, dtype=torch.bfloat16).contiguous()
+        self.register_buffer("img_bank", img16, persistent=False)
+        self.register_buffer("img_coords", torch.as_tensor(img_xy, dtype=torch.float32)[i0:i1].to(dev).contiguous(),
+                             persistent=False)
+        self.register_buffer("img_off", local.to(dev), persistent=False)
+        self.register_buffer("img_group_off", torch.from_numpy(ops.proto_group_cells(local.numpy())).to(dev), persistent=False)
+        self.register_buffer("img_sqnorm", torch.empty(0, dtype=torch.float32, device=dev), persistent=False)
+        self._img_sqnorm_for = None
+
     def _ensure_sqnorm(self):
         """``bank_sqnorm`` of the bank where it lives NOW (the reference idiom is ``ProtoRefiner(...).to(device)``,
         inference.py:177: a bank installed on the CPU has no norms until it reaches the GPU)."""
@@ -215,6 +253,12 @@ class ProtoRefiner(nn.Module):
             self.bank_sqnorm = (ops.row_sqnorm_bf16(self.bank, split=self._split) if self.bank.shape[0]
                                 else torch.empty(0, dtype=torch.float32, device=self.bank.device))
             self._sqnorm_for = key
+        if self.has_images:
+            key = (self.img_bank.data_ptr(), self.img_bank.device)
+            if self._img_sqnorm_for != key:
+                self.img_sqnorm = (ops.row_sqnorm_bf16(self.img_bank, split=self._split) if self.img_bank.shape[0]
+                                   else torch.empty(0, dtype=torch.float32, device=self.img_bank.device))
+                self._img_sqnorm_for = key
 
     def __str__(self):
         rep = "ProtoRefiner(\n"
@@ -240,6 +284,15 @@ class ProtoRefiner(nn.Module):
                                        group_off=self.group_off, metric=self.metric, gather4=self.gather4,
                                        want_meta=True)
         self._last_meta = (meta, q16.shape[0], q16.shape[1], candidate_cells)
+        n_local = int(self.bank.shape[0])
+        if self.has_images and n_local > 0:
+            # stage 1b: the best prototype of every pair is the "cell" of a second retrieval over its member images
+            cand2 = ops.proto_record_ids(rec).view(q16.shape[0], self.topk)
+            img = self.img_bank if self.img_bank.shape[0] > 0 else None
+            rec_img = ops.proto_retrieve(q16, qn, cand2, self.topk, img, self.img_sqnorm, self.img_coords, self.img_off,
+                                         self.proto_base, self.proto_base + n_local, self.img_base,
+                                         group_off=self.img_group_off, metric=self.metric, gather4=self.gather4)
+            ops.proto_take_image_coords(rec, rec_img)
         return rec
 
     gather4 = os.environ.get("GG_RETRIEVE_GATHER4", "1") != "0"  # query rows gathered by the TMA engine (tile::gather4)

@@ -69,6 +69,7 @@ class _GeocellHeadLoss(torch.autograd.Function):
             dlogits, loss_rows = ops.hard_ce(head["logits"], head["lse"], labels_clf, C)
             loss = ops.loss_mean(loss_rows)
         ctx.save_for_backward(dlogits, x16)
+        ctx.w16 = st["w16"] if embedding.requires_grad else None  # dx = dlogits W reuses the forward's operand
         ctx.dbp = dbp
         ctx.set_materialize_grads(False)  # no zero-filled grads for the non-differentiable outputs
         ctx.dims = (C, D, embedding.shape, embedding.requires_grad)
@@ -93,11 +94,32 @@ class _GeocellHeadLoss(torch.autograd.Function):
             else:
                 dW, db = ctx.module._backward_data_parallel(dlogits, x16, C, D, B, gloss, want_b, ctx.dbp)
         if ctx.needs_input_grad[0] and emb_needs_grad:
-            # Only reached when the encoder is trained end to end (outside the BASELINE configs):
-            # dx = dlogits W through cuBLAS, then the mean's 1/V broadcast (super_guessr.py:347).
-            g = (dlogits[:, :C].float() @ ctx.weight.detach().float()) * (gloss / B)
-            demb = g if len(emb_shape) == 2 else (g / emb_shape[1]).unsqueeze(1).expand(emb_shape)
+            # Reached when the encoder is trained (TinyViT's last stage / CLIP's last layer, super_guessr.py:127-153;
+            # main_coordinator_idun_s3.py:423): dx = dlogits W on the tensor cores with the mean's 1/V broadcast
+            # (super_guessr.py:347) in the epilogue (gg_head_dx).
+            demb = ops.head_dx(dlogits, ctx.w16, C, D, 1.0 / B, gloss, emb_shape)
         return demb, (dW if want_w else None), db, None, None, None, None
+
+
+NUM_ATTENTION_HEADS = 16  # models/super_guessr.py:14
+
+
+class PositionalEncoder(nn.Module):
+    """The reference's positional table (models/layers/positional_encoder.py:5-44): (max_len, 1, D), sin on even
+    columns, cos on odd ones, registered as a frozen parameter `pos_encoding` (same state-dict key).  The addition
+    itself -- `x + pos_encoding[:B]`, which indexes the BATCH row -- runs inside gg_split3_bf16."""
+
+    def __init__(self, dim_model: int, dropout_p: float = 0.1, max_len: int = 1000):
+        super().__init__()
+        import math
+
+        self.dropout = nn.Dropout(dropout_p)
+        pos_encoding = torch.zeros(max_len, dim_model)
+        positions = torch.arange(0, max_len, dtype=torch.float).view(-1, 1)
+        division = torch.exp(torch.arange(0, dim_model, 2).float() * (-math.log(10000.0)) / dim_model)
+        pos_encoding[:, 0::2] = torch.sin(positions * division)
+        pos_encoding[:, 1::2] = torch.cos(positions * division)
+        self.register_parameter("pos_encoding", nn.Parameter(pos_encoding.unsqueeze(0).transpose(0, 1), requires_grad=False))
 
 
 def dp_chunk_bounds(C: int, chunks: int, align: int = 256):
@@ -159,10 +181,6 @@ class SuperGuessr(nn.Module):
             print(f"Not using keyword arguments: {list(kwargs.keys())}")
         if precision not in ("bf16", "bf16x3"):
             raise ValueError("precision must be 'bf16' or 'bf16x3'")
-        if hierarchical:
-            raise NotImplementedError(
-                "hierarchical=True (positional encoding + 16-head attention over the 4 headings, "
-                "super_guessr.py:89-99,340-345) is not on the accelerated path yet; no reference caller enables it")
         self.base_model = base_model
         self.panorama = panorama
         self.hidden_size = embed_dim
@@ -180,6 +198,14 @@ class SuperGuessr(nn.Module):
         self.geocell_centroid_coords = nn.Parameter(table, requires_grad=False)
         self.num_cells = table.size(0)
         self.input_dim = self.hidden_size
+        if self.hierarchical:  # super_guessr.py:88-99 (same sub-modules, hence the same state-dict keys)
+            print("Number of attention heads:", NUM_ATTENTION_HEADS)
+            self.heading_pad = 0
+            self.pos_encoder = PositionalEncoder(self.input_dim + self.heading_pad)
+            self.self_attn = nn.MultiheadAttention(self.input_dim + self.heading_pad, NUM_ATTENTION_HEADS, dropout=0.1,
+                                                   batch_first=True)
+            self.relu = nn.ReLU()
+        self._hier_cache = None
         self.cell_layer = nn.Linear(self.input_dim, self.num_cells)
         self.softmax = nn.Softmax(dim=-1)
         self.loss_fnc = nn.CrossEntropyLoss()
@@ -465,6 +491,39 @@ class SuperGuessr(nn.Module):
         cur.wait_stream(comm)
         return dW, db
 
+    # ---- hierarchical fusion (super_guessr.py:340-345) and trainer-side helpers ---------------
+    def _hierarchical_fusion(self, x):
+        """pos_encoder + 16-head self-attention over the headings, token 0, in eval mode (gg_split3_bf16,
+        gg_linear_bf16, gg_hier_attention).  Training this branch (its two dropouts, the attention backward) is not
+        on the accelerated path: no reference caller enables `hierarchical`."""
+        if self.training:
+            raise NotImplementedError(
+                "hierarchical=True is implemented for eval mode (dropout off, attention parameters frozen); training "
+                "the attention fusion is outside the accelerated path (no reference caller enables it)")
+        a = self.self_attn
+        key = tuple((p.data_ptr(), p._version) for p in (a.in_proj_weight, a.out_proj.weight))
+        if self._hier_cache is None or self._hier_cache[0] != key:
+            self._hier_cache = (key, (ops.split3_bf16(a.in_proj_weight.detach().float(), 1),
+                                      ops.split3_bf16(a.out_proj.weight.detach().float(), 1)))
+        with torch.no_grad():
+            return ops.hier_fuse(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias,
+                                 self.pos_encoder.pos_encoding, num_heads=a.num_heads, weights=self._hier_cache[1])
+
+    def labels_from_coords(self, labels: Tensor):
+        """The trainer's label derivation (main_coordinator_idun_s3.py:390-391: haversine_matrix + argmin) as a
+        by-product of the loss's row statistics: (labels_clf (B,) int64, nearest_km (B,) fp32), first index on ties."""
+        labels = labels.to(self.geocell_centroid_coords.device)
+        _, cell, km = ops.hav_row_stats(labels, self._centroid_xyz(), self.num_cells, tau=self.label_smoothing_tau,
+                                        far_km=self.far_km, want_nearest=True)
+        return cell, km
+
+    @staticmethod
+    def accuracy(topk, targets: Tensor) -> Tensor:
+        """The trainer's per-step metrics (main_coordinator_idun_s3.py:399-408) on the device: a (2,) tensor
+        [top-1 accuracy, top-k accuracy]; read it when logging instead of two `.item()` syncs per step."""
+        idx = topk.indices if hasattr(topk, "indices") else topk
+        return ops.topk_accuracy(idx, targets.to(idx.device))
+
     # ---- forward (super_guessr.py:268-395) ---------------------------------------------------
     def forward(self, pixel_values: Tensor = None, embedding: Tensor = None, labels: Tensor = None,
                 labels_clf: Tensor = None, index: Tensor = None):
@@ -502,6 +561,8 @@ class SuperGuessr(nn.Module):
             raise ops._lib.GeoguessrB200Error(
                 "SuperGuessr parameters are on the CPU: this implementation only runs on an sm_100a GPU "
                 "(call .cuda()); there is no CPU fallback")
+        if self.panorama and self.hierarchical:
+            layer_input = self._hierarchical_fusion(layer_input)  # (B, D) fp32: the head sees a single "heading"
 
         serving_now = (not self.training) and self.serving
         needs_loss = not serving_now

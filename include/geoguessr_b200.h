@@ -147,6 +147,34 @@ int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld,
                 const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
                 void* workspace, const unsigned long long* signal_ptrs, int signal_world, gg_stream_t stream);
 
+/* dx of the same layer (autograd of super_guessr.py:354 w.r.t. its input; reached from
+ * main_coordinator_idun_s3.py:423 whenever the encoder is trained -- TinyViT's last stage / CLIP's last layer,
+ * super_guessr.py:127-153) with the heading mean's 1/V broadcast (:347) in the epilogue:
+ * demb (B, V, D) fp32, every heading v: demb[b, v, :] = scale * grad_scale / V * sum_c dlogits[b, c] W[c, :].
+ * w (C, w_ld >= D) bf16 = the forward's operand, consumed as it lies (no transposed copy); tcgen05. */
+int gg_head_dx(const void* dlogits_bf16, int ldc, const void* w_bf16, int w_ld, int B, int C, int D, float scale,
+               const float* grad_scale, int V, float* demb, gg_stream_t stream);
+
+/* ---- f-1: the trainer's per-step accuracy metrics -----------------------------------------------
+ * main_coordinator_idun_s3.py:399-408: top1 = mean(topk_idx[:, 0] == targets), topk = mean(any_j topk_idx[:, j] ==
+ * targets), from the head's top-k indices and the nearest-centroid targets (gg_hav_row_stats' nearest_cell): two
+ * device floats acc[0], acc[1] (deterministic single-CTA sum) instead of two `.item()` syncs per step. */
+int gg_topk_accuracy(const long long* topk_idx, int k, const long long* targets, int B, float* acc, gg_stream_t stream);
+
+/* ---- f-4: `hierarchical=True` heading fusion ----------------------------------------------------
+ * models/super_guessr.py:89-99,340-345 + models/layers/positional_encoder.py:21-44, eval mode: z = x + PE[batch row],
+ * 16-head self-attention over the V headings, token 0, output projection.  The fp32 module is reproduced to fp32
+ * accuracy on the tensor cores by splitting operands into three bf16 terms laid side by side along K (six products):
+ * gg_split3_bf16: src (rows, D) fp32 [+ pos_encoding[row / V] when given] -> (rows, 6D) bf16, role 0 = activation
+ * [h|h|m|h|l|m], role 1 = weight [h|m|h|l|h|m];  gg_linear_bf16: out (M, N) fp32 = a (M, K) w(N, K)^T + bias, tcgen05;
+ * gg_hier_attention: qkv (B*V, 3D) fp32 -> softmax_t(q[b,0,h] . k[b,t,h] / sqrt(D/heads)) weighted values of token 0,
+ * written as the role-0 split operand (B, 6D) of the output projection. */
+int gg_split3_bf16(const float* src, long long rows, int D, int role, const float* pos_encoding, int V, void* dst_bf16,
+                   gg_stream_t stream);
+int gg_linear_bf16(const void* a_bf16, int lda, const void* w_bf16, int ldw, const float* bias, int M, int N, int K,
+                   float* out, int ldo, gg_stream_t stream);
+int gg_hier_attention(const float* qkv, int B, int V, int D, int heads, void* ctx_split_bf16, gg_stream_t stream);
+
 /* ---- a10-a15: ProtoRefiner ----------------------------------------------------------------
  * models/proto_refiner.py:165-203 (retrieval) -- for every (query i, candidate j < topk):
  * score = max_p -||proto_{c,p} - q_i||_2 (:190-193, _euclidean_distance :364-376), arg-best
@@ -183,6 +211,15 @@ int gg_proto_refine(const void* rec, int nranks, long long rank_stride, const fl
                     const long long* cand, int cand_ld, const float* initial_llh, int B, int topk, float temperature,
                     float max_refinement_km, float* out_llh, long long* out_cell, int* out_guess, float* out_score,
                     int* out_proto, gg_stream_t stream);
+
+/* Within-cluster refinement (f-3, second half; the reference's _within_cluster_refinement, proto_refiner.py:239-269,
+ * cannot run and would pick the FARTHEST member): a second gg_proto_retrieve over the member images of each pair's
+ * best prototype (bank = image embeddings sorted by cluster, "cells" = clusters, cand = the stage-1 prototype ids)
+ * finds the NEAREST image; this call then replaces the coordinates of every stage-1 record whose cluster has images:
+ * rec[i].{lng, lat} = rec_img[i].{lng, lat} where rec_img[i].id >= 0.  Scores and prototype ids are kept. */
+int gg_proto_take_image_coords(void* rec, const void* rec_img, long long n, gg_stream_t stream);
+/* prototype ids of a record array as the int64 candidate list of that second retrieval: cand2[i] = rec[i].id */
+int gg_proto_record_ids(const void* rec, long long n, long long* ids, gg_stream_t stream);
 
 /* ---- next row f-3: prototype bank builder --------------------------------------------------------
  * models/proto_refiner.py:391-406 + :461-517 (Embeddings.generate_embeddings) with the encoder replaced by stored

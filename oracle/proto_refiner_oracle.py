@@ -8,7 +8,8 @@ coordinates, :251-252) is restated; the other branch dereferences a
 
 Bank representation: ``protos[c]`` is ``None`` (cell has no prototypes,
 :181-187) or a ``(P_c, D)`` tensor; ``coords[c]`` is the matching ``(P_c, 2)``
-tensor of (lng, lat).
+tensor of (lng, lat).  Optional ``images[c][p]`` / ``image_coords[c][p]``: the
+member images ``(n, D)`` / ``(n, 2)`` of prototype p of cell c.
 """
 from __future__ import annotations
 
@@ -68,6 +69,8 @@ def forward(
     temperature: float = 1.6,
     device="cpu",
     metric: str = "l2",
+    images: list | None = None,
+    image_coords: list | None = None,
 ):
     """ProtoRefiner.forward, proto_refiner.py:129-237.  Returns
     (None, preds_LLH (B,2) fp32, preds_geocell (B,) int64, guess_index (B,))."""
@@ -95,6 +98,13 @@ def forward(
             top_distances.append(torch.max(logits).item())  # :193
             j = torch.argmax(logits, dim=-1).item()  # :194
             lng, lat = coords[cell_id][j, 0].item(), coords[cell_id][j, 1].item()  # :251-252
+            if images is not None and images[cell_id] is not None and images[cell_id][j].shape[0] > 0:
+                # _within_cluster_refinement as it is MEANT (:239-269; as written it dereferences self.dataset, which
+                # is never assigned, and takes argmax of the distances = the farthest member): the cluster's member
+                # image nearest to the query gives the coordinates.  Unpinned: the reference cannot execute this.
+                member_logits = similarity(images[cell_id][j].to(device), emb, metric)
+                jj = torch.argmax(member_logits).item()
+                lng, lat = image_coords[cell_id][j][jj, 0].item(), image_coords[cell_id][j][jj, 1].item()
             top_preds.append([lng, lat])
         top_distances = torch.tensor(top_distances, device=device)  # :205
         probs = temperature_softmax(top_distances, temperature)  # :206

@@ -1,0 +1,173 @@
+"""GPU tests of the rows next to the BASELINE step: dx on the tensor cores (a8), the `hierarchical=True` fusion (f-4),
+the trainer's label derivation / accuracy metrics (f-1) and the within-cluster image refinement (f-3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import geoguessr_ai_b200 as gg
+from geoguessr_ai_b200 import ops, synth
+from oracle import hier_fusion_oracle as hf
+from oracle import proto_refiner_oracle as pro
+from oracle import super_guessr_oracle as sgo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+C = 12647
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("B,D,V,precision", [(96, 256, 4, "bf16"), (300, 576, 4, "bf16"), (64, 128, 1, "bf16x3")])
+def test_embedding_gradient_matches_autograd(B, D, V, precision, centroids):
+    """dL/d(embedding) through gg_head_dx (tcgen05, 1/V broadcast in the epilogue) against the oracle's autograd."""
+    emb, W, b, labels = synth.head_inputs(B, D, C, V=4, seed=31, bf16_round=True)
+    if V == 1:
+        emb = emb[:, 0].contiguous()
+    m = gg.SuperGuessr(None, panorama=V > 1, should_smooth_labels=True, embed_dim=D, centroids=centroids,
+                       precision=precision).to(DEV).train()
+    with torch.no_grad():
+        m.cell_layer.weight.copy_(W)
+        m.cell_layer.bias.copy_(b)
+    e = emb.to(DEV).requires_grad_(True)
+    out = m(embedding=e, labels=labels.to(DEV), labels_clf=torch.zeros(B, dtype=torch.int64, device=DEV))
+    (out.loss * 3.0).backward()  # an upstream factor: read on the device by the kernel
+    assert e.grad is not None and e.grad.shape == emb.shape
+    er = emb.clone().requires_grad_(True)
+    x = er.mean(1) if V > 1 else er
+    logits = torch.nn.functional.linear(x, W, b)
+    t = sgo.soft_targets(labels, centroids)
+    loss = -(t * torch.log_softmax(logits, -1)).sum(-1).mean() * 3.0
+    loss.backward()
+    ref = er.grad
+    err = (e.grad.cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), (err, ref.abs().max().item())
+    if V > 1:  # every heading receives the same gradient (mean's broadcast)
+        assert torch.equal(e.grad[:, 0], e.grad[:, 3])
+    # the head's own gradients are unchanged by asking for dx
+    gW = m.cell_layer.weight.grad.clone()
+    m.zero_grad(set_to_none=True)
+    out2 = m(embedding=emb.to(DEV), labels=labels.to(DEV), labels_clf=torch.zeros(B, dtype=torch.int64, device=DEV))
+    (out2.loss * 3.0).backward()
+    assert torch.equal(gW, m.cell_layer.weight.grad)
+
+
+def test_dx_kernel_against_plain_contraction():
+    """gg_head_dx alone: ragged sizes in every dimension, pad columns of dlogits ignored."""
+    for B, Cc, D, V in ((37, 300, 72, 4), (130, 1000, 264, 2), (5, 70, 8, 1)):
+        g = torch.Generator().manual_seed(B)
+        W = (torch.randn(Cc, D, generator=g) / D ** 0.5).to(torch.bfloat16)
+        dl = torch.full((B, ops.logits_ld(Cc)), 7.0, dtype=torch.bfloat16)  # pad columns hold junk
+        dl[:, :Cc] = (torch.randn(B, Cc, generator=g) * 1e-2).to(torch.bfloat16)
+        gs = torch.tensor(0.5)
+        shape = (B, V, D) if V > 1 else (B, D)
+        demb = ops.head_dx(dl.to(DEV), W.to(DEV), Cc, D, 0.25, gs.to(DEV), shape)
+        ref = (dl[:, :Cc].float() @ W.float()) * (0.25 * 0.5 / V)
+        ref = ref.unsqueeze(1).expand(B, V, D) if V > 1 else ref
+        np.testing.assert_allclose(demb.cpu().numpy(), ref.numpy(), atol=1e-6 + 1e-4 * ref.abs().max().item())
+
+
+def test_hierarchical_fusion_matches_reference_golden():
+    """The reference module executed in eval mode (tests/golden/hier_fusion.npz): the split-operand tensor-core path
+    reproduces the fp32 fusion to 1e-5."""
+    g = np.load(os.path.join(GOLDEN, "hier_fusion.npz"))
+    t = {k: torch.from_numpy(g[k]).to(DEV) for k in ("x", "fused", "in_proj_weight", "in_proj_bias", "out_proj_weight",
+                                                     "out_proj_bias", "pos_encoding")}
+    got = ops.hier_fuse(t["x"], t["in_proj_weight"], t["in_proj_bias"], t["out_proj_weight"], t["out_proj_bias"],
+                        t["pos_encoding"])
+    err = (got - t["fused"]).abs().max().item()
+    assert err <= 1e-5, err
+    # larger, through the module, against the oracle: D = 576 (36-wide heads), B = 200
+    B, V, D = 200, 4, 576
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(B, V, D, generator=gen)
+    cent = torch.stack([torch.rand(50, generator=gen) * 360 - 180, torch.rand(50, generator=gen) * 140 - 60], 1)
+    m = gg.SuperGuessr(None, panorama=True, hierarchical=True, serving=True, embed_dim=D, centroids=cent,
+                       precision="bf16x3").to(DEV).eval()
+    a = m.self_attn
+    want = hf.fuse(x, a.in_proj_weight.detach().cpu(), a.in_proj_bias.detach().cpu(), a.out_proj.weight.detach().cpu(),
+                   a.out_proj.bias.detach().cpu(), m.pos_encoder.pos_encoding.detach().cpu())
+    got = m._hierarchical_fusion(x.to(DEV))
+    assert (got.cpu() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    llh, topk, emb = m(embedding=x.to(DEV))
+    logits = torch.nn.functional.linear(want, m.cell_layer.weight.detach().cpu(), m.cell_layer.bias.detach().cpu())
+    ref = torch.topk(logits, 8, -1)
+    idx = topk.indices.cpu().numpy()
+    for r in range(B):  # top-5 identical except inside 1e-3 logit ties
+        for j in range(5):
+            if idx[r, j] != ref.indices[r, j]:
+                pos = (ref.indices[r] == idx[r, j]).nonzero()
+                assert len(pos) and abs(ref.values[r, pos[0, 0]] - ref.values[r, j]) < 1e-3
+    assert emb.shape == (B, V, D)
+    with pytest.raises(NotImplementedError):
+        m.train()(embedding=x.to(DEV), labels_clf=torch.zeros(B, dtype=torch.int64, device=DEV))
+    with pytest.raises(RuntimeError):
+        m.eval()(embedding=torch.zeros(1001, 4, D, device=DEV))  # the reference's table does not broadcast either
+
+
+def test_label_derivation_and_accuracy_metrics(centroids):
+    """f-1: labels_clf = argmin_c haversine (main_coordinator_idun_s3.py:390-391) and the top-1 / top-5 accuracies
+    (:399-408) on the device."""
+    B, D = 500, 128
+    emb, W, b, labels = synth.head_inputs(B, D, C, seed=12, bf16_round=True)
+    m = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, embed_dim=D, centroids=centroids).to(DEV).train()
+    with torch.no_grad():
+        m.cell_layer.weight.copy_(W)
+        m.cell_layer.bias.copy_(b)
+    cell, km = m.labels_from_coords(labels.to(DEV))
+    idx, d = sgo.nearest_centroid(labels, centroids)
+    chosen = d.gather(1, cell.cpu()[:, None])[:, 0]
+    np.testing.assert_allclose(chosen.numpy(), d.min(-1)[0].numpy(), atol=2e-2)  # duplicate centroids tie
+    out = m(embedding=emb.to(DEV), labels=labels.to(DEV), labels_clf=cell)
+    # make the metrics non-trivial: targets taken from the predictions for a third of the rows
+    targets = cell.clone()
+    targets[::3] = out.top5_geocells.indices[::3, 0]
+    targets[1::3] = out.top5_geocells.indices[1::3, 3]
+    acc = m.accuracy(out.top5_geocells, targets)
+    top1 = (out.top5_geocells.indices[:, 0] == targets).float().mean().item()
+    topk = (out.top5_geocells.indices == targets.unsqueeze(1)).any(1).float().mean().item()
+    assert acc.shape == (2,) and acc.is_cuda
+    assert abs(acc[0].item() - top1) < 1e-6 and abs(acc[1].item() - topk) < 1e-6 and topk > top1 > 0.3
+
+
+def test_within_cluster_image_refinement(centroids):
+    """f-3, second half: after the nearest prototype per candidate, the nearest MEMBER IMAGE of that cluster gives the
+    coordinates (what the reference's _within_cluster_refinement, proto_refiner.py:239-269, is meant to do: as written
+    it cannot run and would take the farthest member).  Against the oracle's restatement of the corrected step."""
+    Cn, D, B, k = 600, 128, 80, 5
+    cent = centroids[:Cn]
+    sizes = synth.cell_sizes(Cn, 2400, seed=4, mode="skewed", missing_frac=0.05)
+    off, bank, xy = synth.proto_bank(sizes, D, cent, seed=4, dtype=torch.bfloat16, jitter_deg=0.3)
+    P = bank.shape[0]
+    rng = np.random.default_rng(6)
+    nimg = rng.integers(0, 6, P)  # 0 members: the prototype keeps its own coordinates (count == 0, :251-252)
+    moff = np.zeros(P + 1, dtype=np.int64)
+    np.cumsum(nimg, out=moff[1:])
+    L = int(moff[-1])
+    img = torch.from_numpy(rng.standard_normal((L, D)).astype(np.float32)).to(torch.bfloat16)
+    img_xy = torch.from_numpy(np.repeat(xy.numpy(), nimg, axis=0) + rng.uniform(-0.05, 0.05, (L, 2)).astype(np.float32))
+    emb = torch.from_numpy(rng.standard_normal((B, 4, D)).astype(np.float32))
+    emb = emb.mean(1).to(torch.bfloat16).float().unsqueeze(1).expand(B, 4, D).contiguous()
+    cand = torch.from_numpy(rng.integers(0, Cn, (B, k)).astype(np.int64))
+    probs = torch.from_numpy(-np.sort(-rng.dirichlet(np.ones(k) * 2, B).astype(np.float32), axis=1))
+    initial = cent[cand[:, 0]].clone()
+    r = gg.ProtoRefiner(topk=k, bank=(off, bank, xy), images=(torch.from_numpy(moff.astype(np.int32)), img, img_xy),
+                        device=DEV, report_changed=False)
+    _, llh, cells, guess, score, proto = r(emb.to(DEV), initial.to(DEV), cand.to(DEV), probs.to(DEV), return_debug=True)
+    protos, coords = synth.bank_as_lists(off, bank, xy)
+    o = off.tolist()
+    images = [None if protos[c] is None else [img[moff[p]:moff[p + 1]].float() for p in range(o[c], o[c + 1])] for c in range(Cn)]
+    images_xy = [None if protos[c] is None else [img_xy[moff[p]:moff[p + 1]] for p in range(o[c], o[c + 1])] for c in range(Cn)]
+    _, o_llh, o_cell, o_guess = pro.forward(emb, initial, cand, probs, protos, coords, topk=k, images=images,
+                                            image_coords=images_xy)
+    ref_score, ref_idx, second = pro.best_per_candidate(emb, cand, protos, k)
+    tie = ((ref_score - second) < 1e-3).any(-1)
+    same = cells.cpu() == o_cell
+    assert int((~same & ~tie).sum()) == 0
+    ok = same & ~tie
+    d = pro.haversine(llh.cpu()[ok].double(), o_llh[ok].double()) * 1000.0
+    assert ok.float().mean() > 0.9 and float(d.max()) <= 1.0
+    # and it differs from the prototype's own coordinates wherever the chosen cluster has images
+    r0 = gg.ProtoRefiner(topk=k, bank=(off, bank, xy), device=DEV, report_changed=False)
+    _, llh0, cells0 = r0(emb.to(DEV), initial.to(DEV), cand.to(DEV), probs.to(DEV))
+    assert (llh0 != llh).any()

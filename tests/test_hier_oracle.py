@@ -1,6 +1,6 @@
 """`hierarchical=True` heading fusion: the oracle against the reference module executed by
-oracle/make_golden_hier.py (tests/golden/hier_fusion.npz).  CPU only; the CUDA kernel for this row is not built
-yet (SuperGuessr(hierarchical=True) raises NotImplementedError), so this pins the checker it will be held to."""
+oracle/make_golden_hier.py (tests/golden/hier_fusion.npz).  CPU part: pins the checker; the CUDA path
+(gg_split3_bf16 / gg_linear_bf16 / gg_hier_attention) is held to the same golden in tests/test_extras_gpu.py."""
 import os
 
 import numpy as np
@@ -35,8 +35,16 @@ def test_batch_beyond_the_positional_table_fails_like_the_reference():
         hf.fuse(x, w, torch.zeros(3 * D), torch.zeros(D, D), torch.zeros(D))
 
 
-def test_product_path_still_refuses_hierarchical():
+def test_product_module_has_the_reference_submodules():
+    """Same sub-modules, hence the same state-dict keys as the reference's hierarchical model; training the branch is
+    refused (eval-mode path only), and there is no CPU path."""
     import geoguessr_ai_b200 as gg
 
-    with pytest.raises(NotImplementedError):
-        gg.SuperGuessr(None, panorama=True, hierarchical=True, embed_dim=64, centroids=torch.zeros(8, 2))
+    m = gg.SuperGuessr(None, panorama=True, hierarchical=True, embed_dim=64, centroids=torch.zeros(8, 2))
+    keys = set(m.state_dict().keys())
+    assert {"pos_encoder.pos_encoding", "self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+            "self_attn.out_proj.bias", "cell_layer.weight", "cell_layer.bias", "geocell_centroid_coords"} == keys
+    assert m.pos_encoder.pos_encoding.shape == (1000, 1, 64) and not m.pos_encoder.pos_encoding.requires_grad
+    assert torch.allclose(m.pos_encoder.pos_encoding.reshape(1000, 64), hf.positional_table(1000, 64), atol=1e-6)
+    with pytest.raises(Exception):
+        m.eval()(embedding=torch.zeros(2, 4, 64))

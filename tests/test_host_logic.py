@@ -28,8 +28,8 @@ def test_superguessr_contract(centroids, capsys):
     assert (m.num_cells, m.num_candidates, m.serving, m.hidden_size) == (12647, 5, False, 1024)
     with pytest.raises(AssertionError):
         m(pixel_values=None, embedding=None)
-    with pytest.raises(NotImplementedError):
-        gg.SuperGuessr(None, hierarchical=True, centroids=centroids)
+    h = gg.SuperGuessr(None, hierarchical=True, centroids=centroids[:16], embed_dim=64)  # reference sub-modules (:88-99)
+    assert isinstance(h.self_attn, torch.nn.MultiheadAttention) and h.self_attn.num_heads == 16
     assert gg.ModelOutput._fields == ("loss", "loss_clf", "preds_LLH", "preds_geocell", "top5_geocells", "embedding")
     v, i = gg.TopK(1, 2)
     assert (v, i) == (1, 2)

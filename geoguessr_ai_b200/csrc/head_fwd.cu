@@ -188,54 +188,12 @@ __device__ __forceinline__ void merge_list(float (&tv)[KTOP], int (&ti)[KTOP], c
 
 constexpr uint32_t kEpiBarrier = 1;  // named barrier of the 16 epilogue warps
 
-// Called by all epilogue warps of the CTA that flushed the last partial of row block (mb, crank).  Warp (quad, cg)
-// folds partials cg, cg + 4, ... of rows quad * 32 + lane; the four column-group warps of a quadrant are then
-// combined through shared memory in a fixed order (deterministic), and cg 0 writes the rows' results.
+// The four column-group warps of a TMEM lane quadrant hold states of the SAME 32 rows: fold them through shared
+// memory in a fixed order (3 <- and 2 <- into 1 and 0, then 1 <- into 0; deterministic); afterwards the warps with
+// cg == 0 hold the combined (max, sum-exp, top-k) of their rows.  Called by all 16 epilogue warps.
 template <int KTOP, bool HAS_CEIL, typename Smem>
-__device__ __forceinline__ void merge_block(Smem& sm, const float* __restrict__ pmax, const float* __restrict__ psum,
-                                            const float* __restrict__ ptopv, const int* __restrict__ ptopi,
-                                            const FwdSched& sc, int mb, int crank, int quad, int cg, int lane, int M,
-                                            const FwdOut& o) {
-  const int rit = quad * 32 + lane;
-  const int row = (2 * mb + crank) * kBM + rit;
-  const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
-  const int nparts = (c_hi - c_lo + 1) * kColGroups;
-
-  float lmax = -INFINITY, lsum = 0.f;
-  float tv[KTOP];
-  int ti[KTOP];
-#pragma unroll
-  for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-
-  // this warp's partials, the next one's loads in flight while the current one is merged (L2 loads: the
-  // partials were written by other SMs during this launch)
-  float m = -INFINITY, sum = 0.f, pv[KTOP];
-  int pi[KTOP];
-  auto load = [&](int i) {
-    const int c = c_lo + i / kColGroups;
-    const int run = mb - sc.start(c) / sc.num_n;
-    const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + (i % kColGroups);
-    if (!HAS_CEIL) {
-      m = __ldcg(pmax + p * kBM + rit);
-      sum = __ldcg(psum + p * kBM + rit);
-    }
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) {
-      pv[j] = __ldcg(ptopv + (p * KTOP + j) * kBM + rit);
-      pi[j] = __ldcg(ptopi + (p * KTOP + j) * kBM + rit);
-    }
-  };
-  if (cg < nparts) load(cg);
-  for (int i = cg; i < nparts; i += kColGroups) {  // warp-uniform
-    const float cm = m, cs = sum;
-    float cv[KTOP];
-    int ci[KTOP];
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) { cv[j] = pv[j]; ci[j] = pi[j]; }
-    if (i + kColGroups < nparts) load(i + kColGroups);
-    if (!HAS_CEIL) lse_merge(lmax, lsum, cm, cs);
-    merge_list<KTOP>(tv, ti, cv, ci);
-  }
+__device__ __forceinline__ void quadrant_tree(Smem& sm, int quad, int cg, int lane, float& lmax, float& lsum,
+                                              float (&tv)[KTOP], int (&ti)[KTOP]) {
   auto publish = [&](int slot) {
     float(*dst)[32] = sm.mrg[slot];
     dst[0][lane] = lmax;
@@ -261,9 +219,44 @@ __device__ __forceinline__ void merge_block(Smem& sm, const float* __restrict__ 
   named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
   if (cg == 1) publish(quad);
   named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
-  if (cg != 0) return;
-  absorb(quad);
-  if (row >= M) return;
+  if (cg == 0) absorb(quad);
+  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);  // the scratch is free again when anyone returns
+}
+
+// Called by all epilogue warps of the CTA that flushed the last partial of row block (mb, crank): one partial per
+// contributing CTA (each already folded over its column groups).  Warp (quad, cg) folds partials cg, cg + 4, ... of
+// rows quad * 32 + lane, the quadrant tree combines the four warps, and cg 0 writes the rows' results.
+template <int KTOP, bool HAS_CEIL, typename Smem>
+__device__ __forceinline__ void merge_block(Smem& sm, const float* __restrict__ pmax, const float* __restrict__ psum,
+                                            const float* __restrict__ ptopv, const int* __restrict__ ptopi,
+                                            const FwdSched& sc, int mb, int crank, int quad, int cg, int lane, int M,
+                                            const FwdOut& o) {
+  const int rit = quad * 32 + lane;
+  const int row = (2 * mb + crank) * kBM + rit;
+  const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
+  const int nparts = c_hi - c_lo + 1;
+
+  float lmax = -INFINITY, lsum = 0.f;
+  float tv[KTOP];
+  int ti[KTOP];
+#pragma unroll
+  for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+  for (int i = cg; i < nparts; i += kColGroups) {  // warp-uniform; L2 loads: written by other SMs during this launch
+    const int c = c_lo + i;
+    const int run = mb - sc.start(c) / sc.num_n;
+    const size_t p = static_cast<size_t>(2 * c + crank) * sc.runs + run;
+    float pv[KTOP];
+    int pi[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) {
+      pv[j] = __ldcg(ptopv + (p * KTOP + j) * kBM + rit);
+      pi[j] = __ldcg(ptopi + (p * KTOP + j) * kBM + rit);
+    }
+    if (!HAS_CEIL) lse_merge(lmax, lsum, __ldcg(pmax + p * kBM + rit), __ldcg(psum + p * kBM + rit));
+    merge_list<KTOP>(tv, ti, pv, pi);
+  }
+  quadrant_tree<KTOP, HAS_CEIL>(sm, quad, cg, lane, lmax, lsum, tv, ti);
+  if (cg != 0 || row >= M) return;
   float lse_row, inv = 1.f;
   if (!HAS_CEIL) {
     inv = 1.f / lsum;
@@ -532,17 +525,21 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
 
-      // end of this CTA's run over row block mb: flush the row state
+      // end of this CTA's run over row block mb: fold the four column-group warps of every quadrant (same rows)
+      // and flush ONE partial per row -- the final merge then reads a handful of partials per row, not dozens
       if (nb == sc.num_n - 1 || t == t_end - 1) {
-        const size_t p = (static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first)) * kColGroups + cg;
-        if (!HAS_CEIL) {
-          __stcg(&pmax[p * kBM + row_in_tile], run_max);
-          __stcg(&psum[p * kBM + row_in_tile], run_sum);
-        }
+        quadrant_tree<KTOP, HAS_CEIL>(sm, quad, cg, lane, run_max, run_sum, tv, ti);
+        if (cg == 0) {
+          const size_t p = static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first);
+          if (!HAS_CEIL) {
+            __stcg(&pmax[p * kBM + row_in_tile], run_max);
+            __stcg(&psum[p * kBM + row_in_tile], run_sum);
+          }
 #pragma unroll
-        for (int j = 0; j < KTOP; ++j) {
-          __stcg(&ptopv[(p * KTOP + j) * kBM + row_in_tile], tv[j]);
-          __stcg(&ptopi[(p * KTOP + j) * kBM + row_in_tile], ti[j]);
+          for (int j = 0; j < KTOP; ++j) {
+            __stcg(&ptopv[(p * KTOP + j) * kBM + row_in_tile], tv[j]);
+            __stcg(&ptopi[(p * KTOP + j) * kBM + row_in_tile], ti[j]);
+          }
         }
         run_max = -INFINITY;
         run_sum = 0.f;
@@ -588,7 +585,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 template <bool WRITE_LOGITS>
 static size_t fwd_smem_bytes() { return sizeof(FwdSmem<WRITE_LOGITS>) + 1024; }
 
-static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(2 * sc.grid) * sc.runs * kColGroups; }
+static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(2 * sc.grid) * sc.runs; }
 
 template <typename Kern, typename... Args>
 static cudaError_t launch_pairs(Kern kern, int pairs, size_t smem, cudaStream_t stream, Args... args) {

@@ -54,79 +54,93 @@ __global__ void proto_count_kernel(const long long* __restrict__ cand, int cand_
   if (mine) atomicAdd(&cnt[c - cell_lo], 1);
 }
 
+// Block-wide exclusive scan of one int per thread (1024 threads): warp shuffles + one pass over the 32 warp totals.
+// Returns the exclusive prefix of `v`; *total receives the block sum.  `red` = 33 ints of shared scratch.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* red, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // (scratch reuse between calls)
+  if (lane == 31) red[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = red[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    red[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  const int base = warp > 0 ? red[warp - 1] : 0;
+  *total = red[31];
+  return base + inc - v;
+}
+
 // Single CTA.  Pass 1: exclusive scan of the pair counts over the owned cells -> pair_off (ncell+1).  Pass 2: scan
 // over the groups -> work list (group, chunk) for every group that has both pairs and prototypes.
 // meta = {work items, pairs, accumulation units (work items x 256-prototype blocks of the group), 0}.
-__global__ void proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off, int ncell,
-                                  const int* __restrict__ group_off, int ngroups, int* __restrict__ pair_off,
-                                  int* __restrict__ cursor, int* __restrict__ work_group, int* __restrict__ work_chunk,
-                                  int* __restrict__ meta) {
-  __shared__ int s_a[1024], s_b[1024];
+__global__ void __launch_bounds__(1024)
+proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off, int ncell,
+                  const int* __restrict__ group_off, int ngroups, int* __restrict__ pair_off,
+                  int* __restrict__ cursor, int* __restrict__ work_group, int* __restrict__ work_chunk,
+                  int* __restrict__ meta) {
+  __shared__ int red[33];
   const int tid = threadIdx.x;
   {
     const int per = (ncell + 1023) / 1024;
     const int c0 = min(ncell, tid * per), c1 = min(ncell, c0 + per);
     int np = 0;
-    for (int c = c0; c < c1; ++c) np += cnt[c];
-    s_a[tid] = np;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-      const int a = tid >= o ? s_a[tid - o] : 0;
-      __syncthreads();
-      s_a[tid] += a;
-      __syncthreads();
-    }
-    int pbase = s_a[tid] - np;
+    for (int c = c0; c < c1; ++c) np += __ldg(cnt + c);
+    int total;
+    int pbase = block_exclusive_scan(np, red, &total);
     for (int c = c0; c < c1; ++c) {
       pair_off[c] = pbase;
       cursor[c] = 0;
-      pbase += cnt[c];
+      pbase += __ldg(cnt + c);
     }
-    if (tid == 1023) {
-      pair_off[ncell] = s_a[1023];
-      meta[1] = s_a[1023];
+    if (tid == 0) {
+      pair_off[ncell] = total;
+      meta[1] = total;
     }
     __syncthreads();  // pair_off complete (block-scope visibility of the global writes)
   }
   const int per = (ngroups + 1023) / 1024;
   const int g0 = min(ngroups, tid * per), g1 = min(ngroups, g0 + per);
+  auto group_chunks = [&](int g, int& units) {
+    const int c0 = __ldg(group_off + g), c1 = __ldg(group_off + g + 1);
+    const int n = pair_off[c1] - pair_off[c0], np = __ldg(cell_off + c1) - __ldg(cell_off + c0);
+    if (n <= 0 || np <= 0) { units = 0; return 0; }
+    const int chunks = (n + kPM - 1) / kPM;
+    units = chunks * ((np + kPN - 1) / kPN);
+    return chunks;
+  };
   int nt = 0, nu = 0;
   for (int g = g0; g < g1; ++g) {
-    const int c0 = group_off[g], c1 = group_off[g + 1];
-    const int n = pair_off[c1] - pair_off[c0], np = cell_off[c1] - cell_off[c0];
-    if (n > 0 && np > 0) {
-      const int chunks = (n + kPM - 1) / kPM;
-      nt += chunks;
-      nu += chunks * ((np + kPN - 1) / kPN);
-    }
+    int u;
+    nt += group_chunks(g, u);
+    nu += u;
   }
-  s_a[tid] = nt;
-  s_b[tid] = nu;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    int a = 0, b = 0;
-    if (tid >= o) { a = s_a[tid - o]; b = s_b[tid - o]; }
-    __syncthreads();
-    s_a[tid] += a;
-    s_b[tid] += b;
-    __syncthreads();
-  }
-  int tbase = s_a[tid] - nt;
+  int total_t, total_u;
+  int tbase = block_exclusive_scan(nt, red, &total_t);
+  block_exclusive_scan(nu, red, &total_u);
   for (int g = g0; g < g1; ++g) {
-    const int c0 = group_off[g], c1 = group_off[g + 1];
-    const int n = pair_off[c1] - pair_off[c0], np = cell_off[c1] - cell_off[c0];
-    if (n > 0 && np > 0) {
-      const int chunks = (n + kPM - 1) / kPM;
-      for (int m = 0; m < chunks; ++m) {
-        work_group[tbase + m] = g;
-        work_chunk[tbase + m] = m;
-      }
-      tbase += chunks;
+    int u;
+    const int chunks = group_chunks(g, u);
+    for (int m = 0; m < chunks; ++m) {
+      work_group[tbase + m] = g;
+      work_chunk[tbase + m] = m;
     }
+    tbase += chunks;
   }
-  if (tid == 1023) {
-    meta[0] = s_a[1023];
-    meta[2] = s_b[1023];
+  if (tid == 0) {
+    meta[0] = total_t;
+    meta[2] = total_u;
     meta[3] = 0;
   }
 }
@@ -234,8 +248,15 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: 
       const int a_row0 = pair_off[c0] + work_chunk[w] * kPM;
       const int a_last = pair_off[c1] - 1;  // last slot of the group: rows past it repeat this one (results unused)
       const int p0 = cell_off[c0], p1 = cell_off[c1];
+      // Only the rows that hold pairs are loaded (32-row granules; a work item of the 1 M bank holds ~65 pairs, of
+      // the 10 M bank ~26): the MMA still spans 128 rows, the rest of the tile keeps stale shared memory whose
+      // accumulator rows nobody reads.
+      const int nq = min(kPM, pair_off[c1] - a_row0);
+      const int granules = (nq + 31) >> 5;
+      const uint32_t a_bytes = static_cast<uint32_t>(granules) * (32 * kPK * 2);
       int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-      if (GATHER4) {
+      const bool my_rows = GATHER4 && 4 * lane < 32 * granules;
+      if (my_rows) {
         r0 = __ldg(slot_q + min(a_row0 + 4 * lane + 0, a_last));
         r1 = __ldg(slot_q + min(a_row0 + 4 * lane + 1, a_last));
         r2 = __ldg(slot_q + min(a_row0 + 4 * lane + 2, a_last));
@@ -245,13 +266,16 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: 
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&sm.empty[s], ph ^ 1);
           if (lane == 0) {
-            mbar_arrive_expect_tx(&sm.full[s], kPStageA + kPStageB);
+            mbar_arrive_expect_tx(&sm.full[s], a_bytes + kPStageB);
             tma_load_2d_hint(sm.b[s], &tm_bank, &sm.full[s], kb * kPK, n0, kPolicyEvictFirst);
-            if (!GATHER4) tma_load_2d(sm.a[s], &tm_q, &sm.full[s], kb * kPK, a_row0);
+            if (!GATHER4) {
+              for (int gq = 0; gq < granules; ++gq)
+                tma_load_2d(sm.a[s] + gq * (32 * kPK * 2), &tm_q, &sm.full[s], kb * kPK, a_row0 + 32 * gq);
+            }
           }
           if (GATHER4) {
             __syncwarp();  // the barrier is armed before any lane's bytes can land
-            tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
+            if (my_rows) tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
           }
           if (++s == kPStages) { s = 0; ph ^= 1; }
         }
@@ -586,7 +610,7 @@ extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int 
     proto_gather_kernel<<<static_cast<int>(ceil_div_ll(npair, 8)), 256, 0, s>>>(static_cast<const bf16*>(q_bf16), w.slot_q,
                                                                              w.meta, D, w.qs);
     GG_LAUNCH_CHECK();
-    rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, kPM);
+    rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, 32);
   }
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPN);

@@ -129,6 +129,7 @@ class ProtoRefiner(nn.Module):
                 "proto_refiner.py:89-103).  With stored embeddings that job is "
                 "geoguessr_ai_b200.proto_builder.build_prototype_bank(embeddings, proto_df, num_cells) -> pass its "
                 "result as bank=(cell_off, bank, coords); or pass protos='load' / protos=[...]+coords=[...].")
+        self.has_images = False
         self._install_bank(cell_off, mat, xy, shard, device, bank_is_local)
         self._install_images(images, device)
 
@@ -207,6 +208,10 @@ class ProtoRefiner(nn.Module):
         self.register_buffer("cell_off", local_off.to(dev), persistent=False)
         groups = ops.proto_group_cells(local_off.numpy())
         self.num_groups = len(groups) - 1
+        # Query rows: gathered by the TMA engine four at a time (tile::gather4, no cell-ordered copy in HBM) when a
+        # work item meets its rows once -- groups of <= 256 prototypes; measured at ~45 ns per gather4 on B200, it
+        # loses to one pre-gathered copy when big cells re-read the rows for every 256-prototype unit.
+        self.gather4 = self._gather4_default and (p1 - p0) <= 256 * max(self.num_groups, 1)
         self.register_buffer("group_off", torch.from_numpy(groups).to(dev), persistent=False)
         # ||p||^2 needs the CUDA library: computed now on a CUDA device, else on the first forward after .to("cuda")
         self.register_buffer("bank_sqnorm", torch.empty(0, dtype=torch.float32, device=dev), persistent=False)
@@ -217,8 +222,7 @@ class ProtoRefiner(nn.Module):
 
     def _install_images(self, images, device):
         """Second-stage bank: member images sorted by prototype; this rank keeps those of its own prototypes."""
-        self.has_images = images is not None
-        if not self.has_images:
+        if images is None:
             return
         member_off, img, img_xy = images
         moff = torch.as_tensor(member_off).to(torch.int64).cpu().numpy()
@@ -237,6 +241,7 @@ class ProtoRefiner(nn.Module):
             img16 = torch.cat([hi, (img.float() - hi.float()).to(torch.bfloat16), hi], 1).to(dev).contiguous()
         else:
             img16 = img.to(device=dev, dtype=torch.bfloat16).contiguous()
+        self.has_images = True
         self.register_buffer("img_bank", img16, persistent=False)
         self.register_buffer("img_coords", torch.as_tensor(img_xy, dtype=torch.float32)[i0:i1].to(dev).contiguous(),
                              persistent=False)
@@ -244,6 +249,8 @@ class ProtoRefiner(nn.Module):
         self.register_buffer("img_group_off", torch.from_numpy(ops.proto_group_cells(local.numpy())).to(dev), persistent=False)
         self.register_buffer("img_sqnorm", torch.empty(0, dtype=torch.float32, device=dev), persistent=False)
         self._img_sqnorm_for = None
+        if dev.type == "cuda":
+            self._ensure_sqnorm()
 
     def _ensure_sqnorm(self):
         """``bank_sqnorm`` of the bank where it lives NOW (the reference idiom is ``ProtoRefiner(...).to(device)``,
@@ -295,7 +302,7 @@ class ProtoRefiner(nn.Module):
             ops.proto_take_image_coords(rec, rec_img)
         return rec
 
-    gather4 = os.environ.get("GG_RETRIEVE_GATHER4", "1") != "0"  # query rows gathered by the TMA engine (tile::gather4)
+    _gather4_default = os.environ.get("GG_RETRIEVE_GATHER4", "1") != "0"
 
     def last_retrieve_stats(self):
         """Work of the last retrieval on this rank (reads 16 bytes back: synchronises): work items, accumulation
@@ -310,9 +317,11 @@ class ProtoRefiner(nn.Module):
         mine = (c >= 0) & (c < sizes.numel())
         algo_flop = 2.0 * K * float(sizes[c.clamp(0, max(sizes.numel() - 1, 0))][mine].sum().item()) if sizes.numel() else 0.0
         row = K * 2
-        executed = units * (256 + 128) * row + pairs * 16 + nq * self.topk * 16
+        # bank boxes of 256 rows per unit + the pairs' rows in 32-row granules per unit + records
+        a_rows = (pairs + 16 * items) * (units / max(items, 1))
+        executed = units * 256 * row + a_rows * row + pairs * 16 + nq * self.topk * 16
         if not self.gather4:
-            executed += 2 * pairs * row
+            executed += 2 * pairs * row  # the cell-ordered copy: read + write
         return dict(work_items=items, pairs=pairs, units=units, executed_bytes=float(executed),
                     executed_flop=float(units) * 2 * 128 * 256 * K,
                     algorithmic_flop=algo_flop, query_rows=nq)

@@ -171,3 +171,63 @@ def test_within_cluster_image_refinement(centroids):
     r0 = gg.ProtoRefiner(topk=k, bank=(off, bank, xy), device=DEV, report_changed=False)
     _, llh0, cells0 = r0(emb.to(DEV), initial.to(DEV), cand.to(DEV), probs.to(DEV))
     assert (llh0 != llh).any()
+
+
+def test_reference_inference_handoff_with_swapped_classes(centroids):
+    """The call sequence of the reference's inference.py:119-186 (the live import sites are
+    `from models.super_guessr import SuperGuessr` / `from models.proto_refiner import ProtoRefiner`, inference.py:13,15)
+    with the two classes swapped: backbone -> SuperGuessr(serving) -> checkpoint filtered by name and shape ->
+    eval forward with a dummy labels_clf -> ProtoRefiner(...).to(device) -> refined (lon, lat); against the oracle."""
+    import types
+
+    device = torch.device(DEV)
+    D, Cn = 64, 12647
+
+    class Backbone(torch.nn.Module):  # stands in for CLIPVisionModel / TinyViTAdapter: .config + .pooler_output
+        def __init__(self):
+            super().__init__()
+            self.config = types.SimpleNamespace(hidden_size=D, _name_or_path="stub-encoder")
+            self.proj = torch.nn.Linear(3 * 8 * 8, D)
+
+        def forward(self, pixel_values):
+            return types.SimpleNamespace(pooler_output=self.proj(pixel_values.flatten(1)))
+
+    torch.manual_seed(3)
+    backbone_model = Backbone().to(device)
+    model = gg.SuperGuessr(base_model=backbone_model, panorama=True, serving=True, should_smooth_labels=False,
+                           centroids=centroids).to(device)
+    assert model.hidden_size == D and all(p.requires_grad for p in backbone_model.parameters())
+    # a checkpoint in the training format, with one foreign and one mis-shaped entry (inference.py:126-156)
+    W = torch.randn(Cn, D) * 0.1
+    state_dict = {"model_state_dict": {"cell_layer.weight": W, "cell_layer.bias": torch.zeros(Cn),
+                                       "cell_layer.extra": torch.zeros(3), "geocell_centroid_coords": torch.zeros(5, 2)}}
+    raw = state_dict.get("model_state_dict", state_dict)
+    model_state = model.state_dict()
+    filtered = {n: p for n, p in raw.items() if n in model_state and model_state[n].shape == p.shape}
+    assert sorted(filtered) == ["cell_layer.bias", "cell_layer.weight"]
+    model.load_state_dict(filtered, strict=False)
+    model.eval()
+    pixel_values = torch.randn(1, 4, 3, 8, 8, device=device)
+    with torch.no_grad():
+        dummy_labels = torch.zeros(1, dtype=torch.long, device=device)
+        pred_llh, topk, embedding = model(pixel_values=pixel_values, labels_clf=dummy_labels)
+    top_indices = topk.indices[0].detach().cpu().tolist()
+    top_probs = topk.values[0].detach().cpu().tolist()
+    assert len(top_indices) == 5 and abs(sum(top_probs)) <= 1.0 and embedding.shape == (1, 4, D)
+
+    sizes = synth.cell_sizes(Cn, 3 * Cn, seed=1, mode="skewed")
+    off, bank, xy = synth.proto_bank(sizes, D, centroids, seed=1, dtype=torch.bfloat16, jitter_deg=0.5)
+    protos, coords = synth.bank_as_lists(off, bank, xy)
+    refiner = gg.ProtoRefiner(topk=topk.indices.size(1), protos=protos, coords=coords, device="cpu").to(device)
+    refiner.eval()
+    with torch.no_grad():
+        _, refined_llh, _ = refiner(embedding=embedding, initial_preds=pred_llh, candidate_cells=topk.indices,
+                                    candidate_probs=topk.values)
+    lon, lat = refined_llh[0].tolist()
+    # oracle on the same numbers (the head in fp32 on the bf16-rounded operands the kernel saw)
+    x = embedding.detach().cpu().mean(1).to(torch.bfloat16).float()
+    logits = torch.nn.functional.linear(x, W.to(torch.bfloat16).float())
+    ref_top = torch.topk(torch.softmax(logits, -1), 5)
+    assert ref_top.indices[0].tolist() == top_indices
+    _, o_llh, _, _ = pro.forward(x.unsqueeze(1), pred_llh.cpu(), topk.indices.cpu(), topk.values.cpu(), protos, coords, topk=5)
+    assert abs(o_llh[0, 0].item() - lon) < 1e-5 and abs(o_llh[0, 1].item() - lat) < 1e-5

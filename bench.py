@@ -489,10 +489,14 @@ def run_b200_train(args, ctx):
             torch.cuda.synchronize()
             return 2.0 * B * C_CELLS * D / (c0.elapsed_time(c1) / 20 * 1e-3) / 1e12
 
-        context = {"cublas_bf16_same_shape_tflops": {"x W^T (4096x1024 . 1024x12647)": cublas_tflops(lambda: xa @ wa.t()),
-                                                      "dlogits^T x (12647x4096 . 4096x1024)": cublas_tflops(lambda: ga.t() @ xa)},
-                   "note": "torch.matmul (cuBLAS) on the head GEMMs' own shapes, 20 back-to-back launches; context for "
-                           "roofline.frac, whose denominator is cuBLAS at 8192^3"}
+        wp = torch.randn((ops.logits_ld(C_CELLS), D), device=dev).to(torch.bfloat16)
+        context = {"cublas_bf16_same_shape_tflops": {
+            "x W^T as nn.Linear calls it (4096x1024 . 1024x12647, N = 12647 is odd)": cublas_tflops(lambda: xa @ wa.t()),
+            "x W^T with the geocells padded to 12800": cublas_tflops(lambda: xa @ wp.t()),
+            "dlogits^T x (12647x4096 . 4096x1024)": cublas_tflops(lambda: ga.t() @ xa)},
+                   "note": "torch.matmul (cuBLAS) on the head GEMMs' own shapes, 20 back-to-back launches, FLOPs counted "
+                           "for the 12647 real geocells; context for roofline.frac, whose denominator is cuBLAS at 8192^3"}
+        del wp
         del xa, wa, ga
 
     grad_comm = None

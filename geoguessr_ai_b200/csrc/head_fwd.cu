@@ -31,6 +31,7 @@
 // Layout: x (M=B, K=D) bf16 row-major; W (N=C, K=D) bf16 row-major (both K-major operands, 128 B
 // swizzled TMA boxes of 64 K-elements); logits (B, ldc) bf16, ldc >= C padded to a multiple of 64.
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -63,7 +64,6 @@ struct FwdSmem {
   // per epilogue warp: 32 rows x 32 bf16 logits (one 32-column chunk), 64-byte swizzled (TMA store box)
   uint8_t out[WRITE_LOGITS ? kEpiWarps : 1][32 * 64];
   int thr[kThrSlots][kBM];           // per row: best known lower bound of the run's k-th largest logit (ordered key)
-  float mrg[8][2 + 2 * 8][32];       // merge tree scratch: 8 publishing warps x (max, sum, 8 values, 8 indices) x lane
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t acc_full[2];
@@ -74,24 +74,86 @@ struct FwdSmem {
 
 // Static schedule shared by the kernel, its merge step and the host.  Units are CTA PAIRS and
 // pair-tiles: num_m = 256-row blocks, grid = number of pairs (clusters); CTA 2c + r of pair c works on
-// row block 2 * mb + r.
+// row block 2 * mb + r.  Pair c owns the contiguous tiles [first[c], first[c + 1]).
+//
+// The ranges are balanced by COST, not by tile count: the first tiles of a run over a new row block are slow in
+// the epilogue (the row's top-k starts empty, so whole chunks go through the insertion path until the thresholds
+// have risen; measured with tools/head_fwd_timeline.py: a pair whose range crosses a row-block boundary finishes
+// 8-10 us = ~1.4 tiles later than its neighbours), and the slowest pair ends the kernel.
+constexpr int kMaxPairs = 96;
+constexpr float kRunPenaltyTiles = 1.4f;  // extra cost of every run after a pair's first, in tiles
 struct FwdSched {
-  int num_m, num_n, tiles, grid, base, rem, runs;  // runs = max row blocks a pair can touch
-  __host__ __device__ int start(int c) const { return c * base + (c < rem ? c : rem); }
-  __host__ __device__ int owner(int t) const {
-    const int cut = rem * (base + 1);
-    return t < cut ? t / (base + 1) : rem + (t - cut) / base;
+  int num_m, num_n, tiles, grid, runs;  // runs = max row blocks a pair can touch
+  int first[kMaxPairs + 1];
+  __host__ __device__ int start(int c) const { return first[c]; }
+  __host__ __device__ int owner(int t) const {  // (cold paths only)
+    int lo = 0, hi = grid - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (first[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
   }
 };
+static FwdSched make_sched_uncached(int M, int N, int sms);
+// (the bisection walks the tile list a few dozen times: memoised, the launch path must stay cheap)
 static FwdSched make_sched(int M, int N, int sms) {
+  struct Entry { int M, N, sms; FwdSched s; };
+  static Entry cache[8];
+  static int used = 0, next = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].M == M && cache[i].N == N && cache[i].sms == sms) return cache[i].s;
+  Entry& e = cache[next];
+  next = (next + 1) % 8;
+  if (used < 8) ++used;
+  e.M = M; e.N = N; e.sms = sms;
+  e.s = make_sched_uncached(M, N, sms);
+  return e.s;
+}
+static FwdSched make_sched_uncached(int M, int N, int sms) {
   FwdSched s;
   s.num_m = ceil_div(M, 2 * kBM);
   s.num_n = ceil_div(N, kBN);
   s.tiles = s.num_m * s.num_n;
-  s.grid = std::max(1, std::min(s.tiles, sms / 2));
-  s.base = s.tiles / s.grid;
-  s.rem = s.tiles % s.grid;
-  s.runs = ceil_div(s.base + 1, s.num_n) + 1;
+  s.grid = std::max(1, std::min(std::min(s.tiles, sms / 2), kMaxPairs));
+  // greedy fill with a cost limit T; the smallest T that needs <= grid pairs (bisection)
+  auto fill = [&](float T, int* first) {
+    int c = 0, t = 0;
+    while (t < s.tiles) {
+      if (first) first[c] = t;
+      float cost = 0.f;
+      int n = 0;
+      while (t < s.tiles) {
+        const float add = 1.0f + ((n > 0 && t % s.num_n == 0) ? kRunPenaltyTiles : 0.f);
+        if (n > 0 && cost + add > T) break;
+        cost += add;
+        ++t;
+        ++n;
+      }
+      ++c;
+      if (c > s.grid && !first) return c;
+      if (c >= s.grid && t < s.tiles && first) {  // (cannot happen for a feasible T; keep the table consistent)
+        t = s.tiles;
+      }
+    }
+    if (first) {
+      for (int i = c; i <= s.grid; ++i) first[i] = s.tiles;
+    }
+    return c;
+  };
+  float lo = static_cast<float>(s.tiles) / s.grid, hi = static_cast<float>(s.tiles) * (1.0f + kRunPenaltyTiles) + 1.0f;
+  for (int it = 0; it < 40; ++it) {
+    const float mid = 0.5f * (lo + hi);
+    if (fill(mid, nullptr) <= s.grid) hi = mid; else lo = mid;
+  }
+  fill(hi, s.first);
+  s.runs = 1;
+  for (int c = 0; c < s.grid; ++c) {
+    if (s.first[c + 1] > s.first[c])
+      s.runs = std::max(s.runs, (s.first[c + 1] - 1) / s.num_n - s.first[c] / s.num_n + 1);
+  }
   return s;
 }
 
@@ -173,90 +235,120 @@ __device__ __forceinline__ void lse_merge(float& lmax, float& lsum, float m, flo
     else lsum += s * expf(m - lmax);
   }
 }
-// merge a descending list (pv, pi) into (tv, ti); stops at the first element that cannot enter
-template <int KTOP>
-__device__ __forceinline__ void merge_list(float (&tv)[KTOP], int (&ti)[KTOP], const float (&pv)[KTOP],
-                                           const int (&pi)[KTOP]) {
-#pragma unroll
-  for (int j = 0; j < KTOP; ++j) {
-    // lists are sorted: once the warp's lanes are all done with this list, skip the rest (warp-uniform exit)
-    const bool enters = pv[j] > tv[KTOP - 1] || (pv[j] == tv[KTOP - 1] && pv[j] > -INFINITY && pi[j] < ti[KTOP - 1]);
-    if (!__any_sync(0xffffffffu, enters)) break;
-    merge_insert<KTOP>(tv, ti, pv[j], pi[j]);
-  }
-}
-
 constexpr uint32_t kEpiBarrier = 1;  // named barrier of the 16 epilogue warps
 
-// The four column-group warps of a TMEM lane quadrant hold states of the SAME 32 rows: fold them through shared
-// memory in a fixed order (3 <- and 2 <- into 1 and 0, then 1 <- into 0; deterministic); afterwards the warps with
-// cg == 0 hold the combined (max, sum-exp, top-k) of their rows.  Called by all 16 epilogue warps.
-template <int KTOP, bool HAS_CEIL, typename Smem>
-__device__ __forceinline__ void quadrant_tree(Smem& sm, int quad, int cg, int lane, float& lmax, float& lsum,
-                                              float (&tv)[KTOP], int (&ti)[KTOP]) {
-  auto publish = [&](int slot) {
-    float(*dst)[32] = sm.mrg[slot];
-    dst[0][lane] = lmax;
-    dst[1][lane] = lsum;
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) {
-      dst[2 + j][lane] = tv[j];
-      dst[2 + 8 + j][lane] = __int_as_float(ti[j]);
-    }
-  };
-  auto absorb = [&](int slot) {
-    float(*src)[32] = sm.mrg[slot];
-    if (!HAS_CEIL) lse_merge(lmax, lsum, src[0][lane], src[1][lane]);
-    float cv[KTOP];
-    int ci[KTOP];
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) { cv[j] = src[2 + j][lane]; ci[j] = __float_as_int(src[2 + 8 + j][lane]); }
-    merge_list<KTOP>(tv, ti, cv, ci);
-  };
-  if (cg >= 2) publish((cg - 2) * 4 + quad);
-  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
-  if (cg < 2) absorb(cg * 4 + quad);  // 0 <- 2, 1 <- 3
-  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
-  if (cg == 1) publish(quad);
-  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
-  if (cg == 0) absorb(quad);
-  named_bar_sync(kEpiBarrier, 32 * kEpiWarps);  // the scratch is free again when anyone returns
+// Optional per-CTA timeline (tools/head_fwd_timeline.py): 16 globaltimer stamps per CTA when a buffer is set.
+__device__ __forceinline__ void stamp(long long* tl, int slot) {
+  if (tl != nullptr) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[static_cast<size_t>(blockIdx.x) * 16 + slot] = t;
+  }
 }
 
-// Called by all epilogue warps of the CTA that flushed the last partial of row block (mb, crank): one partial per
-// contributing CTA (each already folded over its column groups).  Warp (quad, cg) folds partials cg, cg + 4, ... of
-// rows quad * 32 + lane, the quadrant tree combines the four warps, and cg 0 writes the rows' results.
-template <int KTOP, bool HAS_CEIL, typename Smem>
-__device__ __forceinline__ void merge_block(Smem& sm, const float* __restrict__ pmax, const float* __restrict__ psum,
-                                            const float* __restrict__ ptopv, const int* __restrict__ ptopi,
-                                            const FwdSched& sc, int mb, int crank, int quad, int cg, int lane, int M,
-                                            const FwdOut& o) {
-  const int rit = quad * 32 + lane;
+// ---- branch-free merging of sorted top-k lists (the final merge of a row block) ------------------------------
+// The merge runs on 512 threads for 128 rows x ~24 lists: with insertion code every list costs ~200 divergent
+// instructions (any lane inserting stalls the warp) and the merge took 10-17 us at the very end of the kernel
+// (tools/head_fwd_timeline.py).  Here a candidate is one 64-bit key -- ordered logit bits above, inverted geocell
+// index below, so that a plain unsigned compare orders by value and breaks ties towards the LOWER index -- and
+// merging two descending lists is max(A[i], B[K-1-i]) (exactly the K largest of the union) followed by a fixed
+// sorting network: ~100 straight-line instructions per list, no divergence.
+typedef unsigned long long key_t64;
+__device__ __forceinline__ key_t64 make_key(float v, int idx) {
+  return (static_cast<key_t64>(static_cast<uint32_t>(ordered_key(v)) ^ 0x80000000u) << 32) | static_cast<uint32_t>(~idx);
+}
+__device__ __forceinline__ float key_value(key_t64 k) { return key_to_float(static_cast<int>(static_cast<uint32_t>(k >> 32) ^ 0x80000000u)); }
+__device__ __forceinline__ int key_index(key_t64 k) { return static_cast<int>(~static_cast<uint32_t>(k)); }
+__device__ __forceinline__ void key_cx(key_t64& hi, key_t64& lo) {  // compare-exchange: hi >= lo afterwards
+  const key_t64 a = hi, b = lo;
+  const bool sw = a < b;
+  hi = sw ? b : a;
+  lo = sw ? a : b;
+}
+template <int K> __device__ __forceinline__ void sort_keys_desc(key_t64 (&c)[K]);
+template <> __device__ __forceinline__ void sort_keys_desc<5>(key_t64 (&c)[5]) {  // optimal 9-comparator network
+  key_cx(c[0], c[1]); key_cx(c[3], c[4]); key_cx(c[2], c[4]); key_cx(c[2], c[3]); key_cx(c[1], c[4]);
+  key_cx(c[0], c[3]); key_cx(c[0], c[2]); key_cx(c[1], c[3]); key_cx(c[1], c[2]);
+}
+template <> __device__ __forceinline__ void sort_keys_desc<8>(key_t64 (&c)[8]) {  // bitonic merge (the input is bitonic)
+#pragma unroll
+  for (int d = 4; d >= 1; d >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((i & d) == 0) key_cx(c[i], c[i + d]);
+  }
+}
+// a <- the K largest of a U b, descending (both inputs descending)
+template <int K>
+__device__ __forceinline__ void merge_keys(key_t64 (&a)[K], const key_t64 (&b)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) a[i] = a[i] > b[K - 1 - i] ? a[i] : b[K - 1 - i];
+  sort_keys_desc<K>(a);
+}
+
+// (max, sum-exp) pairs combined with the hardware exponential (2 ulp: far below the bf16 logits' own rounding)
+__device__ __forceinline__ void lse_merge_fast(float& lmax, float& lsum, float m, float s) {
+  const float nm = fmaxf(lmax, m);
+  const float a = nm > -INFINITY ? ex2_approx((lmax - nm) * kLog2e) : 0.f;
+  const float b = nm > -INFINITY ? ex2_approx((m - nm) * kLog2e) : 0.f;
+  lsum = lsum * a + s * b;
+  lmax = nm;
+}
+
+// Called by all 512 epilogue threads of the CTA that flushed the last partial of row block (mb, crank).  Four
+// threads share a row: thread `sub` folds the partials of column group `sub` of every contributing CTA -- the next
+// contributor's loads are in flight while the current one is merged -- then two shuffle rounds combine the four
+// threads (no shared memory, no barrier) and sub 0 writes the row's results.  Fixed order: deterministic.
+template <int KTOP, bool HAS_CEIL>
+__device__ __forceinline__ void merge_block(const float* __restrict__ pmax, const float* __restrict__ psum,
+                                            const key_t64* __restrict__ pkeys, const FwdSched& sc, int mb, int crank,
+                                            int M, const FwdOut& o, long long* timeline) {
+  const int te = static_cast<int>(threadIdx.x) - 64;  // 0..511
+  const int rit = te >> 2, sub = te & 3;
   const int row = (2 * mb + crank) * kBM + rit;
   const int c_lo = sc.owner(mb * sc.num_n), c_hi = sc.owner((mb + 1) * sc.num_n - 1);
-  const int nparts = c_hi - c_lo + 1;
 
   float lmax = -INFINITY, lsum = 0.f;
-  float tv[KTOP];
-  int ti[KTOP];
+  key_t64 best[KTOP];
 #pragma unroll
-  for (int j = 0; j < KTOP; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  for (int i = cg; i < nparts; i += kColGroups) {  // warp-uniform; L2 loads: written by other SMs during this launch
-    const int c = c_lo + i;
+  for (int j = 0; j < KTOP; ++j) best[j] = make_key(-INFINITY, 0x7fffffff);
+
+  float m = -INFINITY, s = 0.f;
+  key_t64 nxt[KTOP];
+  auto load = [&](int c) {  // L2 loads: the partials were written by other SMs during this launch
     const int run = mb - sc.start(c) / sc.num_n;
-    const size_t p = static_cast<size_t>(2 * c + crank) * sc.runs + run;
-    float pv[KTOP];
-    int pi[KTOP];
-#pragma unroll
-    for (int j = 0; j < KTOP; ++j) {
-      pv[j] = __ldcg(ptopv + (p * KTOP + j) * kBM + rit);
-      pi[j] = __ldcg(ptopi + (p * KTOP + j) * kBM + rit);
+    const size_t p = (static_cast<size_t>(2 * c + crank) * sc.runs + run) * kColGroups + sub;
+    if (!HAS_CEIL) {
+      m = __ldcg(pmax + p * kBM + rit);
+      s = __ldcg(psum + p * kBM + rit);
     }
-    if (!HAS_CEIL) lse_merge(lmax, lsum, __ldcg(pmax + p * kBM + rit), __ldcg(psum + p * kBM + rit));
-    merge_list<KTOP>(tv, ti, pv, pi);
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) nxt[j] = __ldcg(pkeys + (p * KTOP + j) * kBM + rit);
+  };
+  if (te == 0) stamp(timeline, 12);
+  load(c_lo);
+#pragma unroll 1
+  for (int c = c_lo; c <= c_hi; ++c) {
+    const float cm = m, cs = s;
+    key_t64 cur[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) cur[j] = nxt[j];
+    if (c < c_hi) load(c + 1);
+    if (!HAS_CEIL) lse_merge_fast(lmax, lsum, cm, cs);
+    merge_keys<KTOP>(best, cur);
+    if (te == 0 && c == c_lo) stamp(timeline, 13);
   }
-  quadrant_tree<KTOP, HAS_CEIL>(sm, quad, cg, lane, lmax, lsum, tv, ti);
-  if (cg != 0 || row >= M) return;
+  if (te == 0) stamp(timeline, 14);
+#pragma unroll 1
+  for (int x = 1; x <= 2; x <<= 1) {  // the row's four threads are adjacent lanes
+    const float om = __shfl_xor_sync(0xffffffffu, lmax, x), os = __shfl_xor_sync(0xffffffffu, lsum, x);
+    key_t64 other[KTOP];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) other[j] = __shfl_xor_sync(0xffffffffu, best[j], x);
+    if (!HAS_CEIL) lse_merge_fast(lmax, lsum, om, os);
+    merge_keys<KTOP>(best, other);
+  }
+  if (sub != 0 || row >= M) return;
   float lse_row, inv = 1.f;
   if (!HAS_CEIL) {
     inv = 1.f / lsum;
@@ -268,16 +360,16 @@ __device__ __forceinline__ void merge_block(Smem& sm, const float* __restrict__ 
 #pragma unroll
   for (int j = 0; j < KTOP; ++j) {
     if (j < o.k_cnt) {
-      o.topk_val[static_cast<size_t>(row) * o.k + o.k_off + j] = expf(tv[j] - lmax) * inv;
-      o.topk_idx[static_cast<size_t>(row) * o.k + o.k_off + j] = ti[j];
+      o.topk_val[static_cast<size_t>(row) * o.k + o.k_off + j] = expf(key_value(best[j]) - lmax) * inv;
+      o.topk_idx[static_cast<size_t>(row) * o.k + o.k_off + j] = key_index(best[j]);
     }
   }
   if (o.ceil_v) {
-    o.ceil_v[row] = tv[KTOP - 1];
-    o.ceil_i[row] = ti[KTOP - 1];
+    o.ceil_v[row] = key_value(best[KTOP - 1]);
+    o.ceil_i[row] = key_index(best[KTOP - 1]);
   }
   if (HAS_CEIL) return;
-  const int best0 = ti[0];
+  const int best0 = key_index(best[0]);
   if (o.pred_cell) o.pred_cell[row] = best0;
   if (o.pred_llh) {
     o.pred_llh[2 * row + 0] = o.centroids[2 * best0 + 0];
@@ -290,9 +382,10 @@ template <int KTOP, bool WRITE_LOGITS, bool HAS_CEIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias_pad,
-                float* __restrict__ pmax, float* __restrict__ psum, float* __restrict__ ptopv,
-                int* __restrict__ ptopi, unsigned int* __restrict__ tickets, const float* __restrict__ ceil_in_v,
-                const int* __restrict__ ceil_in_i, int M, int N, int K, FwdSched sc, FwdOut out) {
+                float* __restrict__ pmax, float* __restrict__ psum, key_t64* __restrict__ pkeys,
+                unsigned int* __restrict__ tickets, const float* __restrict__ ceil_in_v,
+                const int* __restrict__ ceil_in_i, int M, int N, int K, FwdSched sc, FwdOut out,
+                long long* __restrict__ timeline) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = FwdSmem<WRITE_LOGITS>;
   constexpr int kStages = Smem::kStages;
@@ -306,6 +399,12 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const int t_begin = sc.start(pair), t_end = sc.start(pair + 1);
 
   if (threadIdx.x == 0) {
+    stamp(timeline, 0);
+    if (timeline != nullptr) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      timeline[static_cast<size_t>(blockIdx.x) * 16 + 15] = smid;
+    }
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
     if (WRITE_LOGITS) tma_prefetch_desc(&tm_out);
@@ -328,6 +427,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   cluster_sync();  // the partner's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  if (threadIdx.x == 0) stamp(timeline, 1);
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -378,7 +478,9 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
+        if (it == 0 && lane == 0) stamp(timeline, 2);  // first tile's MMAs issued
       }
+      if (lane == 0) stamp(timeline, 3);  // last MMA issued
     }
   } else {
     // ===================== epilogue warps (512 threads: row = TMEM lane, 64 columns each) ==========
@@ -417,6 +519,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       }
       mbar_wait(&sm.acc_full[acc], acc_ph);
       tc_fence_after();
+      if (threadIdx.x == 64) {
+        if (it == 0) stamp(timeline, 4);            // first accumulator complete
+        if (t == t_end - 1) stamp(timeline, 5);     // last accumulator complete
+      }
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kBN + cg * kColsPerEpiWarp;
 
@@ -525,22 +631,19 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
 
-      // end of this CTA's run over row block mb: fold the four column-group warps of every quadrant (same rows)
-      // and flush ONE partial per row -- the final merge then reads a handful of partials per row, not dozens
+      // end of this CTA's run over row block mb: flush the row state (one partial per epilogue warp)
       if (nb == sc.num_n - 1 || t == t_end - 1) {
-        quadrant_tree<KTOP, HAS_CEIL>(sm, quad, cg, lane, run_max, run_sum, tv, ti);
-        if (cg == 0) {
-          const size_t p = static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first);
+        if (threadIdx.x == 64 && t == t_end - 1) stamp(timeline, 6);  // last tile's chunks done
+        {
+          const size_t p = (static_cast<size_t>(blockIdx.x) * sc.runs + (mb - mb_first)) * kColGroups + cg;
           if (!HAS_CEIL) {
             __stcg(&pmax[p * kBM + row_in_tile], run_max);
             __stcg(&psum[p * kBM + row_in_tile], run_sum);
           }
 #pragma unroll
-          for (int j = 0; j < KTOP; ++j) {
-            __stcg(&ptopv[(p * KTOP + j) * kBM + row_in_tile], tv[j]);
-            __stcg(&ptopi[(p * KTOP + j) * kBM + row_in_tile], ti[j]);
-          }
+          for (int j = 0; j < KTOP; ++j) __stcg(&pkeys[(p * KTOP + j) * kBM + row_in_tile], make_key(tv[j], ti[j]));
         }
+        if (threadIdx.x == 64 && t == t_end - 1) stamp(timeline, 7);  // partials stored
         run_max = -INFINITY;
         run_sum = 0.f;
 #pragma unroll
@@ -563,19 +666,23 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           sm.is_last = last ? 1u : 0u;
         }
         named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
+        if (threadIdx.x == 64 && t == t_end - 1) stamp(timeline, 8);  // flushed, ticket drawn
         if (sm.is_last != 0u) {
           __threadfence();
-          merge_block<KTOP, HAS_CEIL>(sm, pmax, psum, ptopv, ptopi, sc, mb, crank, quad, cg, lane, M, out);
+          merge_block<KTOP, HAS_CEIL>(pmax, psum, pkeys, sc, mb, crank, M, out, timeline);
+          if (threadIdx.x == 64) stamp(timeline, 9);  // merged a row block (last one wins)
         }
       }
     }
     if (WRITE_LOGITS) {
       if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last bulk store
     }
+    if (threadIdx.x == 64) stamp(timeline, 10);  // epilogue done (bulk stores drained)
   }
 
   tc_fence_before();
   cluster_sync();  // the partner may still be signalling this CTA's barriers / the leader reading its operands
+  if (threadIdx.x == 0) stamp(timeline, 11);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
@@ -585,7 +692,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 template <bool WRITE_LOGITS>
 static size_t fwd_smem_bytes() { return sizeof(FwdSmem<WRITE_LOGITS>) + 1024; }
 
-static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(2 * sc.grid) * sc.runs; }
+static size_t fwd_partials(const FwdSched& sc) { return static_cast<size_t>(2 * sc.grid) * sc.runs * kColGroups; }
 
 template <typename Kern, typename... Args>
 static cudaError_t launch_pairs(Kern kern, int pairs, size_t smem, cudaStream_t stream, Args... args) {
@@ -597,10 +704,10 @@ static cudaError_t launch_pairs(Kern kern, int pairs, size_t smem, cudaStream_t 
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-// workspace: [partials: pmax | psum | ptopv | ptopi][ceil_v (B) | ceil_i (B) | lse (B): passes beyond the first]
+// workspace: [partials: pmax | psum | pkeys (64-bit candidates)][ceil_v (B) | ceil_i (B) | lse (B): passes beyond the first]
 struct FwdWs {
-  float *pmax, *psum, *ptopv;
-  int* ptopi;
+  float *pmax, *psum;
+  key_t64* pkeys;
   float* ceil_v[2];
   int* ceil_i[2];
   float* lse;
@@ -617,8 +724,7 @@ static FwdWs carve_fwd_ws(void* base, const FwdSched& sc, int B, int ktop, bool 
   const size_t np = fwd_partials(sc) * kBM;
   w.pmax = reinterpret_cast<float*>(take(np * sizeof(float)));
   w.psum = reinterpret_cast<float*>(take(np * sizeof(float)));
-  w.ptopv = reinterpret_cast<float*>(take(np * ktop * sizeof(float)));
-  w.ptopi = reinterpret_cast<int*>(take(np * ktop * sizeof(int)));
+  w.pkeys = reinterpret_cast<key_t64*>(take(np * ktop * sizeof(key_t64)));
   for (int i = 0; i < 2; ++i) {
     w.ceil_v[i] = reinterpret_cast<float*>(take(multipass ? sizeof(float) * B : 0));
     w.ceil_i[i] = reinterpret_cast<int*>(take(multipass ? sizeof(int) * B : 0));
@@ -628,6 +734,8 @@ static FwdWs carve_fwd_ws(void* base, const FwdSched& sc, int B, int ktop, bool 
   return w;
 }
 
+static long long* g_fwd_timeline = nullptr;  // gg_debug_head_fwd_timeline
+
 template <int KTOP, bool WRITE_LOGITS, bool HAS_CEIL>
 static int launch_one(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CUtensorMap& tm_out, const float* bias_pad,
                       const FwdWs& w, unsigned int* tickets, const float* ceil_in_v, const int* ceil_in_i, int B, int C,
@@ -635,8 +743,8 @@ static int launch_one(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const CU
   auto kern = head_fwd_kernel<KTOP, WRITE_LOGITS, HAS_CEIL>;
   const size_t smem = fwd_smem_bytes<WRITE_LOGITS>();
   if (int e = set_max_dynamic_smem_once(kern, smem)) return e;
-  GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, w.pmax, w.psum, w.ptopv, w.ptopi,
-                       tickets, ceil_in_v, ceil_in_i, B, C, D, sc, out));
+  GG_CUDA(launch_pairs(kern, sc.grid, smem, stream, tm_x, tm_w, tm_out, bias_pad, w.pmax, w.psum, w.pkeys, tickets,
+                       ceil_in_v, ceil_in_i, B, C, D, sc, out, g_fwd_timeline));
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -652,6 +760,8 @@ extern "C" size_t gg_head_fwd_workspace_bytes(int B, int C, int k) {
   return carve_fwd_ws(nullptr, sc, B, fwd_ktop(k), k > 8).bytes;
 }
 extern "C" size_t gg_head_fwd_ticket_bytes(int B) { return sizeof(unsigned int) * 2 * ceil_div(B, 2 * kBM); }
+
+extern "C" void gg_debug_head_fwd_timeline(long long* device_buf) { g_fwd_timeline = device_buf; }
 
 extern "C" int gg_head_logits_ld(int C) { return ceil_div(C, 256) * 256; }
 extern "C" int gg_head_bias_pad(int C) { return ceil_div(C, kBN) * kBN; }

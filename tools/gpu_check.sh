@@ -37,8 +37,14 @@ for w in $what; do
     p2p)  # needs gpurun --gpus N (N = 2, 4 or 8): gradient exchange kernels against NCCL + data-parallel bench
       N=$(nvidia-smi -L | wc -l)
       T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29540"
-      timeout 200 $T tools/p2p_check.py > gpurun_out/p2p_check_${N}gpu.log 2>&1; tail -9 gpurun_out/p2p_check_${N}gpu.log
-      timeout 200 $T bench.py --gpus $N --no-cpu > gpurun_out/scale${N}_train.json 2> gpurun_out/scale${N}_train.err; echo "bench$N rc=$?" ;;
+      timeout 300 $T tools/p2p_check.py --quick > gpurun_out/p2p_check_${N}gpu.log 2>&1; echo "p2p_check rc=$?"; tail -14 gpurun_out/p2p_check_${N}gpu.log
+      timeout 600 $T bench.py --gpus $N --no-cpu > gpurun_out/scale${N}.json 2> gpurun_out/scale${N}.err; echo "bench$N rc=$?"; tail -3 gpurun_out/scale${N}.err ;;
+    p2pcmp)  # the exchange variants side by side (training half only)
+      N=$(nvidia-smi -L | wc -l)
+      T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541"
+      for c in fused p2p nvls nccl; do
+        timeout 300 $T bench.py --gpus $N --no-cpu --workload train --sustained-s 0 --dp-comm $c > gpurun_out/scale${N}_$c.json 2> gpurun_out/scale${N}_$c.err; echo "bench$N $c rc=$?"
+      done ;;
     klaunch)
       timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -s 30 -c 60 --csv --log-file gpurun_out/klaunch.csv \
         python tools/kbench.py 3 > gpurun_out/klaunch.log 2>&1; echo "klaunch rc=$?" ;;

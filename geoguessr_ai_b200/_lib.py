@@ -44,7 +44,7 @@ SIGNATURES = {
     "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, P, P, P, P, P, F, P]),
     "gg_hard_ce_fwd_bwd": (I, [P, I, P, P, I, I, P, P, P]),
     "gg_loss_mean": (I, [P, I, F, P, P]),
-    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P, I, P]),
+    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P, I, I, P]),
     "gg_head_dx": (I, [P, I, P, I, I, I, I, F, P, I, P, P]),
     "gg_topk_accuracy": (I, [P, I, P, I, P, P]),
     "gg_split3_bf16": (I, [P, L, I, I, P, I, P, P]),
@@ -60,7 +60,8 @@ SIGNATURES = {
     "gg_p2p_allreduce_avg": (I, [P, I, I, c_size_t, P]),
     "gg_nvls_allreduce_avg": (I, [P, I, I, c_size_t, P]),
     "gg_grad_ctrl_bytes": (c_size_t, []),
-    "gg_grad_exchange": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "gg_grad_stage_floats": (c_size_t, [I, I, I]),
+    "gg_grad_exchange": (I, [P, P, P, P, P, I, I, I, I, I, P]),
 }
 
 _lib = None

@@ -85,13 +85,21 @@ struct PairSchedule {
   }
 };
 
-// Data-parallel training (gg_grad_exchange): when the last column tile of a 128-geocell block of dW (and its db
-// rows) has been written, the block is announced to the rank that reduces it -- a system-scope release add on
-// that rank's `ready` counter in symmetric memory -- so the exchange proceeds block by block underneath the GEMM.
-struct GradSignal {
-  unsigned int* blk_count;             // local: finished column tiles per 128-geocell block (self-resetting)
-  unsigned int* ready[kGradMaxWorld];  // every rank's `ready` counters (peer-mapped); block b belongs to rank b % world
-  int world;                           // 0 / 1: no signalling
+// Data-parallel training (gg_grad_exchange): dW is cut into blocks of 128 geocells (one CTA's rows of a pair tile);
+// block b is reduced by rank b % world.  In that mode this kernel does not write the gradient buffer at all: every
+// finished tile -- and, with the first column tile, the block's 128 db entries -- goes straight into the REDUCER's
+// staging slab for this source rank (posted TMA / plain stores over NVLink; the local slab for blocks this rank
+// reduces itself), and when all column tiles of a block have been pushed the block is announced with a system-scope
+// release add on the reducer's `ready` counter.  The transfer thus rides underneath the GEMM tile by tile, without
+// any other kernel sharing the SMs with it.
+struct GradPush {
+  unsigned int* blk_count;             // local: pushed column tiles per 128-geocell block (self-resetting)
+  unsigned int* ready[kGradMaxWorld];  // every rank's `ready` counters (peer-mapped)
+  float* stage_b[kGradMaxWorld];       // rank r's db staging rows for THIS source rank (peer-mapped): [block / world][128]
+  int world;                           // 0 / 1: plain local dW / db
+};
+struct StageMaps {
+  CUtensorMap m[kGradMaxWorld];        // rank r's dW staging slab for this source rank: (rows = blocks-of-r x 128, D) fp32
 };
 __device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -101,9 +109,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
 head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C, rows B
                 const __grid_constant__ CUtensorMap tm_x,   // x:       inner D, rows B
                 const __grid_constant__ CUtensorMap tm_dw,  // dW (C, D) fp32: 32 x 32 store boxes
-                const __grid_constant__ GradSignal sig, int C, int D, int Bk, float scale_in,
+                const __grid_constant__ StageMaps stage, const __grid_constant__ GradPush sig, int C, int D, int Bk,
+                float scale_in,
                 const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags,
-                float* __restrict__ db, const float* __restrict__ db_partials, int db_parts, int db_ld) {
+                float* __restrict__ db, const float* __restrict__ db_partials, int db_parts, int db_ld,
+                const float* __restrict__ db_ready) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,6 +229,12 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         const int row = m0 + rit;
+        // where this CTA's 128 geocells of the tile go: the gradient itself, or the reducer's staging slab
+        const bool push = sig.world > 1;
+        const int blk = m0 / kWM;
+        const int dst_rank = push ? blk % sig.world : 0;
+        const CUtensorMap* const tm_dst = push ? &stage.m[dst_rank] : &tm_dw;
+        const int dst_row0 = push ? (blk / sig.world) * kWM : m0;
         const bool add_prev = k0 > 0;      // the lower pair parked the first k-blocks of this tile
         const bool park = k1 < num_k;      // the higher pair finishes this tile
         mbar_wait(&sm.acc_full[acc], acc_ph);
@@ -249,7 +265,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
           if (park) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) __stcg(my_park + static_cast<size_t>(c * 32 + j) * kWM, __uint_as_float(r[j]));
-          } else if (col0 < D) {  // (warp-uniform)
+          } else if (col0 < D && m0 < C) {  // (warp-uniform)
             // 32 geocells x 32 columns through a swizzled staging tile and one TMA store: full 128-byte lines
             // instead of 32 row-strided 16-byte pieces per store instruction; rows >= C / columns >= D are clipped.
             uint8_t* const buf = sm.out[quad][obuf];
@@ -268,7 +284,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tm_dw, buf, col0, m0 + quad * 32);
+              tma_store_2d(tm_dst, buf, col0, dst_row0 + quad * 32);
               tma_store_commit();
             }
           }
@@ -278,23 +294,30 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
         // bias gradient: whoever finishes a geocell block's first column tile also sums that block's column-sum
         // partials from the loss kernel (fixed order; 128 consecutive geocells per warp-quartet: coalesced)
-        if (db != nullptr && !park && n0 == 0 && row < C) {
-          float s0 = 0.f, s1 = 0.f;
-          int i = 0;
-          for (; i + 1 < db_parts; i += 2) {
-            s0 += __ldg(db_partials + static_cast<size_t>(i) * db_ld + row);
-            s1 += __ldg(db_partials + static_cast<size_t>(i + 1) * db_ld + row);
+        if ((db != nullptr || push) && !park && n0 == 0 && row < C) {
+          float v;
+          if (db_partials != nullptr) {
+            float s0 = 0.f, s1 = 0.f;
+            int i = 0;
+            for (; i + 1 < db_parts; i += 2) {
+              s0 += __ldg(db_partials + static_cast<size_t>(i) * db_ld + row);
+              s1 += __ldg(db_partials + static_cast<size_t>(i + 1) * db_ld + row);
+            }
+            if (i < db_parts) s0 += __ldg(db_partials + static_cast<size_t>(i) * db_ld + row);
+            v = (s0 + s1) * scale;
+          } else {
+            v = __ldg(db_ready + row);  // finished before this launch (column sums of dlogits)
           }
-          if (i < db_parts) s0 += __ldg(db_partials + static_cast<size_t>(i) * db_ld + row);
-          db[row] = (s0 + s1) * scale;
+          if (push) sig.stage_b[dst_rank][(blk / sig.world) * kWM + rit] = v;
+          else db[row] = v;
         }
         if (park) {  // publish: every epilogue thread's stores, then the flag
           __threadfence();
           named_bar_sync(1, 128);
           if (threadIdx.x == 64) atomicExch(&flags[pair * 2 + crank], 1);
-        } else if (sig.world > 1 && m0 < C) {
+        } else if (push && m0 < C) {
           // this CTA's 128 geocells x 256 columns of dW (and, with the first column tile, the block's db rows) are
-          // final on this rank: count the block's column tiles, the last one announces the block to its reducer
+          // on their way to the reducer: count the block's column tiles, the last one announces the block
           if (lane == 0) {
             tma_store_wait_all<0>();  // the bulk stores have been performed, not merely read from shared memory
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -302,11 +325,10 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
           named_bar_sync(1, 128);
           if (threadIdx.x == 64) {
             __threadfence_system();
-            const int blk = m0 / kWM;
             const unsigned int old = atomicAdd(sig.blk_count + blk, 1u);
             if (old + 1u == static_cast<unsigned int>(num_n)) {
               sig.blk_count[blk] = 0u;  // left zeroed for the next step
-              red_release_sys_add(sig.ready[blk % sig.world] + blk, 1u);
+              red_release_sys_add(sig.ready[dst_rank] + blk, 1u);
             }
           }
         }
@@ -390,38 +412,58 @@ using namespace gg;
 static size_t bwd_flag_bytes() { return ((static_cast<size_t>(device_sm_count()) * sizeof(int)) + 255) & ~size_t(255); }
 static size_t bwd_park_bytes() { return static_cast<size_t>(device_sm_count()) * kPartialFloats * sizeof(float); }
 extern "C" size_t gg_head_bwd_workspace_bytes(int C) {
-  return bwd_flag_bytes() + bwd_park_bytes() + static_cast<size_t>(kDbSlices) * C * sizeof(float);
+  // + C floats: db finished ahead of the GEMM when it is pushed to a reducer without the loss kernel's partials
+  return bwd_flag_bytes() + bwd_park_bytes() + static_cast<size_t>(kDbSlices + 1) * C * sizeof(float);
+}
+
+// staging region of one rank: `world` slabs (one per source rank), each = its blocks' dW rows then their db entries
+static size_t grad_blocks_per_rank(int C, int world) { return (static_cast<size_t>(ceil_div(C, kWM)) + world - 1) / world; }
+extern "C" size_t gg_grad_stage_floats(int C, int D, int world) {
+  return static_cast<size_t>(world) * grad_blocks_per_rank(C, world) * kWM * (static_cast<size_t>(D) + 1);
 }
 
 extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
                            float scale, const float* grad_scale, float* dW, float* db, const float* db_partials,
-                           int db_parts, int db_ld, void* workspace, const unsigned long long* signal_ptrs,
-                           int signal_world, gg_stream_t stream) {
+                           int db_parts, int db_ld, void* workspace, const unsigned long long* dp_ptrs, int dp_world,
+                           int dp_rank, gg_stream_t stream) {
   GG_CHECK(B > 0 && C > 0 && D > 0, GG_ERR_ARG, "gg_head_bwd: empty problem B=%d C=%d D=%d", B, C, D);
-  GG_CHECK(dlogits_bf16 && x_bf16 && dW, GG_ERR_ARG, "gg_head_bwd: null pointer");
+  GG_CHECK(dlogits_bf16 && x_bf16, GG_ERR_ARG, "gg_head_bwd: null pointer");
   GG_CHECK(ldc >= C && ldc % 8 == 0, GG_ERR_ARG, "gg_head_bwd: ldc=%d must be >= C and a multiple of 8", ldc);
   GG_CHECK(D % 8 == 0 && x_ld >= D && x_ld % 8 == 0, GG_ERR_ARG, "gg_head_bwd: D=%d / x_ld=%d must be multiples of 8", D, x_ld);
   GG_CHECK(workspace, GG_ERR_ARG, "gg_head_bwd: workspace (gg_head_bwd_workspace_bytes) is required");
   GG_CHECK(!db_partials || (db_parts > 0 && db_ld >= C), GG_ERR_ARG, "gg_head_bwd: bad db_partials shape");
-  GG_CHECK(signal_world >= 0 && signal_world <= kGradMaxWorld && (signal_world <= 1 || signal_ptrs), GG_ERR_ARG,
-           "gg_head_bwd: signal_world=%d (<= %d) needs signal_ptrs", signal_world, kGradMaxWorld);
+  const bool push = dp_world > 1;
+  GG_CHECK(dp_world >= 0 && dp_world <= kGradMaxWorld && (!push || (dp_ptrs && dp_rank >= 0 && dp_rank < dp_world)),
+           GG_ERR_ARG, "gg_head_bwd: dp_world=%d dp_rank=%d (<= %d ranks) needs dp_ptrs", dp_world, dp_rank, kGradMaxWorld);
+  GG_CHECK(push || dW, GG_ERR_ARG, "gg_head_bwd: dW is required");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUtensorMap tm_g, tm_x, tm_dw;
   int rc = make_tmap_bf16_2d(&tm_g, dlogits_bf16, C, B, static_cast<uint64_t>(ldc) * 2, 64, kWK);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tm_x, x_bf16, D, B, static_cast<uint64_t>(x_ld) * 2, 64, kWK);
   if (rc) return rc;
-  rc = make_tmap_f32_2d(&tm_dw, dW, D, C, static_cast<uint64_t>(D) * 4, 32);
-  if (rc) return rc;
-  GradSignal sig = {};
-  if (signal_world > 1) {
-    sig.world = signal_world;
-    sig.blk_count = reinterpret_cast<unsigned int*>(signal_ptrs[0]);
-    for (int r = 0; r < signal_world; ++r) {
-      GG_CHECK(signal_ptrs[1 + r] != 0, GG_ERR_ARG, "gg_head_bwd: ready counters of rank %d missing", r);
-      sig.ready[r] = reinterpret_cast<unsigned int*>(signal_ptrs[1 + r]);
-    }
+  GradPush sig = {};
+  StageMaps maps = {};
+  if (push) {
+    const size_t rows = grad_blocks_per_rank(C, dp_world) * kWM;        // staged geocell rows per (reducer, source)
+    const size_t slab = rows * (static_cast<size_t>(D) + 1);            // floats
+    sig.world = dp_world;
+    sig.blk_count = reinterpret_cast<unsigned int*>(dp_ptrs[0]);
     GG_CHECK(sig.blk_count, GG_ERR_ARG, "gg_head_bwd: block counters missing");
+    for (int r = 0; r < dp_world; ++r) {
+      const unsigned long long ready = dp_ptrs[1 + r], stage_r = dp_ptrs[1 + dp_world + r];
+      GG_CHECK(ready != 0 && stage_r != 0 && (stage_r & 15) == 0, GG_ERR_ARG, "gg_head_bwd: buffers of rank %d missing", r);
+      sig.ready[r] = reinterpret_cast<unsigned int*>(ready);
+      float* my_slab = reinterpret_cast<float*>(stage_r) + static_cast<size_t>(dp_rank) * slab;
+      sig.stage_b[r] = my_slab + rows * D;
+      rc = make_tmap_f32_2d(&maps.m[r], my_slab, D, rows, static_cast<uint64_t>(D) * 4, 32);
+      if (rc) return rc;
+    }
+    tm_dw = maps.m[0];  // (not used in this mode)
+  } else {
+    rc = make_tmap_f32_2d(&tm_dw, dW, D, C, static_cast<uint64_t>(D) * 4, 32);
+    if (rc) return rc;
+    for (int r = 0; r < kGradMaxWorld; ++r) maps.m[r] = tm_dw;
   }
   const int pair_tiles = ceil_div(C, 2 * kWM) * ceil_div(D, kWN);
   const int pairs = std::max(1, std::min(pair_tiles, device_sm_count() / 2));
@@ -430,26 +472,28 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
   int* flags = reinterpret_cast<int*>(wsb);
   float* parked = reinterpret_cast<float*>(wsb + bwd_flag_bytes());
+  float* db_slices = reinterpret_cast<float*>(wsb + bwd_flag_bytes() + bwd_park_bytes());
+  float* db_tmp = db_slices + static_cast<size_t>(kDbSlices) * C;
   // with the loss kernel's column-sum partials at hand the GEMM's epilogue finishes db as well
-  const bool db_fused = db && db_partials;
-  auto db_from_dlogits = [&]() -> int {
-    float* partial = reinterpret_cast<float*>(wsb + bwd_flag_bytes() + bwd_park_bytes());
+  const bool db_fused = (db || push) && db_partials;
+  auto db_from_dlogits = [&](float* out) -> int {
     dim3 blk(32, 8), grd(ceil_div(C, 256), kDbSlices);
-    db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, partial);
+    db_partial_kernel<<<grd, blk, 0, s>>>(static_cast<const bf16*>(dlogits_bf16), ldc, B, C, db_slices);
     GG_LAUNCH_CHECK();
-    db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(partial, C, C, kDbSlices, scale, grad_scale, db);
+    db_final_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(db_slices, C, C, kDbSlices, scale, grad_scale, out);
     GG_LAUNCH_CHECK();
     return GG_OK;
   };
-  // announced blocks carry their db rows: without the partials db is finished BEFORE the GEMM then
-  if (db && !db_fused && sig.world > 1)
-    if (int e = db_from_dlogits()) return e;
+  // pushed blocks carry their db entries: without the partials db is finished BEFORE the GEMM then
+  if (push && !db_fused)
+    if (int e = db_from_dlogits(db_tmp)) return e;
   GG_CUDA(cudaMemsetAsync(flags, 0, bwd_flag_bytes(), s));
   // cluster shape (2,1,1) is compiled into the kernel
-  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, tm_dw, sig, C, D, B, scale, grad_scale, parked, flags,
-                                                       db_fused ? db : nullptr, db_partials, db_parts, db_ld);
+  head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, tm_dw, maps, sig, C, D, B, scale, grad_scale, parked,
+                                                       flags, db_fused && !push ? db : nullptr, db_partials, db_parts, db_ld,
+                                                       db_tmp);
   GG_LAUNCH_CHECK();
-  if (db && !db_fused && sig.world <= 1)
-    if (int e = db_from_dlogits()) return e;
+  if (db && !db_fused && !push)
+    if (int e = db_from_dlogits(db)) return e;
   return GG_OK;
 }

@@ -125,27 +125,31 @@ nvls_allreduce_avg_kernel(float4* __restrict__ mc, size_t lo, size_t hi, float i
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Progressive exchange underneath the dW GEMM (gg_grad_exchange).  The two kernels above run AFTER the GEMM, between
-// two host-issued barriers: the whole exchange is exposed.  Here the exchange kernel is launched NEXT TO gg_head_bwd
-// (another stream; its few small CTAs co-reside with the GEMM's one CTA per SM) and works block by block: dW is cut
-// into blocks of 128 geocells (+ the block's 128 db entries), block b is reduced by rank b % world.  The GEMM
-// announces a finished block with a system-scope release add on the reducer's `ready[b]` counter; the reducer waits
-// for all ranks' announcements, averages the block (multimem.ld_reduce through the NVSwitch, or peer loads in rank
-// order), writes the average into every rank's copy (multimem.st / peer stores) and adds to every rank's `done`
-// counter; each rank's kernel ends when every block of every reducer has landed in its copy.  Only the blocks the
-// GEMM finishes last are exchanged after it.  No host barrier: counters only ever grow (the expected values are
-// multiples of a per-launch epoch kept in the control region), nothing is reset while a peer could still add.
+// Exchange fused into the dW GEMM (gg_head_bwd's push mode + gg_grad_exchange).  The two kernels above run AFTER the
+// GEMM between two host-issued barriers and move the whole buffer then.  Here dW is cut into blocks of 128 geocells
+// (+ the block's 128 db entries); block b is reduced by rank b % world, and the GEMM's epilogue stores every tile
+// straight into the reducer's staging slab for its source rank (posted stores over NVLink, tile by tile under the
+// GEMM; see head_bwd.cu) and announces complete blocks on the reducer's `ready` counters.  What is left for after
+// the GEMM is this kernel: per owned block wait for the last announcements, add the `world` staged copies in rank
+// order from LOCAL memory (deterministic, identical everywhere), scale, and write the average into every rank's
+// gradient buffer -- multimem.st through the NVSwitch when the multicast mapping is given, else posted peer stores
+// -- then tell every rank; it returns when every block of every reducer has landed in this rank's gradient.
+// No peer loads anywhere, no host barrier: counters only ever grow (expected values are multiples of a per-launch
+// epoch kept in the control region), nothing is reset while a peer could still add.
+//
+// (A first version averaged the blocks with a second kernel running NEXT TO the GEMM and peer loads; measured on
+// 2 x B200 it slowed the GEMM 2-4x -- the co-resident CTAs' system-scope fences and polling stall the SM's memory
+// pipeline -- and is gone.)
 //
 // Control region (symmetric memory, GG_GRAD_CTRL_BYTES per rank, zeroed once): u32 words
-//   [0, 1024)     blk_count  finished column tiles per block (gg_head_bwd, local, self-resetting)
+//   [0, 1024)     blk_count  pushed column tiles per block (gg_head_bwd, local, self-resetting)
 //   [1024, 2048)  ready      announcements per block (remote adds by every rank's gg_head_bwd)
 //   [2048]        done       exchanged units landed in this rank's copy (remote adds by the reducers)
 //   [2049]        exit ticket, [2050] epoch (local)
 constexpr int kCtrlReady = 1024, kCtrlDone = 2048, kCtrlExit = 2049, kCtrlEpoch = 2050;
 constexpr int kGradBlockRows = 128;
-constexpr int kGradParts = 4;      // CTAs that share one block
-constexpr int kGradThreads = 256;   // <= 154 registers per thread leaves room next to the GEMM CTA of an SM
-constexpr int kGradMaxCtas = 64;
+constexpr int kGradParts = 8;      // CTAs that share one block
+constexpr int kGradThreads = 256;
 
 struct GradPeers {
   float4* grad[kP2PMaxWorld];        // every rank's [dW | db | pad] buffer
@@ -167,7 +171,7 @@ __device__ __forceinline__ void multimem_red_release_sys(unsigned int* p, unsign
 __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target, const char* what, int a, int b) {
   const long long t0 = clock64();
   while (static_cast<int>(ld_acquire_sys(p) - target) < 0) {
-    __nanosleep(200);
+    __nanosleep(100);
     if (clock64() - t0 > 10000000000LL) {
       printf("gg: grad exchange timeout waiting for %s (rank %d, index %d): have %u want %u\n", what, a, b,
              ld_acquire_sys(p), target);
@@ -176,74 +180,55 @@ __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int t
   }
 }
 
-// average float4 [lo, hi) of every copy (this CTA's threads stride over it)
+// dst[i] (every rank's copy, float4 index dst0 + i) = inv_world * sum_src stage[src * slab4 + src0 + i], i in [0, n)
 template <int WORLD, bool NVLS>
-__device__ __forceinline__ void exchange_range(const GradPeers& peers, float4* mc, size_t lo, size_t hi, float inv_world) {
-  // <= 64 registers: the kernel's CTAs share SMs with the dW GEMM's
-  constexpr int kUnroll = NVLS ? 4 : (WORLD >= 8 ? 1 : (WORLD >= 4 ? 2 : 4));
-  size_t base = lo + threadIdx.x;
-  const size_t stride = kGradThreads;
-  if (NVLS) {
-    for (; base + (kUnroll - 1) * stride < hi; base += stride * kUnroll) {
-      float4 v[kUnroll];
+__device__ __forceinline__ void reduce_range(const GradPeers& peers, float4* mc, const float4* __restrict__ stage,
+                                             size_t slab4, size_t src0, size_t dst0, size_t n, float inv_world) {
+  constexpr int kUnroll = WORLD >= 8 ? 2 : (WORLD >= 4 ? 4 : 8);  // WORLD x unroll local 16-byte loads in flight
+  size_t i = threadIdx.x;
+  auto emit = [&](size_t at, const float4& v) {
+    if (NVLS) {
+      multimem_st(mc + dst0 + at, v);
+    } else {
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) v[u] = multimem_ld_add(mc + base + u * stride);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) pin(v[u]);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        v[u].x *= inv_world; v[u].y *= inv_world; v[u].z *= inv_world; v[u].w *= inv_world;
-        multimem_st(mc + base + u * stride, v[u]);
-      }
+      for (int r = 0; r < WORLD; ++r) st_peer(peers.grad[r] + dst0 + at, v);
     }
-    for (; base < hi; base += stride) {
-      float4 v = multimem_ld_add(mc + base);
-      v.x *= inv_world; v.y *= inv_world; v.z *= inv_world; v.w *= inv_world;
-      multimem_st(mc + base, v);
+  };
+  for (; i + (kUnroll - 1) * kGradThreads < n; i += kUnroll * kGradThreads) {
+    float4 v[kUnroll][WORLD];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) v[u][r] = __ldcs(stage + r * slab4 + src0 + i + u * kGradThreads);
     }
-  } else {
-    for (; base + (kUnroll - 1) * stride < hi; base += stride * kUnroll) {
-      float4 v[kUnroll][WORLD];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kUnroll; ++u) {
+      float4 acc = v[u][0];
 #pragma unroll
-        for (int r = 0; r < WORLD; ++r) v[u][r] = ld_peer(peers.grad[r] + base + u * stride);
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-#pragma unroll
-        for (int r = 0; r < WORLD; ++r) pin(v[u][r]);
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        float4 acc = v[u][0];
-#pragma unroll
-        for (int r = 1; r < WORLD; ++r) {  // rank order: identical on every rank
-          acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w;
-        }
-        acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
-#pragma unroll
-        for (int r = 0; r < WORLD; ++r) st_peer(peers.grad[r] + base + u * stride, acc);
-      }
-    }
-    for (; base < hi; base += stride) {
-      float4 acc = ld_peer(peers.grad[0] + base);
-#pragma unroll
-      for (int r = 1; r < WORLD; ++r) {
-        const float4 t = ld_peer(peers.grad[r] + base);
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      for (int r = 1; r < WORLD; ++r) {  // rank order: identical on every rank
+        acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w;
       }
       acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
-#pragma unroll
-      for (int r = 0; r < WORLD; ++r) st_peer(peers.grad[r] + base, acc);
+      emit(i + u * kGradThreads, acc);
     }
+  }
+  for (; i < n; i += kGradThreads) {
+    float4 acc = __ldcs(stage + src0 + i);
+#pragma unroll
+    for (int r = 1; r < WORLD; ++r) {
+      const float4 t = __ldcs(stage + r * slab4 + src0 + i);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    acc.x *= inv_world; acc.y *= inv_world; acc.z *= inv_world; acc.w *= inv_world;
+    emit(i, acc);
   }
 }
 
 template <int WORLD, bool NVLS>
-__global__ void __launch_bounds__(kGradThreads, 1)
+__global__ void __launch_bounds__(kGradThreads)
 grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict__ mc_grad,
-                     unsigned int* __restrict__ mc_ctrl, int rank, int C, int D, int nblk, float inv_world, int no_wait) {
+                     unsigned int* __restrict__ mc_ctrl, const float4* __restrict__ stage, int rank, int C, int D,
+                     int nblk, int own_max, float inv_world, int no_wait) {
   unsigned int* const ctrl = peers.ctrl[rank];
   __shared__ unsigned int s_epoch;
   if (threadIdx.x == 0) s_epoch = ld_acquire_sys(ctrl + kCtrlEpoch);
@@ -251,17 +236,22 @@ grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict
   const unsigned int epoch = s_epoch + 1u;  // announcements / landed units expected so far = epoch x (per-launch count)
   const int own = nblk > rank ? (nblk - rank + WORLD - 1) / WORLD : 0;  // blocks rank, rank + WORLD, ...
   const size_t row4 = static_cast<size_t>(D) / 4;                       // float4 per geocell row
-  const size_t db4 = static_cast<size_t>(C) * row4;                     // float4 offset of db
+  const size_t db4 = static_cast<size_t>(C) * row4;                     // float4 offset of db in the gradient buffer
+  const size_t rows = static_cast<size_t>(own_max) * kGradBlockRows;    // staged rows per slab
+  const size_t slab4 = rows * (static_cast<size_t>(D) + 1) / 4;         // float4 per slab (dW rows, then db entries)
   for (int u = blockIdx.x; u < own * kGradParts; u += gridDim.x) {
-    const int b = rank + (u / kGradParts) * WORLD, part = u % kGradParts;
+    const int j = u / kGradParts, part = u % kGradParts;
+    const int b = rank + j * WORLD;
     if (threadIdx.x == 0) spin_until(ctrl + kCtrlReady + b, epoch * static_cast<unsigned int>(WORLD), "block", rank, b);
     __syncthreads();
     const int r0 = b * kGradBlockRows, r1 = min(C, r0 + kGradBlockRows);
-    const size_t lo = static_cast<size_t>(r0) * row4, n4 = static_cast<size_t>(r1 - r0) * row4;
-    exchange_range<WORLD, NVLS>(peers, mc_grad, lo + n4 * part / kGradParts, lo + n4 * (part + 1) / kGradParts, inv_world);
-    if (part == 0)  // the block's db entries (128 floats; the last block's ragged end runs into the zero pad)
-      exchange_range<WORLD, NVLS>(peers, mc_grad, db4 + static_cast<size_t>(r0) / 4,
-                                  db4 + (static_cast<size_t>(r1) + 3) / 4, inv_world);
+    const size_t n4 = static_cast<size_t>(r1 - r0) * row4;
+    const size_t lo = n4 * part / kGradParts, hi = n4 * (part + 1) / kGradParts;
+    reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, static_cast<size_t>(j) * kGradBlockRows * row4 + lo,
+                              static_cast<size_t>(r0) * row4 + lo, hi - lo, inv_world);
+    if (part == 0)  // the block's db entries (128 floats; the last block's ragged end runs into the pad)
+      reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, rows * row4 + static_cast<size_t>(j) * (kGradBlockRows / 4),
+                                db4 + static_cast<size_t>(r0) / 4, (static_cast<size_t>(r1 - r0) + 3) / 4, inv_world);
     __syncthreads();  // every thread's stores are issued
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -350,7 +340,8 @@ extern "C" int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, s
 extern "C" size_t gg_grad_ctrl_bytes(void) { return GG_GRAD_CTRL_BYTES; }
 
 extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsigned long long* ctrl_ptrs, void* grad_mc,
-                                void* ctrl_mc, int world, int rank, int C, int D, int flags, gg_stream_t stream) {
+                                void* ctrl_mc, const void* stage, int world, int rank, int C, int D, int flags,
+                                gg_stream_t stream) {
   GG_CHECK(grad_ptrs && ctrl_ptrs && world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, GG_ERR_ARG,
            "gg_grad_exchange: world=%d rank=%d (1 <= world <= %d)", world, rank, kP2PMaxWorld);
   GG_CHECK(world == 1 || world == 2 || world == 4 || world == 8, GG_ERR_UNSUPPORTED,
@@ -360,6 +351,7 @@ extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsig
   GG_CHECK(nblk <= kCtrlReady, GG_ERR_UNSUPPORTED, "gg_grad_exchange: C=%d exceeds %d geocells", C, kCtrlReady * kGradBlockRows);
   GG_CHECK((grad_mc == nullptr) == (ctrl_mc == nullptr), GG_ERR_ARG, "gg_grad_exchange: both multicast addresses or none");
   if (world == 1) return GG_OK;
+  GG_CHECK(stage && (reinterpret_cast<uintptr_t>(stage) & 15) == 0, GG_ERR_ARG, "gg_grad_exchange: staging region missing");
   GradPeers peers = {};
   for (int r = 0; r < world; ++r) {
     GG_CHECK(grad_ptrs[r] != 0 && (grad_ptrs[r] & 15) == 0 && ctrl_ptrs[r] != 0 && (ctrl_ptrs[r] & 15) == 0, GG_ERR_ARG,
@@ -368,16 +360,19 @@ extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsig
     peers.ctrl[r] = reinterpret_cast<unsigned int*>(ctrl_ptrs[r]);
   }
   const int own = nblk > rank ? (nblk - rank + world - 1) / world : 0;
-  const int grid = std::max(1, std::min(kGradMaxCtas, own * kGradParts));
+  const int own_max = (nblk + world - 1) / world;
+  // every CTA must be resident (each waits for units other CTAs of this grid deliver): <= 2 per SM
+  const int grid = std::max(1, std::min(2 * device_sm_count(), own * kGradParts));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float inv = 1.0f / static_cast<float>(world);
   float4* mg = static_cast<float4*>(grad_mc);
   unsigned int* mcc = static_cast<unsigned int*>(ctrl_mc);
+  const float4* st = static_cast<const float4*>(stage);
   const int nw = (flags & GG_GRAD_NO_WAIT) ? 1 : 0;
-#define GG_GX(W)                                                                                              \
-  do {                                                                                                        \
-    if (mg) grad_exchange_kernel<W, true><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, rank, C, D, nblk, inv, nw);  \
-    else grad_exchange_kernel<W, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, rank, C, D, nblk, inv, nw);    \
+#define GG_GX(W)                                                                                                   \
+  do {                                                                                                             \
+    if (mg) grad_exchange_kernel<W, true><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw);  \
+    else grad_exchange_kernel<W, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw);    \
   } while (0)
   if (world == 2) GG_GX(2);
   else if (world == 4) GG_GX(4);

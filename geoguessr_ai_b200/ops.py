@@ -326,129 +326,65 @@ def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tens
 
 
 def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None, c_range=None, out=None,
-                  signal=None):
+                  push=None):
     """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C) (from the loss kernel's column-sum
     partials when given, else from a pass over dlogits).
 
     c_range=(c0, c1) computes only geocells [c0, c1) (c0 a multiple of 8) into rows c0..c1 of ``out=(dW, db)``:
     the NCCL data-parallel path runs the GEMM range by range and all-reduces each range while the next one runs.
-    signal=(blk_count_ptr, [ready_ptr of rank 0, 1, ...]): announce finished 128-geocell blocks to their reducers
-    (gg_grad_exchange runs next to this launch); whole range only."""
+    push=(blk_count_ptr, [ready_ptr of rank 0, 1, ...], [staging region of rank 0, 1, ...], rank): data-parallel
+    mode -- every tile goes straight into its reducer's staging slab (gg_grad_exchange follows on the same stream),
+    nothing is written to ``out``; whole range only.  Returns (None, None) then."""
     dev = _need_cuda(dlogits, x16, grad_scale)
     B, ldc = dlogits.shape
     dev = dlogits.device
     lib = _lib.load()
-    if out is None:
+    c0, c1 = (0, C) if c_range is None else c_range
+    assert 0 <= c0 < c1 <= C and c0 % 8 == 0, "geocell range must start at a multiple of 8"
+    dp_arr, dp_world, dp_rank = None, 0, 0
+    if push is not None:
+        import ctypes
+
+        assert (c0, c1) == (0, C), "the push mode covers the whole geocell range"
+        blk_count, ready, stage, dp_rank = push
+        dp_world = len(ready)
+        dp_arr = (ctypes.c_ulonglong * (1 + 2 * dp_world))(int(blk_count), *[int(p) for p in ready], *[int(p) for p in stage])
+        dW = db = None
+    elif out is None:
         dW = torch.empty((C, D), dtype=torch.float32, device=dev)
         db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
     else:
         dW, db = out
         if not want_db:
             db = None
-    c0, c1 = (0, C) if c_range is None else c_range
-    assert 0 <= c0 < c1 <= C and c0 % 8 == 0, "geocell range must start at a multiple of 8"
     ws = _u8(lib.gg_head_bwd_workspace_bytes(c1 - c0), dev)
-    if not want_db:
+    if not want_db and push is None:
         db_partials = None
     if grad_scale is not None:
         grad_scale = grad_scale.detach().float().contiguous()
     esz = dlogits.element_size()
-    sig_arr, sig_world = None, 0
-    if signal is not None:
-        import ctypes
-
-        assert (c0, c1) == (0, C) and db is not None, "block announcements need the whole geocell range and db"
-        blk_count, ready = signal
-        sig_world = len(ready)
-        sig_arr = (ctypes.c_ulonglong * (1 + sig_world))(int(blk_count), *[int(p) for p in ready])
     _call("gg_head_bwd", lib.gg_head_bwd, dev, _ptr(dlogits) + c0 * esz, ldc, _ptr(x16), x16.shape[1], B, c1 - c0, D, float(scale),
-          _ptr(grad_scale), _ptr(dW) + c0 * D * 4, 0 if db is None else _ptr(db) + c0 * 4,
+          _ptr(grad_scale), 0 if dW is None else _ptr(dW) + c0 * D * 4, 0 if db is None else _ptr(db) + c0 * 4,
           0 if db_partials is None else _ptr(db_partials) + c0 * 4, 0 if db_partials is None else db_partials.shape[0],
           0 if db_partials is None else db_partials.shape[1], _ptr(ws),
-          0 if sig_arr is None else ctypes.cast(sig_arr, ctypes.c_void_p), sig_world, _stream(dev))
+          0 if dp_arr is None else ctypes.cast(dp_arr, ctypes.c_void_p), dp_world, int(dp_rank), _stream(dev))
     return dW, db
-
-
-def head_dx(dlogits, w16, C, D, scale, grad_scale, emb_shape):
-    """demb = scale * grad_scale / V * (dlogits[:, :C] @ W), broadcast over the V headings (gg_head_dx): the gradient
-    with respect to the (B, V, D) / (B, D) embedding input.  w16: the forward's bf16 operand (first D columns used)."""
-    dev = _need_cuda(dlogits, w16, grad_scale)
-    B, ldc = dlogits.shape
-    V = 1 if len(emb_shape) == 2 else int(emb_shape[1])
-    demb = torch.empty(tuple(emb_shape), dtype=torch.float32, device=dlogits.device)
-    if grad_scale is not None:
-        grad_scale = grad_scale.detach().float().contiguous()
-    _call("gg_head_dx", _lib.load().gg_head_dx, dev, _ptr(dlogits), ldc, _ptr(w16), w16.shape[1], B, C, D, float(scale),
-          _ptr(grad_scale), V, _ptr(demb), _stream(dev))
-    return demb
-
-
-def topk_accuracy(topk_idx, targets):
-    """(2,) fp32 on the device: [top-1 accuracy, top-k accuracy] of the trainer's per-step metrics
-    (main_coordinator_idun_s3.py:399-408) -- no host synchronisation."""
-    dev = _need_cuda(topk_idx, targets)
-    topk_idx = topk_idx.detach().to(torch.int64).contiguous()
-    targets = targets.detach().to(torch.int64).contiguous()
-    B, k = topk_idx.shape
-    assert targets.shape == (B,)
-    acc = torch.empty((2,), dtype=torch.float32, device=topk_idx.device)
-    _call("gg_topk_accuracy", _lib.load().gg_topk_accuracy, dev, _ptr(topk_idx), k, _ptr(targets), B, _ptr(acc), _stream(dev))
-    return acc
-
-
-# --------------------------------------------------------------------------- f-4 hierarchical fusion
-def split3_bf16(src, role, pos_encoding=None, V=1):
-    """(rows, D) fp32 -> (rows, 6D) bf16 three-term split operand (gg_split3_bf16): role 0 activation, 1 weight."""
-    dev = _need_cuda(src, pos_encoding)
-    assert src.dtype == torch.float32 and src.dim() == 2
-    src = src.contiguous()
-    rows, D = src.shape
-    out = torch.empty((rows, 6 * D), dtype=torch.bfloat16, device=src.device)
-    _call("gg_split3_bf16", _lib.load().gg_split3_bf16, dev, _ptr(src), rows, D, int(role), _ptr(pos_encoding), int(V),
-          _ptr(out), _stream(dev))
-    return out
-
-
-def linear_bf16(a16, w16, bias, N):
-    """out (M, N) fp32 = a16 (M, K) @ w16 (N, K)^T + bias on the tensor cores (gg_linear_bf16)."""
-    dev = _need_cuda(a16, w16, bias)
-    M, K = a16.shape
-    assert w16.shape == (N, K) and a16.dtype == torch.bfloat16 and w16.dtype == torch.bfloat16
-    out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
-    b = None if bias is None else bias.detach().float().contiguous()
-    _call("gg_linear_bf16", _lib.load().gg_linear_bf16, dev, _ptr(a16), K, _ptr(w16), K, _ptr(b), M, N, K, _ptr(out), N,
-          _stream(dev))
-    return out
-
-
-def hier_fuse(x, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, pos_encoding, num_heads=16, weights=None):
-    """`hierarchical=True` fusion in eval mode (super_guessr.py:340-345): x (B, V, D) fp32 -> (B, D) fp32.
-    weights: optional cached (in_proj split, out_proj split) operands (they only change with the parameters)."""
-    dev = _need_cuda(x, in_proj_weight, out_proj_weight, pos_encoding)
-    assert x.dtype == torch.float32 and x.dim() == 3
-    B, V, D = x.shape
-    pe = pos_encoding.detach().float().reshape(-1, D).contiguous()
-    if B > pe.shape[0]:
-        raise RuntimeError(f"hierarchical fusion: the positional table is indexed by the batch row and holds "
-                           f"{pe.shape[0]} rows (models/layers/positional_encoder.py:44); batch {B} does not broadcast")
-    if weights is None:
-        weights = (split3_bf16(in_proj_weight.detach().float(), 1), split3_bf16(out_proj_weight.detach().float(), 1))
-    w_in, w_out = weights
-    zs = split3_bf16(x.contiguous().view(B * V, D), 0, pos_encoding=pe, V=V)
-    qkv = linear_bf16(zs, w_in, in_proj_bias, 3 * D)
-    ctx = torch.empty((B, 6 * D), dtype=torch.bfloat16, device=x.device)
-    _call("gg_hier_attention", _lib.load().gg_hier_attention, dev, _ptr(qkv), B, V, D, int(num_heads), _ptr(ctx), _stream(dev))
-    return linear_bf16(ctx, w_out, out_proj_bias, D)
 
 
 GRAD_CTRL_BYTES = 16384  # GG_GRAD_CTRL_BYTES
 GRAD_CTRL_READY_OFF = 4096  # GG_GRAD_CTRL_READY_OFF
 
 
-def grad_exchange(grad_ptrs, ctrl_ptrs, grad_mc, ctrl_mc, rank, C, D, no_wait=False):
-    """Block-by-block average of the symmetric-memory gradient buffers next to the dW GEMM (gg_grad_exchange), on
-    the current stream.  grad_ptrs / ctrl_ptrs: every rank's buffer / control region as mapped on this device;
-    grad_mc / ctrl_mc: their multicast addresses (0 = peer loads / stores).  no_wait: GG_GRAD_NO_WAIT (emulation)."""
+def grad_stage_floats(C, D, world):
+    return int(_lib.load().gg_grad_stage_floats(int(C), int(D), int(world)))
+
+
+def grad_exchange(grad_ptrs, ctrl_ptrs, grad_mc, ctrl_mc, stage_ptr, rank, C, D, no_wait=False):
+    """Second half of the fused gradient exchange (gg_grad_exchange), on the current stream, after the dW GEMM that
+    pushed the tiles: per owned block add the staged copies (local memory) in rank order and write the average into
+    every rank's gradient buffer.  grad_ptrs / ctrl_ptrs: every rank's buffer / control region as mapped on this
+    device; grad_mc / ctrl_mc: their multicast addresses (0 = posted peer stores); stage_ptr: this rank's staging
+    region.  no_wait: GG_GRAD_NO_WAIT (emulation)."""
     import ctypes
 
     world = len(grad_ptrs)
@@ -456,8 +392,8 @@ def grad_exchange(grad_ptrs, ctrl_ptrs, grad_mc, ctrl_mc, rank, C, D, no_wait=Fa
     c = (ctypes.c_ulonglong * world)(*[int(p) for p in ctrl_ptrs])
     dev = None  # raw addresses: the caller's current device / stream
     _call("gg_grad_exchange", _lib.load().gg_grad_exchange, dev, ctypes.cast(g, ctypes.c_void_p),
-          ctypes.cast(c, ctypes.c_void_p), int(grad_mc), int(ctrl_mc), world, int(rank), int(C), int(D), int(bool(no_wait)),
-          _stream(dev))
+          ctypes.cast(c, ctypes.c_void_p), int(grad_mc), int(ctrl_mc), int(stage_ptr), world, int(rank), int(C), int(D),
+          int(bool(no_wait)), _stream(dev))
 
 
 def p2p_allreduce_avg(peer_ptrs, rank, n_floats):

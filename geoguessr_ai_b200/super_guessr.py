@@ -320,10 +320,12 @@ class SuperGuessr(nn.Module):
         reference leaves to DDP / Accelerate).  After this call ``.grad`` is already the global average: do not
         wrap the module in DDP as well.
 
-        comm="fused": [dW | db] live in a symmetric-memory buffer mapped into every peer over NVLink; the dW GEMM
-        announces every finished block of 128 geocells to the rank that reduces it and gg_grad_exchange, launched
-        next to the GEMM on a second stream, averages the blocks as they arrive (NVSwitch multicast from 8 ranks,
-        peer loads / stores below) -- only the blocks the GEMM finishes last are exchanged after it; no host barrier.
+        comm="fused": [dW | db] and a staging region live in a symmetric-memory buffer mapped into every peer over
+        NVLink.  The dW GEMM stores every finished tile straight into the staging slab of the rank that reduces its
+        block of 128 geocells (posted stores: the transfer rides under the GEMM) and announces complete blocks;
+        gg_grad_exchange, behind it on the same stream, adds the locally staged copies in rank order and writes the
+        averages into every rank's gradient (NVSwitch multicast stores from 8 ranks, posted peer stores below).
+        No peer loads, no host barrier.
         comm="nvls" / "p2p": the same buffer, ONE exchange kernel after the GEMM between two symmetric-memory
         barriers -- "nvls" through the NVSwitch multicast mapping (gg_nvls_allreduce_avg), "p2p" with peer loads /
         stores (gg_p2p_allreduce_avg: two-shot, rank-order sums).
@@ -378,7 +380,8 @@ class SuperGuessr(nn.Module):
             n = C * D + C
             n_pad = -(-n // (4 * world)) * (4 * world)
             ctrl_words = ops.GRAD_CTRL_BYTES // 4
-            buf = symm.empty(ctrl_words + n_pad, dtype=torch.float32, device=dev)
+            n_stage = ops.grad_stage_floats(C, D, world) if kind == "fused" else 0
+            buf = symm.empty(ctrl_words + n_pad + n_stage, dtype=torch.float32, device=dev)
             handle = symm.rendezvous(buf, group.group_name)
         except Exception as e:  # noqa: BLE001
             if dp["comm"] != "auto":
@@ -392,13 +395,14 @@ class SuperGuessr(nn.Module):
         mc = int(getattr(handle, "multicast_ptr", 0) or 0)
         if kind == "nvls" and mc == 0:
             raise RuntimeError("comm='nvls': this group has no NVSwitch multicast mapping (multicast_ptr == 0)")
-        buf.zero_()  # control words + pad start at zero on every rank ...
+        buf.zero_()  # control words, pad and staging rows start at zero on every rank ...
         torch.cuda.current_stream(dev).synchronize()
         handle.barrier(channel=0)  # ... before any peer can add to them
         base = [int(p) for p in handle.buffer_ptrs]
         off = ops.GRAD_CTRL_BYTES
         use_mc = mc != 0 and (kind == "nvls" or (kind == "fused" and world >= 8))
         dp["symm"] = dict(key=(C, D, dev), buf=buf, handle=handle, ctrl_ptrs=base, ptrs=[p + off for p in base],
+                          stage_ptrs=[p + off + 4 * n_pad for p in base],
                           world=world, rank=rank, n=n_pad, multicast=(mc + off) if mc else 0,
                           ctrl_multicast=mc, kind=kind, use_mc=use_mc, grad_off=ctrl_words)
         return dp["symm"]
@@ -415,8 +419,10 @@ class SuperGuessr(nn.Module):
         path = ("NVSwitch multicast (multimem.ld_reduce / multimem.st)" if sm["use_mc"]
                 else "peer loads in rank order + peer stores")
         if sm["kind"] == "fused":
-            return (f"fused: gg_head_bwd announces finished 128-geocell blocks of [dW | db] (symmetric memory, fp32) and "
-                    f"gg_grad_exchange averages them block by block next to the GEMM via {path}; no host barrier")
+            how = "multimem.st through the NVSwitch" if sm["use_mc"] else "posted peer stores"
+            return ("fused: gg_head_bwd stores every dW / db tile into the reducing rank's staging slab (symmetric memory, "
+                    "fp32, posted over NVLink under the GEMM) and announces complete 128-geocell blocks; gg_grad_exchange "
+                    f"adds the staged copies in rank order and broadcasts the averages ({how}); no peer loads, no host barrier")
         return (f"{sm['kind']}: one exchange kernel ({path}) over [dW | db] in symmetric memory after the dW GEMM, "
                 "between two symmetric-memory barriers")
 
@@ -439,16 +445,13 @@ class SuperGuessr(nn.Module):
             dp["stream"] = torch.cuda.Stream(device=dev)
         comm, cur = dp["stream"], torch.cuda.current_stream(dev)
         if sm["kind"] == "fused":
-            # the exchange kernel is ordered only behind what precedes the GEMM: it runs NEXT TO it, waiting block
-            # by block for every rank's announcement
-            comm.wait_stream(cur)
+            # the dW GEMM pushes every tile into its reducer's staging slab (over NVLink, under the GEMM) and announces
+            # complete blocks; the exchange kernel behind it adds the staged copies and broadcasts the averages
             ready = [p + ops.GRAD_CTRL_READY_OFF for p in sm["ctrl_ptrs"]]
             ops.head_backward(dlogits, x16, C, D, scale=1.0 / B, grad_scale=gloss, want_db=True, db_partials=dbp,
-                              out=(dW, db), signal=(sm["ctrl_ptrs"][sm["rank"]], ready))
-            with torch.cuda.stream(comm):
-                ops.grad_exchange(sm["ptrs"], sm["ctrl_ptrs"], sm["multicast"] if sm["use_mc"] else 0,
-                                  sm["ctrl_multicast"] if sm["use_mc"] else 0, sm["rank"], C, D)
-            cur.wait_stream(comm)
+                              push=(sm["ctrl_ptrs"][sm["rank"]], ready, sm["stage_ptrs"], sm["rank"]))
+            ops.grad_exchange(sm["ptrs"], sm["ctrl_ptrs"], sm["multicast"] if sm["use_mc"] else 0,
+                              sm["ctrl_multicast"] if sm["use_mc"] else 0, sm["stage_ptrs"][sm["rank"]], sm["rank"], C, D)
             return dW, (db if want_b else None)
 
         h = sm["handle"]

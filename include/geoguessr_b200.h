@@ -144,14 +144,15 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * sums from gg_hav_ce_fwd_bwd; when null, db is computed from dlogits.  workspace
  * (gg_head_bwd_workspace_bytes(C) bytes, required): parked partial accumulators + flags of the stream-K
  * schedule, and the column-sum slices of the db pass.
- * Data parallelism (gg_grad_exchange below): with signal_world > 1, dW / db are this rank's gradient buffer in
- * symmetric memory and signal_ptrs (HOST array of 1 + signal_world device addresses) = {this rank's block counters,
- * rank 0's `ready` counters, rank 1's, ...} (gg_grad_ctrl_layout): as soon as all column tiles of a 128-geocell
- * block are written the kernel announces the block to the rank that reduces it (block b -> rank b % world), so
- * the exchange runs block by block underneath this GEMM.  signal_world <= 1: no signalling, signal_ptrs unused. */
+ * Data parallelism (gg_grad_exchange below): with dp_world > 1 the kernel does not write dW / db at all (both may be
+ * null): every finished tile of 128 geocells x 256 columns -- and the block's 128 db entries -- is stored straight
+ * into the staging slab of the rank that reduces the block (block b -> rank b % dp_world), over NVLink for the other
+ * ranks, and complete blocks are announced on that rank's `ready` counters.  dp_ptrs: HOST array of 1 + 2 * dp_world
+ * device addresses as mapped on this device = {this rank's control region + GG_GRAD_CTRL_BLKCOUNT_OFF, control region +
+ * GG_GRAD_CTRL_READY_OFF of rank 0, 1, ..., staging region of rank 0, 1, ...}.  dp_world <= 1: plain local dW / db. */
 int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
                 const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
-                void* workspace, const unsigned long long* signal_ptrs, int signal_world, gg_stream_t stream);
+                void* workspace, const unsigned long long* dp_ptrs, int dp_world, int dp_rank, gg_stream_t stream);
 
 /* dx of the same layer (autograd of super_guessr.py:354 w.r.t. its input; reached from
  * main_coordinator_idun_s3.py:423 whenever the encoder is trained -- TinyViT's last stage / CLIP's last layer,
@@ -255,16 +256,19 @@ int gg_p2p_allreduce_avg(const unsigned long long* peer_ptrs, int world, int ran
  * multicast address of the buffer on this device.  Same ordering contract as gg_p2p_allreduce_avg. */
 int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_floats, gg_stream_t stream);
 
-/* The same average, block by block UNDERNEATH the dW GEMM (no host barrier, only the last blocks are exposed).
- * Every rank owns, in symmetric memory, a control region of GG_GRAD_CTRL_BYTES (zeroed once, before the first step)
- * and its gradient buffer [dW (C,D) | db (C) | pad to a multiple of 4 floats].  gg_head_bwd (signal_ptrs = {ctrl +
- * GG_GRAD_CTRL_BLKCOUNT_OFF of this rank, ctrl + GG_GRAD_CTRL_READY_OFF of rank 0, 1, ...}) announces every finished
- * block of 128 geocells to rank (block % world); gg_grad_exchange, launched on ANOTHER stream next to that GEMM,
- * waits per owned block for all ranks' announcements, averages the block -- multimem.ld_reduce / multimem.st through
- * the NVSwitch when the multicast addresses are given, else peer loads in rank order + peer stores (deterministic,
- * identical on all ranks) -- and tells every rank; it returns when every block of every owner has landed in this
- * rank's copy.  grad_ptrs / ctrl_ptrs: HOST arrays of `world` device addresses (rank order, as mapped on this
- * device); grad_mc / ctrl_mc: multicast addresses of the same buffers or both null.  world in {1, 2, 4, 8}.
+/* The same average with the transfer fused into the dW GEMM (no host barrier; only the reduction of locally staged
+ * copies and the broadcast of the averages are left for after the GEMM).  Every rank owns, in symmetric memory, a
+ * control region of GG_GRAD_CTRL_BYTES (zeroed once, before the first step), its gradient buffer [dW (C,D) | db (C) |
+ * pad to a multiple of 4 floats] and a staging region of gg_grad_stage_floats(C, D, world) floats: `world` slabs (one
+ * per source rank), each = the dW rows of the blocks this rank reduces (block b of 128 geocells -> rank b % world)
+ * followed by their db entries.  gg_head_bwd (dp_world > 1) pushes every tile into the reducer's slab and announces
+ * complete blocks; gg_grad_exchange, launched AFTER it on the same stream, waits per owned block for all ranks'
+ * announcements, adds the staged copies in rank order (deterministic, identical on all ranks), scales by 1 / world and
+ * writes the average into every rank's gradient buffer -- multimem.st through the NVSwitch when the multicast
+ * addresses are given, else posted peer stores -- and returns when every block of every reducer has landed in this
+ * rank's gradient.  grad_ptrs / ctrl_ptrs: HOST arrays of `world` device addresses (rank order, as mapped on this
+ * device); grad_mc / ctrl_mc: multicast addresses of the same buffers or both null; stage: THIS rank's staging
+ * region.  world in {1, 2, 4, 8}.
  * flags: GG_GRAD_NO_WAIT = return once this rank's own blocks are exchanged, without waiting for the other reducers'
  * blocks to land (the caller orders the gradient's consumer behind every rank's exchange by other means; used by
  * the single-process emulation of the tests, where the "ranks" share one GPU's launch queues). */
@@ -273,8 +277,9 @@ int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_flo
 #define GG_GRAD_CTRL_READY_OFF 4096
 #define GG_GRAD_NO_WAIT 1
 size_t gg_grad_ctrl_bytes(void);
+size_t gg_grad_stage_floats(int C, int D, int world);
 int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsigned long long* ctrl_ptrs, void* grad_mc,
-                     void* ctrl_mc, int world, int rank, int C, int D, int flags, gg_stream_t stream);
+                     void* ctrl_mc, const void* stage, int world, int rank, int C, int D, int flags, gg_stream_t stream);
 
 #ifdef __cplusplus
 }

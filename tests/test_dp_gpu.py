@@ -41,23 +41,22 @@ def test_two_shot_allreduce_single_device_emulation(world, n):
 
 @pytest.mark.parametrize("world,Cc,D,B", [(2, 1500, 192, 200), (4, 1500, 576, 200), (8, 2100, 256, 136), (2, 12647, 1024, 512)])
 def test_fused_exchange_single_device_emulation(world, Cc, D, B):
-    """gg_head_bwd announcing finished 128-geocell blocks + gg_grad_exchange averaging them as they arrive, with
-    `world` gradient buffers / control regions of ONE GPU standing in for the ranks (peer pointers are plain
-    addresses; every "rank" runs its dW GEMM and its exchange kernel on its own pair of streams, all concurrently).
-    Two steps back to back (the counters only grow: epochs).  Every copy must end up holding the rank-order
-    average of the per-rank gradients, bit for bit."""
+    """gg_head_bwd pushing its tiles into the reducers' staging slabs + gg_grad_exchange adding the staged copies,
+    with `world` buffers (control | gradient | staging) of ONE GPU standing in for the ranks (peer pointers are plain
+    addresses).  Two steps back to back (the counters only grow: epochs), with / without the loss kernel's db
+    partials.  Every copy must end up holding the rank-order average of the per-rank gradients, bit for bit."""
     from geoguessr_ai_b200 import ops
 
     dev = torch.device("cuda:0")
     ctrl_words = ops.GRAD_CTRL_BYTES // 4
     n = Cc * D + Cc
     n_pad = -(-n // (4 * world)) * (4 * world)
-    bufs = [torch.zeros(ctrl_words + n_pad, dtype=torch.float32, device=dev) for _ in range(world)]
+    n_stage = ops.grad_stage_floats(Cc, D, world)
+    bufs = [torch.zeros(ctrl_words + n_pad + n_stage, dtype=torch.float32, device=dev) for _ in range(world)]
     ctrl_ptrs = [b.data_ptr() for b in bufs]
     grad_ptrs = [p + ops.GRAD_CTRL_BYTES for p in ctrl_ptrs]
+    stage_ptrs = [p + 4 * n_pad for p in grad_ptrs]
     ready = [p + ops.GRAD_CTRL_READY_OFF for p in ctrl_ptrs]
-    mains = [torch.cuda.Stream() for _ in range(world)]
-    comms = [torch.cuda.Stream() for _ in range(world)]
     ldc = ops.logits_ld(Cc)
     for step in range(2):
         g = torch.Generator().manual_seed(100 * world + step)
@@ -75,19 +74,16 @@ def test_fused_exchange_single_device_emulation(world, Cc, D, B):
             want_w = dW if want_w is None else want_w + dW  # rank order, fp32
             want_b = db if want_b is None else want_b + db
         want_w, want_b = want_w * (1.0 / world), want_b * (1.0 / world)
+        for b in bufs:
+            b[ctrl_words: ctrl_words + n_pad].fill_(float("nan"))  # the gradient must be fully overwritten
         torch.cuda.synchronize()
-        # Every GEMM is queued before any exchange kernel, and the exchange kernels do not wait for each other
-        # (GG_GRAD_NO_WAIT): on ONE GPU the "ranks" share hardware launch queues, so a kernel may not depend on one
-        # queued behind it.  The GEMMs take turns (shared memory); the exchange kernels spin beside them.
+        # one stream: every "rank" pushes, then every "rank" reduces what it owns (GG_GRAD_NO_WAIT: on ONE GPU the
+        # exchange kernels run one after the other and must not wait for each other's blocks)
         for r in range(world):
-            dW = bufs[r][ctrl_words: ctrl_words + Cc * D].view(Cc, D)
-            db = bufs[r][ctrl_words + Cc * D: ctrl_words + Cc * D + Cc]
-            with torch.cuda.stream(mains[r]):
-                ops.head_backward(dls[r], xs[r], Cc, D, scale=0.5, db_partials=dbps[r], out=(dW, db),
-                                  signal=(ctrl_ptrs[r], ready))
+            ops.head_backward(dls[r], xs[r], Cc, D, scale=0.5, db_partials=dbps[r],
+                              push=(ctrl_ptrs[r], ready, stage_ptrs, r))
         for r in range(world):
-            with torch.cuda.stream(comms[r]):
-                ops.grad_exchange(grad_ptrs, ctrl_ptrs, 0, 0, r, Cc, D, no_wait=True)
+            ops.grad_exchange(grad_ptrs, ctrl_ptrs, 0, 0, stage_ptrs[r], r, Cc, D, no_wait=True)
         torch.cuda.synchronize()
         for r in range(world):
             dW = bufs[r][ctrl_words: ctrl_words + Cc * D].view(Cc, D)

@@ -333,9 +333,10 @@ class SuperGuessr(nn.Module):
         runs in that many geocell ranges (dp_chunk_bounds), each all-reduced while the next one is computed.
         ``comm_dtype=torch.bfloat16`` (NCCL only) halves the bytes on NVLink by rounding each rank's gradient
         before the sum (opt-in: not bit-faithful to an fp32 all-reduce).
-        comm="auto": "fused" for 2, 4 or 8 ranks when symmetric memory can be set up, else "nccl" (also for
-        CPU / gloo groups, where the path uses whatever all_reduce the group's backend provides).  The transport
-        is decided when the buffer is set up, before any kernel runs."""
+        comm="auto": what measured fastest on B200 NVSwitch boxes for the 51.9 MB head gradient -- "fused" at 8
+        ranks, "p2p" at 2 and 4 -- when symmetric memory can be set up, else "nccl" (also for CPU / gloo groups,
+        where the path uses whatever all_reduce the group's backend provides).  The transport is decided when the
+        buffer is set up, before any kernel runs."""
         import torch.distributed as dist
 
         if not dist.is_initialized():
@@ -353,7 +354,13 @@ class SuperGuessr(nn.Module):
         if comm == "nccl" or not is_cuda or comm_dtype is not None:
             return "nccl"
         if world in (2, 4, 8):
-            return "fused" if comm == "auto" else comm
+            # measured on B200 NVSwitch boxes (profiles/README.md, r02): at 8 ranks the exchange fused into the dW
+            # GEMM wins (0.470 ms per step against 0.515 multicast / 0.522 peer two-shot / 0.593 NCCL); at 2 and 4
+            # ranks a rank's NVLink egress carries its gradient twice in the fused scheme (push + broadcast) and the
+            # two-shot exchange after the GEMM, which uses both directions at once, is as fast or faster
+            if comm == "auto":
+                return "fused" if world >= 8 else "p2p"
+            return comm
         if comm == "auto":
             return "nccl"
         raise ValueError(f"comm='{comm}' covers 2, 4 or 8 ranks; this group has {world} (use comm='auto' or 'nccl')")
@@ -400,7 +407,7 @@ class SuperGuessr(nn.Module):
         handle.barrier(channel=0)  # ... before any peer can add to them
         base = [int(p) for p in handle.buffer_ptrs]
         off = ops.GRAD_CTRL_BYTES
-        use_mc = mc != 0 and (kind == "nvls" or (kind == "fused" and world >= 8))
+        use_mc = mc != 0 and (kind == "nvls" or (kind == "fused" and world >= 4))
         dp["symm"] = dict(key=(C, D, dev), buf=buf, handle=handle, ctrl_ptrs=base, ptrs=[p + off for p in base],
                           stage_ptrs=[p + off + 4 * n_pad for p in base],
                           world=world, rank=rank, n=n_pad, multicast=(mc + off) if mc else 0,

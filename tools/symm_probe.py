@@ -50,6 +50,18 @@ try:
     tb = timeit(lambda: h.barrier(channel=0))
     if rank == 0:
         print(f"multimem_all_reduce_: {t_mm:.1f} us; two_shot: {t_two:.1f} us; symm barrier: {tb:.1f} us", flush=True)
+    # what one direction of NVLink gives for half the buffer (the slice a two-rank exchange moves each way):
+    # the copy engine (cudaMemcpyPeer behind Tensor.copy_) against the same bytes stored by SM threads
+    peer = (rank + 1) % world
+    half = n // 2
+    remote = h.get_buffer(peer, (n,), torch.float32)
+    src = torch.randn(half, device=dev)
+    t_dma = timeit(lambda: remote[:half].copy_(src))
+    t_dma_in = timeit(lambda: src.copy_(remote[:half]))
+    dist.barrier()
+    if rank == 0:
+        print(f"{half * 4 / 1e6:.1f} MB to the peer: copy engine push {t_dma:.1f} us = {half * 4 / t_dma / 1e3:.0f} GB/s, "
+              f"pull {t_dma_in:.1f} us = {half * 4 / t_dma_in / 1e3:.0f} GB/s", flush=True)
 except Exception as e:  # noqa: BLE001
     if rank == 0:
         print("symmetric memory probe failed:", type(e).__name__, str(e)[:500], flush=True)

@@ -371,12 +371,86 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_p
     return dW, db
 
 
+def head_dx(dlogits, w16, C, D, scale, grad_scale, emb_shape):
+    """demb = scale * grad_scale / V * (dlogits[:, :C] @ W), broadcast over the V headings (gg_head_dx): the gradient
+    with respect to the (B, V, D) / (B, D) embedding input.  w16: the forward's bf16 operand (first D columns used)."""
+    dev = _need_cuda(dlogits, w16, grad_scale)
+    B, ldc = dlogits.shape
+    V = 1 if len(emb_shape) == 2 else int(emb_shape[1])
+    demb = torch.empty(tuple(emb_shape), dtype=torch.float32, device=dlogits.device)
+    if grad_scale is not None:
+        grad_scale = grad_scale.detach().float().contiguous()
+    _call("gg_head_dx", _lib.load().gg_head_dx, dev, _ptr(dlogits), ldc, _ptr(w16), w16.shape[1], B, C, D, float(scale),
+          _ptr(grad_scale), V, _ptr(demb), _stream(dev))
+    return demb
+
+
+def topk_accuracy(topk_idx, targets):
+    """(2,) fp32 on the device: [top-1 accuracy, top-k accuracy] of the trainer's per-step metrics
+    (main_coordinator_idun_s3.py:399-408) -- no host synchronisation."""
+    dev = _need_cuda(topk_idx, targets)
+    topk_idx = topk_idx.detach().to(torch.int64).contiguous()
+    targets = targets.detach().to(torch.int64).contiguous()
+    B, k = topk_idx.shape
+    assert targets.shape == (B,)
+    acc = torch.empty((2,), dtype=torch.float32, device=topk_idx.device)
+    _call("gg_topk_accuracy", _lib.load().gg_topk_accuracy, dev, _ptr(topk_idx), k, _ptr(targets), B, _ptr(acc), _stream(dev))
+    return acc
+
+
+# --------------------------------------------------------------------------- f-4 hierarchical fusion
+def split3_bf16(src, role, pos_encoding=None, V=1):
+    """(rows, D) fp32 -> (rows, 6D) bf16 three-term split operand (gg_split3_bf16): role 0 activation, 1 weight."""
+    dev = _need_cuda(src, pos_encoding)
+    assert src.dtype == torch.float32 and src.dim() == 2
+    src = src.contiguous()
+    rows, D = src.shape
+    out = torch.empty((rows, 6 * D), dtype=torch.bfloat16, device=src.device)
+    _call("gg_split3_bf16", _lib.load().gg_split3_bf16, dev, _ptr(src), rows, D, int(role), _ptr(pos_encoding), int(V),
+          _ptr(out), _stream(dev))
+    return out
+
+
+def linear_bf16(a16, w16, bias, N):
+    """out (M, N) fp32 = a16 (M, K) @ w16 (N, K)^T + bias on the tensor cores (gg_linear_bf16)."""
+    dev = _need_cuda(a16, w16, bias)
+    M, K = a16.shape
+    assert w16.shape == (N, K) and a16.dtype == torch.bfloat16 and w16.dtype == torch.bfloat16
+    out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
+    b = None if bias is None else bias.detach().float().contiguous()
+    _call("gg_linear_bf16", _lib.load().gg_linear_bf16, dev, _ptr(a16), K, _ptr(w16), K, _ptr(b), M, N, K, _ptr(out), N,
+          _stream(dev))
+    return out
+
+
+def hier_fuse(x, in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, pos_encoding, num_heads=16, weights=None):
+    """`hierarchical=True` fusion in eval mode (super_guessr.py:340-345): x (B, V, D) fp32 -> (B, D) fp32.
+    weights: optional cached (in_proj split, out_proj split) operands (they only change with the parameters)."""
+    dev = _need_cuda(x, in_proj_weight, out_proj_weight, pos_encoding)
+    assert x.dtype == torch.float32 and x.dim() == 3
+    B, V, D = x.shape
+    pe = pos_encoding.detach().float().reshape(-1, D).contiguous()
+    if B > pe.shape[0]:
+        raise RuntimeError(f"hierarchical fusion: the positional table is indexed by the batch row and holds "
+                           f"{pe.shape[0]} rows (models/layers/positional_encoder.py:44); batch {B} does not broadcast")
+    if weights is None:
+        weights = (split3_bf16(in_proj_weight.detach().float(), 1), split3_bf16(out_proj_weight.detach().float(), 1))
+    w_in, w_out = weights
+    zs = split3_bf16(x.contiguous().view(B * V, D), 0, pos_encoding=pe, V=V)
+    qkv = linear_bf16(zs, w_in, in_proj_bias, 3 * D)
+    ctx = torch.empty((B, 6 * D), dtype=torch.bfloat16, device=x.device)
+    _call("gg_hier_attention", _lib.load().gg_hier_attention, dev, _ptr(qkv), B, V, D, int(num_heads), _ptr(ctx), _stream(dev))
+    return linear_bf16(ctx, w_out, out_proj_bias, D)
+
+
 GRAD_CTRL_BYTES = 16384  # GG_GRAD_CTRL_BYTES
 GRAD_CTRL_READY_OFF = 4096  # GG_GRAD_CTRL_READY_OFF
 
 
 def grad_stage_floats(C, D, world):
-    return int(_lib.load().gg_grad_stage_floats(int(C), int(D), int(world)))
+    lib = _lib.load()
+    assert lib.gg_grad_ctrl_bytes() == GRAD_CTRL_BYTES, "control-region size of the library and of the binding differ"
+    return int(lib.gg_grad_stage_floats(int(C), int(D), int(world)))
 
 
 def grad_exchange(grad_ptrs, ctrl_ptrs, grad_mc, ctrl_mc, stage_ptr, rank, C, D, no_wait=False):

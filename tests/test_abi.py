@@ -53,3 +53,20 @@ def test_no_cpu_fallback():
     m = gg.SuperGuessr(None, panorama=True, embed_dim=64, centroids=torch.zeros(10, 2), serving=True).eval()
     with pytest.raises(_lib.GeoguessrB200Error):
         m(embedding=torch.zeros(2, 4, 64))
+
+
+def test_every_launcher_has_a_python_caller():
+    """Each gg_* entry point of the binding is used by the package itself (ops.py / proto_builder.py / the modules):
+    a wrapper lost in an edit shows up here, on the CPU, not as an AttributeError on the GPU box."""
+    pkg = os.path.join(REPO, "geoguessr_ai_b200")
+    text = ""
+    for name in os.listdir(pkg):
+        if name.endswith(".py") and name != "_lib.py":
+            text += open(os.path.join(pkg, name)).read()
+    text += open(os.path.join(REPO, "tools", "head_fwd_timeline.py")).read()
+    missing = [s for s in _lib.SIGNATURES if s not in text and s not in ("gg_abi_version", "gg_last_error")]
+    assert not missing, f"no Python caller for {missing}"
+    for fn in ("head_dx", "topk_accuracy", "split3_bf16", "linear_bf16", "hier_fuse", "grad_exchange", "grad_stage_floats",
+               "proto_record_ids", "proto_take_image_coords", "cast_bank_bf16", "proto_group_cells", "head_forward",
+               "head_backward", "hav_ce", "hard_ce", "fuse_headings", "fuse_and_prepare", "proto_retrieve", "proto_refine"):
+        assert hasattr(ops, fn), fn

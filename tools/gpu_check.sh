@@ -32,7 +32,7 @@ for w in $what; do
       timeout 300 python bench.py --workload infer --protos 1000000 --steps 10 --warmup 3 > gpurun_out/infer_1m.json 2> gpurun_out/infer_1m.err; echo "infer1m rc=$?"
       timeout 300 python bench.py --workload infer --protos 10000000 --steps 5 --warmup 3 --no-cpu > gpurun_out/infer_10m.json 2> gpurun_out/infer_10m.err; echo "infer10m rc=$?" ;;
     ncuinfer)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(proto_|head_fwd|head_merge|fuse_headings)" -s 27 -c 9 -f -o gpurun_out/prof_infer \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(proto_retrieve|proto_refine|head_fwd|fuse_flat|fuse_rows)" -s 15 -c 5 -f -o gpurun_out/prof_infer \
         python bench.py --workload infer --protos 1000000 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_infer.log 2>&1; echo "ncuinfer rc=$?" ;;
     p2p)  # needs gpurun --gpus N (N = 2, 4 or 8): gradient exchange kernels against NCCL + data-parallel bench
       N=$(nvidia-smi -L | wc -l)
@@ -50,10 +50,10 @@ for w in $what; do
         python tools/kbench.py 3 > gpurun_out/klaunch.log 2>&1; echo "klaunch rc=$?" ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-        python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
+        python bench.py --workload train --sustained-s 0 --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1; echo "launches rc=$?" ;;
     ncu)
       timeout 1200 ncu --set full --clock-control none --import-source on \
         -k regex:"${NCU_KERNELS:-^(cast_weight|fuse_|hav_|head_|label_xyz)}" -s ${NCU_SKIP:-28} -c ${NCU_COUNT:-7} -f -o gpurun_out/prof_train \
-        python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
+        python bench.py --workload train --sustained-s 0 --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?" ;;
   esac
 done

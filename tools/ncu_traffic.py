@@ -17,7 +17,8 @@ from collections import OrderedDict
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LAUNCHER = {"head_fwd_kernel": "gg_head_fwd", "hav_ce_stream_kernel": "gg_hav_ce_fwd_bwd", "head_bwd_kernel": "gg_head_bwd",
-            "fuse_headings_kernel": "gg_fuse_headings", "fuse_and_cast_kernel": "gg_fuse_and_prepare", "cast_weight_kernel": "gg_prepare_head_weights",
+            "fuse_flat_kernel": "gg_fuse_headings", "fuse_rows_kernel": "gg_fuse_headings (with norms)",
+            "fuse_and_cast_kernel": "gg_fuse_and_prepare", "cast_weight_kernel": "gg_prepare_head_weights",
             "proto_retrieve_kernel": "gg_proto_retrieve", "proto_refine_kernel": "gg_proto_refine",
             "hav_row_stats_kernel": "gg_hav_row_stats"}
 METRICS = OrderedDict([

@@ -53,13 +53,14 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
-def profile_traffic(launcher):
+def profile_traffic(launcher, prefix=""):
     """dram read + write bytes per launch of the launcher's main kernel, from the committed ncu capture
-    (profiles/traffic.json, written by tools/ncu_traffic.py from `ncu --set full`); None if not captured."""
+    (profiles/traffic.json, written by tools/ncu_traffic.py from `ncu --set full`; serving captures under
+    "infer:<launcher>", taken at 1 M prototypes); None if not captured."""
     path = os.path.join(REPO, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get(launcher, {}).get("dram_bytes")
+            return json.load(f).get(prefix + launcher, {}).get("dram_bytes")
     except (OSError, ValueError):
         return None
 
@@ -273,11 +274,11 @@ def kernel_table(per, calls, algo, peaks):
     return kernels
 
 
-def dominant_roofline(kernels, peaks, extra=None):
+def dominant_roofline(kernels, peaks, extra=None, traffic_prefix=""):
     dom = max((k for k in kernels if "frac" in kernels[k]),
               key=lambda k: kernels[k]["ms"] * kernels[k].get("calls_per_step", 1))
     roof = {k: v for k, v in kernels[dom].items() if k not in ("ms", "calls_per_step")}
-    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom),
+    roof.update({"kernel": dom, "ms_per_launch": kernels[dom]["ms"], "traffic": profile_traffic(dom, traffic_prefix),
                  "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; "
                                 + ("bf16_tflops, the burst figure: the launcher is timed alone with CUDA events"
                                    if roof["bound"] == "tensor" else "hbm_gbs") + ")"})
@@ -384,24 +385,6 @@ def run_b200_train(args, ctx):
     value = world * B / (ms_step / 1e3)
     final_loss = loss.item()
 
-    # ---------------- the same loop run back to back for >= 2 s: what the step does under the power cap
-    sustained = None
-    if args.sustained_s > 0:
-        n_sus = int(max(K, min(200000, args.sustained_s * 1e3 / ms_step)))
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        barrier()
-        e0.record()
-        for i in range(n_sus):
-            run(("res", i % 3), *resident[i % 3])
-        e1.record()
-        barrier()
-        ms_sus = max_over_ranks(e0.elapsed_time(e1)) / n_sus
-        sus_clocks = sampler.stop() if rank == 0 else None
-        sustained = {"steps": n_sus, "seconds": ms_sus * n_sus / 1e3, "ms_per_step": ms_sus,
-                     "value": world * B / (ms_sus / 1e3), "unit": "samples/s", "clocks": sus_clocks}
-
     # ---------------- per-launcher CUDA-event timing over a second identical timed region
     # Eager launches; a ~1 ms device-side spin queued ahead of every step lets the host run a whole step
     # ahead, so the events bracket device time only (no launch gaps inside the brackets).
@@ -498,6 +481,27 @@ def run_b200_train(args, ctx):
                            "for the 12647 real geocells; context for roofline.frac, whose denominator is cuBLAS at 8192^3"}
         del wp
         del xa, wa, ga
+
+    # ---------------- the same loop run back to back for >= 2 s: what the step does under the power cap
+    sustained = None  # (last: it heats the part; everything above is measured at burst clocks)
+    if args.sustained_s > 0:
+        n_sus = int(max(K, min(200000, args.sustained_s * 1e3 / ms_step)))
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0.record()
+        for i in range(n_sus):
+            run(("res", i % 3), *resident[i % 3])
+        e1.record()
+        barrier()
+        ms_sus = max_over_ranks(e0.elapsed_time(e1)) / n_sus
+        sus_clocks = sampler.stop() if rank == 0 else None
+        sustained = {"steps": n_sus, "seconds": ms_sus * n_sus / 1e3, "ms_per_step": ms_sus,
+                     "value": world * B / (ms_sus / 1e3), "unit": "samples/s", "clocks": sus_clocks}
+
+    if sustained is not None:
+        time.sleep(1.5)  # let the power-cap controller release the clocks before the next workload is timed
 
     grad_comm = None
     if world > 1:
@@ -760,7 +764,8 @@ def run_b200_infer(args, ctx, P, B, K):
                   "work_items": stats["work_items"], "units": stats["units"]}
             kernels["gg_proto_retrieve"].update(ex)
             extra["gg_proto_retrieve"] = ex
-        roof = dominant_roofline(kernels, peaks, extra)
+        # (the committed capture is the 1 M-prototype run on one GPU: no traffic figure for other shapes)
+        roof = dominant_roofline(kernels, peaks, extra, "infer:" if (P <= 1_000_000 and world == 1) else "none:")
         cpu = agree = None
         if not args.no_cpu:
             nq = 256

@@ -69,7 +69,10 @@ def main():
             lines.append(f"| `{name[:48]}` | {a['n']} | " + " | ".join(
                 f"{mean[m]:.0f}" if METRICS[m] in ("regs", "grid", "block") else f"{mean[m]:.2f}" for m in METRICS) + " |")
             if a["base"] in LAUNCHER:
-                traffic[LAUNCHER[a["base"]]] = {
+                # captures of the serving workload (file name contains "infer") get their own keys: the same launcher
+                # runs on another batch there
+                key = ("infer:" if "infer" in os.path.basename(rep) else "") + LAUNCHER[a["base"]]
+                traffic[key] = {
                     "kernel": name, "dram_bytes": (mean["dram__bytes_read.sum"] + mean["dram__bytes_write.sum"]) * 1e6,
                     "dram_read_bytes": mean["dram__bytes_read.sum"] * 1e6, "dram_write_bytes": mean["dram__bytes_write.sum"] * 1e6,
                     "ncu_us": mean["gpu__time_duration.sum"], "source": f"profiles/{rnd}_ncu_kernels.md ({os.path.basename(rep)})"}

@@ -237,12 +237,14 @@ __device__ __forceinline__ void lse_merge(float& lmax, float& lsum, float m, flo
 }
 constexpr uint32_t kEpiBarrier = 1;  // named barrier of the 16 epilogue warps
 
-// Optional per-CTA timeline (tools/head_fwd_timeline.py): 16 globaltimer stamps per CTA when a buffer is set.
+// Optional per-CTA timeline (tools/head_fwd_timeline.py): 64 globaltimer stamps per CTA when a buffer is set
+// (16 named points; then for each of the CTA's first 16 tiles: 16+i accumulator seen complete by epilogue warp 0,
+// 32+i that warp ready for it -- the gap is its wait --, 48+i the tile's last MMA issued).
 __device__ __forceinline__ void stamp(long long* tl, int slot) {
   if (tl != nullptr) {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    tl[static_cast<size_t>(blockIdx.x) * 16 + slot] = t;
+    tl[static_cast<size_t>(blockIdx.x) * 64 + slot] = t;
   }
 }
 
@@ -403,7 +405,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (timeline != nullptr) {
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      timeline[static_cast<size_t>(blockIdx.x) * 16 + 15] = smid;
+      timeline[static_cast<size_t>(blockIdx.x) * 64 + 15] = smid;
     }
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
@@ -479,6 +481,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
         if (it == 0 && lane == 0) stamp(timeline, 2);  // first tile's MMAs issued
+        if (it < 16 && lane == 0) stamp(timeline, 48 + it);
       }
       if (lane == 0) stamp(timeline, 3);  // last MMA issued
     }
@@ -517,10 +520,12 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         ceil_i = row < M ? __ldg(ceil_in_i + row) : 0x7fffffff;
         ceil_mb = mb;
       }
+      if (threadIdx.x == 64 && it < 16) stamp(timeline, 32 + it);
       mbar_wait(&sm.acc_full[acc], acc_ph);
       tc_fence_after();
       if (threadIdx.x == 64) {
         if (it == 0) stamp(timeline, 4);            // first accumulator complete
+        if (it < 16) stamp(timeline, 16 + it);      // every tile's accumulator
         if (t == t_end - 1) stamp(timeline, 5);     // last accumulator complete
       }
       const uint32_t taddr =

@@ -29,6 +29,7 @@ namespace gg {
 constexpr int kPM = 128;  // pairs per work item (UMMA M)
 constexpr int kPN = 256;  // prototypes per accumulation unit (UMMA N)
 constexpr int kPK = 64;
+constexpr int kPBox = 32;  // bank rows per TMA box: a unit loads only the boxes that hold prototypes of its group
 constexpr int kPStages = 4;
 constexpr int kProtoThreads = 192;
 constexpr uint32_t kPStageA = kPM * kPK * 2;
@@ -84,7 +85,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* red, int* total)
 
 // Single CTA.  Pass 1: exclusive scan of the pair counts over the owned cells -> pair_off (ncell+1).  Pass 2: scan
 // over the groups -> work list (group, chunk) for every group that has both pairs and prototypes.
-// meta = {work items, pairs, accumulation units (work items x 256-prototype blocks of the group), 0}.
+// meta = {work items, pairs, accumulation units (work items x 256-prototype blocks of the group), 32-row bank boxes
+// the retrieval kernel loads per k-block (work items x ceil(group size / 32))}.
 __global__ void __launch_bounds__(1024)
 proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off, int ncell,
                   const int* __restrict__ group_off, int ngroups, int* __restrict__ pair_off,
@@ -112,26 +114,29 @@ proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off,
   }
   const int per = (ngroups + 1023) / 1024;
   const int g0 = min(ngroups, tid * per), g1 = min(ngroups, g0 + per);
-  auto group_chunks = [&](int g, int& units) {
+  auto group_chunks = [&](int g, int& units, int& boxes) {
     const int c0 = __ldg(group_off + g), c1 = __ldg(group_off + g + 1);
     const int n = pair_off[c1] - pair_off[c0], np = __ldg(cell_off + c1) - __ldg(cell_off + c0);
-    if (n <= 0 || np <= 0) { units = 0; return 0; }
+    if (n <= 0 || np <= 0) { units = boxes = 0; return 0; }
     const int chunks = (n + kPM - 1) / kPM;
     units = chunks * ((np + kPN - 1) / kPN);
+    boxes = chunks * ((np + kPBox - 1) / kPBox);
     return chunks;
   };
-  int nt = 0, nu = 0;
+  int nt = 0, nu = 0, nb = 0;
   for (int g = g0; g < g1; ++g) {
-    int u;
-    nt += group_chunks(g, u);
+    int u, b;
+    nt += group_chunks(g, u, b);
     nu += u;
+    nb += b;
   }
-  int total_t, total_u;
+  int total_t, total_u, total_b;
   int tbase = block_exclusive_scan(nt, red, &total_t);
   block_exclusive_scan(nu, red, &total_u);
+  block_exclusive_scan(nb, red, &total_b);
   for (int g = g0; g < g1; ++g) {
-    int u;
-    const int chunks = group_chunks(g, u);
+    int u, b;
+    const int chunks = group_chunks(g, u, b);
     for (int m = 0; m < chunks; ++m) {
       work_group[tbase + m] = g;
       work_chunk[tbase + m] = m;
@@ -141,7 +146,7 @@ proto_scan_kernel(const int* __restrict__ cnt, const int* __restrict__ cell_off,
   if (tid == 0) {
     meta[0] = total_t;
     meta[2] = total_u;
-    meta[3] = 0;
+    meta[3] = total_b;
   }
 }
 
@@ -248,14 +253,14 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: 
       const int a_row0 = pair_off[c0] + work_chunk[w] * kPM;
       const int a_last = pair_off[c1] - 1;  // last slot of the group: rows past it repeat this one (results unused)
       const int p0 = cell_off[c0], p1 = cell_off[c1];
-      // Only the rows that hold pairs are loaded (32-row granules; a work item of the 1 M bank holds ~65 pairs, of
-      // the 10 M bank ~26): the MMA still spans 128 rows, the rest of the tile keeps stale shared memory whose
-      // accumulator rows nobody reads.
+      // Only the rows that hold pairs are loaded (a work item of the 1 M bank holds ~65 pairs, of the 10 M bank ~26):
+      // 4-row groups when the TMA engine gathers them, 32-row boxes from the cell-ordered copy.  The MMA still spans
+      // 128 rows; the rest of the tile keeps stale shared memory whose accumulator rows nobody reads.
       const int nq = min(kPM, pair_off[c1] - a_row0);
-      const int granules = (nq + 31) >> 5;
-      const uint32_t a_bytes = static_cast<uint32_t>(granules) * (32 * kPK * 2);
+      const int granules = GATHER4 ? (nq + 3) >> 2 : (nq + 31) >> 5;
+      const uint32_t a_bytes = static_cast<uint32_t>(granules) * (GATHER4 ? 4 : 32) * (kPK * 2);
       int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-      const bool my_rows = GATHER4 && 4 * lane < 32 * granules;
+      const bool my_rows = GATHER4 && lane < granules;
       if (my_rows) {
         r0 = __ldg(slot_q + min(a_row0 + 4 * lane + 0, a_last));
         r1 = __ldg(slot_q + min(a_row0 + 4 * lane + 1, a_last));
@@ -263,20 +268,24 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: 
         r3 = __ldg(slot_q + min(a_row0 + 4 * lane + 3, a_last));
       }
       for (int n0 = p0; n0 < p1; n0 += kPN) {
+        // the bank side the same way: 32-row boxes (one per lane) up to the group's last prototype -- a group of the
+        // 1 M bank holds ~200 prototypes, and a full 256-row box would fetch the next group's rows for nothing
+        const int nbox = (min(kPN, p1 - n0) + kPBox - 1) / kPBox;
+        const uint32_t b_bytes = static_cast<uint32_t>(nbox) * (kPBox * kPK * 2);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&sm.empty[s], ph ^ 1);
           if (lane == 0) {
-            mbar_arrive_expect_tx(&sm.full[s], a_bytes + kPStageB);
-            tma_load_2d_hint(sm.b[s], &tm_bank, &sm.full[s], kb * kPK, n0, kPolicyEvictFirst);
+            mbar_arrive_expect_tx(&sm.full[s], a_bytes + b_bytes);
             if (!GATHER4) {
               for (int gq = 0; gq < granules; ++gq)
                 tma_load_2d(sm.a[s] + gq * (32 * kPK * 2), &tm_q, &sm.full[s], kb * kPK, a_row0 + 32 * gq);
             }
           }
-          if (GATHER4) {
-            __syncwarp();  // the barrier is armed before any lane's bytes can land
-            if (my_rows) tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
-          }
+          __syncwarp();  // the barrier is armed before any lane's bytes can land
+          if (lane < nbox)
+            tma_load_2d_hint(sm.b[s] + lane * (kPBox * kPK * 2), &tm_bank, &sm.full[s], kb * kPK, n0 + kPBox * lane,
+                             kPolicyEvictFirst);
+          if (GATHER4 && my_rows) tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
           if (++s == kPStages) { s = 0; ph ^= 1; }
         }
       }
@@ -613,7 +622,7 @@ extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int 
     rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, 32);
   }
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPN);
+  rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPBox);
   if (rc) return rc;
   const size_t smem = sizeof(ProtoSmem) + 1024;
   const int grid = device_sm_count();

@@ -144,6 +144,30 @@ def fuse_headings(emb: torch.Tensor, split: bool = False, want_sqnorm: bool = Fa
     return (x, sq) if want_sqnorm else x
 
 
+_fused_cache = None  # (weakref to the embedding tensor, its version, split, x16, ||x||^2)
+_FUSE_CACHE = __import__("os").environ.get("GG_FUSE_CACHE", "1") != "0"
+
+
+def fuse_headings_shared(emb: torch.Tensor, split: bool = False):
+    """fuse_headings(emb, split, want_sqnorm=True), remembered for the SAME tensor object at the same version: the
+    serving forward of SuperGuessr and the ProtoRefiner that follows it (inference.py:168,180) both start from the
+    heading mean of one embedding batch -- the second call reuses the first one's bf16 rows and norms instead of
+    streaming the (B,4,D) fp32 batch from HBM again.  Returns (x16, sqnorm)."""
+    global _fused_cache
+    import weakref
+
+    c = _fused_cache
+    if (_FUSE_CACHE and c is not None and c[0]() is emb and c[1] == emb._version and c[2] == bool(split)
+            and c[3].device == emb.device):
+        return c[3], c[4]
+    x16, sq = fuse_headings(emb, split=split, want_sqnorm=True)
+    try:
+        _fused_cache = (weakref.ref(emb), emb._version, bool(split), x16, sq) if _FUSE_CACHE else None
+    except TypeError:
+        _fused_cache = None
+    return x16, sq
+
+
 def prepare_head_weights(weight: torch.Tensor, bias: torch.Tensor, split: bool = False):
     """fp32 nn.Linear parameters -> (bf16 operand (C,D) or (C,3D), zero-padded fp32 bias)."""
     dev = _need_cuda(weight, bias)

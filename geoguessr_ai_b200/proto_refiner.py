@@ -278,7 +278,8 @@ class ProtoRefiner(nn.Module):
 
     # ---- forward (proto_refiner.py:129-237) -------------------------------------------------
     def _fuse(self, embedding: Tensor):
-        q16, qn = ops.fuse_headings(embedding, split=self._split, want_sqnorm=True)  # :150-151 mean over headings
+        # :150-151 mean over headings (shared with the SuperGuessr serving forward that produced the candidates)
+        q16, qn = ops.fuse_headings_shared(embedding, split=self._split)
         if q16.shape[1] != self.embed_dim * (3 if self._split else 1):
             raise ValueError(f"embedding dim {q16.shape[1] // (3 if self._split else 1)} != prototype dim {self.embed_dim}")
         return q16, qn
@@ -311,15 +312,15 @@ class ProtoRefiner(nn.Module):
         if self._last_meta is None:
             return None
         meta, nq, K, cand = self._last_meta
-        items, pairs, units, _ = (int(v) for v in meta.cpu().tolist())
+        items, pairs, units, boxes = (int(v) for v in meta.cpu().tolist())
         sizes = (self.cell_off[1:] - self.cell_off[:-1]).to(torch.int64)
         c = cand[:, :self.topk].to(torch.int64) - self.cell_lo
         mine = (c >= 0) & (c < sizes.numel())
         algo_flop = 2.0 * K * float(sizes[c.clamp(0, max(sizes.numel() - 1, 0))][mine].sum().item()) if sizes.numel() else 0.0
         row = K * 2
-        # bank boxes of 256 rows per unit + the pairs' rows in 32-row granules per unit + records
-        a_rows = (pairs + 16 * items) * (units / max(items, 1))
-        executed = units * 256 * row + a_rows * row + pairs * 16 + nq * self.topk * 16
+        # bank boxes of 32 rows up to each group's end + the pairs' rows (4-row gathers / 32-row boxes) per unit + records
+        a_rows = (pairs + (2 if self.gather4 else 16) * items) * (units / max(items, 1))
+        executed = boxes * 32 * row + a_rows * row + pairs * 16 + nq * self.topk * 16
         if not self.gather4:
             executed += 2 * pairs * row  # the cell-ordered copy: read + write
         return dict(work_items=items, pairs=pairs, units=units, executed_bytes=float(executed),

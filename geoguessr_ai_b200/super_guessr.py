@@ -589,7 +589,8 @@ class SuperGuessr(nn.Module):
 
         with torch.no_grad():
             st = self._operands(weight, bias)
-            x16 = ops.fuse_headings(layer_input, split=st["split"])
+            # (shared with a ProtoRefiner called on the same embedding batch next: one pass over the fp32 batch)
+            x16, _ = ops.fuse_headings_shared(layer_input, split=st["split"])
             head = ops.head_forward(x16, st["w16"], st["bias_pad"], self.num_cells, self.num_candidates,
                                     self.geocell_centroid_coords.data, want_logits=False)
         return head["pred_llh"], TopK(head["topk_val"], head["topk_idx"]), embedding

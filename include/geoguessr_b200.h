@@ -92,7 +92,7 @@ int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, i
                 int ldc, int k, void* workspace, void* tickets, const float* centroids, float* topk_val,
                 long long* topk_idx, long long* pred_cell, float* pred_llh, float* lse, gg_stream_t stream);
 
-/* Tuning aid (tools/head_fwd_timeline.py), not part of the path: while a device buffer of 16 int64 per CTA (2 per
+/* Tuning aid (tools/head_fwd_timeline.py), not part of the path: while a device buffer of 64 int64 per CTA (2 per
  * SM) is set, every gg_head_fwd launch stamps %globaltimer at fixed points of each CTA's life (entry, set-up done,
  * first / last MMA issued, first / last accumulator complete, chunks done, fold, flush, merge, epilogue drained,
  * exit).  null switches it off (the default; the kernel then only tests a pointer). */

@@ -231,3 +231,26 @@ def test_reference_inference_handoff_with_swapped_classes(centroids):
     assert ref_top.indices[0].tolist() == top_indices
     _, o_llh, _, _ = pro.forward(x.unsqueeze(1), pred_llh.cpu(), topk.indices.cpu(), topk.values.cpu(), protos, coords, topk=5)
     assert abs(o_llh[0, 0].item() - lon) < 1e-5 and abs(o_llh[0, 1].item() - lat) < 1e-5
+
+
+def test_fused_embedding_is_shared_but_never_stale():
+    """The serving forward and the refiner share one heading fusion of the same embedding tensor; an in-place update of
+    that tensor (a new batch copied into the same buffer) must invalidate it."""
+    B, V, D = 64, 4, 128
+    g = torch.Generator().manual_seed(1)
+    emb = torch.randn(B, V, D, generator=g).to(DEV)
+    a16, an = ops.fuse_headings_shared(emb)
+    b16, bn = ops.fuse_headings_shared(emb)
+    assert b16 is a16 and bn is an  # second call: no kernel
+    fresh16, fresh_n = ops.fuse_headings(emb, want_sqnorm=True)
+    assert torch.equal(a16, fresh16) and torch.equal(an, fresh_n)
+    emb.copy_(torch.randn(B, V, D, generator=g))  # same object, new contents
+    c16, cn = ops.fuse_headings_shared(emb)
+    assert c16 is not a16
+    fresh16, fresh_n = ops.fuse_headings(emb, want_sqnorm=True)
+    assert torch.equal(c16, fresh16) and torch.equal(cn, fresh_n)
+    other = emb.clone()
+    d16, _ = ops.fuse_headings_shared(other)  # another tensor object: recomputed
+    assert d16 is not c16 and torch.equal(d16, c16)
+    s16, _ = ops.fuse_headings_shared(other, split=True)
+    assert s16.shape == (B, 3 * D)

@@ -24,7 +24,7 @@ x16 = ops.fuse_headings(emb.to(dev))
 w16, bp = ops.prepare_head_weights(W.to(dev), b.to(dev))
 for _ in range(3):
     ops.head_forward(x16, w16, bp, C, k, cent, want_logits=mode == "train")
-tl = torch.zeros((148, 16), dtype=torch.int64, device=dev)
+tl = torch.zeros((148, 64), dtype=torch.int64, device=dev)
 lib = _lib.load()
 names = ["entry", "setup done", "first tile MMAs issued", "last MMA issued", "first acc complete", "last acc complete",
          "last chunks done", "folded", "flushed+ticket", "merged", "epilogue drained", "exit", "merge start",
@@ -51,8 +51,10 @@ for rep in range(3):
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"timeline_{mode}.csv")
 try:
     with open(out, "w") as f:
-        f.write("block,smid," + ",".join(n.replace(" ", "_") for n in names) + "\n")
+        f.write("block,smid," + ",".join(n.replace(" ", "_") for n in names) + ","
+                + ",".join(f"{n}{i}" for n in ("acc", "rdy", "iss") for i in range(16)) + "\n")
         for blk in range(t.shape[0]):
-            f.write(f"{blk},{int(t[blk, 15])}," + ",".join(f"{(t[blk, i] - t0) / 1e3:.2f}" if t[blk, i] > 0 else "" for i in range(len(names))) + "\n")
+            f.write(f"{blk},{int(t[blk, 15])}," + ",".join(f"{(t[blk, i] - t0) / 1e3:.2f}" if t[blk, i] > 0 else "" for i in range(len(names)))
+                    + "," + ",".join(f"{(t[blk, 16 + i] - t0) / 1e3:.2f}" if t[blk, 16 + i] > 0 else "" for i in range(48)) + "\n")
 except OSError:
     pass

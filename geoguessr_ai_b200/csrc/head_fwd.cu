@@ -541,6 +541,16 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 8; ++q) bq[q] = __ldg(bp + q);
         tmem_ld_wait();
+        if (c == kColsPerEpiWarp / 32 - 1) {
+          // The tile's last columns are in registers: hand the TMEM accumulator back to the leader's MMA warp NOW,
+          // before this chunk's soft-max / top-k work.  At the start of a run every logit enters the top-k lists
+          // (~3x the steady-state instructions per chunk); held until the end of the tile, the accumulator kept the
+          // MMA warp waiting ~6 us at the third tile of every CTA and again after every row-block boundary
+          // (tools/head_fwd_timeline.py, rdy/acc/iss stamps).
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
+        }
         float v[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -631,11 +641,6 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
           if (mine && tv[KTOP - 1] > -INFINITY) red_max_s32_shared(thr_slot, ordered_key(tv[KTOP - 1]));
         }
       }
-      // TMEM accumulator drained -> hand it back to the leader's MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
-
       // end of this CTA's run over row block mb: flush the row state (one partial per epilogue warp)
       if (nb == sc.num_n - 1 || t == t_end - 1) {
         if (threadIdx.x == 64 && t == t_end - 1) stamp(timeline, 6);  // last tile's chunks done

@@ -29,7 +29,10 @@ namespace gg {
 constexpr int kPM = 128;  // pairs per work item (UMMA M)
 constexpr int kPN = 256;  // prototypes per accumulation unit (UMMA N)
 constexpr int kPK = 64;
-constexpr int kPBox = 32;  // bank rows per TMA box: a unit loads only the boxes that hold prototypes of its group
+constexpr int kPBox = 32;  // granularity of a bank load: a unit fetches its group's prototypes rounded up to 32 rows
+struct BankMaps {          // the bank (P_local, D) through boxes of 32, 64, ... 256 rows: one TMA per stage whatever the size
+  CUtensorMap m[kPN / kPBox];
+};
 constexpr int kPStages = 4;
 constexpr int kProtoThreads = 192;
 constexpr uint32_t kPStageA = kPM * kPK * 2;
@@ -207,7 +210,7 @@ __device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* m, uin
 template <bool GATHER4, bool COSINE>
 __global__ void __launch_bounds__(kProtoThreads, 1)
 proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: q (B, D), 1-row boxes; else Qs (slots, D)
-                      const __grid_constant__ CUtensorMap tm_bank,  // bank (P_local, D)
+                      const __grid_constant__ BankMaps tm_banks,    // bank (P_local, D), see BankMaps
                       const int* __restrict__ meta, const int* __restrict__ work_group,
                       const int* __restrict__ work_chunk, const int* __restrict__ group_off,
                       const int* __restrict__ pair_off, const int* __restrict__ pair_ids,
@@ -223,7 +226,7 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: 
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_bank);
+    tma_prefetch_desc(&tm_banks.m[kPN / kPBox - 1]);
     for (int s = 0; s < kPStages; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
@@ -268,24 +271,27 @@ proto_retrieve_kernel(const __grid_constant__ CUtensorMap tm_q,     // GATHER4: 
         r3 = __ldg(slot_q + min(a_row0 + 4 * lane + 3, a_last));
       }
       for (int n0 = p0; n0 < p1; n0 += kPN) {
-        // the bank side the same way: 32-row boxes (one per lane) up to the group's last prototype -- a group of the
-        // 1 M bank holds ~200 prototypes, and a full 256-row box would fetch the next group's rows for nothing
+        // the bank side the same way: one box reaching up to the group's last prototype (rounded up to 32 rows) -- a
+        // group of the 1 M bank holds ~200 prototypes, and a full 256-row box would fetch the next group's rows for
+        // nothing.  (One TMA per stage through the map of that height: eight 32-row boxes instead cost more in TMA
+        // issue slots than the bytes saved.)
         const int nbox = (min(kPN, p1 - n0) + kPBox - 1) / kPBox;
         const uint32_t b_bytes = static_cast<uint32_t>(nbox) * (kPBox * kPK * 2);
+        const CUtensorMap* tm_bank = &tm_banks.m[nbox - 1];
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&sm.empty[s], ph ^ 1);
           if (lane == 0) {
             mbar_arrive_expect_tx(&sm.full[s], a_bytes + b_bytes);
+            tma_load_2d_hint(sm.b[s], tm_bank, &sm.full[s], kb * kPK, n0, kPolicyEvictFirst);
             if (!GATHER4) {
               for (int gq = 0; gq < granules; ++gq)
                 tma_load_2d(sm.a[s] + gq * (32 * kPK * 2), &tm_q, &sm.full[s], kb * kPK, a_row0 + 32 * gq);
             }
           }
-          __syncwarp();  // the barrier is armed before any lane's bytes can land
-          if (lane < nbox)
-            tma_load_2d_hint(sm.b[s] + lane * (kPBox * kPK * 2), &tm_bank, &sm.full[s], kb * kPK, n0 + kPBox * lane,
-                             kPolicyEvictFirst);
-          if (GATHER4 && my_rows) tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
+          if (GATHER4) {
+            __syncwarp();  // the barrier is armed before any lane's bytes can land
+            if (my_rows) tma_gather4(sm.a[s] + lane * 512, &tm_q, &sm.full[s], kb * kPK, r0, r1, r2, r3);
+          }
           if (++s == kPStages) { s = 0; ph ^= 1; }
         }
       }
@@ -611,7 +617,8 @@ extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int 
                                           w.pair_ids, w.slot_q, w.slot_range);
   GG_LAUNCH_CHECK();
 
-  CUtensorMap tm_q, tm_bank;
+  CUtensorMap tm_q;
+  BankMaps tm_banks;
   int rc;
   if (gather4) {
     rc = make_tmap_bf16_2d(&tm_q, q_bf16, D, static_cast<uint64_t>(B), static_cast<uint64_t>(D) * 2, kPK, 1);
@@ -622,15 +629,27 @@ extern "C" int gg_proto_retrieve(const void* q_bf16, const float* q_sqnorm, int 
     rc = make_tmap_bf16_2d(&tm_q, w.qs, D, static_cast<uint64_t>(npair), static_cast<uint64_t>(D) * 2, kPK, 32);
   }
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tm_bank, bank_bf16, D, static_cast<uint64_t>(n_protos), static_cast<uint64_t>(D) * 2, kPK, kPBox);
-  if (rc) return rc;
+  {  // the bank's maps only change when another bank is installed: keep the last set per host thread
+    struct Key { const void* p; long long n; int D; };
+    thread_local Key last{nullptr, 0, 0};
+    thread_local BankMaps last_maps;
+    if (last.p != bank_bf16 || last.n != n_protos || last.D != D) {
+      for (int i = 0; i < kPN / kPBox; ++i) {
+        rc = make_tmap_bf16_2d(&last_maps.m[i], bank_bf16, D, static_cast<uint64_t>(n_protos),
+                               static_cast<uint64_t>(D) * 2, kPK, kPBox * (i + 1));
+        if (rc) { last.p = nullptr; return rc; }
+      }
+      last = Key{bank_bf16, static_cast<long long>(n_protos), D};
+    }
+    tm_banks = last_maps;
+  }
   const size_t smem = sizeof(ProtoSmem) + 1024;
   const int grid = device_sm_count();
 #define GG_RETRIEVE(G4, COS)                                                                                       \
   do {                                                                                                             \
     auto kern = proto_retrieve_kernel<G4, COS>;                                                                    \
     if (int e = set_max_dynamic_smem_once(kern, smem)) return e;                                                   \
-    kern<<<grid, kProtoThreads, smem, s>>>(tm_q, tm_bank, w.meta, w.work_group, w.work_chunk, group_off, w.pair_off, \
+    kern<<<grid, kProtoThreads, smem, s>>>(tm_q, tm_banks, w.meta, w.work_group, w.work_chunk, group_off, w.pair_off, \
                                            w.pair_ids, w.slot_q, w.slot_range, cell_off, q_sqnorm, bank_sqnorm,    \
                                            bank_coords, proto_base, D, rec);                                       \
   } while (0)

@@ -242,7 +242,7 @@ def run_reference(args):
                         "sample": f"{nq} queries: eager CPU head + the reference's Python (query x candidate) refiner "
                                   "loop (oracle port), prototypes of the touched cells generated on the host"}
         line["infer"] = inf
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def train_config(n_gpus, cfg):
@@ -288,7 +288,7 @@ def dominant_roofline(kernels, peaks, extra=None, traffic_prefix=""):
 
 
 # ------------------------------------------------------------------------------------------------ training
-def run_b200_train(args, ctx):
+def run_b200_train(args, ctx, brief=False, dp_optimizer=None):
     import geoguessr_ai_b200 as gg
     from geoguessr_ai_b200 import ops
     from geoguessr_ai_b200.geocells import load_packaged_centroids
@@ -307,13 +307,21 @@ def run_b200_train(args, ctx):
         model.cell_layer.weight.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
         model.cell_layer.bias.uniform_(-1 / D ** 0.5, 1 / D ** 0.5)
     model.train()
-    if world > 1:  # gradients are averaged inside backward()
-        model.enable_data_parallel(chunks=args.dp_chunks,
-                                   comm_dtype=torch.bfloat16 if args.dp_bf16 else None,
-                                   comm="nccl" if args.dp_bf16 else args.dp_comm)
+    which = dp_optimizer or args.dp_optimizer
+    sharded = which == "sharded" or (which == "auto" and world > 1 and not args.dp_bf16
+                                     and args.dp_comm in ("auto", "fused") and args.dp_chunks == 1)
     params = [model.cell_layer.weight, model.cell_layer.bias]
     use_graph = not args.no_graph
-    opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=use_graph)
+    if sharded:
+        # AdamW sharded over the ranks and fused into the gradient exchange (geoguessr_ai_b200/sharded_adamw.py):
+        # same update as torch.optim.AdamW, applied by the rank that reduces a block; checked below
+        opt = model.sharded_adamw(lr=1e-4)
+    else:
+        if world > 1:  # gradients are averaged inside backward()
+            model.enable_data_parallel(chunks=args.dp_chunks,
+                                       comm_dtype=torch.bfloat16 if args.dp_bf16 else None,
+                                       comm="nccl" if args.dp_bf16 else args.dp_comm)
+        opt = torch.optim.AdamW(params, lr=1e-4, fused=True, capturable=use_graph)
 
     host = make_batches(3, B, D, V, seed0=100 + 10 * rank)
     host = [(e.pin_memory(), l.pin_memory()) for e, l in host]
@@ -328,6 +336,9 @@ def run_b200_train(args, ctx):
         return out.loss
 
     barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
+    dp_check = None
+    if sharded:  # first step of the fresh optimizer against NCCL average + torch.optim.AdamW (all ranks take part)
+        dp_check = check_sharded_step(model, opt, resident[0], dummy_clf, dist if world > 1 else None)
 
     # One CUDA graph per input buffer: the launches of a step (ours, the fused AdamW, the gradient exchange)
     # replay without host work in between.  Falls back to eager launches if capture fails.
@@ -384,6 +395,14 @@ def run_b200_train(args, ctx):
     ms_step = ms_total / K
     value = world * B / (ms_step / 1e3)
     final_loss = loss.item()
+    if brief:  # the comparison arm of a data-parallel run: throughput, what exchanged the gradient, its check
+        if world > 1 and not sharded:
+            dp_check = check_dp_gradient(model, resident[0], dummy_clf, dist)
+        what = opt.describe() if sharded else (model.describe_data_parallel() if world > 1 else None)
+        del graphs
+        return {"value": value, "unit": "samples/s", "ms_per_step": ms_step, "steps": K, "clocks": clocks,
+                "optimizer": "sharded AdamW (model.sharded_adamw)" if sharded else "torch.optim.AdamW(fused=True)",
+                "grad_allreduce": what, "dp_check": dp_check}
 
     # ---------------- per-launcher CUDA-event timing over a second identical timed region
     # Eager launches; a ~1 ms device-side spin queued ahead of every step lets the host run a whole step
@@ -399,8 +418,7 @@ def run_b200_train(args, ctx):
     per = {k: sum(v) / n_timed for k, v in tms.items()}  # per step (a launcher may run more than once: --dp-chunks)
 
     # ---------------- N > 1: the averaged gradient of one step against NCCL (all ranks take part)
-    dp_check = None
-    if world > 1:
+    if world > 1 and not sharded:
         dp_check = check_dp_gradient(model, resident[0], dummy_clf, dist)
 
     # ---------------- end to end from host buffers (`e2e`): H2D of the batch + D2H of the loss every step
@@ -504,7 +522,9 @@ def run_b200_train(args, ctx):
         time.sleep(1.5)  # let the power-cap controller release the clocks before the next workload is timed
 
     grad_comm = None
-    if world > 1:
+    if sharded:
+        grad_comm = opt.describe()
+    elif world > 1:
         grad_comm = model.describe_data_parallel()
     del graphs
     if rank != 0:
@@ -534,7 +554,7 @@ def run_b200_train(args, ctx):
 
     launches_per_step = sum(1 for _ in per)  # launcher calls; kernels per launcher below
     kernels_per_launcher = {"gg_fuse_and_prepare": 1, "gg_head_fwd": 1, "gg_hav_row_stats": 2, "gg_hav_ce_fwd_bwd": 1,
-                            "gg_head_bwd": 1, "gg_grad_exchange": 1, "gg_p2p_allreduce_avg": 1,
+                            "gg_head_bwd": 1, "gg_grad_exchange": 1, "gg_grad_exchange_adamw": 1, "gg_p2p_allreduce_avg": 1,
                             "gg_nvls_allreduce_avg": 1}
     launches_per_step = sum(kernels_per_launcher.get(n, 1) * max(1, round(len(tms[n]) / n_timed)) for n in tms)
     line = {
@@ -551,7 +571,48 @@ def run_b200_train(args, ctx):
     }
     if dp_check is not None:
         line["dp_check"] = dp_check
+    line["config"]["optimizer"] = ("AdamW sharded over the ranks and fused into the gradient exchange "
+                                   "(model.sharded_adamw)" if sharded else "torch.optim.AdamW(fused=True)")
     return line
+
+
+def check_sharded_step(model, opt, batch, dummy_clf, dist):
+    """The FIRST step of a fresh ShardedAdamW (moments zero) against the reference sequence: per-rank gradient with the
+    optimizer detached, NCCL all_reduce / world, torch.optim.AdamW with the same hyper-parameters."""
+    emb, labels = batch
+    world = dist.get_world_size() if dist is not None else 1
+    g = opt.param_groups[0]
+    model._sharded = None
+    model.zero_grad(set_to_none=True)
+    model(embedding=emb, labels=labels, labels_clf=dummy_clf).loss.backward()
+    gw = model.cell_layer.weight.grad.detach().clone() / world
+    gb = model.cell_layer.bias.grad.detach().clone() / world
+    if dist is not None:
+        dist.all_reduce(gw, op=dist.ReduceOp.SUM)
+        dist.all_reduce(gb, op=dist.ReduceOp.SUM)
+    model.zero_grad(set_to_none=True)
+    model._op_cache = None
+    model._sharded = opt
+    rw = torch.nn.Parameter(model.cell_layer.weight.detach().clone())
+    rb = torch.nn.Parameter(model.cell_layer.bias.detach().clone())
+    ref = torch.optim.AdamW([rw, rb], lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+    rw.grad, rb.grad = gw, gb
+    ref.step()
+    model(embedding=emb, labels=labels, labels_clf=dummy_clf).loss.backward()
+    opt.step()
+    torch.cuda.synchronize()
+    w16 = opt.w16.clone()
+    opt.gather_master()
+    w, b = model.cell_layer.weight.data, model.cell_layer.bias.data
+    err = torch.stack([(w - rw.data).abs().max(), (b - rb.data).abs().max(), rw.data.abs().max(),
+                       (w16.float() != rw.data.to(torch.bfloat16).float()).float().mean()])
+    if dist is not None:
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    err = err.tolist()
+    return {"against": "first step: NCCL all_reduce(SUM) / world of the per-rank gradients + torch.optim.AdamW",
+            "max_abs_diff_W": err[0], "max_abs_diff_b": err[1], "max_abs_W": err[2],
+            "bf16_operand_entries_off_by_one_rounding": err[3],
+            "ok": bool(err[0] <= 2e-6 * err[2] and err[1] <= 2e-6 * err[2] and err[3] < 1e-3)}
 
 
 def check_dp_gradient(model, batch, dummy_clf, dist):
@@ -811,10 +872,28 @@ def finish(world):
         os._exit(0)
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The result line, to the process's original stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
-    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; the bench contract is ONE JSON line
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # The bench contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    # fd 1 from C): everything that is not the result line is sent to stderr at the file-descriptor level, and the
+    # line itself goes to the saved stdout (emit()).
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -830,6 +909,9 @@ def main():
     ap.add_argument("--sustained-s", type=float, default=2.0,
                     help="train: seconds of back-to-back steps for the 'sustained' key (0 = skip)")
     ap.add_argument("--dp-chunks", type=int, default=1, help="comm=nccl: geocell ranges of the dW GEMM + all-reduce (N > 1)")
+    ap.add_argument("--dp-optimizer", default="auto", choices=["auto", "torch", "sharded"],
+                    help="train: torch = torch.optim.AdamW (fused) after the gradient exchange; sharded = AdamW sharded "
+                         "over the ranks and fused into the exchange (model.sharded_adamw); auto = sharded when N > 1")
     ap.add_argument("--dp-comm", default="auto", choices=["auto", "fused", "nvls", "p2p", "nccl"],
                     help="gradient exchange for N > 1: fused = progressive exchange under the dW GEMM (own kernels over "
                          "symmetric memory), nvls / p2p = one exchange kernel after the GEMM, nccl = NCCL all-reduce")
@@ -844,6 +926,13 @@ def main():
     if args.workload in ("all", "train"):
         line = run_b200_train(args, ctx)
         torch.cuda.empty_cache()
+        if ctx.world > 1 and args.dp_optimizer == "auto":
+            # the same step with the reference trainer's own optimizer object (torch.optim.AdamW after the fp32
+            # gradient exchange), for comparison beside the default
+            alt = run_b200_train(args, ctx, brief=True, dp_optimizer="torch")
+            torch.cuda.empty_cache()
+            if ctx.rank == 0:
+                line["torch_adamw"] = alt
     if args.workload in ("all", "infer"):
         configs = INFER_CONFIGS if args.protos == 0 else ((f"protos_{args.protos}", args.protos),)
         inf = {}
@@ -859,7 +948,7 @@ def main():
             else:
                 line["infer"] = inf
     if ctx.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     finish(ctx.world)
 
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "gg_grad_ctrl_bytes": (c_size_t, []),
     "gg_grad_stage_floats": (c_size_t, [I, I, I]),
     "gg_grad_exchange": (I, [P, P, P, P, P, I, I, I, I, I, P]),
+    "gg_grad_exchange_adamw": (I, [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, P, I, P]),
 }
 
 _lib = None

@@ -96,7 +96,7 @@ struct GradPush {
   unsigned int* blk_count;             // local: pushed column tiles per 128-geocell block (self-resetting)
   unsigned int* ready[kGradMaxWorld];  // every rank's `ready` counters (peer-mapped)
   float* stage_b[kGradMaxWorld];       // rank r's db staging rows for THIS source rank (peer-mapped): [block / world][128]
-  int world;                           // 0 / 1: plain local dW / db
+  int world;                           // 0: plain local dW / db
 };
 struct StageMaps {
   CUtensorMap m[kGradMaxWorld];        // rank r's dW staging slab for this source rank: (rows = blocks-of-r x 128, D) fp32
@@ -230,7 +230,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         const uint32_t acc_ph = (it >> 1) & 1;
         const int row = m0 + rit;
         // where this CTA's 128 geocells of the tile go: the gradient itself, or the reducer's staging slab
-        const bool push = sig.world > 1;
+        const bool push = sig.world >= 1;
         const int blk = m0 / kWM;
         const int dst_rank = push ? blk % sig.world : 0;
         const CUtensorMap* const tm_dst = push ? &stage.m[dst_rank] : &tm_dw;
@@ -432,7 +432,7 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   GG_CHECK(D % 8 == 0 && x_ld >= D && x_ld % 8 == 0, GG_ERR_ARG, "gg_head_bwd: D=%d / x_ld=%d must be multiples of 8", D, x_ld);
   GG_CHECK(workspace, GG_ERR_ARG, "gg_head_bwd: workspace (gg_head_bwd_workspace_bytes) is required");
   GG_CHECK(!db_partials || (db_parts > 0 && db_ld >= C), GG_ERR_ARG, "gg_head_bwd: bad db_partials shape");
-  const bool push = dp_world > 1;
+  const bool push = dp_ptrs != nullptr && dp_world >= 1;  // (one rank: gg_grad_exchange_adamw's single-GPU form)
   GG_CHECK(dp_world >= 0 && dp_world <= kGradMaxWorld && (!push || (dp_ptrs && dp_rank >= 0 && dp_rank < dp_world)),
            GG_ERR_ARG, "gg_head_bwd: dp_world=%d dp_rank=%d (<= %d ranks) needs dp_ptrs", dp_world, dp_rank, kGradMaxWorld);
   GG_CHECK(push || dW, GG_ERR_ARG, "gg_head_bwd: dW is required");

@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace gg {
 
@@ -224,15 +225,151 @@ __device__ __forceinline__ void reduce_range(const GradPeers& peers, float4* mc,
   }
 }
 
+// ---- sharded AdamW inside the exchange (gg_grad_exchange_adamw) ------------------------------------------------
+// The averaged gradient of a block exists only in the reducer's registers: the reducer applies AdamW to ITS blocks of
+// the fp32 master weights (torch.optim.AdamW's update, main_coordinator_idun_s3.py:286-291,424) and broadcasts what
+// the next forward needs -- the bf16 operand rows (half the bytes of the fp32 gradient) and the fp32 bias -- into
+// every rank's operand buffer.  The separate optimizer pass over all of W on every rank and the per-step fp32 -> bf16
+// recast of W disappear; each rank keeps moments and current master weights only for the blocks it reduces.
+struct AdamwArgs {
+  float* w; float* m; float* v;      // master weight (C, D) and moments: rows of this rank's blocks are current
+  float* b; float* mb; float* vb;    // bias (C) and moments
+  const float* hyper;                // device: lr, beta1, beta2, eps, weight_decay
+  long long* step;                   // device: optimizer steps taken so far (incremented by the kernel)
+  uint4* w16[kP2PMaxWorld];          // every rank's bf16 operand (C, D)
+  float4* bias[kP2PMaxWorld];        // every rank's padded fp32 bias
+  uint4* w16_mc;                     // multicast addresses of the two (NVLS)
+  float4* bias_mc;
+};
+struct AdamwStep {
+  float lr, beta1, beta2, eps, lr_wd, step_size, inv_bc2_sqrt;
+};
+__device__ __forceinline__ void adamw_update(float& w, float& m, float& v, float g, const AdamwStep& h) {
+  w -= h.lr_wd * w;                       // decoupled weight decay
+  m += (1.f - h.beta1) * (g - m);         // lerp(m, g, 1 - beta1)
+  v = h.beta2 * v + (1.f - h.beta2) * g * g;
+  const float denom = sqrtf(v) * h.inv_bc2_sqrt + h.eps;
+  w -= h.step_size * m / denom;
+}
+__device__ __forceinline__ void st_peer16(uint4* p, const uint4& v) { __stcg(p, v); }
+__device__ __forceinline__ void multimem_st16(uint4* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w) : "memory");
+}
+
+// n8 items of 8 floats: staged floats [8 (src8 + i), +8) of every slab -> averaged gradient -> AdamW on master floats
+// [8 (dst8 + i), +8) -> 8 bf16 into every rank's operand
 template <int WORLD, bool NVLS>
+__device__ __forceinline__ void adamw_range(const AdamwArgs& aw, const AdamwStep& h, const float4* __restrict__ stage,
+                                            size_t slab4, size_t src8, size_t dst8, size_t n8, float inv_world) {
+  constexpr int kU = WORLD >= 8 ? 1 : 2;  // items in flight per thread: (2 WORLD + 6) kU 16-byte loads
+  float4* const w4 = reinterpret_cast<float4*>(aw.w);
+  float4* const m4 = reinterpret_cast<float4*>(aw.m);
+  float4* const v4 = reinterpret_cast<float4*>(aw.v);
+  for (size_t i0 = threadIdx.x; i0 < n8; i0 += kU * kGradThreads) {
+    float4 a[kU][WORLD], c[kU][WORLD], w0[kU], w1[kU], m0[kU], m1[kU], v0[kU], v1[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t i = i0 + u * kGradThreads;
+      if (i < n8) {
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) {
+          a[u][r] = __ldcs(stage + r * slab4 + 2 * (src8 + i));
+          c[u][r] = __ldcs(stage + r * slab4 + 2 * (src8 + i) + 1);
+        }
+        const size_t at = 2 * (dst8 + i);
+        w0[u] = __ldcs(w4 + at); w1[u] = __ldcs(w4 + at + 1);
+        m0[u] = __ldcs(m4 + at); m1[u] = __ldcs(m4 + at + 1);
+        v0[u] = __ldcs(v4 + at); v1[u] = __ldcs(v4 + at + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t i = i0 + u * kGradThreads;
+      if (i >= n8) break;
+      float4 g0 = a[u][0], g1 = c[u][0];
+#pragma unroll
+      for (int r = 1; r < WORLD; ++r) {  // rank order: identical on every rank
+        g0.x += a[u][r].x; g0.y += a[u][r].y; g0.z += a[u][r].z; g0.w += a[u][r].w;
+        g1.x += c[u][r].x; g1.y += c[u][r].y; g1.z += c[u][r].z; g1.w += c[u][r].w;
+      }
+      adamw_update(w0[u].x, m0[u].x, v0[u].x, g0.x * inv_world, h); adamw_update(w0[u].y, m0[u].y, v0[u].y, g0.y * inv_world, h);
+      adamw_update(w0[u].z, m0[u].z, v0[u].z, g0.z * inv_world, h); adamw_update(w0[u].w, m0[u].w, v0[u].w, g0.w * inv_world, h);
+      adamw_update(w1[u].x, m1[u].x, v1[u].x, g1.x * inv_world, h); adamw_update(w1[u].y, m1[u].y, v1[u].y, g1.y * inv_world, h);
+      adamw_update(w1[u].z, m1[u].z, v1[u].z, g1.z * inv_world, h); adamw_update(w1[u].w, m1[u].w, v1[u].w, g1.w * inv_world, h);
+      const size_t at = 2 * (dst8 + i);
+      __stcs(w4 + at, w0[u]); __stcs(w4 + at + 1, w1[u]);
+      __stcs(m4 + at, m0[u]); __stcs(m4 + at + 1, m1[u]);
+      __stcs(v4 + at, v0[u]); __stcs(v4 + at + 1, v1[u]);
+      uint4 o;
+      o.x = pack_bf16x2(w0[u].x, w0[u].y); o.y = pack_bf16x2(w0[u].z, w0[u].w);
+      o.z = pack_bf16x2(w1[u].x, w1[u].y); o.w = pack_bf16x2(w1[u].z, w1[u].w);
+      if (NVLS) {
+        multimem_st16(aw.w16_mc + dst8 + i, o);
+      } else {
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) st_peer16(aw.w16[r] + dst8 + i, o);
+      }
+    }
+  }
+}
+
+// the block's bias entries [c0, c0 + 128) (entries >= C: the pad, kept at zero); staged at float4 index src4
+template <int WORLD, bool NVLS>
+__device__ __forceinline__ void adamw_bias(const AdamwArgs& aw, const AdamwStep& h, const float4* __restrict__ stage,
+                                           size_t slab4, size_t src4, int c0, int C, float inv_world) {
+  const int i = threadIdx.x;
+  if (i >= kGradBlockRows / 4 || c0 + 4 * i >= C) return;
+  float4 g = __ldcs(stage + src4 + i);
+#pragma unroll
+  for (int r = 1; r < WORLD; ++r) {
+    const float4 t = __ldcs(stage + r * slab4 + src4 + i);
+    g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  }
+  const float gs[4] = {g.x * inv_world, g.y * inv_world, g.z * inv_world, g.w * inv_world};
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = c0 + 4 * i + e;
+    if (c < C) {
+      float w = aw.b[c], m = aw.mb[c], v = aw.vb[c];
+      adamw_update(w, m, v, gs[e], h);
+      aw.b[c] = w; aw.mb[c] = m; aw.vb[c] = v;
+      o[e] = w;
+    }
+  }
+  const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+  const size_t at = static_cast<size_t>(c0) / 4 + i;
+  if (NVLS) {
+    multimem_st(aw.bias_mc + at, ov);
+  } else {
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) st_peer(aw.bias[r] + at, ov);
+  }
+}
+
+template <int WORLD, bool NVLS, bool ADAMW>
 __global__ void __launch_bounds__(kGradThreads)
 grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict__ mc_grad,
                      unsigned int* __restrict__ mc_ctrl, const float4* __restrict__ stage, int rank, int C, int D,
-                     int nblk, int own_max, float inv_world, int no_wait) {
+                     int nblk, int own_max, float inv_world, int no_wait, const __grid_constant__ AdamwArgs aw) {
   unsigned int* const ctrl = peers.ctrl[rank];
   __shared__ unsigned int s_epoch;
-  if (threadIdx.x == 0) s_epoch = ld_acquire_sys(ctrl + kCtrlEpoch);
+  __shared__ AdamwStep s_h;
+  if (threadIdx.x == 0) {
+    s_epoch = ld_acquire_sys(ctrl + kCtrlEpoch);
+    if (ADAMW) {
+      // every CTA reads the step count before the last one out (below) advances it
+      const double t = static_cast<double>(*reinterpret_cast<volatile long long*>(aw.step) + 1);
+      const float lr = aw.hyper[0], b1 = aw.hyper[1], b2 = aw.hyper[2];
+      s_h.lr = lr; s_h.beta1 = b1; s_h.beta2 = b2; s_h.eps = aw.hyper[3];
+      s_h.lr_wd = lr * aw.hyper[4];
+      s_h.step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), t)));
+      s_h.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), t)));
+    }
+  }
   __syncthreads();
+  const AdamwStep h = s_h;
   const unsigned int epoch = s_epoch + 1u;  // announcements / landed units expected so far = epoch x (per-launch count)
   const int own = nblk > rank ? (nblk - rank + WORLD - 1) / WORLD : 0;  // blocks rank, rank + WORLD, ...
   const size_t row4 = static_cast<size_t>(D) / 4;                       // float4 per geocell row
@@ -246,12 +383,22 @@ grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict
     __syncthreads();
     const int r0 = b * kGradBlockRows, r1 = min(C, r0 + kGradBlockRows);
     const size_t n4 = static_cast<size_t>(r1 - r0) * row4;
-    const size_t lo = n4 * part / kGradParts, hi = n4 * (part + 1) / kGradParts;
-    reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, static_cast<size_t>(j) * kGradBlockRows * row4 + lo,
-                              static_cast<size_t>(r0) * row4 + lo, hi - lo, inv_world);
-    if (part == 0)  // the block's db entries (128 floats; the last block's ragged end runs into the pad)
-      reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, rows * row4 + static_cast<size_t>(j) * (kGradBlockRows / 4),
-                                db4 + static_cast<size_t>(r0) / 4, (static_cast<size_t>(r1 - r0) + 3) / 4, inv_world);
+    if (ADAMW) {
+      const size_t n8 = n4 / 2;  // D is a multiple of 8 in this mode
+      const size_t lo = n8 * part / kGradParts, hi = n8 * (part + 1) / kGradParts;
+      adamw_range<WORLD, NVLS>(aw, h, stage, slab4, static_cast<size_t>(j) * kGradBlockRows * (row4 / 2) + lo,
+                               static_cast<size_t>(r0) * (row4 / 2) + lo, hi - lo, inv_world);
+      if (part == 0)
+        adamw_bias<WORLD, NVLS>(aw, h, stage, slab4, rows * row4 + static_cast<size_t>(j) * (kGradBlockRows / 4), r0, C,
+                                inv_world);
+    } else {
+      const size_t lo = n4 * part / kGradParts, hi = n4 * (part + 1) / kGradParts;
+      reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, static_cast<size_t>(j) * kGradBlockRows * row4 + lo,
+                                static_cast<size_t>(r0) * row4 + lo, hi - lo, inv_world);
+      if (part == 0)  // the block's db entries (128 floats; the last block's ragged end runs into the pad)
+        reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, rows * row4 + static_cast<size_t>(j) * (kGradBlockRows / 4),
+                                  db4 + static_cast<size_t>(r0) / 4, (static_cast<size_t>(r1 - r0) + 3) / 4, inv_world);
+    }
     __syncthreads();  // every thread's stores are issued
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -270,6 +417,7 @@ grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict
     __threadfence_system();
     if (atomicAdd(ctrl + kCtrlExit, 1u) == gridDim.x - 1) {  // last CTA out: next launch's epoch
       ctrl[kCtrlExit] = 0u;
+      if (ADAMW) *aw.step += 1;
       __threadfence();
       atomicExch(ctrl + kCtrlEpoch, epoch);
     }
@@ -371,13 +519,78 @@ extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsig
   const int nw = (flags & GG_GRAD_NO_WAIT) ? 1 : 0;
 #define GG_GX(W)                                                                                                   \
   do {                                                                                                             \
-    if (mg) grad_exchange_kernel<W, true><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw);  \
-    else grad_exchange_kernel<W, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw);    \
+    if (mg) grad_exchange_kernel<W, true, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw, AdamwArgs{});  \
+    else grad_exchange_kernel<W, false, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw, AdamwArgs{});    \
   } while (0)
   if (world == 2) GG_GX(2);
   else if (world == 4) GG_GX(4);
   else GG_GX(8);
 #undef GG_GX
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+extern "C" int gg_grad_exchange_adamw(const unsigned long long* w16_ptrs, const unsigned long long* bias_ptrs,
+                                      const unsigned long long* ctrl_ptrs, void* w16_mc, void* bias_mc, void* ctrl_mc,
+                                      const void* stage, int world, int rank, int C, int D, float* master_w,
+                                      float* master_b, float* m_w, float* v_w, float* m_b, float* v_b,
+                                      const float* hyper, long long* step, int flags, gg_stream_t stream) {
+  GG_CHECK(w16_ptrs && bias_ptrs && ctrl_ptrs && world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world,
+           GG_ERR_ARG, "gg_grad_exchange_adamw: world=%d rank=%d (1 <= world <= %d)", world, rank, kP2PMaxWorld);
+  GG_CHECK(world == 1 || world == 2 || world == 4 || world == 8, GG_ERR_UNSUPPORTED,
+           "gg_grad_exchange_adamw: world=%d (1, 2, 4 or 8 GPUs of one NVSwitch domain)", world);
+  GG_CHECK(C > 0 && D > 0 && D % 8 == 0, GG_ERR_ARG, "gg_grad_exchange_adamw: C=%d D=%d (D a multiple of 8)", C, D);
+  GG_CHECK(master_w && master_b && m_w && v_w && m_b && v_b && hyper && step, GG_ERR_ARG,
+           "gg_grad_exchange_adamw: optimizer state missing");
+  const int nblk = (C + kGradBlockRows - 1) / kGradBlockRows;
+  GG_CHECK(nblk <= kCtrlReady, GG_ERR_UNSUPPORTED, "gg_grad_exchange_adamw: C=%d exceeds %d geocells", C,
+           kCtrlReady * kGradBlockRows);
+  const bool nvls = w16_mc != nullptr;
+  GG_CHECK(nvls == (bias_mc != nullptr) && nvls == (ctrl_mc != nullptr), GG_ERR_ARG,
+           "gg_grad_exchange_adamw: all three multicast addresses or none");
+  GG_CHECK(stage && (reinterpret_cast<uintptr_t>(stage) & 15) == 0, GG_ERR_ARG, "gg_grad_exchange_adamw: staging region missing");
+  GradPeers peers = {};
+  AdamwArgs aw = {};
+  for (int r = 0; r < world; ++r) {
+    GG_CHECK(w16_ptrs[r] != 0 && (w16_ptrs[r] & 15) == 0 && bias_ptrs[r] != 0 && (bias_ptrs[r] & 15) == 0 &&
+                 ctrl_ptrs[r] != 0 && (ctrl_ptrs[r] & 15) == 0,
+             GG_ERR_ARG, "gg_grad_exchange_adamw: buffers of rank %d missing or not 16-byte aligned", r);
+    peers.ctrl[r] = reinterpret_cast<unsigned int*>(ctrl_ptrs[r]);
+    aw.w16[r] = reinterpret_cast<uint4*>(w16_ptrs[r]);
+    aw.bias[r] = reinterpret_cast<float4*>(bias_ptrs[r]);
+  }
+  aw.w = master_w; aw.m = m_w; aw.v = v_w;
+  aw.b = master_b; aw.mb = m_b; aw.vb = v_b;
+  aw.hyper = hyper; aw.step = step;
+  aw.w16_mc = static_cast<uint4*>(w16_mc);
+  aw.bias_mc = static_cast<float4*>(bias_mc);
+  const int own = nblk > rank ? (nblk - rank + world - 1) / world : 0;
+  const int own_max = (nblk + world - 1) / world;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float inv = 1.0f / static_cast<float>(world);
+  unsigned int* mcc = static_cast<unsigned int*>(ctrl_mc);
+  const float4* st = static_cast<const float4*>(stage);
+  const int nw = (flags & GG_GRAD_NO_WAIT) ? 1 : 0;
+  // every CTA must be resident (each waits for units other CTAs of this grid deliver): as many as the instance fits
+#define GG_GXA_ONE(W, NV)                                                                                          \
+  do {                                                                                                             \
+    auto kern = grad_exchange_kernel<W, NV, true>;                                                                 \
+    int per_sm = 0;                                                                                                \
+    GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGradThreads, 0));                        \
+    const int g = std::max(1, std::min(std::max(1, per_sm) * device_sm_count(), own * kGradParts));                \
+    kern<<<g, kGradThreads, 0, s>>>(peers, nullptr, mcc, st, rank, C, D, nblk, own_max, inv, nw, aw);              \
+  } while (0)
+#define GG_GXA(W)                                                                                                  \
+  do {                                                                                                             \
+    if (nvls) GG_GXA_ONE(W, true);                                                                                 \
+    else GG_GXA_ONE(W, false);                                                                                     \
+  } while (0)
+  if (world == 1) GG_GXA(1);
+  else if (world == 2) GG_GXA(2);
+  else if (world == 4) GG_GXA(4);
+  else GG_GXA(8);
+#undef GG_GXA
+#undef GG_GXA_ONE
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -494,6 +494,29 @@ def grad_exchange(grad_ptrs, ctrl_ptrs, grad_mc, ctrl_mc, stage_ptr, rank, C, D,
           int(bool(no_wait)), _stream(dev))
 
 
+def grad_exchange_adamw(w16_ptrs, bias_ptrs, ctrl_ptrs, w16_mc, bias_mc, ctrl_mc, stage_ptr, rank, C, D, master_w,
+                        master_b, m_w, v_w, m_b, v_b, hyper, step, no_wait=False):
+    """The fused exchange with the optimizer in it (gg_grad_exchange_adamw): per owned block add the staged copies,
+    apply AdamW to this rank's rows of the fp32 master weights / bias (in place, with the moments) and write the bf16
+    operand rows and the fp32 bias into every rank's operand buffers.  hyper: device fp32 [lr, beta1, beta2, eps,
+    weight_decay]; step: device int64 counter (incremented by the kernel)."""
+    import ctypes
+
+    world = len(w16_ptrs)
+    dev = _need_cuda(master_w, master_b, m_w, v_w, m_b, v_b, hyper, step)
+    for t in (master_w, master_b, m_w, v_w, m_b, v_b, hyper):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert step.dtype == torch.int64 and hyper.numel() >= 5
+    assert master_w.shape == (C, D) and m_w.shape == (C, D) and v_w.shape == (C, D)
+    w = (ctypes.c_ulonglong * world)(*[int(p) for p in w16_ptrs])
+    b = (ctypes.c_ulonglong * world)(*[int(p) for p in bias_ptrs])
+    c = (ctypes.c_ulonglong * world)(*[int(p) for p in ctrl_ptrs])
+    _call("gg_grad_exchange_adamw", _lib.load().gg_grad_exchange_adamw, dev, ctypes.cast(w, ctypes.c_void_p),
+          ctypes.cast(b, ctypes.c_void_p), ctypes.cast(c, ctypes.c_void_p), int(w16_mc), int(bias_mc), int(ctrl_mc),
+          int(stage_ptr), world, int(rank), int(C), int(D), _ptr(master_w), _ptr(master_b), _ptr(m_w), _ptr(v_w),
+          _ptr(m_b), _ptr(v_b), _ptr(hyper), _ptr(step), int(bool(no_wait)), _stream(dev))
+
+
 def p2p_allreduce_avg(peer_ptrs, rank, n_floats):
     """In-place two-shot average of a symmetric-memory fp32 buffer over the ranks (gg_p2p_allreduce_avg) on the
     current stream.  peer_ptrs: every rank's buffer address as mapped on this device (rank order).  The caller

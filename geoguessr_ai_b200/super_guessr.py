@@ -44,7 +44,11 @@ class _GeocellHeadLoss(torch.autograd.Function):
                               tau=module.label_smoothing_tau, far_km=module.far_km, out=stats)
         elif smooth and not under_gemm:
             stats = module._row_stats_async(labels, C)
-        if module.training:
+        if module._sharded is not None:
+            # sharded AdamW: the bf16 operand is persistent (the reducers of the last step wrote it): fusion only
+            st = module._sharded.operands()
+            x16 = ops.fuse_headings(embedding)
+        elif module.training:
             # the weights move every step: their bf16 operand is rebuilt in the same launch as the fusion
             split = module.precision == "bf16x3"
             x16, w16, bias_pad = ops.fuse_and_prepare(embedding, weight, bias, split=split)
@@ -86,6 +90,15 @@ class _GeocellHeadLoss(torch.autograd.Function):
         B = dlogits.shape[0]
         want_w, want_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dW = db = demb = None
+        sharded = ctx.module._sharded is not None and ctx.module.training
+        if sharded and ctx.needs_input_grad[0] and emb_needs_grad:
+            # the reducers overwrite this rank's operand as soon as it has announced a block: dx reads W first
+            demb = ops.head_dx(dlogits, ctx.w16, C, D, 1.0 / B, gloss, emb_shape)
+        if sharded:
+            if not (want_w and want_b):
+                raise RuntimeError("sharded AdamW updates cell_layer.weight and .bias together: both must require grad")
+            ctx.module._sharded.backward_and_step(dlogits, x16, C, D, B, gloss, ctx.dbp)
+            return demb, None, None, None, None, None, None
         if want_w or want_b:
             dp = ctx.module._dp
             if dp is None:
@@ -215,6 +228,7 @@ class SuperGuessr(nn.Module):
         self._side_stream = None
         self._stats_under_gemm = os.environ.get("GG_STATS_UNDER_GEMM", "1") != "0"
         self._dp = None
+        self._sharded = None
         print(f"Initialized SuperGuessr classification model with {self.num_cells} geocells.")
 
     # ---- reference helpers (super_guessr.py:114-206) ---------------------------------------
@@ -273,6 +287,8 @@ class SuperGuessr(nn.Module):
         rebuilt every step (fused optimisers update parameters without bumping ``_version``, so a
         version key cannot be trusted while weights are moving); in eval mode it is cached and
         rebuilt when the fp32 parameters change (load_state_dict, .to(), manual edits)."""
+        if self._sharded is not None:
+            return self._sharded.operands()
         key = (weight.data_ptr(), weight._version, bias.data_ptr(), bias._version, self.precision, weight.device)
         if self.training or self._op_cache is None or self._op_cache["key"] != key:
             split = self.precision == "bf16x3"
@@ -346,6 +362,16 @@ class SuperGuessr(nn.Module):
         self._dp = dict(group=process_group, chunks=int(chunks), comm_dtype=comm_dtype, stream=None, comm=comm,
                         symm=None)
         return self
+
+    def sharded_adamw(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, process_group=None):
+        """The optimizer for the head in place of ``torch.optim.AdamW(model.parameters(), ...)``
+        (main_coordinator_idun_s3.py:286-291): AdamW sharded over the data-parallel ranks and fused into the gradient
+        exchange (sharded_adamw.ShardedAdamW).  With an initialised process group the head is data parallel over it
+        (do not also call enable_data_parallel / wrap in DDP); without one it is a single-GPU fused optimizer step.
+        Returns a torch.optim.Optimizer: ``loss.backward(); optimizer.step()`` as before."""
+        from .sharded_adamw import ShardedAdamW
+
+        return ShardedAdamW(self, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, process_group=process_group)
 
     @staticmethod
     def _dp_transport(comm: str, world: int, is_cuda: bool, comm_dtype=None) -> str:

@@ -144,12 +144,12 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * sums from gg_hav_ce_fwd_bwd; when null, db is computed from dlogits.  workspace
  * (gg_head_bwd_workspace_bytes(C) bytes, required): parked partial accumulators + flags of the stream-K
  * schedule, and the column-sum slices of the db pass.
- * Data parallelism (gg_grad_exchange below): with dp_world > 1 the kernel does not write dW / db at all (both may be
+ * Data parallelism (gg_grad_exchange below): with dp_ptrs given (dp_world >= 1) the kernel does not write dW / db at all (both may be
  * null): every finished tile of 128 geocells x 256 columns -- and the block's 128 db entries -- is stored straight
  * into the staging slab of the rank that reduces the block (block b -> rank b % dp_world), over NVLink for the other
  * ranks, and complete blocks are announced on that rank's `ready` counters.  dp_ptrs: HOST array of 1 + 2 * dp_world
  * device addresses as mapped on this device = {this rank's control region + GG_GRAD_CTRL_BLKCOUNT_OFF, control region +
- * GG_GRAD_CTRL_READY_OFF of rank 0, 1, ..., staging region of rank 0, 1, ...}.  dp_world <= 1: plain local dW / db. */
+ * GG_GRAD_CTRL_READY_OFF of rank 0, 1, ..., staging region of rank 0, 1, ...}.  dp_ptrs null: plain local dW / db. */
 int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
                 const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
                 void* workspace, const unsigned long long* dp_ptrs, int dp_world, int dp_rank, gg_stream_t stream);
@@ -261,7 +261,7 @@ int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_flo
  * control region of GG_GRAD_CTRL_BYTES (zeroed once, before the first step), its gradient buffer [dW (C,D) | db (C) |
  * pad to a multiple of 4 floats] and a staging region of gg_grad_stage_floats(C, D, world) floats: `world` slabs (one
  * per source rank), each = the dW rows of the blocks this rank reduces (block b of 128 geocells -> rank b % world)
- * followed by their db entries.  gg_head_bwd (dp_world > 1) pushes every tile into the reducer's slab and announces
+ * followed by their db entries.  gg_head_bwd (dp_ptrs given) pushes every tile into the reducer's slab and announces
  * complete blocks; gg_grad_exchange, launched AFTER it on the same stream, waits per owned block for all ranks'
  * announcements, adds the staged copies in rank order (deterministic, identical on all ranks), scales by 1 / world and
  * writes the average into every rank's gradient buffer -- multimem.st through the NVSwitch when the multicast
@@ -280,6 +280,29 @@ size_t gg_grad_ctrl_bytes(void);
 size_t gg_grad_stage_floats(int C, int D, int world);
 int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsigned long long* ctrl_ptrs, void* grad_mc,
                      void* ctrl_mc, const void* stage, int world, int rank, int C, int D, int flags, gg_stream_t stream);
+
+/* The same exchange with the optimizer in it (sharded AdamW; replaces gg_grad_exchange AND the trainer's
+ * torch.optim.AdamW step, main_coordinator_idun_s3.py:286-291,424, for the head's weight and bias).  After adding a
+ * block's staged copies the reducer holds the averaged gradient in registers: it applies AdamW --
+ *     p -= lr wd p;  m += (1 - b1)(g - m);  v = b2 v + (1 - b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+ * (torch's fused kernel, fp32) -- to the rows of ITS blocks of the fp32 master weights master_w (C, D) / master_b (C)
+ * with moments m_*, v_* (all local to this rank; rows of other ranks' blocks are not touched and go stale), and
+ * writes what the next forward consumes into EVERY rank's operand buffers: the rows as bf16 (w16, (C, D): half the
+ * bytes of the fp32 gradient the plain exchange broadcasts) and the bias as fp32 (bias, gg_head_bias_pad(C) entries,
+ * pad kept at zero).  No gradient is materialised, no rank runs an optimizer pass over all of W, and the per-step
+ * fp32 -> bf16 cast of W (gg_prepare_head_weights) is gone.  hyper: DEVICE floats {lr, beta1, beta2, eps,
+ * weight_decay}; step: DEVICE counter of optimizer steps taken so far (t = *step + 1; incremented by the kernel), so a
+ * captured CUDA graph replays correctly.  w16_ptrs / bias_ptrs / ctrl_ptrs: host arrays of `world` device addresses
+ * in symmetric memory; *_mc: multicast addresses of the same three buffers or all null.  world in {1, 2, 4, 8}
+ * (world = 1: gg_head_bwd with dp_world = 1 stages into the local slab; a single-GPU fused optimizer step).
+ * A rank returns when every reducer's rows have landed in ITS operands.  Other ranks' operands are only overwritten
+ * after that rank announced the block, i.e. after its dW GEMM: anything of the step that still reads w16 (gg_head_dx)
+ * must be launched before gg_head_bwd. */
+int gg_grad_exchange_adamw(const unsigned long long* w16_ptrs, const unsigned long long* bias_ptrs,
+                           const unsigned long long* ctrl_ptrs, void* w16_mc, void* bias_mc, void* ctrl_mc,
+                           const void* stage, int world, int rank, int C, int D, float* master_w, float* master_b,
+                           float* m_w, float* v_w, float* m_b, float* v_b, const float* hyper, long long* step,
+                           int flags, gg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
      (bit-exact at N = 2)
   2. three consecutive data-parallel SuperGuessr training steps with comm="fused" (gg_head_bwd announcing blocks +
      gg_grad_exchange next to it), "nvls", "p2p" == the same steps with comm="nccl"
+  2b. three steps with model.sharded_adamw() (AdamW inside gg_grad_exchange_adamw) == NCCL average + torch.optim.AdamW
   3. timing of the exchanges for the 51.8 MB head gradient (CUDA events, max over ranks)
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/p2p_check.py [--quick]
@@ -114,6 +115,69 @@ for D, B in ((256, 512), (576, 256)):
         gathered_w = [torch.empty_like(got[-1][0]) for _ in range(world)]
         dist.all_gather(gathered_w, got[-1][0])
         assert all(torch.equal(gathered_w[0], g) for g in gathered_w), f"{kind}: ranks hold different gradients"
+
+
+# ---- 2b. sharded AdamW fused into the exchange vs NCCL average + torch.optim.AdamW
+def adamw_steps(sharded, D=256, B=512, steps=3):
+    import contextlib
+    import io
+
+    cent = load_packaged_centroids()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = gg.SuperGuessr(None, panorama=True, should_smooth_labels=True, embed_dim=D, centroids=cent).to(dev)
+    emb, W, b, labels = synth.head_inputs(B * world, D, cent.shape[0], seed=9, bf16_round=True)
+    with torch.no_grad():
+        m.cell_layer.weight.copy_(W)
+        m.cell_layer.bias.copy_(b)
+    m.train()
+    kw = dict(lr=2e-3, betas=(0.9, 0.98), weight_decay=0.02)
+    if sharded:
+        opt = m.sharded_adamw(**kw)
+    else:
+        m.enable_data_parallel(comm="nccl")
+        opt = torch.optim.AdamW(m.cell_layer.parameters(), **kw)
+    sl = slice(rank * B, (rank + 1) * B)
+    losses, first = [], None
+    for i in range(steps):
+        opt.zero_grad(set_to_none=True)
+        out = m(embedding=emb[sl].to(dev), labels=labels[sl].to(dev), labels_clf=torch.zeros(B, dtype=torch.int64, device=dev))
+        out.loss.backward()
+        opt.step()
+        losses.append(out.loss.item())
+        if i == 0:  # (a collective in the sharded case: every rank takes part)
+            if sharded:
+                opt.gather_master()
+            first = (m.cell_layer.weight.data.clone(), m.cell_layer.bias.data.clone())
+    torch.cuda.synchronize()
+    w16 = None
+    if sharded:
+        w16 = opt.w16.clone()
+        opt.gather_master()
+    return first, (m.cell_layer.weight.data.clone(), m.cell_layer.bias.data.clone()), w16, losses, (opt.describe() if sharded else None)
+
+
+lr_check = 2e-3
+for D, B in ((256, 512), (576, 256)):
+    first_ref, (w_ref, b_ref), _, l_ref, _ = adamw_steps(False, D, B)
+    first_got, (w_got, b_got), w16, l_got, what = adamw_steps(True, D, B)
+    # step 1 (identical inputs on both sides): the two AdamW implementations agree to fp32 rounding
+    rel_w1 = ((first_got[0] - first_ref[0]).abs().max() / first_ref[0].abs().max()).item()
+    rel_b1 = ((first_got[1] - first_ref[1]).abs().max() / first_ref[1].abs().max()).item()
+    # later steps: the persistent bf16 operand and the re-cast one differ in a few entries by one rounding, and AdamW
+    # turns a tiny change of a tiny gradient (|g| ~ eps) into a visible fraction of one update (lr): bound by that
+    abs_w = (w_got - w_ref).abs().max().item()
+    abs_b = (b_got - b_ref).abs().max().item()
+    flips = (w16.float() != w_ref.to(torch.bfloat16).float()).float().mean().item()
+    say(f"sharded AdamW D={D} vs nccl + torch.optim.AdamW: step 1 master W rel diff {rel_w1:.2e}, bias {rel_b1:.2e}; after 3 "
+        f"steps max abs diff W {abs_w:.2e}, bias {abs_b:.2e} (one update = lr = {lr_check:.0e}), bf16 operand entries "
+        f"differing {flips:.2e}, losses {l_got} vs {l_ref}")
+    assert rel_w1 < 5e-6 and rel_b1 < 5e-6
+    assert abs_w < 0.25 * lr_check and abs_b < 0.25 * lr_check and flips < 5e-3
+    assert all(abs(a - c) <= 1e-4 * abs(c) for a, c in zip(l_got, l_ref))
+    gathered_w = [torch.empty_like(w16) for _ in range(world)]
+    dist.all_gather(gathered_w, w16)
+    assert all(torch.equal(gathered_w[0], g) for g in gathered_w), "ranks hold different bf16 operands"
+say(what)
 
 
 # ---- 3. timing

@@ -474,7 +474,7 @@ def run_b200_train(args, ctx, brief=False, dp_optimizer=None):
     # context for the tensor-bound launchers: what cuBLAS reaches on the SAME shapes (the roofline denominator is
     # cuBLAS at 8192^3); library call, outside every timed region above, not part of the product path
     context = None
-    if rank == 0:
+    if rank == 0 and not args.no_cpu:  # (--no-cpu = profiler runs: keep library GEMMs out of the launch list)
         xa = torch.randn((B, D), device=dev).to(torch.bfloat16)
         wa = torch.randn((C_CELLS, D), device=dev).to(torch.bfloat16)
         ga = torch.randn((B, ops.logits_ld(C_CELLS)), device=dev).to(torch.bfloat16)[:, :C_CELLS]
@@ -612,7 +612,10 @@ def check_sharded_step(model, opt, batch, dummy_clf, dist):
     return {"against": "first step: NCCL all_reduce(SUM) / world of the per-rank gradients + torch.optim.AdamW",
             "max_abs_diff_W": err[0], "max_abs_diff_b": err[1], "max_abs_W": err[2],
             "bf16_operand_entries_off_by_one_rounding": err[3],
-            "ok": bool(err[0] <= 2e-6 * err[2] and err[1] <= 2e-6 * err[2] and err[3] < 1e-3)}
+            "lr": g["lr"],
+            # NCCL's summation order differs from the rank order from 4 ranks on (fp32 rounding of the gradient), and
+            # step 1 of AdamW moves an entry by lr g / (|g| + eps): for |g| ~ eps a visible fraction of lr
+            "ok": bool(max(err[0], err[1]) <= 2e-2 * g["lr"] and err[3] < 1e-3)}
 
 
 def check_dp_gradient(model, batch, dummy_clf, dist):

@@ -161,17 +161,20 @@ for D, B in ((256, 512), (576, 256)):
     first_ref, (w_ref, b_ref), _, l_ref, _ = adamw_steps(False, D, B)
     first_got, (w_got, b_got), w16, l_got, what = adamw_steps(True, D, B)
     # step 1 (identical inputs on both sides): the two AdamW implementations agree to fp32 rounding
-    rel_w1 = ((first_got[0] - first_ref[0]).abs().max() / first_ref[0].abs().max()).item()
-    rel_b1 = ((first_got[1] - first_ref[1]).abs().max() / first_ref[1].abs().max()).item()
+    # (NCCL's summation order differs from the rank order from 4 ranks on: the averaged gradient differs by fp32
+    # rounding, and step 1 of AdamW moves an entry by lr g / (|g| + eps) -- for |g| ~ eps that is a visible fraction
+    # of lr; bound 2 % of one update)
+    rel_w1 = ((first_got[0] - first_ref[0]).abs().max() / lr_check).item()
+    rel_b1 = ((first_got[1] - first_ref[1]).abs().max() / lr_check).item()
     # later steps: the persistent bf16 operand and the re-cast one differ in a few entries by one rounding, and AdamW
     # turns a tiny change of a tiny gradient (|g| ~ eps) into a visible fraction of one update (lr): bound by that
     abs_w = (w_got - w_ref).abs().max().item()
     abs_b = (b_got - b_ref).abs().max().item()
     flips = (w16.float() != w_ref.to(torch.bfloat16).float()).float().mean().item()
-    say(f"sharded AdamW D={D} vs nccl + torch.optim.AdamW: step 1 master W rel diff {rel_w1:.2e}, bias {rel_b1:.2e}; after 3 "
+    say(f"sharded AdamW D={D} vs nccl + torch.optim.AdamW: step 1 master W max abs diff {rel_w1:.2e} lr, bias {rel_b1:.2e} lr; after 3 "
         f"steps max abs diff W {abs_w:.2e}, bias {abs_b:.2e} (one update = lr = {lr_check:.0e}), bf16 operand entries "
         f"differing {flips:.2e}, losses {l_got} vs {l_ref}")
-    assert rel_w1 < 5e-6 and rel_b1 < 5e-6
+    assert rel_w1 < 2e-2 and rel_b1 < 2e-2
     assert abs_w < 0.25 * lr_check and abs_b < 0.25 * lr_check and flips < 5e-3
     assert all(abs(a - c) <= 1e-4 * abs(c) for a, c in zip(l_got, l_ref))
     gathered_w = [torch.empty_like(w16) for _ in range(world)]

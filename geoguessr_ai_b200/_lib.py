@@ -29,6 +29,7 @@ SIGNATURES = {
     "gg_head_fwd_workspace_bytes": (c_size_t, [I, I, I]),
     "gg_head_fwd_ticket_bytes": (c_size_t, [I]),
     "gg_debug_head_fwd_timeline": (None, [P]),
+    "gg_debug_head_bwd_timeline": (None, [P]),
     "gg_head_bwd_workspace_bytes": (c_size_t, [I]),
     "gg_hav_ce_workspace_bytes": (c_size_t, [I, I]),
     "gg_hav_ce_db_parts": (I, [I, I]),

@@ -16,12 +16,18 @@
 // pairs that run concurrently work on the few geocell blocks whose dlogits then sit in L2, so dlogits is
 // streamed from HBM once).  The last, incomplete round is cut stream-K style: its (tile, k-block) units
 // are split into one contiguous, equally long range per pair (at cfg2: 200 pair-tiles over 74 pairs = 2
-// whole rounds + 52 tiles x 64 k-blocks = 45 units per pair instead of a third, 70 %-idle round).  A pair
-// walks its range downwards.  A tile that straddles two ranges is finished by the HIGHER pair: the lower
-// pair meets its part first, parks the raw fp32 partial in the workspace and raises a flag; the higher pair
-// reaches its part last, adds the parked partial in its epilogue and writes dW.  Waits therefore only ever
-// point at lower-numbered, earlier-scheduled pairs that did the awaited work first: no deadlock, and a fixed
-// summation order (deterministic).
+// whole rounds + 52 tiles x 64 k-blocks = 45 units per pair instead of a third, 70 %-idle round).  A tile
+// whose k-blocks are spread over two or three ranges is FINISHED by the pair that holds its last k-blocks; the
+// others PARK their raw fp32 partial in the workspace and raise a flag.  A pair does its parking part FIRST,
+// before the whole rounds, and its finishing part LAST: partials are parked ~10 us into the launch and nobody
+// waits for anybody at the end (tools/head_bwd_timeline.py: with the tail round walked at the end and the
+// finisher adding the parked partial in its epilogue, a middle pair parked at 72 us what the next pair needed to
+// finish, and the launch ended at 81 us with the last MMA issued at 65).  The finisher does not add in its
+// epilogue either: while the MMAs of its last whole tile run, its epilogue warps -- idle then -- sum the parked
+// partials in pair order and write them INTO the TMEM accumulator its finishing part will use (tcgen05.st); the
+// MMAs of that part accumulate on top and the epilogue is the ordinary one.  Waits only ever point at pairs
+// that parked as their first piece of work, depending on nobody: no deadlock, and a fixed summation order
+// (deterministic).
 #include <algorithm>
 
 #include "common.cuh"
@@ -48,6 +54,7 @@ struct BwdSmem {
   uint64_t empty[kWStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t preload;  // leader's: the finishing part's accumulator holds the parked partials (8 epilogue warps arrive)
   uint32_t tmem_base;
 };
 
@@ -64,24 +71,39 @@ struct PairSchedule {
     u0 = tail_total * pair / npairs;
     u1 = tail_total * (pair + 1) / npairs;
   }
-  // the pair whose range ends where mine begins (owner of tail unit u0 - 1): with few tail units most ranges
-  // are empty, so this need not be pair - 1
-  __device__ int lower_neighbour() const {
-    const long long total = tail_total;
-    if (u0 <= 0 || total <= 0) return -1;
-    return static_cast<int>((u0 * npairs + total - 1) / total) - 1;  // ceil(u0 * P / total) - 1
+  // Does my range end inside a tile (its top part is parked for the pair that holds the tile's last k-blocks)?
+  __device__ bool parks() const { return u1 > u0 && (u1 % num_k) != 0; }
+  __device__ int tail_segments() const {
+    return u1 > u0 ? static_cast<int>((u1 - 1) / num_k - u0 / num_k) + 1 : 0;
   }
-  __device__ int segments() const {
-    return rounds + (u1 > u0 ? static_cast<int>((u1 - 1) / num_k - u0 / num_k) + 1 : 0);
-  }
-  // i-th segment: tile and k-block range [k0, k1)
+  __device__ int segments() const { return rounds + tail_segments(); }
+  // i-th segment in execution order: the parking part (if any), the whole rounds, the rest of the tail range from the
+  // top down (whole tiles, then the finishing part); tile and k-block range [k0, k1)
   __device__ void get(int i, int& tile, int& k0, int& k1) const {
-    if (i < rounds) { tile = i * npairs + pair; k0 = 0; k1 = num_k; return; }
-    const int t = static_cast<int>((u1 - 1) / num_k) - (i - rounds);  // tail tiles from the top of the range down
+    const int pk = parks() ? 1 : 0;
+    int j;  // tail segment, 0 = top of the range
+    if (pk && i == 0) {
+      j = 0;
+    } else if (i - pk < rounds) {
+      tile = (i - pk) * npairs + pair; k0 = 0; k1 = num_k;
+      return;
+    } else {
+      j = i - rounds;
+    }
+    const int t = static_cast<int>((u1 - 1) / num_k) - j;
     const long long base = static_cast<long long>(t) * num_k;
     k0 = static_cast<int>((u0 > base ? u0 : base) - base);
     k1 = static_cast<int>((u1 < base + num_k ? u1 : base + num_k) - base);
     tile = tail_base + t;
+  }
+  // does pair q hold any of the tail units [a, b)?  (ranges of a short tail round can be empty)
+  __device__ bool holds(int q, long long a, long long b) const {
+    const long long q0 = tail_total * q / npairs, q1 = tail_total * (q + 1) / npairs;
+    return q1 > q0 && q0 < b && q1 > a;
+  }
+  // owner of tail unit u
+  __device__ int owner(long long u) const {
+    return static_cast<int>(((u + 1) * npairs + tail_total - 1) / tail_total) - 1;  // ceil((u + 1) P / total) - 1
   }
 };
 
@@ -105,6 +127,17 @@ __device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned in
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Optional per-CTA timeline (tools/head_bwd_timeline.py, gg_debug_head_bwd_timeline): 64 globaltimer stamps per CTA.
+// 0 entry, 1 set-up done, 2 exit, 3 last MMA issued, 4 number of segments, 5 parked-partial wait over; per segment i < 16:
+// 8+i accumulator seen complete by the epilogue, 24+i epilogue done with it, 40+i its last MMA issued.
+__device__ __forceinline__ void bwd_stamp(long long* tl, int slot) {
+  if (tl != nullptr) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[static_cast<size_t>(blockIdx.x) * 64 + slot] = t;
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBwdThreads, 1)
 head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C, rows B
                 const __grid_constant__ CUtensorMap tm_x,   // x:       inner D, rows B
@@ -113,7 +146,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
                 float scale_in,
                 const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags,
                 float* __restrict__ db, const float* __restrict__ db_partials, int db_parts, int db_ld,
-                const float* __restrict__ db_ready) {
+                const float* __restrict__ db_ready, long long* __restrict__ timeline) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,6 +161,8 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
   const int nseg = ps.segments();
 
   if (threadIdx.x == 0) {
+    bwd_stamp(timeline, 0);
+    if (timeline != nullptr) timeline[static_cast<size_t>(blockIdx.x) * 64 + 4] = nseg;
     tma_prefetch_desc(&tm_g);
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_dw);
@@ -139,6 +174,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
       mbar_init(&sm.acc_full[a], 1);
       mbar_init(&sm.acc_empty[a], 2 * 4);  // leader's: one arrive per epilogue warp of BOTH CTAs
     }
+    mbar_init(&sm.preload, 2 * 4);
     fence_barrier_init();
   }
   if (warp == 1) {  // collective over the pair: one warp in each CTA
@@ -149,6 +185,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
   cluster_sync();  // the partner's barriers exist before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  if (threadIdx.x == 0) bwd_stamp(timeline, 1);
 
   {
     if (warp == 0) {
@@ -191,6 +228,10 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
           int t, k0, k1;
           ps.get(it, t, k0, k1);
           mbar_wait(&sm.acc_empty[acc], acc_ph ^ 1);  // both CTAs' epilogues have drained this accumulator
+          // finishing part of a tile other pairs started: the epilogue warps have written the sum of the parked
+          // partials into this accumulator; the MMAs go on top of it
+          const bool finishing = k0 > 0 && k1 == num_k;
+          if (finishing) mbar_wait(&sm.preload, 0);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kWN;
           for (int kb = k0; kb < k1; ++kb) {
@@ -199,7 +240,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
             if (elect_one()) {
               const uint64_t da = da_base + static_cast<uint64_t>(s * (kWStageA >> 4));
               const uint64_t db = db_base + static_cast<uint64_t>(s * (kWStageB >> 4));
-              umma_pair_f16(d_tmem, da, db, idesc, kb != k0);
+              umma_pair_f16(d_tmem, da, db, idesc, kb != k0 || finishing);
 #pragma unroll
               for (int k = 1; k < kWK / 16; ++k)
                 umma_pair_f16_acc(d_tmem, da + k * (2048 >> 4), db + k * (2048 >> 4), idesc);
@@ -209,7 +250,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
             __syncwarp();
             if (++s == kWStages) { s = 0; ph ^= 1; }
           }
+          if (lane == 0 && it < 16) bwd_stamp(timeline, 40 + it);
         }
+        if (lane == 0) bwd_stamp(timeline, 3);
       }
     } else {
       // ===== epilogue: 4 warps, thread = one geocell row of this CTA's accumulator half =====
@@ -218,8 +261,57 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
       const uint32_t leader_acc_empty = mapa_u32(smem_u32(&sm.acc_empty[0]), 0);
       // parked partials: [pair][cta][column][row] so that a warp's accesses are contiguous
       float* const my_park = parked + (static_cast<size_t>(pair) * 2 + crank) * kPartialFloats + rit;
-      const int lower = ps.lower_neighbour();  // whose parked partial a straddling first tile continues
-      const float* const prev_park = parked + (static_cast<size_t>(lower < 0 ? 0 : lower) * 2 + crank) * kPartialFloats + rit;
+      // Finishing part (always the last segment): which pairs parked the tile's earlier k-blocks, and when to fetch them
+      int fin_seg = -1, fin_q0 = 0;
+      long long fin_a = 0, fin_b = 0;  // the tail units the other pairs parked: [fin_a, fin_b)
+      if (nseg > 0) {
+        int t, k0, k1;
+        ps.get(nseg - 1, t, k0, k1);
+        if (k0 > 0 && k1 == num_k) {
+          fin_seg = nseg - 1;
+          fin_a = static_cast<long long>(t - ps.tail_base) * num_k;
+          fin_b = fin_a + k0;
+          fin_q0 = ps.owner(fin_a);
+        }
+      }
+      const uint32_t leader_preload = mapa_u32(smem_u32(&sm.preload), 0);
+      // sum of the parked partials (pair order) -> the accumulator the finishing part will use
+      auto preload = [&]() {
+        if (threadIdx.x == 64) {
+          for (int q = fin_q0; q < pair; ++q) {
+            if (!ps.holds(q, fin_a, fin_b)) continue;
+            const long long t0 = clock64();
+            while (atomicAdd(&flags[q * 2 + crank], 0) == 0) {
+              __nanosleep(64);
+              if (clock64() - t0 > 8000000000LL) { printf("gg: head_bwd partial of pair %d never arrived\n", q); __trap(); }
+            }
+          }
+          __threadfence();
+          bwd_stamp(timeline, 5);
+        }
+        named_bar_sync(1, 128);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (fin_seg & 1) * kWN;
+#pragma unroll 1
+        for (int c = 0; c < kWN / 32; ++c) {
+          uint32_t r[32];
+          const float* src = parked + (static_cast<size_t>(fin_q0) * 2 + crank) * kPartialFloats + rit;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__ldcg(src + static_cast<size_t>(c * 32 + j) * kWM));
+          for (int q = fin_q0 + 1; q < pair; ++q) {
+            if (!ps.holds(q, fin_a, fin_b)) continue;  // (warp-uniform)
+            src = parked + (static_cast<size_t>(q) * 2 + crank) * kPartialFloats + rit;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(src + static_cast<size_t>(c * 32 + j) * kWM));
+          }
+          tmem_st_32x32b_x32(taddr + c * 32, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_preload);
+      };
+      if (fin_seg >= 0 && fin_seg < 2) preload();  // (no earlier segment uses that accumulator)
       int it = 0;
       int obuf = 0;  // staging buffer of the next dW store (alternates per store)
       for (; it < nseg; ++it) {
@@ -235,21 +327,10 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         const int dst_rank = push ? blk % sig.world : 0;
         const CUtensorMap* const tm_dst = push ? &stage.m[dst_rank] : &tm_dw;
         const int dst_row0 = push ? (blk / sig.world) * kWM : m0;
-        const bool add_prev = k0 > 0;      // the lower pair parked the first k-blocks of this tile
-        const bool park = k1 < num_k;      // the higher pair finishes this tile
+        const bool park = k1 < num_k;      // another pair holds this tile's last k-blocks and finishes it
         mbar_wait(&sm.acc_full[acc], acc_ph);
         tc_fence_after();
-        if (add_prev) {  // (set long ago: the lower pair did that part first)
-          if (threadIdx.x == 64) {
-            const long long t0 = clock64();
-            while (atomicAdd(&flags[lower * 2 + crank], 0) == 0) {
-              __nanosleep(64);
-              if (clock64() - t0 > 8000000000LL) { printf("gg: head_bwd partial of pair %d never arrived\n", lower); __trap(); }
-            }
-            __threadfence();
-          }
-          named_bar_sync(1, 128);
-        }
+        if (threadIdx.x == 64 && it < 16) bwd_stamp(timeline, 8 + it);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kWN;
 #pragma unroll 1
         for (int c = 0; c < kWN / 32; ++c) {
@@ -257,11 +338,6 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
-          if (add_prev) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(prev_park + static_cast<size_t>(c * 32 + j) * kWM));
-          }
           if (park) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) __stcg(my_park + static_cast<size_t>(c * 32 + j) * kWM, __uint_as_float(r[j]));
@@ -291,7 +367,11 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         }
         tc_fence_before();
         __syncwarp();
+        // the accumulator this segment used is the finishing part's: fill it with the parked partials before the
+        // MMA warp gets there (it is busy with the segment in between for another ~20 us)
+        if (it == fin_seg - 2) preload();
         if (lane == 0) mbar_arrive_cluster(leader_acc_empty + 8 * acc);
+        if (threadIdx.x == 64 && it < 16) bwd_stamp(timeline, 24 + it);
         // bias gradient: whoever finishes a geocell block's first column tile also sums that block's column-sum
         // partials from the loss kernel (fixed order; 128 consecutive geocells per warp-quartet: coalesced)
         if ((db != nullptr || push) && !park && n0 == 0 && row < C) {
@@ -338,6 +418,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
   }
   tc_fence_before();
   cluster_sync();  // the partner may still be signalling this CTA's barriers / the leader reading its operands
+  if (threadIdx.x == 0) bwd_stamp(timeline, 2);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
@@ -422,6 +503,9 @@ extern "C" size_t gg_grad_stage_floats(int C, int D, int world) {
   return static_cast<size_t>(world) * grad_blocks_per_rank(C, world) * kWM * (static_cast<size_t>(D) + 1);
 }
 
+static long long* g_bwd_timeline = nullptr;  // gg_debug_head_bwd_timeline
+extern "C" void gg_debug_head_bwd_timeline(long long* device_buf) { g_bwd_timeline = device_buf; }
+
 extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
                            float scale, const float* grad_scale, float* dW, float* db, const float* db_partials,
                            int db_parts, int db_ld, void* workspace, const unsigned long long* dp_ptrs, int dp_world,
@@ -491,7 +575,7 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   // cluster shape (2,1,1) is compiled into the kernel
   head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, tm_dw, maps, sig, C, D, B, scale, grad_scale, parked,
                                                        flags, db_fused && !push ? db : nullptr, db_partials, db_parts, db_ld,
-                                                       db_tmp);
+                                                       db_tmp, g_bwd_timeline);
   GG_LAUNCH_CHECK();
   if (db && !db_fused && !push)
     if (int e = db_from_dlogits(db)) return e;

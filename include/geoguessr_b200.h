@@ -97,6 +97,10 @@ int gg_head_fwd(const void* x_bf16, const void* w_bf16, const float* bias_pad, i
  * first / last MMA issued, first / last accumulator complete, chunks done, fold, flush, merge, epilogue drained,
  * exit).  null switches it off (the default; the kernel then only tests a pointer). */
 void gg_debug_head_fwd_timeline(long long* device_buf);
+/* The same for gg_head_bwd (tools/head_bwd_timeline.py): 64 int64 per CTA -- entry, set-up done, exit, last MMA issued,
+ * number of segments, end of the wait for a parked partial; per segment (tile or part of a tail tile) accumulator
+ * complete / epilogue done / last MMA issued. */
+void gg_debug_head_bwd_timeline(long long* device_buf);
 
 /* ---- a5-a8: haversine label-smoothed cross-entropy, forward + gradient ---------------------
  * models/utils.py:39-57 haversine_matrix; :20-32 smooth_labels (tau = config.py:52 = 65 km);

@@ -63,10 +63,12 @@ def test_every_launcher_has_a_python_caller():
     for name in os.listdir(pkg):
         if name.endswith(".py") and name != "_lib.py":
             text += open(os.path.join(pkg, name)).read()
-    text += open(os.path.join(REPO, "tools", "head_fwd_timeline.py")).read()
+    for tool in ("head_fwd_timeline.py", "head_bwd_timeline.py"):
+        text += open(os.path.join(REPO, "tools", tool)).read()
     missing = [s for s in _lib.SIGNATURES if s not in text and s not in ("gg_abi_version", "gg_last_error")]
     assert not missing, f"no Python caller for {missing}"
-    for fn in ("head_dx", "topk_accuracy", "split3_bf16", "linear_bf16", "hier_fuse", "grad_exchange", "grad_stage_floats",
+    for fn in ("head_dx", "topk_accuracy", "split3_bf16", "linear_bf16", "hier_fuse", "grad_exchange", "grad_exchange_adamw",
+               "grad_stage_floats",
                "proto_record_ids", "proto_take_image_coords", "cast_bank_bf16", "proto_group_cells", "head_forward",
                "head_backward", "hav_ce", "hard_ce", "fuse_headings", "fuse_and_prepare", "proto_retrieve", "proto_refine"):
         assert hasattr(ops, fn), fn

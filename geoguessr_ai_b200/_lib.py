@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgeoguessr_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
@@ -30,6 +30,7 @@ SIGNATURES = {
     "gg_head_fwd_ticket_bytes": (c_size_t, [I]),
     "gg_debug_head_fwd_timeline": (None, [P]),
     "gg_debug_head_bwd_timeline": (None, [P]),
+    "gg_debug_nvlink_store_probe": (I, [P, c_size_t, I, I, I, P]),
     "gg_head_bwd_workspace_bytes": (c_size_t, [I]),
     "gg_hav_ce_workspace_bytes": (c_size_t, [I, I]),
     "gg_hav_ce_db_parts": (I, [I, I]),
@@ -45,7 +46,7 @@ SIGNATURES = {
     "gg_hav_ce_fwd_bwd": (I, [P, I, P, P, P, I, I, F, P, P, P, P, P, F, P]),
     "gg_hard_ce_fwd_bwd": (I, [P, I, P, P, I, I, P, P, P]),
     "gg_loss_mean": (I, [P, I, F, P, P]),
-    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P, I, I, P]),
+    "gg_head_bwd": (I, [P, I, P, I, I, I, I, F, P, P, P, P, I, I, P, P, I, I, I, P]),
     "gg_head_dx": (I, [P, I, P, I, I, I, I, F, P, I, P, P]),
     "gg_topk_accuracy": (I, [P, I, P, I, P, P]),
     "gg_split3_bf16": (I, [P, L, I, I, P, I, P, P]),

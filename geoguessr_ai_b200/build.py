@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libgeoguessr_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 SOURCES = ["common.cu", "elementwise.cu", "head_fwd.cu", "hav_ce.cu", "head_bwd.cu", "proto.cu", "p2p.cu", "gemm.cu",
-           "hier.cu"]
+           "hier.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

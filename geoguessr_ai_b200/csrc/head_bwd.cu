@@ -54,6 +54,7 @@ struct BwdSmem {
   uint64_t empty[kWStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  float dbrow[kWM];  // push mode: a block's 128 db entries on their way to the reducer (one bulk store)
   uint64_t preload;  // leader's: the finishing part's accumulator holds the parked partials (8 epilogue warps arrive)
   uint32_t tmem_base;
 };
@@ -63,9 +64,12 @@ struct PairSchedule {
   int pair, npairs, num_k, rounds, tail_base;
   long long tail_total;
   long long u0, u1;  // tail units [u0, u1): unit = tail_tile * num_k + k-block
-  __device__ PairSchedule(int pair_, int npairs_, int num_tiles, int nk)
+  // all_streamk: no whole rounds -- every pair gets one contiguous range of ALL (tile, k-block) units.  Same work and
+  // the same number of parked partials (one per pair), but the pairs' tiles then complete at times spread evenly over
+  // the launch instead of in three bursts: what the push mode needs (see gg_head_bwd)
+  __device__ PairSchedule(int pair_, int npairs_, int num_tiles, int nk, bool all_streamk)
       : pair(pair_), npairs(npairs_), num_k(nk) {
-    rounds = num_tiles / npairs;
+    rounds = all_streamk ? 0 : num_tiles / npairs;
     tail_base = rounds * npairs;
     tail_total = static_cast<long long>(num_tiles - tail_base) * nk;
     u0 = tail_total * pair / npairs;
@@ -115,7 +119,7 @@ struct PairSchedule {
 // release add on the reducer's `ready` counter.  The transfer thus rides underneath the GEMM tile by tile, without
 // any other kernel sharing the SMs with it.
 struct GradPush {
-  unsigned int* blk_count;             // local: pushed column tiles per 128-geocell block (self-resetting)
+  unsigned int* blk_count;             // (unused since every tile is counted on the reducer's own counter)
   unsigned int* ready[kGradMaxWorld];  // every rank's `ready` counters (peer-mapped)
   float* stage_b[kGradMaxWorld];       // rank r's db staging rows for THIS source rank (peer-mapped): [block / world][128]
   int world;                           // 0: plain local dW / db
@@ -146,7 +150,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
                 float scale_in,
                 const float* __restrict__ grad_scale, float* __restrict__ parked, int* __restrict__ flags,
                 float* __restrict__ db, const float* __restrict__ db_partials, int db_parts, int db_ld,
-                const float* __restrict__ db_ready, long long* __restrict__ timeline) {
+                const float* __restrict__ db_ready, long long* __restrict__ timeline, int all_streamk) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,7 +161,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int num_k = (Bk + kWK - 1) / kWK;
   const float scale = grad_scale ? scale_in * __ldg(grad_scale) : scale_in;
-  const PairSchedule ps(pair, npairs, num_tiles, num_k);
+  const PairSchedule ps(pair, npairs, num_tiles, num_k, all_streamk != 0);
   const int nseg = ps.segments();
 
   if (threadIdx.x == 0) {
@@ -312,6 +316,16 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         if (lane == 0) mbar_arrive_cluster(leader_preload);
       };
       if (fin_seg >= 0 && fin_seg < 2) preload();  // (no earlier segment uses that accumulator)
+      // push mode: count a tile whose stores have been performed; the block's last column tile announces the block
+      int pend_blk = -1, pend_dst = 0;
+      auto announce = [&](int blk, int dst_rank) {
+        named_bar_sync(1, 128);  // every warp's bulk stores of that tile have been performed at the reducer
+        // One add per (tile, CTA) on the reducer's counter of the block (it waits for num_n per rank).  Relaxed: the
+        // ordering IS the completion of the bulk stores (cp.async.bulk.wait_group) this thread and, through the
+        // barrier, the other warps waited for before this instruction was issued.
+        if (threadIdx.x == 64)
+          asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(sig.ready[dst_rank] + blk), "r"(1u) : "memory");
+      };
       int it = 0;
       int obuf = 0;  // staging buffer of the next dW store (alternates per store)
       for (; it < nseg; ++it) {
@@ -332,6 +346,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         tc_fence_after();
         if (threadIdx.x == 64 && it < 16) bwd_stamp(timeline, 8 + it);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kWN;
+        int ngroups = 0;  // bulk stores (one group each) this warp issues for this segment
 #pragma unroll 1
         for (int c = 0; c < kWN / 32; ++c) {
           uint32_t r[32];
@@ -363,6 +378,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
               tma_store_2d(tm_dst, buf, col0, dst_row0 + quad * 32);
               tma_store_commit();
             }
+            ++ngroups;
           }
         }
         tc_fence_before();
@@ -374,8 +390,10 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
         if (threadIdx.x == 64 && it < 16) bwd_stamp(timeline, 24 + it);
         // bias gradient: whoever finishes a geocell block's first column tile also sums that block's column-sum
         // partials from the loss kernel (fixed order; 128 consecutive geocells per warp-quartet: coalesced)
-        if ((db != nullptr || push) && !park && n0 == 0 && row < C) {
-          float v;
+        const bool db_tile = (db != nullptr || push) && !park && n0 == 0 && m0 < C;  // (warp-uniform)
+        if (db_tile) {
+          float v = 0.f;
+          if (row < C) {
           if (db_partials != nullptr) {
             float s0 = 0.f, s1 = 0.f;
             int i = 0;
@@ -388,8 +406,27 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
           } else {
             v = __ldg(db_ready + row);  // finished before this launch (column sums of dlogits)
           }
-          if (push) sig.stage_b[dst_rank][(blk / sig.world) * kWM + rit] = v;
-          else db[row] = v;
+          }
+          if (push) {
+            // the block's 128 entries leave as ONE bulk store issued by thread 64, whose completion is awaited with the
+            // tile's other bulk stores (below): no fence instruction in this epilogue -- every membar stalled the SM's
+            // memory pipeline, operand loads included, for microseconds (tools/dp_overlap_probe.py: 14 us per launch)
+            if (threadIdx.x == 64) tma_store_wait_read<0>();  // the previous block's entries have left shared memory
+            named_bar_sync(1, 128);
+            sm.dbrow[rit] = v;
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (threadIdx.x == 64) {
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                               sig.stage_b[dst_rank] + static_cast<size_t>(blk / sig.world) * kWM),
+                           "r"(smem_u32(sm.dbrow)), "r"(static_cast<uint32_t>(kWM * sizeof(float)))
+                           : "memory");
+              tma_store_commit();
+            }
+            if (warp == 2) ++ngroups;  // (thread 64's warp)
+          } else if (row < C) {
+            db[row] = v;
+          }
         }
         if (park) {  // publish: every epilogue thread's stores, then the flag
           __threadfence();
@@ -397,23 +434,23 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
           if (threadIdx.x == 64) atomicExch(&flags[pair * 2 + crank], 1);
         } else if (push && m0 < C) {
           // this CTA's 128 geocells x 256 columns of dW (and, with the first column tile, the block's db rows) are
-          // on their way to the reducer: count the block's column tiles, the last one announces the block
+          // on their way to the reducer.  Counting a tile needs its bulk stores PERFORMED (acknowledged by the reducer's memory), which under a busy
+          // NVLink takes a while: the wait is for the PREVIOUS pushed tile -- everything but the groups just issued --
+          // and that tile is counted now; this one when the next tile has been issued (or after the loop).
           if (lane == 0) {
-            tma_store_wait_all<0>();  // the bulk stores have been performed, not merely read from shared memory
+            tma_store_wait_all_but(ngroups);
             asm volatile("fence.proxy.async;" ::: "memory");
           }
-          named_bar_sync(1, 128);
-          if (threadIdx.x == 64) {
-            __threadfence_system();
-            const unsigned int old = atomicAdd(sig.blk_count + blk, 1u);
-            if (old + 1u == static_cast<unsigned int>(num_n)) {
-              sig.blk_count[blk] = 0u;  // left zeroed for the next step
-              red_release_sys_add(sig.ready[dst_rank] + blk, 1u);
-            }
-          }
+          if (pend_blk >= 0) announce(pend_blk, pend_dst);
+          pend_blk = blk;
+          pend_dst = dst_rank;
         }
       }
-      if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last bulk store
+      if (lane == 0) {
+        tma_store_wait_all<0>();  // shared memory must outlive the last bulk store; the last pushed tile is performed
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      if (pend_blk >= 0) announce(pend_blk, pend_dst);
     }
   }
   tc_fence_before();
@@ -509,7 +546,7 @@ extern "C" void gg_debug_head_bwd_timeline(long long* device_buf) { g_bwd_timeli
 extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D,
                            float scale, const float* grad_scale, float* dW, float* db, const float* db_partials,
                            int db_parts, int db_ld, void* workspace, const unsigned long long* dp_ptrs, int dp_world,
-                           int dp_rank, gg_stream_t stream) {
+                           int dp_rank, int schedule, gg_stream_t stream) {
   GG_CHECK(B > 0 && C > 0 && D > 0, GG_ERR_ARG, "gg_head_bwd: empty problem B=%d C=%d D=%d", B, C, D);
   GG_CHECK(dlogits_bf16 && x_bf16, GG_ERR_ARG, "gg_head_bwd: null pointer");
   GG_CHECK(ldc >= C && ldc % 8 == 0, GG_ERR_ARG, "gg_head_bwd: ldc=%d must be >= C and a multiple of 8", ldc);
@@ -572,10 +609,18 @@ extern "C" int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16
   if (push && !db_fused)
     if (int e = db_from_dlogits(db_tmp)) return e;
   GG_CUDA(cudaMemsetAsync(flags, 0, bwd_flag_bytes(), s));
+  // Push mode: 7/8 of the fp32 tiles leave through NVLink (606 GB/s for SM-issued stores, tools/symm_probe.py).  With
+  // whole rounds every CTA finishes its tiles at the same three moments, 19 MB each time, and the launch became a
+  // sequence of bursts (137 us at 8 ranks); with one contiguous unit range per pair the completions -- and the pushes --
+  // are spread over the whole launch.  On one GPU the rounds are 3-6 us faster (dlogits tiles shared in L2 by the
+  // pairs that run the same geocell block at the same time).
+  GG_CHECK(schedule == GG_BWD_SCHEDULE_AUTO || schedule == GG_BWD_ROUNDS || schedule == GG_BWD_STREAMK, GG_ERR_ARG,
+           "gg_head_bwd: flags=%d", schedule);
+  const int all_streamk = schedule == GG_BWD_SCHEDULE_AUTO ? (push ? 1 : 0) : (schedule == GG_BWD_STREAMK ? 1 : 0);
   // cluster shape (2,1,1) is compiled into the kernel
   head_bwd_kernel<<<2 * pairs, kBwdThreads, smem, s>>>(tm_g, tm_x, tm_dw, maps, sig, C, D, B, scale, grad_scale, parked,
                                                        flags, db_fused && !push ? db : nullptr, db_partials, db_parts, db_ld,
-                                                       db_tmp, g_bwd_timeline);
+                                                       db_tmp, g_bwd_timeline, all_streamk);
   GG_LAUNCH_CHECK();
   if (db && !db_fused && !push)
     if (int e = db_from_dlogits(db)) return e;

@@ -149,7 +149,7 @@ nvls_allreduce_avg_kernel(float4* __restrict__ mc, size_t lo, size_t hi, float i
 //   [2049]        exit ticket, [2050] epoch (local)
 constexpr int kCtrlReady = 1024, kCtrlDone = 2048, kCtrlExit = 2049, kCtrlEpoch = 2050;
 constexpr int kGradBlockRows = 128;
-constexpr int kGradParts = 8;      // CTAs that share one block
+constexpr int kGradMaxParts = 16;  // CTAs that share one block: chosen per launch (grad_parts) so that one wave covers all units
 constexpr int kGradThreads = 256;
 
 struct GradPeers {
@@ -352,7 +352,8 @@ template <int WORLD, bool NVLS, bool ADAMW>
 __global__ void __launch_bounds__(kGradThreads)
 grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict__ mc_grad,
                      unsigned int* __restrict__ mc_ctrl, const float4* __restrict__ stage, int rank, int C, int D,
-                     int nblk, int own_max, float inv_world, int no_wait, const __grid_constant__ AdamwArgs aw) {
+                     int nblk, int own_max, float inv_world, int no_wait, int parts,
+                     const __grid_constant__ AdamwArgs aw) {
   unsigned int* const ctrl = peers.ctrl[rank];
   __shared__ unsigned int s_epoch;
   __shared__ AdamwStep s_h;
@@ -376,23 +377,25 @@ grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict
   const size_t db4 = static_cast<size_t>(C) * row4;                     // float4 offset of db in the gradient buffer
   const size_t rows = static_cast<size_t>(own_max) * kGradBlockRows;    // staged rows per slab
   const size_t slab4 = rows * (static_cast<size_t>(D) + 1) / 4;         // float4 per slab (dW rows, then db entries)
-  for (int u = blockIdx.x; u < own * kGradParts; u += gridDim.x) {
-    const int j = u / kGradParts, part = u % kGradParts;
+  for (int u = blockIdx.x; u < own * parts; u += gridDim.x) {
+    const int j = u / parts, part = u % parts;
     const int b = rank + j * WORLD;
-    if (threadIdx.x == 0) spin_until(ctrl + kCtrlReady + b, epoch * static_cast<unsigned int>(WORLD), "block", rank, b);
+    // every rank's gg_head_bwd adds one per column tile (256 embedding columns) of the block it has delivered
+    if (threadIdx.x == 0)
+      spin_until(ctrl + kCtrlReady + b, epoch * static_cast<unsigned int>(WORLD * ((D + 255) / 256)), "block", rank, b);
     __syncthreads();
     const int r0 = b * kGradBlockRows, r1 = min(C, r0 + kGradBlockRows);
     const size_t n4 = static_cast<size_t>(r1 - r0) * row4;
     if (ADAMW) {
       const size_t n8 = n4 / 2;  // D is a multiple of 8 in this mode
-      const size_t lo = n8 * part / kGradParts, hi = n8 * (part + 1) / kGradParts;
+      const size_t lo = n8 * part / parts, hi = n8 * (part + 1) / parts;
       adamw_range<WORLD, NVLS>(aw, h, stage, slab4, static_cast<size_t>(j) * kGradBlockRows * (row4 / 2) + lo,
                                static_cast<size_t>(r0) * (row4 / 2) + lo, hi - lo, inv_world);
       if (part == 0)
         adamw_bias<WORLD, NVLS>(aw, h, stage, slab4, rows * row4 + static_cast<size_t>(j) * (kGradBlockRows / 4), r0, C,
                                 inv_world);
     } else {
-      const size_t lo = n4 * part / kGradParts, hi = n4 * (part + 1) / kGradParts;
+      const size_t lo = n4 * part / parts, hi = n4 * (part + 1) / parts;
       reduce_range<WORLD, NVLS>(peers, mc_grad, stage, slab4, static_cast<size_t>(j) * kGradBlockRows * row4 + lo,
                                 static_cast<size_t>(r0) * row4 + lo, hi - lo, inv_world);
       if (part == 0)  // the block's db entries (128 floats; the last block's ragged end runs into the pad)
@@ -413,7 +416,7 @@ grad_exchange_kernel(const __grid_constant__ GradPeers peers, float4* __restrict
   // every unit of every reducer has landed in this rank's copy
   if (threadIdx.x == 0) {
     if (!no_wait)
-      spin_until(ctrl + kCtrlDone, epoch * static_cast<unsigned int>(nblk * kGradParts), "landed units", rank, -1);
+      spin_until(ctrl + kCtrlDone, epoch * static_cast<unsigned int>(nblk * parts), "landed units", rank, -1);
     __threadfence_system();
     if (atomicAdd(ctrl + kCtrlExit, 1u) == gridDim.x - 1) {  // last CTA out: next launch's epoch
       ctrl[kCtrlExit] = 0u;
@@ -485,6 +488,15 @@ extern "C" int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, s
   return GG_OK;
 }
 
+// CTAs per block: as many as keep every unit of the rank with the most blocks in ONE wave of resident CTAs (a second,
+// partly filled wave doubled the kernel's time at 2 ranks: 400 units on 296 CTAs).  Every rank must arrive at the same
+// number (the `done` counter counts units of all ranks): it depends on the problem, the world size and the
+// instance's occupancy only.
+static int grad_parts(int nblk, int world, int resident) {
+  const int own_max = (nblk + world - 1) / world;
+  return std::max(1, std::min(kGradMaxParts, resident / std::max(1, own_max)));
+}
+
 extern "C" size_t gg_grad_ctrl_bytes(void) { return GG_GRAD_CTRL_BYTES; }
 
 extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsigned long long* ctrl_ptrs, void* grad_mc,
@@ -510,7 +522,9 @@ extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsig
   const int own = nblk > rank ? (nblk - rank + world - 1) / world : 0;
   const int own_max = (nblk + world - 1) / world;
   // every CTA must be resident (each waits for units other CTAs of this grid deliver): <= 2 per SM
-  const int grid = std::max(1, std::min(2 * device_sm_count(), own * kGradParts));
+  const int resident = 2 * device_sm_count();  // (<= 128 registers in every instance of the plain exchange)
+  const int parts = grad_parts(nblk, world, resident);
+  const int grid = std::max(1, std::min(resident, own * parts));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float inv = 1.0f / static_cast<float>(world);
   float4* mg = static_cast<float4*>(grad_mc);
@@ -519,8 +533,8 @@ extern "C" int gg_grad_exchange(const unsigned long long* grad_ptrs, const unsig
   const int nw = (flags & GG_GRAD_NO_WAIT) ? 1 : 0;
 #define GG_GX(W)                                                                                                   \
   do {                                                                                                             \
-    if (mg) grad_exchange_kernel<W, true, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw, AdamwArgs{});  \
-    else grad_exchange_kernel<W, false, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw, AdamwArgs{});    \
+    if (mg) grad_exchange_kernel<W, true, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw, parts, AdamwArgs{});  \
+    else grad_exchange_kernel<W, false, false><<<grid, kGradThreads, 0, s>>>(peers, mg, mcc, st, rank, C, D, nblk, own_max, inv, nw, parts, AdamwArgs{});    \
   } while (0)
   if (world == 2) GG_GX(2);
   else if (world == 4) GG_GX(4);
@@ -577,8 +591,10 @@ extern "C" int gg_grad_exchange_adamw(const unsigned long long* w16_ptrs, const 
     auto kern = grad_exchange_kernel<W, NV, true>;                                                                 \
     int per_sm = 0;                                                                                                \
     GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGradThreads, 0));                        \
-    const int g = std::max(1, std::min(std::max(1, per_sm) * device_sm_count(), own * kGradParts));                \
-    kern<<<g, kGradThreads, 0, s>>>(peers, nullptr, mcc, st, rank, C, D, nblk, own_max, inv, nw, aw);              \
+    const int resident = std::max(1, per_sm) * device_sm_count();                                                  \
+    const int parts = grad_parts(nblk, world, resident);                                                           \
+    const int g = std::max(1, std::min(resident, own * parts));                                                    \
+    kern<<<g, kGradThreads, 0, s>>>(peers, nullptr, mcc, st, rank, C, D, nblk, own_max, inv, nw, parts, aw);       \
   } while (0)
 #define GG_GXA(W)                                                                                                  \
   do {                                                                                                             \

@@ -123,6 +123,22 @@ __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// all but the newest n (0..9, run-time) bulk groups of this thread are complete
+__device__ __forceinline__ void tma_store_wait_all_but(int n) {
+  switch (n) {
+    case 0: tma_store_wait_all<0>(); break;
+    case 1: tma_store_wait_all<1>(); break;
+    case 2: tma_store_wait_all<2>(); break;
+    case 3: tma_store_wait_all<3>(); break;
+    case 4: tma_store_wait_all<4>(); break;
+    case 5: tma_store_wait_all<5>(); break;
+    case 6: tma_store_wait_all<6>(); break;
+    case 7: tma_store_wait_all<7>(); break;
+    case 8: tma_store_wait_all<8>(); break;
+    default: tma_store_wait_all<9>(); break;
+  }
+}
+
 // ------------------------------------------------------------------ clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

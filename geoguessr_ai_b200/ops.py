@@ -349,8 +349,11 @@ def loss_mean(loss_rows: torch.Tensor, scale: float | None = None) -> torch.Tens
     return out
 
 
+BWD_SCHEDULES = {None: 0, "auto": 0, "rounds": 1, "streamk": 2}  # GG_BWD_SCHEDULE_AUTO / GG_BWD_ROUNDS / GG_BWD_STREAMK
+
+
 def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_partials=None, c_range=None, out=None,
-                  push=None):
+                  push=None, schedule=None):
     """dW (C,D) fp32 = scale * grad_scale * dlogits^T x[:, :D]; db (C) (from the loss kernel's column-sum
     partials when given, else from a pass over dlogits).
 
@@ -358,7 +361,9 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_p
     the NCCL data-parallel path runs the GEMM range by range and all-reduces each range while the next one runs.
     push=(blk_count_ptr, [ready_ptr of rank 0, 1, ...], [staging region of rank 0, 1, ...], rank): data-parallel
     mode -- every tile goes straight into its reducer's staging slab (gg_grad_exchange follows on the same stream),
-    nothing is written to ``out``; whole range only.  Returns (None, None) then."""
+    nothing is written to ``out``; whole range only.  Returns (None, None) then.
+    schedule: "rounds" / "streamk" / None = auto (stream-K ranges in push mode, whole rounds + a stream-K tail else);
+    the two add the same products in different orders (equal to fp32 rounding, bit-equal under the same schedule)."""
     dev = _need_cuda(dlogits, x16, grad_scale)
     B, ldc = dlogits.shape
     dev = dlogits.device
@@ -391,7 +396,8 @@ def head_backward(dlogits, x16, C, D, scale, grad_scale=None, want_db=True, db_p
           _ptr(grad_scale), 0 if dW is None else _ptr(dW) + c0 * D * 4, 0 if db is None else _ptr(db) + c0 * 4,
           0 if db_partials is None else _ptr(db_partials) + c0 * 4, 0 if db_partials is None else db_partials.shape[0],
           0 if db_partials is None else db_partials.shape[1], _ptr(ws),
-          0 if dp_arr is None else ctypes.cast(dp_arr, ctypes.c_void_p), dp_world, int(dp_rank), _stream(dev))
+          0 if dp_arr is None else ctypes.cast(dp_arr, ctypes.c_void_p), dp_world, int(dp_rank), BWD_SCHEDULES[schedule],
+          _stream(dev))
     return dW, db
 
 

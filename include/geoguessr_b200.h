@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 3
+#define GG_ABI_VERSION 4
 
 #define GG_OK 0
 #define GG_ERR_ARG 1         /* bad shape / alignment / null pointer */
@@ -101,6 +101,10 @@ void gg_debug_head_fwd_timeline(long long* device_buf);
  * number of segments, end of the wait for a parked partial; per segment (tile or part of a tail tile) accumulator
  * complete / epilogue done / last MMA issued. */
 void gg_debug_head_bwd_timeline(long long* device_buf);
+/* Hardware probe (tools/symm_probe.py), not part of the path: stores `bytes` to dst -- e.g. a peer's symmetric-memory
+ * mapping -- from `ctas` CTAs, mode 0 = coalesced 16-byte st.global, mode 1 = cp.async.bulk (TMA, 1-D) of `chunk` bytes
+ * per instruction from shared memory. */
+int gg_debug_nvlink_store_probe(void* dst, size_t bytes, int mode, int chunk, int ctas, gg_stream_t stream);
 
 /* ---- a5-a8: haversine label-smoothed cross-entropy, forward + gradient ---------------------
  * models/utils.py:39-57 haversine_matrix; :20-32 smooth_labels (tau = config.py:52 = 65 km);
@@ -153,10 +157,19 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * into the staging slab of the rank that reduces the block (block b -> rank b % dp_world), over NVLink for the other
  * ranks, and complete blocks are announced on that rank's `ready` counters.  dp_ptrs: HOST array of 1 + 2 * dp_world
  * device addresses as mapped on this device = {this rank's control region + GG_GRAD_CTRL_BLKCOUNT_OFF, control region +
- * GG_GRAD_CTRL_READY_OFF of rank 0, 1, ..., staging region of rank 0, 1, ...}.  dp_ptrs null: plain local dW / db. */
+ * GG_GRAD_CTRL_READY_OFF of rank 0, 1, ..., staging region of rank 0, 1, ...}.  dp_ptrs null: plain local dW / db.
+ * flags: GG_BWD_SCHEDULE_AUTO (0), or which work split to use -- GG_BWD_ROUNDS: whole rounds of tiles + a stream-K tail
+ * round (fastest on one GPU), GG_BWD_STREAMK: one contiguous range of (tile, k-block) units per CTA pair, so that tiles
+ * complete -- and, in push mode, leave over NVLink -- evenly over the launch (auto picks it when dp_ptrs is given).
+ * The two splits add the same products in different orders: results agree to fp32 rounding, and bit for bit only
+ * under the same split. */
+#define GG_BWD_SCHEDULE_AUTO 0
+#define GG_BWD_ROUNDS 1
+#define GG_BWD_STREAMK 2
 int gg_head_bwd(const void* dlogits_bf16, int ldc, const void* x_bf16, int x_ld, int B, int C, int D, float scale,
                 const float* grad_scale, float* dW, float* db, const float* db_partials, int db_parts, int db_ld,
-                void* workspace, const unsigned long long* dp_ptrs, int dp_world, int dp_rank, gg_stream_t stream);
+                void* workspace, const unsigned long long* dp_ptrs, int dp_world, int dp_rank, int flags,
+                gg_stream_t stream);
 
 /* dx of the same layer (autograd of super_guessr.py:354 w.r.t. its input; reached from
  * main_coordinator_idun_s3.py:423 whenever the encoder is trained -- TinyViT's last stage / CLIP's last layer,

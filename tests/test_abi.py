@@ -63,7 +63,7 @@ def test_every_launcher_has_a_python_caller():
     for name in os.listdir(pkg):
         if name.endswith(".py") and name != "_lib.py":
             text += open(os.path.join(pkg, name)).read()
-    for tool in ("head_fwd_timeline.py", "head_bwd_timeline.py"):
+    for tool in ("head_fwd_timeline.py", "head_bwd_timeline.py", "symm_probe.py"):
         text += open(os.path.join(REPO, "tools", tool)).read()
     missing = [s for s in _lib.SIGNATURES if s not in text and s not in ("gg_abi_version", "gg_last_error")]
     assert not missing, f"no Python caller for {missing}"

@@ -70,7 +70,7 @@ def test_fused_exchange_single_device_emulation(world, Cc, D, B):
             xs.append(x)
             dls.append(dl)
             dbps.append(dbp)
-            dW, db = ops.head_backward(dl, x, Cc, D, scale=0.5, db_partials=dbp)
+            dW, db = ops.head_backward(dl, x, Cc, D, scale=0.5, db_partials=dbp, schedule="streamk")  # the push mode's split
             want_w = dW if want_w is None else want_w + dW  # rank order, fp32
             want_b = db if want_b is None else want_b + db
         want_w, want_b = want_w * (1.0 / world), want_b * (1.0 / world)
@@ -143,7 +143,7 @@ def test_exchange_with_sharded_adamw_single_device_emulation(world, Cc, D, B):
             dl = dl.to(dev)
             dbp = torch.randn(3, ldc, generator=g).to(dev) if step == 0 else None
             xs.append(x); dls.append(dl); dbps.append(dbp)
-            dW, db = ops.head_backward(dl, x, Cc, D, scale=0.5, db_partials=dbp)
+            dW, db = ops.head_backward(dl, x, Cc, D, scale=0.5, db_partials=dbp, schedule="streamk")  # the push mode's split
             gw = dW if gw is None else gw + dW
             gb = db if gb is None else gb + db
         gw, gb = gw * (1.0 / world), gb * (1.0 / world)

@@ -63,8 +63,19 @@ def reduce_pair():
 
 
 t_plain = timed(plain)
-t_push = timed(push_pair, iters=1) if False else None
-print(f"gg_head_bwd alone                               {t_plain:8.1f} us")
+print(f"gg_head_bwd alone (rounds + stream-K tail)      {t_plain:8.1f} us")
+t_sk = timed(lambda: ops.head_backward(dl, x, C, D, 1.0 / B, out=views[0], schedule="streamk"))
+print(f"gg_head_bwd alone (stream-K ranges)             {t_sk:8.1f} us")
+
+
+def push_one():  # rank 0's GEMM in push mode; every slab is local memory here: the cost of the push code itself
+    ops.head_backward(dl, x, C, D, 1.0 / B, push=(ctrl[0], ready, stage, 0))
+    for b in bufs:  # (the counters only make sense with both ranks pushing: reset what one push leaves behind)
+        b[:ctrl_words].zero_()
+
+
+t_push1 = timed(push_one)
+print(f"gg_head_bwd in push mode, slabs local (+ reset)  {t_push1:8.1f} us")
 
 
 def both():

@@ -62,6 +62,33 @@ try:
     if rank == 0:
         print(f"{half * 4 / 1e6:.1f} MB to the peer: copy engine push {t_dma:.1f} us = {half * 4 / t_dma / 1e3:.0f} GB/s, "
               f"pull {t_dma_in:.1f} us = {half * 4 / t_dma_in / 1e3:.0f} GB/s", flush=True)
+    # the same bytes stored by the SMs, by the form of the store (gg_debug_nvlink_store_probe): every rank stores into
+    # its neighbour at once, as the fused gradient exchange does
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from geoguessr_ai_b200 import _lib  # noqa: E402
+
+    lib = _lib.load()
+    nbytes = half * 4 // (1 << 16) * (1 << 16)
+    dst = int(h.buffer_ptrs[peer])
+    stream = torch.cuda.current_stream().cuda_stream
+    for mode, chunk, ctas in ((0, 0, 148), (0, 0, 592), (1, 4096, 148), (1, 32768, 148), (2, 0, 148), (2, 0, 296)):
+        def store():
+            rc = lib.gg_debug_nvlink_store_probe(dst, nbytes, mode, chunk, ctas, stream)
+            assert rc == 0, lib.gg_last_error().decode()
+        t_s = timeit(store)
+        dist.barrier()
+        if rank == 0:
+            what = ("coalesced 16-byte st.global" if mode == 0 else f"cp.async.bulk, {chunk} B per instruction" if mode == 1
+                    else "cp.async.bulk.tensor 2-D, 32 x 32 fp32 boxes of a (rows, 1024) matrix")
+            print(f"{nbytes / 1e6:.1f} MB to the peer by SM stores ({what}, {ctas} CTAs): {t_s:.1f} us = "
+                  f"{nbytes / t_s / 1e3:.0f} GB/s", flush=True)
+    local = torch.empty(n, dtype=torch.float32, device=dev)
+    for mode, chunk, ctas in ((0, 0, 592), (1, 32768, 148), (2, 0, 148)):
+        def store_local():
+            lib.gg_debug_nvlink_store_probe(local.data_ptr(), nbytes, mode, chunk, ctas, stream)
+        t_s = timeit(store_local)
+        if rank == 0:
+            print(f"  (same kernel into local HBM, mode {mode}: {t_s:.1f} us = {nbytes / t_s / 1e3:.0f} GB/s)", flush=True)
 except Exception as e:  # noqa: BLE001
     if rank == 0:
         print("symmetric memory probe failed:", type(e).__name__, str(e)[:500], flush=True)

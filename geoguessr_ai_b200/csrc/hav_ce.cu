@@ -729,12 +729,16 @@ hav_ce_stream_kernel(const __grid_constant__ CUtensorMap tm_logits, int ldc, con
   // ---- (C) folded in: whichever strip CTA of this row block finishes last turns the rows' accumulators into
   // loss_b = lse_b - sum_c t*l, and whichever row block finishes last sums the row-block partials in block
   // order: deterministic, and no second launch.
-  __threadfence();  // my row_acc adds are performed device-wide before this CTA takes its ticket
   __syncwarp();
   named_bar_sync(1, nactive * 32);  // the warps that own a slice (idle warps of the last strip have returned)
   if (warp != 0) return;
   unsigned int ticket = 0;
-  if (lane == 0) ticket = atomicAdd(counters + 1 + rb, 1u);
+  if (lane == 0) {
+    // the CTA's row_acc adds are performed device-wide before it takes its ticket: ONE fence, cumulative through the
+    // barrier (a membar in each of the 128 threads stalled the memory pipeline the SM's other three CTAs stream through)
+    __threadfence();
+    ticket = atomicAdd(counters + 1 + rb, 1u);
+  }
   ticket = __shfl_sync(0xffffffffu, ticket, 0);
   if (ticket != static_cast<unsigned int>(nstrips - 1)) return;
   __threadfence();

@@ -428,10 +428,12 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tm_g,   // dlogits: inner C,
             db[row] = v;
           }
         }
-        if (park) {  // publish: every epilogue thread's stores, then the flag
-          __threadfence();
+        if (park) {  // publish: every epilogue thread's stores (one fence, cumulative through the barrier), then the flag
           named_bar_sync(1, 128);
-          if (threadIdx.x == 64) atomicExch(&flags[pair * 2 + crank], 1);
+          if (threadIdx.x == 64) {
+            __threadfence();
+            atomicExch(&flags[pair * 2 + crank], 1);
+          }
         } else if (push && m0 < C) {
           // this CTA's 128 geocells x 256 columns of dW (and, with the first column tile, the block's db rows) are
           // on their way to the reducer.  Counting a tile needs its bulk stores PERFORMED (acknowledged by the reducer's memory), which under a busy

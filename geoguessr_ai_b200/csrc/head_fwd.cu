@@ -666,19 +666,23 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
         // Ticket of row block (mb, crank): one per contributing CTA.  Whoever draws the last one finds every
         // partial of these 128 rows in L2 and merges them (the other CTAs go on with their next run).
-        __threadfence();
-        named_bar_sync(kEpiBarrier, 32 * kEpiWarps);  // all 16 epilogue warps have flushed (and fenced)
+        // all 16 epilogue warps have flushed; ONE fence then publishes their stores (cumulative through the barrier)
+        // before the ticket is drawn -- 512 membars per flush stalled the SM's memory pipeline for nothing
+        named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
         if (threadIdx.x == 64) {
+          __threadfence();
           const int contrib = sc.owner((mb + 1) * sc.num_n - 1) - sc.owner(mb * sc.num_n) + 1;
           const unsigned int old = atomicAdd(&tickets[2 * mb + crank], 1u);
           const bool last = old + 1u == static_cast<unsigned int>(contrib);
-          if (last) tickets[2 * mb + crank] = 0u;  // left zeroed for the next launch
+          if (last) {
+            tickets[2 * mb + crank] = 0u;  // left zeroed for the next launch
+            __threadfence();               // (acquire side, once: the merge below reads the partials with ld.cg)
+          }
           sm.is_last = last ? 1u : 0u;
         }
         named_bar_sync(kEpiBarrier, 32 * kEpiWarps);
         if (threadIdx.x == 64 && t == t_end - 1) stamp(timeline, 8);  // flushed, ticket drawn
         if (sm.is_last != 0u) {
-          __threadfence();
           merge_block<KTOP, HAS_CEIL>(pmax, psum, pkeys, sc, mb, crank, M, out, timeline);
           if (threadIdx.x == 64) stamp(timeline, 9);  // merged a row block (last one wins)
         }

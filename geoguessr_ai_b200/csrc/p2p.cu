@@ -130,7 +130,7 @@ nvls_allreduce_avg_kernel(float4* __restrict__ mc, size_t lo, size_t hi, float i
 // GEMM between two host-issued barriers and move the whole buffer then.  Here dW is cut into blocks of 128 geocells
 // (+ the block's 128 db entries); block b is reduced by rank b % world, and the GEMM's epilogue stores every tile
 // straight into the reducer's staging slab for its source rank (posted stores over NVLink, tile by tile under the
-// GEMM; see head_bwd.cu) and announces complete blocks on the reducer's `ready` counters.  What is left for after
+// GEMM; see head_bwd.cu) and counts every delivered tile on the reducer's `ready` counter of the block.  What is left for after
 // the GEMM is this kernel: per owned block wait for the last announcements, add the `world` staged copies in rank
 // order from LOCAL memory (deterministic, identical everywhere), scale, and write the average into every rank's
 // gradient buffer -- multimem.st through the NVSwitch when the multicast mapping is given, else posted peer stores
@@ -143,8 +143,8 @@ nvls_allreduce_avg_kernel(float4* __restrict__ mc, size_t lo, size_t hi, float i
 // pipeline -- and is gone.)
 //
 // Control region (symmetric memory, GG_GRAD_CTRL_BYTES per rank, zeroed once): u32 words
-//   [0, 1024)     blk_count  pushed column tiles per block (gg_head_bwd, local, self-resetting)
-//   [1024, 2048)  ready      announcements per block (remote adds by every rank's gg_head_bwd)
+//   [0, 1024)     (reserved)
+//   [1024, 2048)  ready      delivered column tiles per block (remote adds by every rank's gg_head_bwd: ceil(D / 256) per rank)
 //   [2048]        done       exchanged units landed in this rank's copy (remote adds by the reducers)
 //   [2049]        exit ticket, [2050] epoch (local)
 constexpr int kCtrlReady = 1024, kCtrlDone = 2048, kCtrlExit = 2049, kCtrlEpoch = 2050;

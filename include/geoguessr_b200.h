@@ -155,8 +155,9 @@ int gg_loss_mean(const float* loss_rows, int B, float scale, float* loss_out, gg
  * Data parallelism (gg_grad_exchange below): with dp_ptrs given (dp_world >= 1) the kernel does not write dW / db at all (both may be
  * null): every finished tile of 128 geocells x 256 columns -- and the block's 128 db entries -- is stored straight
  * into the staging slab of the rank that reduces the block (block b -> rank b % dp_world), over NVLink for the other
- * ranks, and complete blocks are announced on that rank's `ready` counters.  dp_ptrs: HOST array of 1 + 2 * dp_world
- * device addresses as mapped on this device = {this rank's control region + GG_GRAD_CTRL_BLKCOUNT_OFF, control region +
+ * ranks, and every delivered tile is counted on that rank's `ready` counter of the block (one relaxed add per tile and
+ * CTA, issued after the tile's bulk stores have completed -- that completion is the ordering: no fence instruction).  dp_ptrs: HOST array of 1 + 2 * dp_world
+ * device addresses as mapped on this device = {this rank's control region + GG_GRAD_CTRL_BLKCOUNT_OFF (reserved, unused), control region +
  * GG_GRAD_CTRL_READY_OFF of rank 0, 1, ..., staging region of rank 0, 1, ...}.  dp_ptrs null: plain local dW / db.
  * flags: GG_BWD_SCHEDULE_AUTO (0), or which work split to use -- GG_BWD_ROUNDS: whole rounds of tiles + a stream-K tail
  * round (fastest on one GPU), GG_BWD_STREAMK: one contiguous range of (tile, k-block) units per CTA pair, so that tiles
@@ -278,9 +279,9 @@ int gg_nvls_allreduce_avg(void* multicast_ptr, int world, int rank, size_t n_flo
  * control region of GG_GRAD_CTRL_BYTES (zeroed once, before the first step), its gradient buffer [dW (C,D) | db (C) |
  * pad to a multiple of 4 floats] and a staging region of gg_grad_stage_floats(C, D, world) floats: `world` slabs (one
  * per source rank), each = the dW rows of the blocks this rank reduces (block b of 128 geocells -> rank b % world)
- * followed by their db entries.  gg_head_bwd (dp_ptrs given) pushes every tile into the reducer's slab and announces
- * complete blocks; gg_grad_exchange, launched AFTER it on the same stream, waits per owned block for all ranks'
- * announcements, adds the staged copies in rank order (deterministic, identical on all ranks), scales by 1 / world and
+ * followed by their db entries.  gg_head_bwd (dp_ptrs given) pushes every tile into the reducer's slab and counts it
+ * on the block's `ready` counter there (ceil(D / 256) column tiles per rank make a block complete); gg_grad_exchange,
+ * launched AFTER it on the same stream, waits per owned block for all ranks' tiles, adds the staged copies in rank order (deterministic, identical on all ranks), scales by 1 / world and
  * writes the average into every rank's gradient buffer -- multimem.st through the NVSwitch when the multicast
  * addresses are given, else posted peer stores -- and returns when every block of every reducer has landed in this
  * rank's gradient.  grad_ptrs / ctrl_ptrs: HOST arrays of `world` device addresses (rank order, as mapped on this

@@ -1,3 +1,6 @@
+#!/bin/bash
+# Multi-GPU pass (under `gpurun --gpus N`): bash tools/scale_check.sh N [check]
+#   check: tests/test_dp_gpu.py, tools/p2p_check.py and tools/symm_probe.py first; then the default bench line on N GPUs
 N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 if [ "$2" = "check" ]; then

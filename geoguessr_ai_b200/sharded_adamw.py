@@ -141,10 +141,16 @@ class ShardedAdamW(torch.optim.Optimizer):
         for p in (self.module.cell_layer.weight, self.module.cell_layer.bias):
             p.grad = None
 
+    @staticmethod
+    def owned_mask(C: int, world: int, rank: int, device=None):
+        """Boolean (C,) mask of the geocell rows rank `rank` of `world` reduces and updates: blocks of 128 geocells,
+        block b belongs to rank b % world (the rule gg_head_bwd's push mode and gg_grad_exchange_adamw share)."""
+        rows = torch.arange(C, device=device)
+        return (rows // _BLOCK) % world == rank
+
     def owned_rows(self):
         """Boolean (C,) mask of the geocell rows whose master weights / moments this rank keeps current."""
-        rows = torch.arange(self.C, device=self.hyper.device)
-        return (rows // _BLOCK) % self.world == self.rank
+        return self.owned_mask(self.C, self.world, self.rank, self.hyper.device)
 
     @torch.no_grad()
     def gather_master(self):

@@ -320,3 +320,30 @@ def test_gradient_transport_is_decided_before_any_kernel_runs():
     assert T("auto", 2, False) == "nccl"  # CPU / gloo groups
     assert T("auto", 2, True, torch.bfloat16) == "nccl"  # rounded communication is an NCCL option
     assert T("nccl", 8, True) == "nccl"
+
+
+def test_sharded_adamw_ownership_partitions_the_geocells():
+    """Every geocell row is owned by exactly one rank, in blocks of 128 dealt round-robin (the rule the push epilogue
+    and the exchange kernel share); and the optimizer refuses a CPU model loudly (no CPU path)."""
+    import torch
+
+    from geoguessr_ai_b200.sharded_adamw import ShardedAdamW
+
+    for C in (1, 127, 128, 129, 12647):
+        for world in (1, 2, 4, 8):
+            masks = torch.stack([ShardedAdamW.owned_mask(C, world, r) for r in range(world)])
+            assert torch.all(masks.sum(0) == 1)
+            for r in range(world):
+                rows = torch.nonzero(masks[r]).flatten()
+                assert torch.all((rows // 128) % world == r)
+    import contextlib
+    import io
+
+    import geoguessr_ai_b200 as gg
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = gg.SuperGuessr(None, panorama=True, embed_dim=64)
+    import pytest
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.sharded_adamw(lr=1e-3)

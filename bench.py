@@ -546,7 +546,7 @@ def run_b200_train(args, ctx, brief=False, dp_optimizer=None):
     roof = dominant_roofline(kernels, peaks)
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # (the contract: the CPU baseline is timed on rank 0 at N = 1 only)
         cval, cms, cores = cpu_reference_train(2, 1, B, D, V)
         cpu = {"value": cval, "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": cms,
                "sample": f"2 full steps of batch {B} after 1 warm-up (oracle: eager CPU PyTorch restatement of the "
@@ -834,7 +834,7 @@ def run_b200_infer(args, ctx, P, B, K):
         # (the committed capture is the 1 M-prototype run on one GPU: no traffic figure for other shapes)
         roof = dominant_roofline(kernels, peaks, extra, "infer:" if (P <= 1_000_000 and world == 1) else "none:")
         cpu = agree = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # (N = 1 only, as above)
             nq = 256
             cval, cores, (o_head, o_ref) = cpu_reference_infer(model.cell_layer.weight, model.cell_layer.bias, cent,
                                                                resident[0], refiner, nq)

@@ -115,9 +115,9 @@ struct PairSchedule {
 // block b is reduced by rank b % world.  In that mode this kernel does not write the gradient buffer at all: every
 // finished tile -- and, with the first column tile, the block's 128 db entries -- goes straight into the REDUCER's
 // staging slab for this source rank (posted TMA / plain stores over NVLink; the local slab for blocks this rank
-// reduces itself), and when all column tiles of a block have been pushed the block is announced with a system-scope
-// release add on the reducer's `ready` counter.  The transfer thus rides underneath the GEMM tile by tile, without
-// any other kernel sharing the SMs with it.
+// reduces itself), and every delivered tile is counted on the reducer's `ready` counter of the block with one relaxed
+// add, issued after the tile's bulk stores have completed.  The transfer thus rides underneath the GEMM tile by tile,
+// without any other kernel sharing the SMs with it and without a fence instruction in the epilogue.
 struct GradPush {
   unsigned int* blk_count;             // (unused since every tile is counted on the reducer's own counter)
   unsigned int* ready[kGradMaxWorld];  // every rank's `ready` counters (peer-mapped)
